@@ -1,0 +1,178 @@
+/*
+ * mclcar_b200 -- C ABI of the B200-native engine for the Monte Carlo likelihood
+ * hot path of the R package shazhe/mclcar.
+ *
+ * The reference is pure R (DESCRIPTION:16 "NeedsCompilation: no"): there is no
+ * existing FFI for this path.  The boundary is therefore the set of R functions
+ * listed in SURVEY.md section 8(b); every entry point below names the R function
+ * (file:line under /root/reference/mclcar_0.2-0/) whose body it replaces behind an
+ * unchanged R signature.  The `.Call` glue that binds these from R is in
+ * r/mclcar_b200_glue.c and documented in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no torch / R / C++ types; every function returns an int status
+ *    (MCLCAR_OK == 0) and never throws or longjmps; mclcar_last_error() gives the text.
+ *  - all host buffers are owned by the caller and are not retained past the call.
+ *  - "sigma" is the VARIANCE, as in the reference: Q = (I - rho W)/sigma (R/mcl.dCAR.R:175).
+ *  - a candidate parameter batch `psi` holds K candidates of P doubles each,
+ *    candidate-contiguous: psi[k*P + j].  Matrix outputs per candidate are P x P,
+ *    symmetric, stored densely: out[k*P*P + a*P + b].
+ *  - direct CAR: pars = (rho, sigma, beta[p]);   P == 2 (no regression) or 2 + p.
+ *    GLM:        pars = (rho, sigma, beta[p]),   P == 2 + p.
+ *    HCAR:       pars = (rho, lambda, sigma.e, sigma.u, beta[p]) or, when no
+ *                individual-level W was given, (lambda, sigma.e, sigma.u, beta[p]).
+ *  - entry points are not re-entrant per ctx; distinct ctx objects are independent.
+ *  - there is NO CPU fallback: compute entry points fail with MCLCAR_ENODEV on a
+ *    host-only context (device < 0) or when no CUDA device is usable.
+ */
+#ifndef MCLCAR_B200_H
+#define MCLCAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mclcar_ctx mclcar_ctx;
+typedef struct mclcar_samples mclcar_samples;
+
+/* ---- status codes ------------------------------------------------------------- */
+#define MCLCAR_OK 0
+#define MCLCAR_EINVAL 1     /* bad argument                                           */
+#define MCLCAR_ERHO 2       /* rho outside (1/min(ew), 1/max(ew)): R/CAR.simLM.R:9-11  */
+#define MCLCAR_ECUDA 3      /* CUDA runtime error                                     */
+#define MCLCAR_ENOMEM 4     /* device or host allocation failed                       */
+#define MCLCAR_ESTATE 5     /* graph / design / observation / psi0 not set yet        */
+#define MCLCAR_ENODEV 6     /* compute call on a host-only context                    */
+#define MCLCAR_ENCCL 7      /* NCCL could not be loaded or reported an error          */
+#define MCLCAR_ELIMIT 8     /* P, p or K beyond the compiled limits                   */
+
+/* ---- enums (plain ints at the ABI) -------------------------------------------- */
+/* memory layout of a sample matrix, in R terms */
+#define MCLCAR_COL_IS_SAMPLE 0 /* simY (n x N), u.y (K x N): each sample's sites contiguous  */
+#define MCLCAR_ROW_IS_SAMPLE 1 /* Zy (N x n): for each site the N samples are contiguous      */
+#define MCLCAR_F64 0
+#define MCLCAR_F32 1
+#define MCLCAR_FAMILY_DCAR 0
+#define MCLCAR_FAMILY_BINOM 1
+#define MCLCAR_FAMILY_POISSON 2
+#define MCLCAR_FAMILY_HCAR 3
+#define MCLCAR_SHIFT_MEAN 0 /* the reference's mean shift (R/mcl.dCAR.R:26-30)              */
+#define MCLCAR_SHIFT_MAX 1  /* max shift: same value where both are finite, cannot overflow */
+
+#define MCLCAR_MAX_P 12     /* largest parameter-vector length the reduction kernels take  */
+#define MCLCAR_MAX_COV 8    /* largest number of regression columns p                       */
+
+/* ---- context -------------------------------------------------------------------- */
+/* device >= 0: CUDA device ordinal.  device < 0: host-only context (graph / design /
+ * observation bookkeeping, tuple merge and finish stages work; compute calls fail with
+ * MCLCAR_ENODEV).  `seed` is the Philox key; in R the glue draws it from R's RNG so that
+ * set.seed() still makes runs reproducible. */
+int mclcar_ctx_create(int device, uint64_t seed, mclcar_ctx** out);
+void mclcar_ctx_destroy(mclcar_ctx* ctx);
+const char* mclcar_last_error(const mclcar_ctx* ctx); /* ctx may be NULL: last create error */
+/* run all work on the given cudaStream_t (NULL: the context's own stream) */
+int mclcar_ctx_set_stream(mclcar_ctx* ctx, void* cuda_stream);
+int mclcar_ctx_sync(mclcar_ctx* ctx);
+/* this context is shard `rank` of `world`: samplers draw global chains rank, rank+world,
+ * ... so that the union over ranks does not depend on `world`. */
+int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world);
+/* NCCL (dlopen'ed on first use, libnccl.so.2): rank 0 obtains a 128-byte unique id,
+ * hands it to the other ranks by any channel, then every rank calls comm_init.  Once
+ * initialised, every *_eval/_grad/_hess call all-gathers its partial tuples with ONE
+ * ncclAllGather per candidate batch and merges them in rank order on every rank. */
+int mclcar_nccl_unique_id(mclcar_ctx* ctx, unsigned char id_out[128]);
+int mclcar_nccl_comm_init(mclcar_ctx* ctx, const unsigned char id[128]);
+
+/* ---- model: graph, design, observations ------------------------------------------ */
+/* rook-neighbour n1 x n2 torus, site (i, j) at index i*n2 + j; equals the W built by
+ * CAR.simTorus (R/CAR.simLM.R:4-7) when n1 == n2.  Eigenvalues are analytic. */
+int mclcar_graph_torus(mclcar_ctx* ctx, int n1, int n2);
+/* general neighbourhood matrix W in CSR (0-based, symmetric, zero diagonal; val NULL =
+ * binary).  Replaces `data$W` (dense n x n in the reference).  Validated on upload. */
+int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val);
+/* eigenvalues of W (`data$lambda`, eigen(W) at R/mcl.bin.R:176): needed by the GLM
+ * gradient / Hessian and for the rho range check on CSR graphs.  Optional. */
+int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, int n);
+/* design matrix X = model.matrix(y ~ ., data.vec) / covX, n x p column-major; p may be 0 */
+int mclcar_set_design(mclcar_ctx* ctx, const double* X, int p);
+/* observed response y (n) and, for the binomial family, n.trial (n, or NULL) */
+int mclcar_set_obs(mclcar_ctx* ctx, const double* y, const double* ntrial);
+int mclcar_graph_n(const mclcar_ctx* ctx);
+int mclcar_graph_ncolors(const mclcar_ctx* ctx);
+
+/* ---- sample sets ------------------------------------------------------------------- */
+typedef struct mclcar_sampler_opts {
+    int64_t n_chains;  /* parallel chains on this context (0: chosen from N and memory)    */
+    int32_t burn;      /* sweeps discarded at the start of every chain (0: default)         */
+    int32_t thin;      /* sweeps between kept states (0: default)                            */
+    int32_t keep;      /* 1: keep the sample matrix in HBM; 0: keep sufficient statistics only */
+    int32_t dtype;     /* MCLCAR_F32 (default) or MCLCAR_F64 chain state and stored samples */
+    int32_t reserved[4];
+} mclcar_sampler_opts;
+
+/* the reference's own sample matrix (simY / Zy / u.y) copied to the device: parity path.
+ * `sites` is n for dCAR / GLM and K (districts) for HCAR. */
+int mclcar_samples_from_host(mclcar_ctx* ctx, const void* M, int dtype, int layout, int64_t sites,
+                             int64_t N, int64_t ld, mclcar_samples** out);
+/* same, for a matrix already resident in device memory (not copied, not owned) */
+int mclcar_samples_from_device(mclcar_ctx* ctx, const void* M_dev, int dtype, int layout, int64_t sites,
+                               int64_t N, int64_t ld, mclcar_samples** out);
+void mclcar_samples_free(mclcar_samples* s);
+int64_t mclcar_samples_count(const mclcar_samples* s);
+/* copy the sample matrix back as fp64 in the given layout (ld >= leading extent) */
+int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double* out, int64_t ld);
+/* sampler diagnostics: mean acceptance rate (1 for pure Gibbs) and sweeps actually run */
+int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate, int64_t* sweeps);
+
+/* ---- direct CAR (R/mcl.dCAR.R) --------------------------------------------------------- */
+/* per-sample sufficient statistics q_i = (Y'Y, Y'WY, X'Y[p], X'WY[p]) in one pass over the
+ * samples; replaces the per-sample dense products of logunnorm / D.log.unorm
+ * (R/mcl.dCAR.R:168-210).  q_out: N x (2+2p) column-major, may be NULL. */
+int mclcar_dcar_stats(mclcar_ctx* ctx, mclcar_samples* s, double* q_out);
+/* attach the importance point to a sample set built with samples_from_*: t20 NULL means
+ * "compute h(Y_i; psi0) from the statistics", otherwise the reference's own t20 (N). */
+int mclcar_dcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* t20);
+int mclcar_dcar_t10_t20(mclcar_ctx* ctx, mclcar_samples* s, double* t10, double* t20 /* N or NULL */);
+/* mcl.dCAR(pars, data, simdata, rho.cons, Evar=TRUE) for K candidates at once
+ * (R/mcl.dCAR.R:11-50; batch call sites R/rsmSub.R:78-95,110).  rho_cons NULL disables the
+ * guard (R: rho.cons = NULL), else candidates outside get (-1e8, 1e8).  A candidate k uses
+ * the sample subset subset_idx[subset_ptr[k] .. subset_ptr[k+1]) (0-based) when subset_ptr
+ * is not NULL and the range is non-empty -- the centre-point subsampling of
+ * R/rsmSub.R:81-86 -- else all samples.  var may be NULL (Evar = FALSE). */
+int mclcar_dcar_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, const double* rho_cons,
+                     const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* lr,
+                     double* var);
+/* mc.gradlik.dCAR(pars, data, simdata, Evar), R/mcl.dCAR.R:213-283; evar in {0, 1, 2};
+ * grad: K x P; gradvar: K x P x P or NULL. */
+int mclcar_dcar_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
+                     int shift_mode, double* grad, double* gradvar);
+/* mc.Hesslik.dCAR, R/mcl.dCAR.R:287-394; hess: K x P x P */
+int mclcar_dcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
+                     double* hess);
+/* MCMLE.var, R/mcl.dCAR.R:156-165 (un-normalised, un-shifted weights); out: K x P x P */
+int mclcar_dcar_mcmle_var(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, double* out);
+
+/* ---- staged evaluation (what the one-shot calls above are made of) ------------------------
+ * stage 1, device: per-candidate partial tuples of this context's samples, to host memory;
+ * stage 2, host only: merge the tuples of G shards in shard order (mclcar_tuples_merge);
+ * stage 3, host only: tuples -> the reference's outputs (mclcar_dcar_finish).
+ * `what`: 0 = lr/var, 1 = gradient (+ variance forms), 2 = Hessian.  A tuple is
+ * mclcar_tuple_len(what, F, d) doubles with F = P gradient features and d = 2 + 2p
+ * statistics for the direct CAR model (layouts: mclcar_b200/csrc/tuples.cu). */
+int64_t mclcar_tuple_len(int what, int F, int d);
+int mclcar_dcar_partial(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int what,
+                        const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* tuples);
+/* tuples_in: [G][K][T], tuples_out: [K][T] */
+int mclcar_tuples_merge(int what, int F, int d, int G, int K, const double* tuples_in, double* tuples_out);
+/* what = 0: out0 = lr[K], out1 = var[K] or NULL.  what = 1: out0 = grad[K*P], out1 =
+ * gradvar[K*P*P] or NULL with evar 1 | 2 as in mc.gradlik.dCAR, 3 = MCMLE.var.
+ * what = 2: out0 = hess[K*P*P].  Works on a host-only context. */
+int mclcar_dcar_finish(mclcar_ctx* ctx, const double* psi0, int P0, const double* psi, int K, int P, int what,
+                       int evar, const double* rho_cons, const double* tuples, double* out0, double* out1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCLCAR_B200_H */

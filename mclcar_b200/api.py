@@ -1,0 +1,285 @@
+"""Host-side mirror of the reference's R interface for the Monte Carlo likelihood hot path.
+
+Function names, argument meaning, defaults, return shapes and error behaviour follow the R
+functions of shazhe/mclcar (file:line under /root/reference/mclcar_0.2-0/) with dots turned
+into underscores; each body is argument unpacking plus one call into the C ABI
+(include/mclcar_b200.h), exactly what the `.Call` glue in r/ does.  R is not available in
+this image, so this module is what the parity tests drive.
+
+`data` objects: the reference passes a list(W, data.vec) (direct CAR) or
+list(y, covX, W, n.trial) (GLM).  Here `CarData` holds the same members plus the engine
+context that owns their device copies.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as L
+from ._lib import lib, check, dptr, i64ptr, iptr, MclcarError  # noqa: F401
+
+
+class Context:
+    """Owns a mclcar_ctx*."""
+
+    def __init__(self, device: int = 0, seed: int = 0):
+        h = C.c_void_p()
+        check(lib.mclcar_ctx_create(int(device), int(seed) & (2**64 - 1), C.byref(h)), None)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.mclcar_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr: int):
+        check(lib.mclcar_ctx_set_stream(self.h, C.c_void_p(stream_ptr)), self.h)
+
+    def sync(self):
+        check(lib.mclcar_ctx_sync(self.h), self.h)
+
+    def set_shard(self, rank: int, world: int):
+        check(lib.mclcar_ctx_set_shard(self.h, rank, world), self.h)
+
+
+@dataclass
+class CarData:
+    """The reference's `data` list plus the engine context holding its device copy."""
+    ctx: Context
+    n: int
+    X: Optional[np.ndarray]          # model.matrix(y ~ ., data.vec) / covX   (n x p)
+    y: np.ndarray
+    W: Optional[sp.csr_matrix] = None
+    torus: Optional[tuple] = None
+    n_trial: Optional[np.ndarray] = None
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def p(self) -> int:
+        return 0 if self.X is None else self.X.shape[1]
+
+
+def make_data(y, X=None, W=None, torus=None, n_trial=None, eigenvalues=None, device: int = 0, seed: int = 0,
+              ctx: Optional[Context] = None) -> CarData:
+    """Upload graph, design and observations.  Exactly one of `W` (symmetric scipy sparse /
+    dense, zero diagonal -- `data$W`) or `torus=(n1, n2)` (the W of CAR.simTorus,
+    R/CAR.simLM.R:4-7) must be given."""
+    ctx = ctx or Context(device, seed)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if (W is None) == (torus is None):
+        raise ValueError("give exactly one of W and torus")
+    if torus is not None:
+        check(lib.mclcar_graph_torus(ctx.h, int(torus[0]), int(torus[1])), ctx.h)
+        Wc = None
+    else:
+        Wc = sp.csr_matrix(W, dtype=np.float64)
+        Wc.sort_indices()
+        rp = np.ascontiguousarray(Wc.indptr, dtype=np.int32)
+        ci = np.ascontiguousarray(Wc.indices, dtype=np.int32)
+        vals = np.ascontiguousarray(Wc.data, dtype=np.float64)
+        check(lib.mclcar_graph_csr(ctx.h, Wc.shape[0], iptr(rp), iptr(ci), dptr(vals)), ctx.h)
+    n = lib.mclcar_graph_n(ctx.h)
+    if y.shape[0] != n:
+        raise ValueError(f"y has {y.shape[0]} entries, graph has {n} sites")
+    if eigenvalues is not None:
+        ew = np.ascontiguousarray(eigenvalues, dtype=np.float64).ravel()
+        check(lib.mclcar_graph_set_eigenvalues(ctx.h, dptr(ew), ew.size), ctx.h)
+    Xc = None
+    if X is not None:
+        X = np.asarray(X, dtype=np.float64)
+        if X.shape[0] != n:
+            raise ValueError("X has the wrong number of rows")
+        Xc = np.asfortranarray(X)  # column-major, as an R matrix
+        check(lib.mclcar_set_design(ctx.h, Xc.ctypes.data_as(C.POINTER(C.c_double)), X.shape[1]), ctx.h)
+    else:
+        check(lib.mclcar_set_design(ctx.h, None, 0), ctx.h)
+    nt = None
+    if n_trial is not None:
+        nt = np.ascontiguousarray(np.broadcast_to(np.asarray(n_trial, dtype=np.float64), (n,)))
+    check(lib.mclcar_set_obs(ctx.h, dptr(y), dptr(nt)), ctx.h)
+    return CarData(ctx=ctx, n=n, X=X, y=y, W=Wc, torus=tuple(torus) if torus is not None else None, n_trial=nt)
+
+
+class SimData:
+    """The reference's `simdata` = list(simY, t10, t20) (R/mcl.dCAR.R:7) as a device handle."""
+
+    def __init__(self, data: CarData, handle: C.c_void_p, psi):
+        self.data = data
+        self.h = handle
+        self.psi = np.asarray(psi, dtype=np.float64)
+
+    @property
+    def n_samples(self) -> int:
+        return int(lib.mclcar_samples_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.mclcar_samples_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # materialise the members of the R list on demand
+    @property
+    def simY(self) -> np.ndarray:
+        """n x N matrix, column = sample (R/mcl.dCAR.R:3)."""
+        N, n = self.n_samples, self.data.n
+        out = np.empty((N, n), dtype=np.float64)
+        check(lib.mclcar_samples_fetch(self.data.ctx.h, self.h, L.COL_IS_SAMPLE, dptr(out), n), self.data.ctx.h)
+        return out.T
+
+    @property
+    def t10(self) -> float:
+        v = C.c_double()
+        check(lib.mclcar_dcar_t10_t20(self.data.ctx.h, self.h, C.byref(v), None), self.data.ctx.h)
+        return v.value
+
+    @property
+    def t20(self) -> np.ndarray:
+        out = np.empty(self.n_samples, dtype=np.float64)
+        v = C.c_double()
+        check(lib.mclcar_dcar_t10_t20(self.data.ctx.h, self.h, C.byref(v), dptr(out)), self.data.ctx.h)
+        return out
+
+    def stats(self) -> np.ndarray:
+        """Per-sample sufficient statistics, N x (2+2p)."""
+        d = 2 + 2 * self.data.p
+        out = np.empty((d, self.n_samples), dtype=np.float64)
+        check(lib.mclcar_dcar_stats(self.data.ctx.h, self.h, dptr(out)), self.data.ctx.h)
+        return out.T
+
+
+def simdata_from_matrix(psi, data: CarData, simY, t20=None, dtype=np.float64) -> SimData:
+    """Wrap the reference's own `simY` (n x N, column = sample): the parity path.  `t20`
+    may be the reference's vector; None recomputes h(Y_i; psi) from the statistics."""
+    simY = np.asarray(simY)
+    if simY.shape[0] != data.n:
+        raise ValueError("simY must be n x N")
+    M = np.ascontiguousarray(simY.T, dtype=dtype)  # [sample][site] == column-major n x N
+    h = C.c_void_p()
+    ctx = data.ctx
+    check(lib.mclcar_samples_from_host(ctx.h, M.ctypes.data_as(C.c_void_p), L.F64 if dtype == np.float64 else L.F32,
+                                       L.COL_IS_SAMPLE, data.n, M.shape[0], data.n, C.byref(h)), ctx.h)
+    sd = SimData(data, h, psi)
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    t20c = None if t20 is None else np.ascontiguousarray(t20, dtype=np.float64)
+    check(lib.mclcar_dcar_attach(ctx.h, h, dptr(psi), psi.size, dptr(t20c)), ctx.h)
+    return sd
+
+
+def _subsets(subsets, K):
+    if subsets is None:
+        return None, None, None
+    ptr = np.zeros(K + 1, dtype=np.int64)
+    chunks = []
+    for k in range(K):
+        s = subsets[k]
+        ln = 0 if s is None else len(s)
+        ptr[k + 1] = ptr[k] + ln
+        if ln:
+            chunks.append(np.asarray(s, dtype=np.int64))
+    idx = np.concatenate(chunks) if chunks else np.zeros(1, dtype=np.int64)
+    return np.ascontiguousarray(idx), ptr, (idx, ptr)
+
+
+def mcl_dCAR_batch(psis, data: CarData, simdata: SimData, rho_cons=None, subsets=None, Evar=True,
+                   shift=L.SHIFT_MEAN) -> np.ndarray:
+    """The psi-batch evaluator behind Exp.dCAR / ExpPath.dCAR (R/rsmSub.R:78-95, 110):
+    row k = mcl.dCAR(psis[k], ..., Evar=TRUE) -> (K, 2), or (K,) when Evar is False.
+    `subsets[k]`: optional 0-based sample indices (centre points, R/rsmSub.R:81-86)."""
+    psis = np.ascontiguousarray(np.atleast_2d(psis), dtype=np.float64)
+    K, P = psis.shape
+    lr = np.empty(K)
+    var = np.empty(K) if Evar else None
+    rc = None if rho_cons is None else np.ascontiguousarray(rho_cons, dtype=np.float64)
+    idx, ptr, _keep = _subsets(subsets, K)
+    ctx = data.ctx
+    check(lib.mclcar_dcar_eval(ctx.h, simdata.h, dptr(psis), K, P, dptr(rc), i64ptr(idx), i64ptr(ptr), shift,
+                               dptr(lr), dptr(var)), ctx.h)
+    return np.stack([lr, var], axis=1) if Evar else lr
+
+
+def mcl_dCAR(pars, data: CarData, simdata: SimData, rho_cons=(-0.249, 0.249), Evar=False):
+    """mcl.dCAR, R/mcl.dCAR.R:11-50."""
+    r = mcl_dCAR_batch(np.asarray(pars, dtype=np.float64)[None, :], data, simdata, rho_cons=rho_cons, Evar=True)[0]
+    return r if Evar else float(r[0])
+
+
+def sigmabeta(rho, data: CarData) -> np.ndarray:
+    """GLS (sigma, beta) given rho, R/loglik.dCAR.R:72-86 (host; depends on the observed
+    data only)."""
+    W = _host_W(data)
+    X, y = data.X, data.y
+    Q1X = X - rho * (W @ X)
+    Q1y = y - rho * (W @ y)
+    beta = np.linalg.solve(X.T @ Q1X, X.T @ Q1y)
+    res = y - X @ beta
+    return np.concatenate([[res @ (res - rho * (W @ res)) / data.n], beta])
+
+
+def _host_W(data: CarData):
+    if data.W is not None:
+        return data.W
+    if "W" not in data.extra:
+        n1, n2 = data.torus
+        idx = np.arange(n1 * n2).reshape(n1, n2)
+        rows = np.repeat(idx.ravel(), 4)
+        cols = np.stack([np.roll(idx, 1, 0), np.roll(idx, -1, 0), np.roll(idx, 1, 1), np.roll(idx, -1, 1)], -1).ravel()
+        data.extra["W"] = sp.csr_matrix((np.ones(rows.size), (rows, cols)), shape=(n1 * n2, n1 * n2))
+    return data.extra["W"]
+
+
+def mcl_profile_dCAR(rho, data: CarData, simdata: SimData, rho_cons=(-0.249, 0.249), Evar=False):
+    """mcl.profile.dCAR, R/mcl.dCAR.R:53-96."""
+    return mcl_dCAR(np.concatenate([[rho], sigmabeta(rho, data)]), data, simdata, rho_cons, Evar)
+
+
+def mc_gradlik_dCAR(pars, data: CarData, simdata: SimData, Evar=0, shift=L.SHIFT_MEAN):
+    """mc.gradlik.dCAR, R/mcl.dCAR.R:213-283."""
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    P = pars.size
+    grad = np.empty(P)
+    gv = np.empty((P, P)) if Evar else None
+    ctx = data.ctx
+    check(lib.mclcar_dcar_grad(ctx.h, simdata.h, dptr(pars), 1, P, int(Evar), shift, dptr(grad), dptr(gv)), ctx.h)
+    return {"grad": grad, "grad.var": gv} if Evar else grad
+
+
+def mc_Hesslik_dCAR(pars, data: CarData, simdata: SimData, shift=L.SHIFT_MEAN) -> np.ndarray:
+    """mc.Hesslik.dCAR, R/mcl.dCAR.R:287-394."""
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    P = pars.size
+    H = np.empty((P, P))
+    check(lib.mclcar_dcar_hess(data.ctx.h, simdata.h, dptr(pars), 1, P, shift, dptr(H)), data.ctx.h)
+    return H
+
+
+def MCMLE_var(pars, data: CarData, simdata: SimData) -> np.ndarray:
+    """MCMLE.var, R/mcl.dCAR.R:156-165."""
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    P = pars.size
+    out = np.empty((P, P))
+    check(lib.mclcar_dcar_mcmle_var(data.ctx.h, simdata.h, dptr(pars), 1, P, dptr(out)), data.ctx.h)
+    return out
+
+
+def vmle_dCAR(MLE: dict, data: CarData, simdata: SimData) -> np.ndarray:
+    """vmle.dCAR, R/mcl.dCAR.R:99-106."""
+    A = mc_gradlik_dCAR(MLE["par"], data, simdata, Evar=2)["grad.var"]
+    Binv = np.linalg.inv(np.asarray(MLE["hessian"], dtype=np.float64))
+    return Binv @ A @ Binv

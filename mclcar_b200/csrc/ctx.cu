@@ -1,0 +1,378 @@
+// Context, model upload (graph / design / observations) and small host utilities.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "engine.hpp"
+
+namespace mclcar {
+
+static thread_local std::string g_last_error;
+
+void set_global_error(const char* msg) { g_last_error = msg; }
+
+int fail(mclcar_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_last_error = buf;
+    return code;
+}
+
+int require_device(mclcar_ctx* ctx) {
+    if (!ctx) return MCLCAR_EINVAL;
+    if (ctx->host_only) return fail(ctx, MCLCAR_ENODEV, "compute call on a host-only context: there is no CPU fallback");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, MCLCAR_ECUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return MCLCAR_OK;
+}
+
+int ensure(mclcar_ctx* ctx, DeviceBuf& b, size_t bytes) {
+    if (bytes <= b.bytes && b.p) return MCLCAR_OK;
+    if (b.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    MCL_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return MCLCAR_OK;
+}
+
+int ensure_pinned(mclcar_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->h_pinned_bytes && ctx->h_pinned) return MCLCAR_OK;
+    if (ctx->h_pinned) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(ctx->h_pinned);
+        ctx->h_pinned = nullptr;
+        ctx->h_pinned_bytes = 0;
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    MCL_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, want));
+    ctx->h_pinned_bytes = want;
+    return MCLCAR_OK;
+}
+
+template <class T>
+static int upload(mclcar_ctx* ctx, T*& dptr, const std::vector<T>& h) {
+    if (ctx->host_only) return MCLCAR_OK;
+    if (dptr) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(dptr);
+        dptr = nullptr;
+    }
+    if (h.empty()) return MCLCAR_OK;
+    MCL_CUDA(ctx, cudaMalloc((void**)&dptr, h.size() * sizeof(T)));
+    MCL_CUDA(ctx, cudaMemcpy(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MCLCAR_OK;
+}
+
+// y = W x on the host CSR copy
+static void spmv(const mclcar_ctx* c, const double* x, double* y) {
+    for (int i = 0; i < c->n; ++i) {
+        double a = 0.0;
+        for (int e = c->rowptr[i]; e < c->rowptr[i + 1]; ++e) a += (c->binary ? 1.0 : c->val[e]) * x[c->colidx[e]];
+        y[i] = a;
+    }
+}
+
+static void invalidate_model(mclcar_ctx* ctx) {
+    ctx->has_design = false;
+    ctx->has_obs = false;
+    ctx->p = 0;
+    ctx->X.clear(); ctx->WX.clear(); ctx->G0.clear(); ctx->G1.clear();
+    ctx->y.clear(); ctx->ntrial.clear(); ctx->qobs.clear();
+}
+
+// greedy colouring in natural order (smallest free colour); colour classes keep site order
+static void colour_graph(mclcar_ctx* c) {
+    const int n = c->n;
+    c->color_of.assign(n, -1);
+    int nc = 0;
+    if (c->kind == GRAPH_TORUS && c->n1 % 2 == 0 && c->n2 % 2 == 0) {
+        for (int i = 0; i < c->n1; ++i)
+            for (int j = 0; j < c->n2; ++j) c->color_of[i * c->n2 + j] = (i + j) & 1;
+        nc = 2;
+    } else {
+        std::vector<int> mark(c->max_deg + 2, -1);
+        for (int i = 0; i < n; ++i) {
+            for (int e = c->rowptr[i]; e < c->rowptr[i + 1]; ++e) {
+                const int cj = c->color_of[c->colidx[e]];
+                if (cj >= 0 && cj < (int)mark.size()) mark[cj] = i;
+            }
+            int col = 0;
+            while (mark[col] == i) ++col;
+            c->color_of[i] = col;
+            nc = std::max(nc, col + 1);
+        }
+    }
+    c->ncolors = nc;
+    c->color_ptr.assign(nc + 1, 0);
+    for (int i = 0; i < n; ++i) c->color_ptr[c->color_of[i] + 1]++;
+    for (int k = 0; k < nc; ++k) c->color_ptr[k + 1] += c->color_ptr[k];
+    c->order.resize(n);
+    std::vector<int> pos(c->color_ptr.begin(), c->color_ptr.end() - 1);
+    for (int i = 0; i < n; ++i) c->order[pos[c->color_of[i]]++] = i;
+}
+
+static int finish_graph(mclcar_ctx* ctx) {
+    ctx->max_deg = 0;
+    for (int i = 0; i < ctx->n; ++i) ctx->max_deg = std::max(ctx->max_deg, ctx->rowptr[i + 1] - ctx->rowptr[i]);
+    colour_graph(ctx);
+    MCL_TRY(upload(ctx, ctx->d_rowptr, ctx->rowptr));
+    MCL_TRY(upload(ctx, ctx->d_colidx, ctx->colidx));
+    MCL_TRY(upload(ctx, ctx->d_val, ctx->val));
+    MCL_TRY(upload(ctx, ctx->d_order, ctx->order));
+    return MCLCAR_OK;
+}
+
+}  // namespace mclcar
+
+using namespace mclcar;
+
+extern "C" {
+
+int mclcar_ctx_create(int device, uint64_t seed, mclcar_ctx** out) {
+    if (!out) return MCLCAR_EINVAL;
+    *out = nullptr;
+    mclcar_ctx* ctx = new (std::nothrow) mclcar_ctx();
+    if (!ctx) return MCLCAR_ENOMEM;
+    ctx->seed = seed;
+    ctx->device = device;
+    ctx->host_only = device < 0;
+    if (!ctx->host_only) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || device >= ndev) {
+            fail(nullptr, MCLCAR_ENODEV, "CUDA device %d not available (%s, %d devices): no CPU fallback", device,
+                 e == cudaSuccess ? "ok" : cudaGetErrorString(e), ndev);
+            delete ctx;
+            return MCLCAR_ENODEV;
+        }
+        cudaDeviceProp prop;
+        if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            fail(nullptr, MCLCAR_ECUDA, "device %d initialisation failed: %s", device, cudaGetErrorString(e));
+            delete ctx;
+            return MCLCAR_ECUDA;
+        }
+        if (prop.major != 10) {
+            fail(nullptr, MCLCAR_ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only", device,
+                 prop.major, prop.minor);
+            cudaStreamDestroy(ctx->own_stream);
+            delete ctx;
+            return MCLCAR_ENODEV;
+        }
+        ctx->n_sm = prop.multiProcessorCount;
+        ctx->stream = ctx->own_stream;
+    }
+    *out = ctx;
+    return MCLCAR_OK;
+}
+
+void mclcar_ctx_destroy(mclcar_ctx* ctx) {
+    if (!ctx) return;
+    if (!ctx->host_only) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        void* ptrs[] = {ctx->d_rowptr, ctx->d_colidx, ctx->d_val, ctx->d_order, ctx->d_X, ctx->d_WX, ctx->d_y,
+                        ctx->d_ntrial, ctx->d_coef.p, ctx->d_partial.p, ctx->d_tuples.p, ctx->d_subidx.p,
+                        ctx->d_gather.p};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+        comm_destroy(ctx);
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    }
+    delete ctx;
+}
+
+const char* mclcar_last_error(const mclcar_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int mclcar_ctx_set_stream(mclcar_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return MCLCAR_OK;
+}
+
+int mclcar_ctx_sync(mclcar_ctx* ctx) {
+    if (!ctx) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MCLCAR_OK;
+}
+
+int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world) {
+    if (!ctx) return MCLCAR_EINVAL;
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, MCLCAR_EINVAL, "bad shard %d of %d", rank, world);
+    ctx->rank = rank;
+    ctx->world = world;
+    return MCLCAR_OK;
+}
+
+int mclcar_graph_n(const mclcar_ctx* ctx) { return ctx ? ctx->n : 0; }
+int mclcar_graph_ncolors(const mclcar_ctx* ctx) { return ctx ? ctx->ncolors : 0; }
+
+int mclcar_graph_torus(mclcar_ctx* ctx, int n1, int n2) {
+    if (!ctx) return MCLCAR_EINVAL;
+    if (n1 < 3 || n2 < 3 || (int64_t)n1 * n2 > (int64_t)1 << 30)
+        return fail(ctx, MCLCAR_EINVAL, "torus sides must be >= 3 and n1*n2 <= 2^30 (got %d x %d)", n1, n2);
+    if (!ctx->host_only) MCL_TRY(require_device(ctx));
+    invalidate_model(ctx);
+    ctx->kind = GRAPH_TORUS;
+    ctx->n1 = n1; ctx->n2 = n2; ctx->n = n1 * n2;
+    ctx->binary = true;
+    ctx->val.clear();
+    const int n = ctx->n;
+    ctx->rowptr.resize(n + 1);
+    ctx->colidx.resize((size_t)4 * n);
+    for (int i = 0; i < n1; ++i)
+        for (int j = 0; j < n2; ++j) {
+            const int s = i * n2 + j;
+            int nb[4] = {((i + n1 - 1) % n1) * n2 + j, i * n2 + (j + n2 - 1) % n2, i * n2 + (j + 1) % n2,
+                         ((i + 1) % n1) * n2 + j};
+            std::sort(nb, nb + 4);
+            ctx->rowptr[s] = 4 * s;
+            for (int t = 0; t < 4; ++t) ctx->colidx[(size_t)4 * s + t] = nb[t];
+        }
+    ctx->rowptr[n] = 4 * n;
+    // analytic spectrum: 2cos(2 pi j/n1) + 2cos(2 pi k/n2) (replaces eigen(W), R/CAR.simLM.R:8)
+    ctx->eigs.resize(n);
+    std::vector<double> a(n1), b(n2);
+    for (int j = 0; j < n1; ++j) a[j] = 2.0 * std::cos(2.0 * M_PI * j / n1);
+    for (int k = 0; k < n2; ++k) b[k] = 2.0 * std::cos(2.0 * M_PI * k / n2);
+    for (int j = 0; j < n1; ++j)
+        for (int k = 0; k < n2; ++k) ctx->eigs[(size_t)j * n2 + k] = a[j] + b[k];
+    ctx->ew_min = *std::min_element(ctx->eigs.begin(), ctx->eigs.end());
+    ctx->ew_max = *std::max_element(ctx->eigs.begin(), ctx->eigs.end());
+    return finish_graph(ctx);
+}
+
+int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val) {
+    if (!ctx || !rowptr || !colidx) return MCLCAR_EINVAL;
+    if (n < 1) return fail(ctx, MCLCAR_EINVAL, "n must be positive");
+    if (!ctx->host_only) MCL_TRY(require_device(ctx));
+    if (rowptr[0] != 0) return fail(ctx, MCLCAR_EINVAL, "rowptr[0] must be 0");
+    const int64_t nnz = rowptr[n];
+    for (int i = 0; i < n; ++i)
+        if (rowptr[i + 1] < rowptr[i]) return fail(ctx, MCLCAR_EINVAL, "rowptr not monotone at row %d", i);
+    // validate: indices in range, zero diagonal, symmetric (W is used as a symmetric matrix by
+    // the reference without checking: eigen(W, symmetric = TRUE), R/loglik.dCAR.R:25)
+    std::map<std::pair<int, int>, double> ent;
+    for (int i = 0; i < n; ++i)
+        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+            const int j = colidx[e];
+            if (j < 0 || j >= n) return fail(ctx, MCLCAR_EINVAL, "column index %d out of range in row %d", j, i);
+            if (j == i) return fail(ctx, MCLCAR_EINVAL, "W must have a zero diagonal (row %d)", i);
+            if (!ent.emplace(std::make_pair(i, j), val ? val[e] : 1.0).second)
+                return fail(ctx, MCLCAR_EINVAL, "duplicate entry (%d, %d)", i, j);
+        }
+    for (auto& kv : ent) {
+        auto it = ent.find(std::make_pair(kv.first.second, kv.first.first));
+        if (it == ent.end() || it->second != kv.second)
+            return fail(ctx, MCLCAR_EINVAL, "W is not symmetric at (%d, %d)", kv.first.first, kv.first.second);
+    }
+    invalidate_model(ctx);
+    ctx->kind = GRAPH_CSR;
+    ctx->n = n; ctx->n1 = ctx->n2 = 0;
+    ctx->rowptr.assign(rowptr, rowptr + n + 1);
+    ctx->colidx.assign(colidx, colidx + nnz);
+    ctx->binary = true;
+    if (val)
+        for (int64_t e = 0; e < nnz; ++e)
+            if (val[e] != 1.0) ctx->binary = false;
+    if (ctx->binary) ctx->val.clear();
+    else ctx->val.assign(val, val + nnz);
+    ctx->eigs.clear();
+    ctx->ew_min = ctx->ew_max = 0.0;
+    return finish_graph(ctx);
+}
+
+int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, int n) {
+    if (!ctx || !ew) return MCLCAR_EINVAL;
+    if (ctx->kind == GRAPH_NONE) return fail(ctx, MCLCAR_ESTATE, "set the graph first");
+    if (n != ctx->n) return fail(ctx, MCLCAR_EINVAL, "expected %d eigenvalues, got %d", ctx->n, n);
+    ctx->eigs.assign(ew, ew + n);
+    ctx->ew_min = *std::min_element(ctx->eigs.begin(), ctx->eigs.end());
+    ctx->ew_max = *std::max_element(ctx->eigs.begin(), ctx->eigs.end());
+    return MCLCAR_OK;
+}
+
+int mclcar_set_design(mclcar_ctx* ctx, const double* X, int p) {
+    if (!ctx) return MCLCAR_EINVAL;
+    if (ctx->kind == GRAPH_NONE) return fail(ctx, MCLCAR_ESTATE, "set the graph before the design");
+    if (p < 0 || p > MCLCAR_MAX_COV) return fail(ctx, MCLCAR_ELIMIT, "p = %d outside [0, %d]", p, MCLCAR_MAX_COV);
+    if (p > 0 && !X) return MCLCAR_EINVAL;
+    if (!ctx->host_only) MCL_TRY(require_device(ctx));
+    const int n = ctx->n;
+    ctx->p = p;
+    ctx->X.assign(X, X + (size_t)n * p);
+    ctx->WX.resize((size_t)n * p);
+    for (int a = 0; a < p; ++a) spmv(ctx, ctx->X.data() + (size_t)a * n, ctx->WX.data() + (size_t)a * n);
+    ctx->G0.assign((size_t)p * p, 0.0);
+    ctx->G1.assign((size_t)p * p, 0.0);
+    for (int a = 0; a < p; ++a)
+        for (int b = 0; b < p; ++b) {
+            long double s0 = 0, s1 = 0;
+            const double *xa = ctx->X.data() + (size_t)a * n, *xb = ctx->X.data() + (size_t)b * n,
+                         *wb = ctx->WX.data() + (size_t)b * n;
+            for (int i = 0; i < n; ++i) {
+                s0 += (long double)xa[i] * xb[i];
+                s1 += (long double)xa[i] * wb[i];
+            }
+            ctx->G0[(size_t)a * p + b] = (double)s0;
+            ctx->G1[(size_t)a * p + b] = (double)s1;
+        }
+    MCL_TRY(upload(ctx, ctx->d_X, ctx->X));
+    MCL_TRY(upload(ctx, ctx->d_WX, ctx->WX));
+    ctx->has_design = true;
+    ctx->has_obs = false;  // qobs depends on X
+    return MCLCAR_OK;
+}
+
+int mclcar_set_obs(mclcar_ctx* ctx, const double* y, const double* ntrial) {
+    if (!ctx || !y) return MCLCAR_EINVAL;
+    if (ctx->kind == GRAPH_NONE) return fail(ctx, MCLCAR_ESTATE, "set the graph before the observations");
+    if (!ctx->has_design) {  // no regression part: p = 0
+        MCL_TRY(mclcar_set_design(ctx, nullptr, 0));
+    }
+    if (!ctx->host_only) MCL_TRY(require_device(ctx));
+    const int n = ctx->n, p = ctx->p;
+    ctx->y.assign(y, y + n);
+    if (ntrial) ctx->ntrial.assign(ntrial, ntrial + n);
+    else ctx->ntrial.clear();
+    std::vector<double> Wy(n);
+    spmv(ctx, ctx->y.data(), Wy.data());
+    ctx->qobs.assign(2 + 2 * p, 0.0);
+    long double s0 = 0, s1 = 0;
+    for (int i = 0; i < n; ++i) {
+        s0 += (long double)y[i] * y[i];
+        s1 += (long double)y[i] * Wy[i];
+    }
+    ctx->qobs[0] = (double)s0;
+    ctx->qobs[1] = (double)s1;
+    for (int a = 0; a < p; ++a) {
+        long double u = 0, v = 0;
+        const double* xa = ctx->X.data() + (size_t)a * n;
+        for (int i = 0; i < n; ++i) {
+            u += (long double)xa[i] * y[i];
+            v += (long double)xa[i] * Wy[i];
+        }
+        ctx->qobs[2 + a] = (double)u;
+        ctx->qobs[2 + p + a] = (double)v;
+    }
+    MCL_TRY(upload(ctx, ctx->d_y, ctx->y));
+    MCL_TRY(upload(ctx, ctx->d_ntrial, ctx->ntrial));
+    ctx->has_obs = true;
+    return MCLCAR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// Internal declarations shared by the translation units of libmclcar_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/mclcar_b200.h"
+
+namespace mclcar {
+
+enum GraphKind { GRAPH_NONE = 0, GRAPH_TORUS = 1, GRAPH_CSR = 2 };
+
+// tuple kinds ("what" at the ABI)
+enum { WHAT_LR = 0, WHAT_GRAD = 1, WHAT_HESS = 2 };
+
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace mclcar
+
+struct mclcar_ctx {
+    int device = -1;
+    bool host_only = true;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    uint64_t seed = 0;
+    int rank = 0, world = 1;
+    int n_sm = 148;
+    std::string err;
+
+    // ---- graph (host copy is always CSR; the torus keeps n1, n2 as well)
+    int kind = mclcar::GRAPH_NONE;
+    int n = 0, n1 = 0, n2 = 0;
+    bool binary = true;
+    std::vector<int> rowptr, colidx;
+    std::vector<double> val;   // empty when binary
+    std::vector<double> eigs;  // eigenvalues of W (analytic on the torus, else user-supplied)
+    double ew_min = 0, ew_max = 0;
+    int max_deg = 0;
+    // greedy colouring: sites of colour c are order[color_ptr[c] .. color_ptr[c+1])
+    int ncolors = 0;
+    std::vector<int> color_ptr, order, color_of;
+    int* d_rowptr = nullptr;
+    int* d_colidx = nullptr;
+    double* d_val = nullptr;
+    int* d_order = nullptr;
+
+    // ---- design
+    bool has_design = false;
+    int p = 0;
+    std::vector<double> X, WX;   // n x p column-major
+    std::vector<double> G0, G1;  // p x p: X'X, X'WX
+    double* d_X = nullptr;       // [p][n] fp64
+    double* d_WX = nullptr;
+
+    // ---- observations
+    bool has_obs = false;
+    std::vector<double> y, ntrial;
+    std::vector<double> qobs;  // (y'y, y'Wy, X'y[p], X'Wy[p])
+    double* d_y = nullptr;
+    double* d_ntrial = nullptr;
+
+    // ---- scratch reused across calls (grown on demand)
+    mclcar::DeviceBuf d_coef, d_partial, d_tuples, d_subidx, d_gather;
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+
+    // ---- NCCL (dlopen'ed)
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+};
+
+struct mclcar_samples {
+    mclcar_ctx* ctx = nullptr;
+    int dtype = MCLCAR_F64;
+    int layout = MCLCAR_COL_IS_SAMPLE;
+    int64_t sites = 0, N = 0, ld = 0;
+    void* d_M = nullptr;  // may be null (statistics-only sample set)
+    bool owned = false;
+    // sufficient statistics, device, [d][N] fp64
+    int d = 0;
+    double* d_q = nullptr;
+    bool stats_ready = false;
+    std::vector<double> qbar;  // column means of q (host)
+    // importance point
+    bool attached = false;
+    std::vector<double> psi0;
+    double t10 = 0.0;
+    double* d_base = nullptr;  // user-supplied t20 (N) or null => computed from psi0 and q
+    double base_mean = 0.0;
+    // sampler diagnostics
+    double accept = 1.0;
+    int64_t sweeps = 0;
+};
+
+namespace mclcar {
+
+int fail(mclcar_ctx* ctx, int code, const char* fmt, ...);
+void set_global_error(const char* msg);
+
+#define MCL_CUDA(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return ::mclcar::fail((ctx), _e == cudaErrorMemoryAllocation ? MCLCAR_ENOMEM : MCLCAR_ECUDA, \
+                                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define MCL_TRY(expr)                    \
+    do {                                 \
+        int _s = (expr);                 \
+        if (_s != MCLCAR_OK) return _s;  \
+    } while (0)
+
+int ensure(mclcar_ctx* ctx, DeviceBuf& b, size_t bytes);
+int ensure_pinned(mclcar_ctx* ctx, size_t bytes);
+int require_device(mclcar_ctx* ctx);
+
+// ---- statistics kernels (stats_torus.cu / stats_csr.cu) -----------------------------------
+// q layout: [d][ldq]; d = 2 + 2p: (x'x, x'Wx, X'x[p], (WX)'x[p])
+int launch_stats_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, double* d_q,
+                            int64_t ldq);
+int launch_transpose(mclcar_ctx* ctx, const void* in, int dtype, int64_t rows, int64_t cols, int64_t ld_in,
+                     void* out, int64_t ld_out);
+int launch_stats_torus_fast(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, double* d_q,
+                            int64_t ldq, bool* handled);
+int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, int n,
+                                const int* d_rowptr, const int* d_colidx, const double* d_val, int L,
+                                const double* const* d_vecs, double* d_out, int64_t ldq);
+int samples_alloc_stats(mclcar_ctx* ctx, mclcar_samples* s, int d);
+int samples_update_qbar(mclcar_ctx* ctx, mclcar_samples* s);
+int merge_tuples(int what, int F, int d, int G, int K, const double* in, double* out);
+void centred_moments(const double* tup, int V, double* vbar, double* C);
+int gather_and_merge(mclcar_ctx* ctx, int what, int F, int d, int K, double* tuples);
+void comm_destroy(mclcar_ctx* ctx);
+
+// ---- reduction kernels (reduce.cu) ----------------------------------------------------------
+struct ReducePlan {
+    const double* d_q = nullptr;  // [d][ldq]
+    int64_t ldq = 0;
+    int d = 0;
+    const double* d_base = nullptr;  // [N] or null
+    int64_t N = 0;
+    int K = 0;
+    int F = 0;       // features with second moments (0 for lr/var)
+    int what = WHAT_LR;
+    int shift_mode = MCLCAR_SHIFT_MEAN;
+    // host coefficient blocks, K x coef_stride (see coef_* helpers)
+    std::vector<double> coef;
+    int coef_stride = 0;
+    // subsets (host, 0-based) or null
+    const int64_t* subset_idx = nullptr;
+    const int64_t* subset_ptr = nullptr;
+};
+// coefficient block of one candidate: c0, c[d], shift, n, centre[1+F], feat[F][1+d] (a0 then A)
+inline int coef_stride_of(int d, int F) { return 3 + d + (1 + F) + F * (1 + d); }
+inline int coef_off_shift(int d) { return 1 + d; }
+inline int coef_off_n(int d) { return 2 + d; }
+inline int coef_off_centre(int d) { return 3 + d; }
+inline int coef_off_feat(int d, int F) { return 3 + d + (1 + F); }
+int64_t tuple_len(int what, int F, int d);
+// runs the reduction; leaves K tuples in ctx->d_tuples (device) and copies them to `tuples` (host)
+int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples);
+
+}  // namespace mclcar

@@ -1,0 +1,205 @@
+// Sample-set handles: the reference's simY / Zy / u.y matrices on the device.
+#include <cstring>
+
+#include "common.cuh"
+#include "engine.hpp"
+
+namespace mclcar {
+
+namespace {
+
+// column means of q [d][ldq] over the first N entries of each row; one CTA per row
+__global__ void rowmean_kernel(const double* q, int64_t ldq, int64_t N, double* out) {
+    __shared__ double scratch[8];
+    double a[1] = {0.0};
+    const double* r = q + (size_t)blockIdx.x * ldq;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) a[0] += r[i];
+    block_sum<1>(a, scratch);
+    if (threadIdx.x == 0) out[blockIdx.x] = a[0] / (double)N;
+}
+
+template <typename T>
+__global__ void to_f64_kernel(const T* in, double* out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (c < cols && r < rows) out[r * ld_out + c] = (double)in[r * ld_in + c];
+}
+
+}  // namespace
+
+int samples_alloc_stats(mclcar_ctx* ctx, mclcar_samples* s, int d) {
+    if (s->d_q && s->d == d) return MCLCAR_OK;
+    if (s->d_q) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(s->d_q);
+        s->d_q = nullptr;
+    }
+    s->d = d;
+    MCL_CUDA(ctx, cudaMalloc((void**)&s->d_q, (size_t)d * s->N * sizeof(double)));
+    s->stats_ready = false;
+    return MCLCAR_OK;
+}
+
+int samples_update_qbar(mclcar_ctx* ctx, mclcar_samples* s) {
+    MCL_TRY(ensure(ctx, ctx->d_tuples, (size_t)s->d * sizeof(double)));
+    rowmean_kernel<<<s->d, 256, 0, ctx->stream>>>(s->d_q, s->N, s->N, (double*)ctx->d_tuples.p);
+    MCL_CUDA(ctx, cudaGetLastError());
+    s->qbar.assign(s->d, 0.0);
+    MCL_CUDA(ctx, cudaMemcpyAsync(s->qbar.data(), ctx->d_tuples.p, (size_t)s->d * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MCLCAR_OK;
+}
+
+}  // namespace mclcar
+
+using namespace mclcar;
+
+static int make_samples(mclcar_ctx* ctx, int dtype, int layout, int64_t sites, int64_t N, int64_t ld,
+                        mclcar_samples** out) {
+    if (!ctx || !out) return MCLCAR_EINVAL;
+    *out = nullptr;
+    if (dtype != MCLCAR_F64 && dtype != MCLCAR_F32) return fail(ctx, MCLCAR_EINVAL, "bad dtype %d", dtype);
+    if (layout != MCLCAR_COL_IS_SAMPLE && layout != MCLCAR_ROW_IS_SAMPLE) return fail(ctx, MCLCAR_EINVAL, "bad layout %d", layout);
+    if (sites < 1 || N < 1) return fail(ctx, MCLCAR_EINVAL, "empty sample matrix (%lld sites x %lld samples)", (long long)sites, (long long)N);
+    if (N >= ((int64_t)1 << 31)) return fail(ctx, MCLCAR_ELIMIT, "more than 2^31 samples on one context");
+    const int64_t lead = layout == MCLCAR_COL_IS_SAMPLE ? sites : N;
+    if (ld < lead) return fail(ctx, MCLCAR_EINVAL, "ld %lld smaller than the leading extent %lld", (long long)ld, (long long)lead);
+    mclcar_samples* s = new (std::nothrow) mclcar_samples();
+    if (!s) return fail(ctx, MCLCAR_ENOMEM, "out of host memory");
+    s->ctx = ctx; s->dtype = dtype; s->layout = layout; s->sites = sites; s->N = N; s->ld = ld;
+    *out = s;
+    return MCLCAR_OK;
+}
+
+extern "C" {
+
+int mclcar_samples_from_host(mclcar_ctx* ctx, const void* M, int dtype, int layout, int64_t sites, int64_t N,
+                             int64_t ld, mclcar_samples** out) {
+    if (!ctx || !M) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    mclcar_samples* s = nullptr;
+    MCL_TRY(make_samples(ctx, dtype, layout, sites, N, ld, &s));
+    const size_t es = dtype == MCLCAR_F32 ? 4 : 8;
+    const int64_t outer = layout == MCLCAR_COL_IS_SAMPLE ? N : sites;
+    const int64_t lead = layout == MCLCAR_COL_IS_SAMPLE ? sites : N;
+    // device copy is packed to a 16-byte aligned leading dimension (bulk-copy requirement)
+    const int64_t align = 16 / es;
+    const int64_t ldd = (lead + align - 1) / align * align;
+    cudaError_t e = cudaMalloc(&s->d_M, (size_t)outer * ldd * es);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(ctx, MCLCAR_ENOMEM, "cudaMalloc of %zu bytes for the sample matrix failed: %s", (size_t)outer * ldd * es,
+                    cudaGetErrorString(e));
+    }
+    s->owned = true;
+    s->ld = ldd;
+    e = cudaMemcpy2DAsync(s->d_M, (size_t)ldd * es, M, (size_t)ld * es, (size_t)lead * es, (size_t)outer,
+                          cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        mclcar_samples_free(s);
+        return fail(ctx, MCLCAR_ECUDA, "host to device copy of the sample matrix failed: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return MCLCAR_OK;
+}
+
+int mclcar_samples_from_device(mclcar_ctx* ctx, const void* M_dev, int dtype, int layout, int64_t sites, int64_t N,
+                               int64_t ld, mclcar_samples** out) {
+    if (!ctx || !M_dev) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    mclcar_samples* s = nullptr;
+    MCL_TRY(make_samples(ctx, dtype, layout, sites, N, ld, &s));
+    s->d_M = const_cast<void*>(M_dev);
+    s->owned = false;
+    *out = s;
+    return MCLCAR_OK;
+}
+
+void mclcar_samples_free(mclcar_samples* s) {
+    if (!s) return;
+    mclcar_ctx* ctx = s->ctx;
+    if (ctx && !ctx->host_only) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (s->owned && s->d_M) cudaFree(s->d_M);
+        if (s->d_q) cudaFree(s->d_q);
+        if (s->d_base) cudaFree(s->d_base);
+    }
+    delete s;
+}
+
+int64_t mclcar_samples_count(const mclcar_samples* s) { return s ? s->N : 0; }
+
+int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double* out, int64_t ld) {
+    if (!ctx || !s || !out) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    if (!s->d_M) return fail(ctx, MCLCAR_ESTATE, "this sample set keeps sufficient statistics only (keep = 0)");
+    const int64_t rows_src = s->layout == MCLCAR_COL_IS_SAMPLE ? s->N : s->sites;
+    const int64_t cols_src = s->layout == MCLCAR_COL_IS_SAMPLE ? s->sites : s->N;
+    const bool same = layout == s->layout;
+    const int64_t rows = same ? rows_src : cols_src, cols = same ? cols_src : rows_src;
+    if (ld < cols) return fail(ctx, MCLCAR_EINVAL, "ld too small");
+    double* tmp = nullptr;
+    MCL_CUDA(ctx, cudaMalloc((void**)&tmp, (size_t)rows * cols * sizeof(double)));
+    cudaStream_t st = ctx->stream;
+    int status = MCLCAR_OK;
+    if (same) {
+        dim3 grid((unsigned)((cols + 255) / 256), (unsigned)rows);
+        if (rows > 65535) {
+            // one launch per block of rows
+            for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+                const int64_t nr = std::min<int64_t>(65535, rows - r0);
+                dim3 g((unsigned)((cols + 255) / 256), (unsigned)nr);
+                if (s->dtype == MCLCAR_F32)
+                    to_f64_kernel<float><<<g, 256, 0, st>>>((const float*)s->d_M + r0 * s->ld, tmp + r0 * cols, nr, cols, s->ld, cols);
+                else
+                    to_f64_kernel<double><<<g, 256, 0, st>>>((const double*)s->d_M + r0 * s->ld, tmp + r0 * cols, nr, cols, s->ld, cols);
+            }
+        } else if (s->dtype == MCLCAR_F32) {
+            to_f64_kernel<float><<<grid, 256, 0, st>>>((const float*)s->d_M, tmp, rows, cols, s->ld, cols);
+        } else {
+            to_f64_kernel<double><<<grid, 256, 0, st>>>((const double*)s->d_M, tmp, rows, cols, s->ld, cols);
+        }
+    } else {
+        // transpose in the source dtype, then widen
+        void* t2 = nullptr;
+        const size_t es = s->dtype == MCLCAR_F32 ? 4 : 8;
+        cudaError_t e = cudaMalloc(&t2, (size_t)rows * cols * es);
+        if (e != cudaSuccess) {
+            cudaFree(tmp);
+            return fail(ctx, MCLCAR_ENOMEM, "cudaMalloc failed in samples_fetch");
+        }
+        status = launch_transpose(ctx, s->d_M, s->dtype, rows_src, cols_src, s->ld, t2, cols);
+        if (status == MCLCAR_OK) {
+            for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+                const int64_t nr = std::min<int64_t>(65535, rows - r0);
+                dim3 g((unsigned)((cols + 255) / 256), (unsigned)nr);
+                if (s->dtype == MCLCAR_F32)
+                    to_f64_kernel<float><<<g, 256, 0, st>>>((const float*)t2 + r0 * cols, tmp + r0 * cols, nr, cols, cols, cols);
+                else
+                    to_f64_kernel<double><<<g, 256, 0, st>>>((const double*)t2 + r0 * cols, tmp + r0 * cols, nr, cols, cols, cols);
+            }
+        }
+        cudaStreamSynchronize(st);
+        cudaFree(t2);
+    }
+    if (status == MCLCAR_OK) {
+        cudaError_t e = cudaMemcpy2DAsync(out, (size_t)ld * 8, tmp, (size_t)cols * 8, (size_t)cols * 8, (size_t)rows,
+                                          cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) status = fail(ctx, MCLCAR_ECUDA, "device to host copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(tmp);
+    return status;
+}
+
+int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate, int64_t* sweeps) {
+    if (!ctx || !s) return MCLCAR_EINVAL;
+    if (accept_rate) *accept_rate = s->accept;
+    if (sweeps) *sweeps = s->sweeps;
+    return MCLCAR_OK;
+}
+
+}  // extern "C"

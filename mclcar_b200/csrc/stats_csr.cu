@@ -1,0 +1,169 @@
+// K2 (general neighbourhood matrix) -- per-sample quadratic and linear forms for a sample
+// matrix stored site-major ("row = sample" of the R matrix Zy, R/postZsub.R:427: for every
+// site the N samples are contiguous).  One lane = one sample, so every load of a site's
+// row is a coalesced run over samples and the CSR indices are warp-uniform:
+//     out[0][i] = x_i'x_i,   out[1][i] = x_i'A x_i,   out[2+l][i] = v_l'x_i
+// with A a symmetric CSR matrix (W of the CAR prior, or M / Z'Z / Z'WZ of the hierarchical
+// model) visited through its upper triangle, and v_l dense vectors (columns of X and WX).
+// Replaces the per-sample dense products at R/mcl.dCAR.R:168-210, R/mcl.bin.R:188-196,
+// R/mcl.HCAR.R:187-196.  Sites are split into chunks over blockIdx.y; the chunk partials
+// are added in chunk order (deterministic).
+//
+// Sample-major matrices on a general graph are transposed on the device first
+// (transpose_kernel) -- those are the small parity-path inputs.
+#include "common.cuh"
+#include "engine.hpp"
+
+namespace mclcar {
+namespace {
+
+constexpr int kThreads = 128;
+
+struct SiteMajorParams {
+    const void* M;
+    int64_t ld, N;
+    int n;
+    const int* rowptr;
+    const int* colidx;
+    const double* val;  // null = binary
+    int L;
+    const double* vec[2 * MCLCAR_MAX_COV];
+    int chunk;     // sites per chunk
+    double* out;   // [chunks][2+L][ldq]
+    int64_t ldq;
+};
+
+template <typename T, int LT>
+__global__ void __launch_bounds__(kThreads) stats_site_major_kernel(const SiteMajorParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.N) return;
+    const T* M = reinterpret_cast<const T*>(p.M);
+    const int s0 = blockIdx.y * p.chunk;
+    const int s1 = min(p.n, s0 + p.chunk);
+    double xx = 0.0, xax = 0.0, lin[LT > 0 ? LT : 1];
+#pragma unroll
+    for (int l = 0; l < LT; ++l) lin[l] = 0.0;
+    for (int s = s0; s < s1; ++s) {
+        const double x = (double)ld_stream(M + (size_t)s * p.ld + i);
+        xx = fma(x, x, xx);
+        double nb = 0.0;
+        const int e1 = p.rowptr[s + 1];
+        for (int e = p.rowptr[s]; e < e1; ++e) {
+            const int j = p.colidx[e];
+            if (j < s) continue;
+            const double w = p.val ? p.val[e] : 1.0;
+            if (j == s) nb = fma(0.5 * w, x, nb);
+            else nb = fma(w, (double)__ldg(M + (size_t)j * p.ld + i), nb);
+        }
+        xax = fma(x, nb, xax);
+#pragma unroll
+        for (int l = 0; l < LT; ++l)
+            if (l < p.L) lin[l] = fma(__ldg(p.vec[l] + s), x, lin[l]);
+    }
+    double* o = p.out + (size_t)blockIdx.y * (2 + p.L) * p.ldq + i;
+    o[0] = xx;
+    o[p.ldq] = 2.0 * xax;
+#pragma unroll
+    for (int l = 0; l < LT; ++l)
+        if (l < p.L) o[(size_t)(2 + l) * p.ldq] = lin[l];
+}
+
+__global__ void chunk_sum_kernel(const double* partial, double* q, int S, int d, int64_t ldq, int64_t N) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (int j = 0; j < d; ++j) {
+        double a = 0.0;
+        for (int s = 0; s < S; ++s) a += partial[((size_t)s * d + j) * ldq + i];
+        q[(size_t)j * ldq + i] = a;
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void transpose_kernel(const TI* in, TO* out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out) {
+    __shared__ TO tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int64_t r = r0 + k, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[k][threadIdx.x] = (TO)in[r * ld_in + c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int64_t c = c0 + k, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[c * ld_out + r] = tile[threadIdx.x][k];
+    }
+}
+
+template <typename T>
+int launch_typed(mclcar_ctx* ctx, const SiteMajorParams& p, dim3 grid) {
+    cudaStream_t st = ctx->stream;
+    if (p.L == 0) stats_site_major_kernel<T, 0><<<grid, kThreads, 0, st>>>(p);
+    else if (p.L <= 2) stats_site_major_kernel<T, 2><<<grid, kThreads, 0, st>>>(p);
+    else if (p.L <= 4) stats_site_major_kernel<T, 4><<<grid, kThreads, 0, st>>>(p);
+    else if (p.L <= 8) stats_site_major_kernel<T, 8><<<grid, kThreads, 0, st>>>(p);
+    else stats_site_major_kernel<T, 16><<<grid, kThreads, 0, st>>>(p);
+    MCL_CUDA(ctx, cudaGetLastError());
+    return MCLCAR_OK;
+}
+
+}  // namespace
+
+// generic form: any symmetric CSR matrix on the device, any list of dense vectors
+int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, int n,
+                                const int* d_rowptr, const int* d_colidx, const double* d_val, int L,
+                                const double* const* d_vecs, double* d_out, int64_t ldq) {
+    if (L > 2 * MCLCAR_MAX_COV) return fail(ctx, MCLCAR_ELIMIT, "too many linear forms (%d)", L);
+    SiteMajorParams p{};
+    p.M = M; p.ld = ld; p.N = N; p.n = n;
+    p.rowptr = d_rowptr; p.colidx = d_colidx; p.val = d_val;
+    p.L = L;
+    for (int l = 0; l < L; ++l) p.vec[l] = d_vecs[l];
+    p.ldq = ldq;
+    const int d = 2 + L;
+    // split the sites so that the grid fills the machine about four times over
+    const int64_t xblocks = (N + kThreads - 1) / kThreads;
+    int chunks = (int)std::max<int64_t>(1, ((int64_t)8 * ctx->n_sm + xblocks - 1) / xblocks);
+    chunks = std::min(chunks, std::max(1, n / 64));
+    chunks = std::min(chunks, 65535);
+    p.chunk = (n + chunks - 1) / chunks;
+    chunks = (n + p.chunk - 1) / p.chunk;
+    double* partial = d_out;
+    if (chunks > 1) {
+        MCL_TRY(ensure(ctx, ctx->d_partial, (size_t)chunks * d * ldq * sizeof(double)));
+        partial = (double*)ctx->d_partial.p;
+    }
+    p.out = partial;
+    dim3 grid((unsigned)xblocks, (unsigned)chunks);
+    if (dtype == MCLCAR_F32) MCL_TRY(launch_typed<float>(ctx, p, grid));
+    else MCL_TRY(launch_typed<double>(ctx, p, grid));
+    if (chunks > 1) {
+        chunk_sum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(partial, d_out, chunks, d, ldq, N);
+        MCL_CUDA(ctx, cudaGetLastError());
+    }
+    return MCLCAR_OK;
+}
+
+int launch_stats_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, double* d_q,
+                            int64_t ldq) {
+    const double* vecs[2 * MCLCAR_MAX_COV];
+    const int p = ctx->p;
+    for (int l = 0; l < p; ++l) {
+        vecs[l] = ctx->d_X + (size_t)l * ctx->n;
+        vecs[p + l] = ctx->d_WX + (size_t)l * ctx->n;
+    }
+    return launch_quadforms_site_major(ctx, M, dtype, N, ld, ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_val, 2 * p,
+                                       vecs, d_q, ldq);
+}
+
+int launch_transpose(mclcar_ctx* ctx, const void* in, int dtype, int64_t rows, int64_t cols, int64_t ld_in,
+                     void* out, int64_t ld_out) {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    if (grid.y > 65535) return fail(ctx, MCLCAR_ELIMIT, "transpose: too many rows (%lld)", (long long)rows);
+    if (dtype == MCLCAR_F32)
+        transpose_kernel<float, float><<<grid, block, 0, ctx->stream>>>((const float*)in, (float*)out, rows, cols, ld_in, ld_out);
+    else
+        transpose_kernel<double, double><<<grid, block, 0, ctx->stream>>>((const double*)in, (double*)out, rows, cols, ld_in, ld_out);
+    MCL_CUDA(ctx, cudaGetLastError());
+    return MCLCAR_OK;
+}
+
+}  // namespace mclcar

@@ -1,0 +1,130 @@
+"""CPU tests: the C-ABI library loads, exports every symbol the header declares, and its
+host-only stages (model bookkeeping, tuple merge, finish) reproduce the oracle."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from mclcar_b200 import _lib as L
+from mclcar_b200 import api
+from oracle import dcar
+from tests import helpers, tuple_ref
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def declared_functions():
+    txt = (ROOT / "include" / "mclcar_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mclcar_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported_and_bound():
+    names = declared_functions()
+    assert len(names) >= 30
+    for nm in names:
+        assert hasattr(L.lib, nm), f"{nm} declared in the header but not exported"
+        assert nm in L.SIGNATURES, f"{nm} has no ctypes signature"
+    assert set(L.SIGNATURES) == set(names)
+
+
+def test_no_cpu_fallback_on_host_only_context():
+    ctx = api.Context(device=-1)
+    n1 = n2 = 6
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(n1 * n2)
+    data = api.make_data(y, X=np.ones((n1 * n2, 1)), torus=(n1, n2), ctx=ctx)
+    M = np.zeros((4, n1 * n2))
+    h = C.c_void_p()
+    st = L.lib.mclcar_samples_from_host(ctx.h, M.ctypes.data_as(C.c_void_p), L.F64, L.COL_IS_SAMPLE, n1 * n2, 4,
+                                        n1 * n2, C.byref(h))
+    assert st == L.ENODEV
+    assert b"no CPU fallback" in L.lib.mclcar_last_error(ctx.h)
+    assert data.n == 36
+
+
+def test_argument_validation():
+    ctx = api.Context(device=-1)
+    assert L.lib.mclcar_graph_torus(ctx.h, 2, 5) == L.EINVAL
+    # asymmetric W is rejected
+    rp = np.array([0, 1, 1], dtype=np.int32)
+    ci = np.array([1], dtype=np.int32)
+    assert L.lib.mclcar_graph_csr(ctx.h, 2, L.iptr(rp), L.iptr(ci), None) == L.EINVAL
+    assert b"symmetric" in L.lib.mclcar_last_error(ctx.h)
+    # non-zero diagonal is rejected
+    rp = np.array([0, 1, 1], dtype=np.int32)
+    ci = np.array([0], dtype=np.int32)
+    assert L.lib.mclcar_graph_csr(ctx.h, 2, L.iptr(rp), L.iptr(ci), None) == L.EINVAL
+    # design before graph
+    ctx2 = api.Context(device=-1)
+    assert L.lib.mclcar_set_design(ctx2.h, None, 0) == L.ESTATE
+    assert L.lib.mclcar_ctx_set_shard(ctx.h, 3, 2) == L.EINVAL
+
+
+def test_colouring():
+    ctx = api.Context(device=-1)
+    assert L.lib.mclcar_graph_torus(ctx.h, 6, 8) == 0
+    assert L.lib.mclcar_graph_ncolors(ctx.h) == 2
+    assert L.lib.mclcar_graph_torus(ctx.h, 5, 7) == 0  # odd sides: greedy colouring
+    assert 3 <= L.lib.mclcar_graph_ncolors(ctx.h) <= 5
+
+
+@pytest.mark.parametrize("what,evar", [(0, 0), (1, 1), (1, 2), (1, 3), (2, 0)])
+@pytest.mark.parametrize("G", [1, 3])
+def test_merge_and_finish_match_oracle(what, evar, G):
+    """Tuples built in numpy for G shards -> C merge -> C finish == oracle on all samples."""
+    odata, psi0, simdata, rng = helpers.torus_case(8, 8, 600, seed=11)
+    ctx = api.Context(device=-1)
+    api.make_data(odata["y"], X=odata["X"], torus=(8, 8), ctx=ctx)
+    psis = np.stack([psi0 * np.array([0.9, 1.1, 1.02, 0.97]), psi0 * np.array([1.1, 0.93, 0.99, 1.04])])
+    K, P = psis.shape
+    p = 2
+    d = 2 + 2 * p
+    F = 0 if what == 0 else P
+    T = L.lib.mclcar_tuple_len(what, F, d)
+    parts = np.array_split(np.arange(600), G)
+    tin = np.stack([tuple_ref.dcar_tuples(psis, psi0, odata["W"], odata["X"], simdata["simY"][:, ix], what,
+                                           shift="mean" if g % 2 == 0 else "max") for g, ix in enumerate(parts)])
+    assert tin.shape == (G, K, T)
+    tin = np.ascontiguousarray(tin)
+    merged = np.empty((K, T))
+    assert L.lib.mclcar_tuples_merge(what, F, d, G, K, L.dptr(tin), L.dptr(merged)) == 0
+    out0 = np.empty(K if what == 0 else (K * P if what == 1 else K * P * P))
+    out1 = np.empty(K if what == 0 else K * P * P)
+    psi0c = np.ascontiguousarray(psi0)
+    psic = np.ascontiguousarray(psis)
+    st = L.lib.mclcar_dcar_finish(ctx.h, L.dptr(psi0c), P, L.dptr(psic), K, P, what, evar, None, L.dptr(merged),
+                                  L.dptr(out0), L.dptr(out1))
+    assert st == 0, L.lib.mclcar_last_error(ctx.h)
+    for k in range(K):
+        if what == 0:
+            ref = dcar.mcl_dCAR(psis[k], odata, simdata, rho_cons=None, Evar=True)
+            np.testing.assert_allclose([out0[k], out1[k]], ref, rtol=1e-10)
+        elif what == 1:
+            if evar == 3:
+                np.testing.assert_allclose(out1.reshape(K, P, P)[k], dcar.MCMLE_var(psis[k], odata, simdata), rtol=1e-9)
+            else:
+                ref = dcar.mc_gradlik_dCAR(psis[k], odata, simdata, Evar=evar)
+                np.testing.assert_allclose(out0.reshape(K, P)[k], ref["grad"], rtol=1e-9, atol=1e-9)
+                np.testing.assert_allclose(out1.reshape(K, P, P)[k], ref["grad.var"], rtol=1e-9)
+        else:
+            ref = dcar.mc_Hesslik_dCAR(psis[k], odata, simdata)
+            np.testing.assert_allclose(out0.reshape(K, P, P)[k], ref, rtol=1e-9, atol=1e-8)
+
+
+def test_rho_cons_sentinels():
+    odata, psi0, simdata, rng = helpers.torus_case(6, 6, 50, seed=3)
+    ctx = api.Context(device=-1)
+    api.make_data(odata["y"], X=odata["X"], torus=(6, 6), ctx=ctx)
+    psis = np.ascontiguousarray(np.stack([psi0, psi0]))
+    psis[1, 0] = 0.2495
+    tin = np.ascontiguousarray(tuple_ref.dcar_tuples(psis, psi0, odata["W"], odata["X"], simdata["simY"], 0))
+    lr, var = np.empty(2), np.empty(2)
+    rc = np.array([-0.249, 0.249])
+    psi0c = np.ascontiguousarray(psi0)
+    assert L.lib.mclcar_dcar_finish(ctx.h, L.dptr(psi0c), 4, L.dptr(psis), 2, 4, 0, 0, L.dptr(rc), L.dptr(tin),
+                                    L.dptr(lr), L.dptr(var)) == 0
+    assert lr[1] == -1e8 and var[1] == 1e8          # R/mcl.dCAR.R:39-42
+    assert abs(lr[0]) < 1e-12 and abs(var[0]) < 1e-20  # psi == psi0: ratio 1, weights constant
