@@ -131,6 +131,10 @@ int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate,
  * samples; replaces the per-sample dense products of logunnorm / D.log.unorm
  * (R/mcl.dCAR.R:168-210).  q_out: N x (2+2p) column-major, may be NULL. */
 int mclcar_dcar_stats(mclcar_ctx* ctx, mclcar_samples* s, double* q_out);
+/* mcl.prep.dCAR(psi, n.samples, data), R/mcl.dCAR.R:2-8: draws N samples at psi0 with the
+ * chromatic Gibbs sampler and attaches t10 = h(y; psi0), t20_i = h(Y_i; psi0). */
+int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
+                     mclcar_samples** out);
 /* attach the importance point to a sample set built with samples_from_*: t20 NULL means
  * "compute h(Y_i; psi0) from the statistics", otherwise the reference's own t20 (N). */
 int mclcar_dcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* t20);

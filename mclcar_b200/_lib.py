@@ -76,6 +76,7 @@ SIGNATURES = {
     "mclcar_samples_fetch": (_i, [_vp, _vp, _i, _pd, _i64]),
     "mclcar_samples_diag": (_i, [_vp, _vp, _pd, _pi64]),
     "mclcar_dcar_stats": (_i, [_vp, _vp, _pd]),
+    "mclcar_dcar_prep": (_i, [_vp, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
     "mclcar_dcar_attach": (_i, [_vp, _vp, _pd, _i, _pd]),
     "mclcar_dcar_t10_t20": (_i, [_vp, _vp, _pd, _pd]),
     "mclcar_dcar_eval": (_i, [_vp, _vp, _pd, _i, _i, _pd, _pi64, _pi64, _i, _pd, _pd]),

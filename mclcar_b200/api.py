@@ -283,3 +283,37 @@ def vmle_dCAR(MLE: dict, data: CarData, simdata: SimData) -> np.ndarray:
     A = mc_gradlik_dCAR(MLE["par"], data, simdata, Evar=2)["grad.var"]
     Binv = np.linalg.inv(np.asarray(MLE["hessian"], dtype=np.float64))
     return Binv @ A @ Binv
+
+
+def _sampler_opts(control: Optional[dict]) -> L.SamplerOpts:
+    """GPU keys appended to the reference's control-list idiom (`con[names(control)] <-
+    control`, R/OptimMCL.R:6-11): n.chains, burn, thin, keep, dtype."""
+    con = {"n.chains": 0, "burn": 0, "thin": 0, "keep": True, "dtype": "f32"}
+    for k, v in (control or {}).items():
+        if k not in con:
+            raise ValueError(f"unknown sampler control '{k}'")
+        con[k] = v
+    o = L.SamplerOpts()
+    o.n_chains = int(con["n.chains"])
+    o.burn = int(con["burn"])
+    o.thin = int(con["thin"])
+    o.keep = 1 if con["keep"] else 0
+    o.dtype = L.F64 if con["dtype"] in ("f64", np.float64) else L.F32
+    return o
+
+
+def mcl_prep_dCAR(psi, n_samples: int, data: CarData, control: Optional[dict] = None) -> SimData:
+    """mcl.prep.dCAR(psi, n.samples, data), R/mcl.dCAR.R:2-8.  Raises MclcarError(ERHO,
+    "rho should be within ...") like CAR.simTorus's stop() (R/CAR.simLM.R:11)."""
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    h = C.c_void_p()
+    o = _sampler_opts(control)
+    check(lib.mclcar_dcar_prep(data.ctx.h, dptr(psi), psi.size, int(n_samples), C.byref(o), C.byref(h)), data.ctx.h)
+    return SimData(data, h, psi)
+
+
+def sampler_diag(data: CarData, simdata) -> dict:
+    acc = C.c_double()
+    sw = C.c_int64()
+    check(lib.mclcar_samples_diag(data.ctx.h, simdata.h, C.byref(acc), C.byref(sw)), data.ctx.h)
+    return {"accept": acc.value, "sweeps": sw.value}

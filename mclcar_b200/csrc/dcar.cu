@@ -14,14 +14,6 @@
 
 namespace mclcar {
 
-int samples_alloc_stats(mclcar_ctx* ctx, mclcar_samples* s, int d);
-int samples_update_qbar(mclcar_ctx* ctx, mclcar_samples* s);
-int launch_stats_torus_fast(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, double* d_q,
-                            int64_t ldq, bool* handled);
-int merge_tuples(int what, int F, int d, int G, int K, const double* in, double* out);
-void centred_moments(const double* tup, int V, double* vbar, double* C);
-int gather_and_merge(mclcar_ctx* ctx, int what, int F, int d, int K, double* tuples);
-
 namespace {
 
 // affine maps of one candidate: h = c0 + c.q ; features f_a = a0[a] + A[a].q ; X'Wr_l = xw0[l] + q[2+p+l]

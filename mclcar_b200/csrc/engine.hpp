@@ -168,4 +168,37 @@ int64_t tuple_len(int what, int F, int d);
 // runs the reduction; leaves K tuples in ctx->d_tuples (device) and copies them to `tuples` (host)
 int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples);
 
+
+// ---- samplers (sampler_torus.cu / sampler_csr.cu) ---------------------------------------------
+struct TorusChains {
+    float* red = nullptr;
+    float* black = nullptr;
+    int64_t C = 0;
+};
+int torus_chains_alloc(mclcar_ctx* ctx, int64_t C, TorusChains& t);
+void torus_chains_free(mclcar_ctx* ctx, TorusChains& t);
+int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, uint32_t sweep);
+int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, int dtype, int64_t ld, int64_t slot0,
+               int64_t nch);
+
+enum { FAM_GAUSS = 0, FAM_BINOM = 1, FAM_POIS = 2 };
+// host description (site order, fp64) of a Gaussian Markov random field exp(-x'Qx/2 + b'x)
+struct GmrfHost {
+    int n = 0;
+    const std::vector<int>* rowptr = nullptr;  // CSR of the off-diagonal pattern of Q
+    const std::vector<int>* colidx = nullptr;
+    std::vector<double> qoff;   // Q_sj per CSR entry
+    std::vector<double> qdiag;  // Q_ss
+    std::vector<double> b;      // linear term (empty = 0)
+    const std::vector<int>* color_ptr = nullptr;  // colouring: positions -> sites
+    const std::vector<int>* order = nullptr;
+};
+int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* mu_host, const double* y,
+                    const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
+                    void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out);
+int check_rho(mclcar_ctx* ctx, double rho);
+void default_schedule(const mclcar_ctx* ctx, double rho, int* burn, int* thin);
+int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N);
+int dcar_ensure_stats(mclcar_ctx* ctx, mclcar_samples* s);
+
 }  // namespace mclcar

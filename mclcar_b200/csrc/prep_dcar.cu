@@ -1,0 +1,175 @@
+// mcl.prep.dCAR (R/mcl.dCAR.R:2-8): draw N samples at the importance point psi0 and attach
+// t10 = h(y; psi0), t20_i = h(Y_i; psi0).  The reference replicates CAR.simLM N times (one
+// sparse Cholesky per sample); here N/C kept states of C parallel Gibbs chains.
+#include <algorithm>
+#include <cmath>
+
+#include "engine.hpp"
+
+namespace mclcar {
+
+// rho must keep I - rho W positive definite: (1/min(ew), 1/max(ew)), R/CAR.simLM.R:9-11
+int check_rho(mclcar_ctx* ctx, double rho) {
+    if (!ctx->eigs.empty()) {
+        const double lo = 1.0 / ctx->ew_min, hi = 1.0 / ctx->ew_max;
+        if (rho < lo || rho > hi) return fail(ctx, MCLCAR_ERHO, "rho should be within %.10g %.10g", lo, hi);
+        return MCLCAR_OK;
+    }
+    // no spectrum supplied: Gershgorin bound |rho| * max row sum < 1 is sufficient
+    double rs = 0;
+    for (int i = 0; i < ctx->n; ++i) {
+        double a = 0;
+        for (int e = ctx->rowptr[i]; e < ctx->rowptr[i + 1]; ++e) a += ctx->binary ? 1.0 : std::fabs(ctx->val[e]);
+        rs = std::max(rs, a);
+    }
+    if (std::fabs(rho) * rs >= 1.0)
+        return fail(ctx, MCLCAR_ERHO, "rho should be within %.10g %.10g (Gershgorin bound; supply the eigenvalues of W for the exact range)",
+                    -1.0 / rs, 1.0 / rs);
+    return MCLCAR_OK;
+}
+
+// contraction factor per chromatic Gauss-Seidel sweep ~ (|rho| * spectral radius)^2
+void default_schedule(const mclcar_ctx* ctx, double rho, int* burn, int* thin) {
+    double lam = 0;
+    if (!ctx->eigs.empty()) lam = std::max(std::fabs(ctx->ew_min), std::fabs(ctx->ew_max));
+    else
+        for (int i = 0; i < ctx->n; ++i) {
+            double a = 0;
+            for (int e = ctx->rowptr[i]; e < ctx->rowptr[i + 1]; ++e) a += ctx->binary ? 1.0 : std::fabs(ctx->val[e]);
+            lam = std::max(lam, a);
+        }
+    double gam = std::pow(std::fabs(rho) * lam, 2.0);
+    gam = std::min(std::max(gam, 1e-3), 0.9995);
+    if (*thin <= 0) *thin = (int)std::min(4000.0, std::max(1.0, std::ceil(std::log(0.01) / std::log(gam))));
+    if (*burn <= 0) *burn = (int)std::min(40000.0, std::max(8.0, std::ceil(std::log(1e-6) / std::log(gam))));
+}
+
+int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N) {
+    const size_t cap = 200 * 1024;
+    int cbmax = 0;
+    for (int cb : {32, 16, 8, 4, 2})
+        if ((size_t)n * cb * sizeof(float) <= cap) { cbmax = cb; break; }
+    if (!cbmax) return std::min<int64_t>(N + (N & 1), (int64_t)ctx->n_sm * 2 * 32);
+    int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, cap / ((size_t)n * cbmax * sizeof(float))));
+    const int64_t c_auto = (int64_t)ctx->n_sm * per_sm * cbmax;
+    return std::max<int64_t>(2, std::min<int64_t>(c_auto, N + (N & 1)));
+}
+
+}  // namespace mclcar
+
+using namespace mclcar;
+
+extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
+                                mclcar_samples** out) {
+    if (!ctx || !psi0 || !out) return MCLCAR_EINVAL;
+    *out = nullptr;
+    MCL_TRY(require_device(ctx));
+    if (ctx->kind == GRAPH_NONE || !ctx->has_obs) return fail(ctx, MCLCAR_ESTATE, "set graph, design and observations first");
+    if (P != 2 && P != 2 + ctx->p) return fail(ctx, MCLCAR_EINVAL, "psi0 has length %d; expected 2 or %d", P, 2 + ctx->p);
+    if (N < 1 || N >= ((int64_t)1 << 31)) return fail(ctx, MCLCAR_EINVAL, "bad sample count %lld", (long long)N);
+    const double rho = psi0[0], sigma = psi0[1];
+    if (!(sigma > 0)) return fail(ctx, MCLCAR_EINVAL, "sigma must be positive");
+    MCL_TRY(check_rho(ctx, rho));
+    mclcar_sampler_opts o{};
+    if (opts) o = *opts;
+    else o.keep = 1;
+    if (o.dtype != MCLCAR_F64) o.dtype = MCLCAR_F32;
+    int burn = o.burn, thin = o.thin;
+    default_schedule(ctx, rho, &burn, &thin);
+    const int n = ctx->n;
+    const size_t es = o.dtype == MCLCAR_F32 ? 4 : 8;
+
+    // mean of the sampled field: X beta0
+    std::vector<double> mu;
+    if (P > 2) {
+        mu.assign(n, 0.0);
+        for (int l = 0; l < ctx->p; ++l)
+            for (int i = 0; i < n; ++i) mu[i] += ctx->X[(size_t)l * n + i] * psi0[2 + l];
+    }
+
+    mclcar_samples* s = new (std::nothrow) mclcar_samples();
+    if (!s) return fail(ctx, MCLCAR_ENOMEM, "out of host memory");
+    s->ctx = ctx; s->dtype = o.dtype; s->sites = n; s->N = N; s->owned = true;
+    int st = MCLCAR_OK;
+    const bool use_torus = ctx->kind == GRAPH_TORUS && ctx->n1 % 2 == 0 && ctx->n2 % 2 == 0 &&
+                           (size_t)n * 8 * sizeof(float) > 200 * 1024;
+    double* d_mu = nullptr;
+    if (use_torus) {
+        // ---- spatially tiled red-black sampler, sample-major output
+        int64_t C = o.n_chains > 0 ? o.n_chains : std::max<int64_t>(1, ((int64_t)32 << 20) / n);
+        C = std::min<int64_t>(std::min<int64_t>(C, N), 65535);
+        const int64_t E = (N + C - 1) / C;
+        const int64_t align = 16 / es;
+        const int64_t ld = (n + align - 1) / align * align;
+        s->layout = MCLCAR_COL_IS_SAMPLE;
+        s->ld = ld;
+        TorusChains tc;
+        void* staging = nullptr;
+        do {
+            cudaError_t e = cudaSuccess;
+            if (!mu.empty()) {
+                e = cudaMalloc((void**)&d_mu, (size_t)n * sizeof(double));
+                if (e == cudaSuccess) e = cudaMemcpyAsync(d_mu, mu.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+            }
+            if (e == cudaSuccess) e = cudaMalloc(o.keep ? &s->d_M : &staging, (size_t)(o.keep ? N : C) * ld * es);
+            if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ENOMEM, "cudaMalloc for %lld samples of %d sites failed: %s", (long long)(o.keep ? N : C), n, cudaGetErrorString(e)); break; }
+            if ((st = torus_chains_alloc(ctx, C, tc))) break;
+            if (!o.keep && (st = samples_alloc_stats(ctx, s, 2 + 2 * ctx->p))) break;
+            uint32_t sweep = 0;
+            for (int b = 0; b < burn && st == MCLCAR_OK; ++b) st = torus_sweep(ctx, tc, rho, sigma, sweep++);
+            for (int64_t e_i = 0; e_i < E && st == MCLCAR_OK; ++e_i) {
+                for (int t = 0; t < thin && st == MCLCAR_OK; ++t) st = torus_sweep(ctx, tc, rho, sigma, sweep++);
+                if (st) break;
+                const int64_t nch = std::min<int64_t>(C, N - e_i * C);
+                if (o.keep) {
+                    st = torus_emit(ctx, tc, d_mu, s->d_M, o.dtype, ld, e_i * C, nch);
+                } else {
+                    st = torus_emit(ctx, tc, d_mu, staging, o.dtype, ld, 0, nch);
+                    bool handled = false;
+                    if (st == MCLCAR_OK) st = launch_stats_torus_fast(ctx, staging, o.dtype, nch, ld, s->d_q + e_i * C, N, &handled);
+                    if (st == MCLCAR_OK && !handled) st = fail(ctx, MCLCAR_ELIMIT, "statistics-only sampling needs n2 %% 4 == 0 and rows <= 24 KB");
+                }
+            }
+            s->sweeps = sweep;
+            if (st == MCLCAR_OK && !o.keep) {
+                if ((st = samples_update_qbar(ctx, s))) break;
+                s->stats_ready = true;
+            }
+        } while (0);
+        torus_chains_free(ctx, tc);
+        if (staging) cudaFree(staging);
+    } else {
+        // ---- generic chromatic sampler with shared-memory-resident chains, site-major output
+        s->layout = MCLCAR_ROW_IS_SAMPLE;
+        const int64_t align = 16 / es;
+        const int64_t ld = (N + align - 1) / align * align;
+        s->ld = ld;
+        GmrfHost g;
+        g.n = n; g.rowptr = &ctx->rowptr; g.colidx = &ctx->colidx; g.color_ptr = &ctx->color_ptr; g.order = &ctx->order;
+        g.qdiag.assign(n, 1.0 / sigma);
+        g.qoff.resize(ctx->colidx.size());
+        for (size_t e = 0; e < g.qoff.size(); ++e) g.qoff[e] = -rho * (ctx->binary ? 1.0 : ctx->val[e]) / sigma;
+        cudaError_t e = cudaMalloc(&s->d_M, (size_t)n * ld * es);
+        if (e != cudaSuccess) st = fail(ctx, MCLCAR_ENOMEM, "cudaMalloc for the sample matrix failed: %s", cudaGetErrorString(e));
+        const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
+        if (st == MCLCAR_OK)
+            st = run_csr_sampler(ctx, g, 0, mu.empty() ? nullptr : mu.data(), nullptr, nullptr, nullptr, N, C, burn, thin,
+                                 s->d_M, o.dtype == MCLCAR_F64, ld, &s->accept, &s->sweeps);
+    }
+    if (d_mu) { cudaStreamSynchronize(ctx->stream); cudaFree(d_mu); }
+    if (st == MCLCAR_OK) st = mclcar_dcar_attach(ctx, s, psi0, P, nullptr);
+    if (st == MCLCAR_OK && !o.keep && s->d_M) {  // statistics only on the generic path: compute, then drop the matrix
+        st = dcar_ensure_stats(ctx, s);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(s->d_M);
+        s->d_M = nullptr;
+    }
+    if (st != MCLCAR_OK) {
+        std::string keep_err = ctx->err;
+        mclcar_samples_free(s);
+        ctx->err = keep_err;
+        return st;
+    }
+    *out = s;
+    return MCLCAR_OK;
+}

@@ -1,0 +1,276 @@
+// K1 (general graph) -- batched chromatic Gibbs / Metropolis-within-Gibbs sampler for a
+// Gaussian Markov random field  pi(x) ~ exp(-x'Qx/2 + b'x) [ * prod_s L_s(x_s) ],  Q sparse.
+//
+//   GAUSS : x_s | rest ~ N(m_s, 1/Q_ss),  m_s = (b_s - sum_{j != s} Q_sj x_j)/Q_ss        (exact Gibbs)
+//           - direct CAR on a neighbourhood matrix W: Q = (I - rho W)/sigma, b = 0, sample = X beta0 + x.
+//             Replaces CAR.simWmat's Cholesky draw (R/CAR.simLM.R:25-34).
+//           - hierarchical CAR: Q = Z'Qe Z + Qu, b = Z'Qe (y - X beta): the u | y draw of sim.HCAR
+//             (R/HCAR.sim.R:64-69).
+//   BINOM / POISSON : latent CAR field of the GLM, target log pi(z) = y'z - sum n log(1+e^{xb+z})
+//           - z'Qz/2 (R/postZsub.R:431) | y'z - sum e^{xb+z} - z'Qz/2 (:976).  Per site the prior
+//           conditional N(m_s, 1/Q_ss) is the proposal, so the Metropolis ratio is the likelihood
+//           ratio only.  Replaces the single-chain whole-vector MALA of postZ (R/postZsub.R:393-529).
+//
+// Parallelisation: chains are independent, so one CTA owns CB chains for the WHOLE run
+// (burn-in, thinning, all kept states) with their state resident in shared memory, [site][CB]
+// floats; colour classes are separated by __syncthreads() only -- no grid-wide barrier and
+// one launch per sample set.  One thread = (site slot, chain pair): the pair's two normals
+// and two uniforms come from ONE Philox4x32-10 call keyed by (seed; site, sweep, global pair
+// id).  Kept states are written site-major ("row = sample" of the R matrix Zy): for every
+// site the CB chains of a CTA form one contiguous run.
+#include "common.cuh"
+#include "engine.hpp"
+
+namespace mclcar {
+
+struct CsrSamplerParams {
+    int n, ncolors;
+    const int* color_ptr;  // [ncolors + 1] positions
+    const int* site_of;    // [n] position -> site
+    const int* rowptr;     // [n + 1] by position
+    const int* colidx;     // neighbour SITE ids
+    const float* coef;     // -Q_sj / Q_ss per entry
+    const float* hm;       // b_s / Q_ss per site
+    const float* sd;       // 1/sqrt(Q_ss) per site
+    const double* mu;      // added to kept states (site order) or null
+    // GLM data (site order)
+    const float* yv;
+    const float* nt;
+    const float* xb;
+    int CB;            // chains per CTA (even)
+    int64_t C;         // chains on this context = CB * gridDim.x
+    int burn, thin, E; // E kept states per chain
+    int64_t N;         // samples wanted on this context (<= E * C)
+    void* out;         // [n][ld] site-major, float or double
+    int64_t ld;
+    int out_f64;
+    float* state_g;    // global-memory state [grid][n][CB] when it does not fit in smem, else null
+    uint32_t seed_lo, seed_hi;
+    int64_t pair0, pair_stride;  // global pair id = pair0 + local_pair * pair_stride
+    unsigned long long* counters;  // [0] accepted, [1] proposed
+};
+
+namespace {
+
+constexpr uint32_t kTagCsr = 0x4373u;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float softplusf(float t) { return t > 15.f ? t : __logf(1.f + __expf(t)); }
+
+template <int FAM>
+__global__ void __launch_bounds__(kThreads) gibbs_csr_kernel(const CsrSamplerParams p) {
+    extern __shared__ float sm_state[];
+    const int CB = p.CB, hp = CB / 2;           // pairs per site row
+    const int pr = threadIdx.x % hp;            // chain pair within the CTA
+    const int slot = threadIdx.x / hp;
+    const int nslots = kThreads / hp;
+    float* x = p.state_g ? p.state_g + (size_t)blockIdx.x * p.n * CB : sm_state;
+    for (int t = threadIdx.x; t < p.n * CB; t += kThreads) x[t] = 0.f;
+    __syncthreads();
+
+    const uint64_t gpair = (uint64_t)(p.pair0 + ((int64_t)blockIdx.x * hp + pr) * p.pair_stride);
+    const int64_t chain_local = (int64_t)blockIdx.x * CB + 2 * pr;
+    unsigned int acc_cnt = 0, prop_cnt = 0;
+    const int total = p.burn + p.E * p.thin;
+    int e_next = 0;
+    for (int sweep = 0; sweep < total; ++sweep) {
+        for (int col = 0; col < p.ncolors; ++col) {
+            const int t1 = p.color_ptr[col + 1];
+            for (int t = p.color_ptr[col] + slot; t < t1; t += nslots) {
+                const int s = p.site_of[t];
+                float m0 = p.hm[s], m1 = m0;
+                const int e1 = p.rowptr[t + 1];
+                for (int e = p.rowptr[t]; e < e1; ++e) {
+                    const float2 v = *reinterpret_cast<const float2*>(x + (size_t)p.colidx[e] * CB + 2 * pr);
+                    const float c = p.coef[e];
+                    m0 = fmaf(c, v.x, m0);
+                    m1 = fmaf(c, v.y, m1);
+                }
+                const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)sweep, (uint32_t)gpair,
+                                                (uint32_t)(gpair >> 32) ^ (kTagCsr << 16), p.seed_lo, p.seed_hi);
+                float z0, z1;
+                box_muller(r.x, r.y, z0, z1);
+                const float sdv = p.sd[s];
+                float2 nv;
+                nv.x = fmaf(sdv, z0, m0);
+                nv.y = fmaf(sdv, z1, m1);
+                if constexpr (FAM != FAM_GAUSS) {
+                    const float2 cur = *reinterpret_cast<const float2*>(x + (size_t)s * CB + 2 * pr);
+                    const float ys = p.yv[s], xbs = p.xb[s];
+                    float la0, la1;
+                    if constexpr (FAM == FAM_BINOM) {
+                        const float ns = p.nt[s];
+                        la0 = ys * (nv.x - cur.x) - ns * (softplusf(xbs + nv.x) - softplusf(xbs + cur.x));
+                        la1 = ys * (nv.y - cur.y) - ns * (softplusf(xbs + nv.y) - softplusf(xbs + cur.y));
+                    } else {
+                        la0 = ys * (nv.x - cur.x) - (__expf(xbs + nv.x) - __expf(xbs + cur.x));
+                        la1 = ys * (nv.y - cur.y) - (__expf(xbs + nv.y) - __expf(xbs + cur.y));
+                    }
+                    const bool a0 = __logf(u01(r.z)) < la0, a1 = __logf(u01(r.w)) < la1;
+                    if (!a0) nv.x = cur.x;
+                    if (!a1) nv.y = cur.y;
+                    acc_cnt += (a0 ? 1u : 0u) + (a1 ? 1u : 0u);
+                    prop_cnt += 2u;
+                }
+                *reinterpret_cast<float2*>(x + (size_t)s * CB + 2 * pr) = nv;
+            }
+            __syncthreads();
+        }
+        if (sweep + 1 == p.burn + (e_next + 1) * p.thin) {
+            // keep this state: sample index = e * C + chain
+            const int64_t i0 = (int64_t)e_next * p.C + chain_local;
+            for (int s = slot; s < p.n; s += nslots) {
+                const float2 v = *reinterpret_cast<const float2*>(x + (size_t)s * CB + 2 * pr);
+                const double m = p.mu ? p.mu[s] : 0.0;
+                if (p.out_f64) {
+                    double* o = reinterpret_cast<double*>(p.out) + (size_t)s * p.ld;
+                    if (i0 < p.N) o[i0] = (double)v.x + m;
+                    if (i0 + 1 < p.N) o[i0 + 1] = (double)v.y + m;
+                } else {
+                    float* o = reinterpret_cast<float*>(p.out) + (size_t)s * p.ld;
+                    if (i0 < p.N) o[i0] = (float)((double)v.x + m);
+                    if (i0 + 1 < p.N) o[i0 + 1] = (float)((double)v.y + m);
+                }
+            }
+            ++e_next;
+        }
+    }
+    if constexpr (FAM != FAM_GAUSS) {
+        // block totals -> two atomics per CTA
+        __shared__ unsigned int s_acc, s_prop;
+        if (threadIdx.x == 0) s_acc = s_prop = 0;
+        __syncthreads();
+        atomicAdd(&s_acc, acc_cnt);
+        atomicAdd(&s_prop, prop_cnt);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(p.counters, (unsigned long long)s_acc);
+            atomicAdd(p.counters + 1, (unsigned long long)s_prop);
+        }
+    }
+}
+
+}  // namespace
+
+int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* mu_host, const double* y,
+                    const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
+                    void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out) {
+    MCL_TRY(require_device(ctx));
+    const int n = g.n;
+    const int ncol = (int)g.color_ptr->size() - 1;
+    // ---- permute the CSR into colour-major position order, convert to the conditional form
+    std::vector<int> rp(n + 1, 0), ci;
+    std::vector<float> coef, hm(n), sd(n);
+    ci.reserve(g.colidx->size());
+    coef.reserve(g.colidx->size());
+    for (int t = 0; t < n; ++t) {
+        const int s = (*g.order)[t];
+        const double qss = g.qdiag[s];
+        if (!(qss > 0)) return fail(ctx, MCLCAR_EINVAL, "precision matrix has a non-positive diagonal at site %d", s);
+        for (int e = (*g.rowptr)[s]; e < (*g.rowptr)[s + 1]; ++e) {
+            ci.push_back((*g.colidx)[e]);
+            coef.push_back((float)(-g.qoff[e] / qss));
+        }
+        rp[t + 1] = (int)ci.size();
+        hm[s] = g.b.empty() ? 0.f : (float)(g.b[s] / qss);
+        sd[s] = (float)(1.0 / std::sqrt(qss));
+    }
+    // ---- chains per CTA: largest CB whose state fits in shared memory and still fills the SMs
+    const size_t smem_cap = 200 * 1024;
+    int CB = 0;
+    for (int cb : {32, 16, 8, 4, 2})
+        if ((size_t)n * cb * sizeof(float) <= smem_cap) {
+            CB = cb;
+            if ((C_want + cb - 1) / cb >= ctx->n_sm) break;
+        }
+    const bool in_smem = CB != 0;
+    if (!in_smem) CB = 32;
+    int64_t grid = (C_want + CB - 1) / CB;
+    if (grid < 1) grid = 1;
+    const int64_t C = grid * CB;
+    int E = (int)((N + C - 1) / C);
+    if (E < 1) E = 1;
+
+    // ---- upload
+    auto up = [&](const void* h, size_t bytes, void** d) -> int {
+        MCL_CUDA(ctx, cudaMalloc(d, bytes ? bytes : 4));
+        if (bytes) MCL_CUDA(ctx, cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return MCLCAR_OK;
+    };
+    std::vector<void*> owned;
+    auto upv = [&](const void* h, size_t bytes, void** d) -> int {
+        int st = up(h, bytes, d);
+        if (st == MCLCAR_OK) owned.push_back(*d);
+        return st;
+    };
+    CsrSamplerParams p{};
+    int st = MCLCAR_OK;
+    std::vector<float> yf, ntf, xbf;
+    std::vector<double> mu;
+    void *d_cp = nullptr, *d_so = nullptr, *d_rp = nullptr, *d_ci = nullptr, *d_coef = nullptr, *d_hm = nullptr,
+         *d_sd = nullptr, *d_mu = nullptr, *d_y = nullptr, *d_nt = nullptr, *d_xb = nullptr, *d_cnt = nullptr,
+         *d_state = nullptr;
+    do {
+        if ((st = upv(g.color_ptr->data(), (ncol + 1) * sizeof(int), &d_cp))) break;
+        if ((st = upv(g.order->data(), n * sizeof(int), &d_so))) break;
+        if ((st = upv(rp.data(), (n + 1) * sizeof(int), &d_rp))) break;
+        if ((st = upv(ci.data(), ci.size() * sizeof(int), &d_ci))) break;
+        if ((st = upv(coef.data(), coef.size() * sizeof(float), &d_coef))) break;
+        if ((st = upv(hm.data(), n * sizeof(float), &d_hm))) break;
+        if ((st = upv(sd.data(), n * sizeof(float), &d_sd))) break;
+        if (mu_host) {
+            if ((st = upv(mu_host, n * sizeof(double), &d_mu))) break;
+        }
+        if (fam != FAM_GAUSS) {
+            yf.resize(n); ntf.resize(n); xbf.resize(n);
+            for (int s = 0; s < n; ++s) {
+                yf[s] = (float)y[s];
+                ntf[s] = ntrial ? (float)ntrial[s] : 1.f;
+                xbf[s] = (float)xb[s];
+            }
+            if ((st = upv(yf.data(), n * sizeof(float), &d_y))) break;
+            if ((st = upv(ntf.data(), n * sizeof(float), &d_nt))) break;
+            if ((st = upv(xbf.data(), n * sizeof(float), &d_xb))) break;
+        }
+        unsigned long long zero[2] = {0, 0};
+        if ((st = upv(zero, sizeof zero, &d_cnt))) break;
+        if (!in_smem) {
+            cudaError_t e = cudaMalloc(&d_state, (size_t)grid * n * CB * sizeof(float));
+            if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ENOMEM, "cudaMalloc of the chain state failed"); break; }
+            owned.push_back(d_state);
+        }
+        p.n = n; p.ncolors = ncol;
+        p.color_ptr = (const int*)d_cp; p.site_of = (const int*)d_so; p.rowptr = (const int*)d_rp;
+        p.colidx = (const int*)d_ci; p.coef = (const float*)d_coef; p.hm = (const float*)d_hm; p.sd = (const float*)d_sd;
+        p.mu = (const double*)d_mu; p.yv = (const float*)d_y; p.nt = (const float*)d_nt; p.xb = (const float*)d_xb;
+        p.CB = CB; p.C = C; p.burn = burn; p.thin = thin; p.E = E; p.N = N;
+        p.out = d_out; p.ld = ld; p.out_f64 = out_f64; p.state_g = (float*)d_state;
+        p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
+        p.pair0 = ctx->rank; p.pair_stride = ctx->world;
+        p.counters = (unsigned long long*)d_cnt;
+        const size_t smem = in_smem ? (size_t)n * CB * sizeof(float) : 0;
+        cudaError_t e = cudaSuccess;
+        if (fam == FAM_GAUSS) {
+            e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+            if (e == cudaSuccess) gibbs_csr_kernel<FAM_GAUSS><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(p);
+        } else if (fam == FAM_BINOM) {
+            e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_BINOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+            if (e == cudaSuccess) gibbs_csr_kernel<FAM_BINOM><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(p);
+        } else {
+            e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_POIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+            if (e == cudaSuccess) gibbs_csr_kernel<FAM_POIS><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(p);
+        }
+        if (e == cudaSuccess) e = cudaGetLastError();
+        unsigned long long cnt[2] = {0, 0};
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ECUDA, "CSR sampler: %s", cudaGetErrorString(e)); break; }
+        if (accept_rate) *accept_rate = cnt[1] ? (double)cnt[0] / (double)cnt[1] : 1.0;
+        if (sweeps_out) *sweeps_out = (int64_t)burn + (int64_t)E * thin;
+    } while (0);
+    cudaStreamSynchronize(ctx->stream);
+    for (void* d : owned) cudaFree(d);
+    return st;
+}
+
+}  // namespace mclcar

@@ -1,0 +1,161 @@
+// K1 (torus) -- batched red-black Gibbs sampler for the zero-mean CAR field
+//     z ~ N(0, sigma (I - rho W)^-1),   z_s | rest ~ N(rho * sum_{j~s} z_j, sigma)
+// on the rook torus of CAR.simTorus (R/CAR.simLM.R:2-22).  It replaces the reference's
+// exact draw (a fresh sparse Cholesky + backsolve per sample, R/CAR.simLM.R:28-31); its RNG
+// stream (Philox4x32-10) differs from R's, so it is validated statistically.
+//
+// Layout: every chain keeps its lattice as two half-lattices ("red": (i + j) even, "black":
+// (i + j) odd), each n1 x n2/2 row-major, so that a half sweep reads only the other colour
+// and writes only its own with unit-stride 16-byte accesses: 2 * sizeof(float) = 8 bytes of
+// HBM traffic per site update.  Site (i, j) of colour col sits at half-column c with
+// j = 2c + ((i & 1) ^ col); its four neighbours are other[i-1][c], other[i+1][c], other[i][c]
+// and other[i][c + s], s = +1 if ((i & 1) ^ col) else -1 (cyclic).
+// One thread updates 4 consecutive half-columns from ONE Philox4x32-10 call keyed by
+// (seed; half-lattice vector index, sweep*2+colour, global chain id) -- results do not
+// depend on the launch geometry nor on how chains are sharded over GPUs.
+#include "common.cuh"
+#include "engine.hpp"
+
+namespace mclcar {
+namespace {
+
+constexpr uint32_t kTagTorus = 0x7052u;
+
+struct TorusSweepParams {
+    float* red;    // [C][n1][h]
+    float* black;  // [C][n1][h]
+    int n1, h;     // h = n2 / 2
+    int64_t C;
+    float rho, sd;
+    uint32_t seed_lo, seed_hi;
+    uint32_t sweep;
+    int64_t chain0, chain_stride;  // global chain id = chain0 + local * chain_stride
+};
+
+// VEC = 4: h % 4 == 0, float4 path.  VEC = 1: any h.
+template <int VEC>
+__global__ void __launch_bounds__(256) gibbs_torus_half_sweep(const TorusSweepParams p, const int col) {
+    const int h = p.h, n1 = p.n1;
+    const int hv = h / VEC;
+    const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int64_t ch = blockIdx.z;
+    if (cv >= hv || i >= n1) return;
+    const size_t plane = (size_t)n1 * h;
+    float* own = (col == 0 ? p.red : p.black) + ch * plane;
+    const float* oth = (col == 0 ? p.black : p.red) + ch * plane;
+    const int iu = i == 0 ? n1 - 1 : i - 1, id = i + 1 == n1 ? 0 : i + 1;
+    const bool fwd = ((i & 1) ^ col) != 0;  // neighbour in the same row sits at c + 1, else at c - 1
+    const int c0 = cv * VEC;
+
+    const uint64_t gch = (uint64_t)(p.chain0 + ch * p.chain_stride);
+    const Philox4 r = philox4x32_10((uint32_t)((size_t)i * hv + cv), p.sweep * 2u + (uint32_t)col, (uint32_t)gch,
+                                    (uint32_t)(gch >> 32) ^ (kTagTorus << 16), p.seed_lo, p.seed_hi);
+    float z[4];
+    box_muller(r.x, r.y, z[0], z[1]);
+    box_muller(r.z, r.w, z[2], z[3]);
+
+    if constexpr (VEC == 4) {
+        const float4 o = *reinterpret_cast<const float4*>(oth + (size_t)i * h + c0);
+        const float4 u = *reinterpret_cast<const float4*>(oth + (size_t)iu * h + c0);
+        const float4 d = *reinterpret_cast<const float4*>(oth + (size_t)id * h + c0);
+        float e;  // the one neighbour outside this thread's vector
+        if (fwd) e = oth[(size_t)i * h + (c0 + 4 == h ? 0 : c0 + 4)];
+        else e = oth[(size_t)i * h + (c0 == 0 ? h - 1 : c0 - 1)];
+        float4 s;
+        if (fwd) {
+            s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e;
+        } else {
+            s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w;
+        }
+        float4 v;
+        v.x = fmaf(p.rho, s.x + u.x + d.x, p.sd * z[0]);
+        v.y = fmaf(p.rho, s.y + u.y + d.y, p.sd * z[1]);
+        v.z = fmaf(p.rho, s.z + u.z + d.z, p.sd * z[2]);
+        v.w = fmaf(p.rho, s.w + u.w + d.w, p.sd * z[3]);
+        *reinterpret_cast<float4*>(own + (size_t)i * h + c0) = v;
+    } else {
+        const int c = c0;
+        const int cn = fwd ? (c + 1 == h ? 0 : c + 1) : (c == 0 ? h - 1 : c - 1);
+        const float s = oth[(size_t)i * h + c] + oth[(size_t)i * h + cn] + oth[(size_t)iu * h + c] + oth[(size_t)id * h + c];
+        own[(size_t)i * h + c] = fmaf(p.rho, s, p.sd * z[0]);
+    }
+}
+
+// write the current state of chains [0, nch) as samples: out[(slot0 + ch)*ld + site] = mu[site] + z
+template <typename TO>
+__global__ void __launch_bounds__(256) torus_emit_kernel(const float* red, const float* black, int n1, int h,
+                                                         const double* mu, TO* out, int64_t ld, int64_t slot0,
+                                                         int64_t nch) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    const int64_t ch = blockIdx.z;
+    if (c >= h || ch >= nch) return;
+    const size_t plane = (size_t)n1 * h;
+    const float r = red[ch * plane + (size_t)i * h + c];
+    const float b = black[ch * plane + (size_t)i * h + c];
+    const int par = i & 1;  // red sits at column 2c + par, black at 2c + 1 - par
+    const size_t site = (size_t)i * 2 * h + 2 * c;
+    const double m0 = mu ? mu[site] : 0.0, m1 = mu ? mu[site + 1] : 0.0;
+    const double v0 = (par ? (double)b : (double)r) + m0;
+    const double v1 = (par ? (double)r : (double)b) + m1;
+    TO* o = out + (size_t)(slot0 + ch) * ld + site;
+    o[0] = (TO)v0;
+    o[1] = (TO)v1;
+}
+
+}  // namespace
+
+int torus_chains_alloc(mclcar_ctx* ctx, int64_t C, TorusChains& t) {
+    const size_t plane = (size_t)ctx->n1 * (ctx->n2 / 2);
+    MCL_CUDA(ctx, cudaMalloc((void**)&t.red, (size_t)C * plane * sizeof(float)));
+    MCL_CUDA(ctx, cudaMalloc((void**)&t.black, (size_t)C * plane * sizeof(float)));
+    MCL_CUDA(ctx, cudaMemsetAsync(t.red, 0, (size_t)C * plane * sizeof(float), ctx->stream));
+    MCL_CUDA(ctx, cudaMemsetAsync(t.black, 0, (size_t)C * plane * sizeof(float), ctx->stream));
+    t.C = C;
+    return MCLCAR_OK;
+}
+
+void torus_chains_free(mclcar_ctx* ctx, TorusChains& t) {
+    cudaStreamSynchronize(ctx->stream);
+    if (t.red) cudaFree(t.red);
+    if (t.black) cudaFree(t.black);
+    t.red = t.black = nullptr;
+}
+
+// one full sweep (both colours) of all chains
+int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, uint32_t sweep) {
+    TorusSweepParams p{};
+    p.red = t.red; p.black = t.black; p.n1 = ctx->n1; p.h = ctx->n2 / 2; p.C = t.C;
+    p.rho = (float)rho; p.sd = (float)std::sqrt(sigma);
+    p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
+    p.sweep = sweep;
+    p.chain0 = ctx->rank; p.chain_stride = ctx->world;
+    const bool vec4 = (p.h % 4) == 0;
+    const int hv = vec4 ? p.h / 4 : p.h;
+    dim3 block(32, 8);
+    while ((int)block.x / 2 >= hv && block.x > 1) { block.x /= 2; block.y *= 2; }
+    dim3 grid((hv + block.x - 1) / block.x, (p.n1 + block.y - 1) / block.y, (unsigned)t.C);
+    if (t.C > 65535) return fail(ctx, MCLCAR_ELIMIT, "more than 65535 chains in one torus sampler launch");
+    for (int col = 0; col < 2; ++col) {
+        if (vec4) gibbs_torus_half_sweep<4><<<grid, block, 0, ctx->stream>>>(p, col);
+        else gibbs_torus_half_sweep<1><<<grid, block, 0, ctx->stream>>>(p, col);
+    }
+    MCL_CUDA(ctx, cudaGetLastError());
+    return MCLCAR_OK;
+}
+
+int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, int dtype, int64_t ld, int64_t slot0,
+               int64_t nch) {
+    const int h = ctx->n2 / 2;
+    dim3 block(128);
+    dim3 grid((h + 127) / 128, ctx->n1, (unsigned)nch);
+    if (dtype == MCLCAR_F32)
+        torus_emit_kernel<float><<<grid, block, 0, ctx->stream>>>(t.red, t.black, ctx->n1, h, d_mu, (float*)out, ld, slot0, nch);
+    else
+        torus_emit_kernel<double><<<grid, block, 0, ctx->stream>>>(t.red, t.black, ctx->n1, h, d_mu, (double*)out, ld, slot0, nch);
+    MCL_CUDA(ctx, cudaGetLastError());
+    return MCLCAR_OK;
+}
+
+}  // namespace mclcar

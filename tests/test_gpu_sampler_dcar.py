@@ -1,0 +1,150 @@
+"""Statistical validation of the chromatic Gibbs sampler for the direct CAR model against
+closed forms: marginal quadratic-form moments, the torus covariance
+sigma (I - rho W)^-1, the mean X beta0, and the MC likelihood ratio against the exact one.
+The sampler cannot be bit-compared with the reference (R's RNG stream)."""
+import numpy as np
+import pytest
+
+from mclcar_b200 import api, _lib as L
+from oracle import dcar, graphs
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _z(stat, mean, var, N, ess_factor=1.0):
+    return (np.mean(stat) - mean) / np.sqrt(var / (N * ess_factor))
+
+
+@pytest.mark.parametrize("n1,n2,N,rho", [(20, 20, 4000, 0.2), (10, 10, 4000, -0.15), (64, 64, 1500, 0.2),
+                                         (128, 96, 600, 0.22), (9, 15, 3000, 0.15)])
+def test_torus_moments(n1, n2, N, rho):
+    """(20,20)/(10,10)/(9,15): generic shared-memory sampler (odd sizes: greedy colouring);
+    (64,64)/(128,96): spatially tiled red-black sampler."""
+    sigma = 1.3
+    n = n1 * n2
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal(n)
+    data = api.make_data(y, X=None, torus=(n1, n2), seed=1234)
+    sd = api.mcl_prep_dCAR([rho, sigma], N, data)
+    q = sd.stats()
+    assert q.shape == (N, 2)
+    mom = graphs.car_moments(graphs.torus_eigenvalues(n1, n2), rho, sigma)
+    assert abs(_z(q[:, 0], mom["E_xx"], mom["V_xx"], N)) < 5
+    assert abs(_z(q[:, 1], mom["E_xWx"], mom["V_xWx"], N)) < 5
+    # sample variance of the statistics themselves (chi-square mixture): within 15 %
+    assert np.var(q[:, 0]) == pytest.approx(mom["V_xx"], rel=0.15)
+    assert np.var(q[:, 1]) == pytest.approx(mom["V_xWx"], rel=0.15)
+    # statistics computed by K2 on the stored fp32 samples equal the oracle's on the fetched matrix
+    Y = sd.simY
+    np.testing.assert_allclose(q, dcar.suffstats(graphs.torus_W(n1, n2), None, Y), rtol=1e-12)
+
+
+def test_torus_covariance_and_mean():
+    n1 = n2 = 12
+    n = n1 * n2
+    rho, sigma = 0.21, 0.8
+    rng = np.random.default_rng(5)
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    beta = np.array([1.5, -0.7])
+    data = api.make_data(rng.standard_normal(n), X=X, torus=(n1, n2), seed=99)
+    N = 6000
+    sd = api.mcl_prep_dCAR(np.concatenate([[rho, sigma], beta]), N, data)
+    Y = sd.simY  # n x N
+    Z = Y - (X @ beta)[:, None]
+    assert np.abs(Z.mean(axis=1)).max() < 5 * np.sqrt(sigma / (1 - 4 * rho) / N)
+    # covariance with the (0,0) site, averaged over translations (stationary field)
+    F = np.fft.fft2(Z.T.reshape(N, n1, n2), axes=(1, 2))
+    emp = np.fft.ifft2((np.abs(F) ** 2).mean(axis=0)).real / n
+    exact = graphs.torus_covariance_row(n1, n2, rho, sigma)
+    assert np.abs(emp - exact).max() < 0.01 * exact[0, 0]
+
+
+@pytest.mark.parametrize("kind", ["lattice", "planar"])
+def test_general_graph_moments(kind):
+    W = graphs.lattice_W(9, 11) if kind == "lattice" else graphs.random_planar_map(300, seed=7)
+    n = W.shape[0]
+    ew = np.linalg.eigvalsh(W.toarray())
+    rho, sigma = 0.7 / ew.max(), 1.1
+    rng = np.random.default_rng(2)
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    beta = np.array([0.4, 0.9])
+    data = api.make_data(rng.standard_normal(n), X=X, W=W, eigenvalues=ew, seed=7)
+    N = 5000
+    sd = api.mcl_prep_dCAR(np.concatenate([[rho, sigma], beta]), N, data)
+    Y = sd.simY
+    Z = Y - (X @ beta)[:, None]
+    cov_exact = sigma * np.linalg.inv(np.eye(n) - rho * W.toarray())
+    emp = Z @ Z.T / N
+    # entrywise standard error of a covariance estimate ~ sqrt((c_ii c_jj + c_ij^2)/N)
+    se = np.sqrt((np.outer(np.diag(cov_exact), np.diag(cov_exact)) + cov_exact**2) / N)
+    assert (np.abs(emp - cov_exact) / se).max() < 6
+    mom = graphs.car_moments(ew, rho, sigma)
+    zz = np.einsum("ij,ij->j", Z, Z)
+    assert abs(_z(zz, mom["E_xx"], mom["V_xx"], N)) < 5
+
+
+def test_rho_out_of_range_raises_like_the_reference():
+    data = api.make_data(np.zeros(100), X=None, torus=(10, 10))
+    with pytest.raises(api.MclcarError) as ei:
+        api.mcl_prep_dCAR([0.26, 1.0], 10, data)
+    assert ei.value.code == L.ERHO and "rho should be within" in str(ei.value)
+
+
+def test_seed_reproducible_and_shard_invariant():
+    n1, n2 = 64, 64
+    y = np.zeros(n1 * n2)
+    ctl = {"n.chains": 4, "burn": 5, "thin": 2}
+    a = api.mcl_prep_dCAR([0.2, 1.0], 8, api.make_data(y, torus=(n1, n2), seed=42), ctl).simY
+    b = api.mcl_prep_dCAR([0.2, 1.0], 8, api.make_data(y, torus=(n1, n2), seed=42), ctl).simY
+    c = api.mcl_prep_dCAR([0.2, 1.0], 8, api.make_data(y, torus=(n1, n2), seed=43), ctl).simY
+    np.testing.assert_array_equal(a, b)
+    assert np.abs(a - c).max() > 0.1
+    # two shards of two chains each draw the same four global chains
+    parts = []
+    for r in range(2):
+        d = api.make_data(y, torus=(n1, n2), seed=42)
+        d.ctx.set_shard(r, 2)
+        parts.append(api.mcl_prep_dCAR([0.2, 1.0], 4, d, {"n.chains": 2, "burn": 5, "thin": 2}).simY)
+    # world=1 sample e*4 + ch  <->  rank ch % 2, sample e*2 + ch // 2
+    for e in range(2):
+        for ch in range(4):
+            np.testing.assert_array_equal(a[:, e * 4 + ch], parts[ch % 2][:, e * 2 + ch // 2])
+
+
+def test_statistics_only_mode_matches_kept_samples():
+    n1, n2 = 64, 64
+    rng = np.random.default_rng(0)
+    n = n1 * n2
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    y = rng.standard_normal(n)
+    psi = [0.2, 1.0, 0.3, -0.2]
+    ctl = {"n.chains": 8, "burn": 6, "thin": 3}
+    d1 = api.make_data(y, X=X, torus=(n1, n2), seed=11)
+    s1 = api.mcl_prep_dCAR(psi, 24, d1, dict(ctl, keep=True))
+    d2 = api.make_data(y, X=X, torus=(n1, n2), seed=11)
+    s2 = api.mcl_prep_dCAR(psi, 24, d2, dict(ctl, keep=False))
+    np.testing.assert_allclose(s2.stats(), s1.stats(), rtol=1e-13)
+    with pytest.raises(api.MclcarError):
+        _ = s2.simY
+    th = np.array([0.18, 1.1, 0.32, -0.18])
+    np.testing.assert_allclose(api.mcl_dCAR(th, d2, s2, Evar=True), api.mcl_dCAR(th, d1, s1, Evar=True), rtol=1e-12)
+
+
+def test_mcl_estimate_matches_exact_likelihood_ratio():
+    """BASELINE config 1 geometry (20 x 20 torus, N = 1000 -> here 8000 for a tight check):
+    MC ratio from GPU-drawn samples vs the exact likelihood ratio, within MC error."""
+    n1 = n2 = 20
+    odata, psi0, _, rng = helpers.torus_case(n1, n2, 10, seed=77)
+    data = api.make_data(odata["y"], X=odata["X"], torus=(n1, n2), seed=2024)
+    N = 8000
+    sd = api.mcl_prep_dCAR(psi0, N, data)
+    eig = graphs.torus_eigenvalues(n1, n2)
+    zs = []
+    for f in ([0.9, 1.05, 1.02, 0.98], [1.1, 0.95, 0.99, 1.03], [1.0, 1.1, 1.0, 1.0]):
+        th = psi0 * np.array(f)
+        r = api.mcl_dCAR(th, data, sd, Evar=True)
+        exact = dcar.loglik_dCAR(th, odata, eig) - dcar.loglik_dCAR(psi0, odata, eig)
+        zs.append((r[0] - exact) / np.sqrt(r[1]))
+        assert r[1] == pytest.approx(dcar.Avar_lik_dCAR(th, psi0, eig, N), rel=0.3)
+    assert np.abs(zs).max() < 4.5
