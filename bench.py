@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the Monte Carlo likelihood hot path (BASELINE.json metric) on B200.
+
+Workload (BASELINE config 5, one GPU's shard): linear CAR on a 1000 x 1000 torus, intercept
+design (p = 1), importance point psi0 = (rho 0.2, sigma^2 1, beta 1), 200-point (rho, sigma^2)
+grid, 12,500 samples per GPU (= 10^5 samples over 8 GPUs).  A step is one pass of the whole
+hot path over one batch:  draw the samples (chromatic Gibbs, K1)  ->  per-sample sufficient
+statistics (K2)  ->  importance-weight reduction for all 200 candidates (K3).
+`value` = samples x candidates / step time, everything resident in HBM; `e2e` = the same
+through the reference-facing API with HOST buffers (observations, design, candidates up;
+results down) inside the timed region.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+    python bench.py --impl reference ...                      (CPU restatement, host cores)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mc_loglik_sample_x_psi_evals_per_s"
+UNIT = "sample*psi evals/s"
+N1 = N2 = 1000
+K_PSI = 200
+PSI0 = np.array([0.2, 1.0, 1.0])
+SEED = 20260101
+
+
+def psi_grid():
+    """20 x 10 (rho, sigma^2) grid inside the finite-variance box (sigma^2 < 2 sigma0^2,
+    R/rsmMCL.R:113-114), beta held at the importance beta (R/rsmSub.R:75)."""
+    rho = np.linspace(0.1990, 0.2010, 20)
+    sig = np.linspace(0.9990, 1.0010, 10)
+    g = np.array([[r, s, PSI0[2]] for r in rho for s in sig])
+    assert g.shape == (K_PSI, 3)
+    return g
+
+
+def synthetic_obs(seed=SEED):
+    """One exact draw at the true parameter (FFT sampler of the oracle-free kind: numpy only)."""
+    rng = np.random.default_rng(seed)
+    a = 2.0 * np.cos(2.0 * np.pi * np.arange(N1) / N1)
+    b = 2.0 * np.cos(2.0 * np.pi * np.arange(N2) / N2)
+    d = np.sqrt(1.0 - 0.2 * (a[:, None] + b[None, :]))
+    z = rng.standard_normal((N1, N2))
+    x = np.fft.irfft2(np.fft.rfft2(z) / d[:, : N2 // 2 + 1], s=(N1, N2))
+    return x.ravel() + 1.0
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's CPU restatement on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_hot_path(n_samples: int, y, psis):
+    from oracle import cpu_path
+    X = np.ones((N1 * N2, 1))
+    t0 = time.perf_counter()
+    lr, var = cpu_path.hot_path_torus(N1, N2, X, y, PSI0, psis, n_samples, seed=SEED)
+    dt = time.perf_counter() - t0
+    assert np.all(np.isfinite(lr))
+    return dt, cpu_path.host_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    y = synthetic_obs()
+    psis = psi_grid()
+    from oracle import cpu_path
+    cores = cpu_path.host_threads()
+    n_s = args.cpu_samples or 8 * cores
+    for _ in range(args.warmup):
+        cpu_hot_path(min(n_s, cores), y, psis)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_hot_path(n_s, y, psis)
+        t += dt
+    value = n_s * K_PSI * args.steps / t
+    sample = f"{n_s} samples x {K_PSI} psi per step (bounded sample of the 12500-sample shard)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(), "samples_per_step": n_s, "psi_points": K_PSI},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name():
+    return (f"BASELINE config 5 shard: linear CAR on {N1}x{N2} torus, p=1, psi0=(0.2,1,1), {K_PSI}-point psi grid; "
+            "step = draw samples (chromatic Gibbs) + sufficient statistics + reduction over all psi")
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from mclcar_b200 import api, _lib as L
+    import ctypes as C
+
+    n = N1 * N2
+    N_gpu = args.samples_per_gpu
+    psis = psi_grid()
+    y = synthetic_obs()
+    X = np.ones((n, 1))
+    # pinned host staging for the e2e leg
+    y_pin = torch.from_numpy(y).pin_memory()
+    X_pin = torch.from_numpy(X).pin_memory()
+    psis_pin = torch.from_numpy(np.ascontiguousarray(psis)).pin_memory()
+
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(device=local, seed=SEED)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_shard(rank, world)
+    if world > 1:  # the library's own NCCL communicator: one all-gather of partial tuples per psi batch
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = C.create_string_buffer(128)
+            L.check(L.lib.mclcar_nccl_unique_id(ctx.h, raw), ctx.h)
+            idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        L.check(L.lib.mclcar_nccl_comm_init(ctx.h, bytes(idbuf.cpu().numpy().tobytes())), ctx.h)
+    control = {"n.chains": args.chains, "burn": args.burn, "thin": args.thin, "keep": not args.stats_only}
+
+    data = api.make_data(y_pin.numpy(), X=X_pin.numpy(), torus=(N1, N2), ctx=ctx)
+
+    def step_resident():
+        sd = api.mcl_prep_dCAR(PSI0, N_gpu, data, control)
+        res = api.mcl_dCAR_batch(psis, data, sd, rho_cons=None)
+        sd.close()
+        return res
+
+    def step_e2e():
+        d = api.set_design_obs(data, X_pin.numpy(), y_pin.numpy())                   # H2D of y and X
+        sd = api.mcl_prep_dCAR(PSI0, N_gpu, d, control)
+        res = api.mcl_dCAR_batch(psis_pin.numpy(), d, sd, rho_cons=None)             # psi up, (lr, var) down
+        sd.close()
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        # the calls end with host-side finishing after the last kernel: take the larger clock
+        t = max(ms * 1e-3, wall if steps else 0.0)
+        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), out
+
+    for _ in range(args.warmup):
+        res = step_resident()
+    assert np.all(np.isfinite(res)), "non-finite result in warm-up"
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    L.check(L.lib.mclcar_ctx_profile(ctx.h, 1), ctx.h)
+    t_res, res = timed(step_resident, args.steps)
+    ms_cat = np.zeros(8)
+    launches = np.zeros(8, dtype=np.int64)
+    L.check(L.lib.mclcar_ctx_profile_read(ctx.h, L.dptr(ms_cat), L.i64ptr(launches)), ctx.h)
+    L.check(L.lib.mclcar_ctx_profile(ctx.h, 0), ctx.h)
+    clk = clocks.stop() if rank == 0 else None
+
+    for _ in range(1):
+        step_e2e()
+    t_e2e, res2 = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = read_peaks()
+    N_tot = N_gpu * world
+    evals = N_tot * K_PSI * args.steps
+    value = evals / t_res
+    # per-kernel numbers from the CUDA-event spans recorded inside the library (this rank)
+    sweep_launches = int(launches[0])
+    sweep_ms = float(ms_cat[0])
+    sd_diag_sweeps = sweep_launches // 2 // max(args.steps, 1)
+    chains = args.chains if args.chains > 0 else max(1, (32 << 20) // n)
+    chains = min(chains, N_gpu)
+    bytes_per_half_sweep = chains * (n // 2) * 8.0  # read other colour + write own colour, fp32
+    sweep_gbs = bytes_per_half_sweep * sweep_launches / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
+    site_updates_per_s = chains * (n / 2) * sweep_launches / (sweep_ms * 1e-3) * world if sweep_ms > 0 else None
+    like_ms = float(ms_cat[2] + ms_cat[3])
+    like_bytes = N_gpu * n * 4.0 * args.steps
+    like_gbs = like_bytes / (like_ms * 1e-3) / 1e9 if like_ms > 0 and not args.stats_only else None
+    stats_gbs = like_bytes / (float(ms_cat[2]) * 1e-3) / 1e9 if ms_cat[2] > 0 and not args.stats_only else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(), "samples_per_gpu": N_gpu, "psi_points": K_PSI, "chains_per_gpu": chains,
+                   "sweeps_per_step": sd_diag_sweeps, "sample_storage": "fp32 in HBM" if not args.stats_only else "statistics only",
+                   "arithmetic": "fp32 chain state and normals; fp64 statistics, weights and reductions",
+                   "l2": "inputs larger than L2 (chain state %.0f MB, sample matrix %.1f GB per GPU)" % (chains * n * 4 / 1e6, N_gpu * n * 4 / 1e9),
+                   "parallelism": f"chains sharded over {world} GPU(s), one NCCL all-gather of partial tuples per psi batch"},
+        "e2e": {"value": evals / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
+                "h2d_bytes_per_step": int(y.nbytes + X.nbytes + psis.nbytes + PSI0.nbytes),
+                "d2h_bytes_per_step": int(K_PSI * 5 * 8 + 2 * 8)},
+        "gpu_launches": int(launches.sum()),
+        "roofline": {"kernel": "gibbs_torus_half_sweep<4>", "bound": "hbm", "achieved": sweep_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": (sweep_gbs / peak) if sweep_gbs else None, "traffic": None,
+                     "algorithmic_bytes_per_launch": bytes_per_half_sweep, "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
+                     "launches": sweep_launches, "peak_source": peak_src,
+                     "share_of_step": sweep_ms / (1e3 * t_res) if t_res > 0 else None},
+        "phases": {
+            "sampler": {"metric": "gibbs_site_updates_per_s", "value": site_updates_per_s, "ms_per_step": sweep_ms / args.steps,
+                        "bytes_per_site_update": 8, "roofline_site_updates_per_s": peak * 1e9 / 8 * world},
+            "emit": {"ms_per_step": float(ms_cat[1]) / args.steps},
+            "likelihood": {"metric": METRIC, "value": (N_tot * K_PSI * args.steps / (like_ms * 1e-3)) if like_ms > 0 else None,
+                           "ms_per_step": like_ms / args.steps, "achieved_GBps": like_gbs,
+                           "frac_of_hbm_peak": (like_gbs / peak) if like_gbs else None,
+                           "stats_kernel_GBps": stats_gbs, "stats_kernel_frac": (stats_gbs / peak) if stats_gbs else None,
+                           "reduce_ms_per_step": float(ms_cat[3]) / args.steps,
+                           "algorithmic_bytes_per_sample": n * 4},
+        },
+        "clocks": clk,
+        "result_check": {"lr_min": float(res[:, 0].min()), "lr_max": float(res[:, 0].max()),
+                         "var_max": float(res[:, 1].max()), "e2e_equal": bool(np.allclose(res, res2, rtol=1e-9, atol=1e-12))},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import cpu_path
+        cores = cpu_path.host_threads()
+        n_s = args.cpu_samples or 8 * cores
+        cpu_hot_path(min(n_s, cores), y, psis)
+        dt, _ = cpu_hot_path(n_s, y, psis)
+        line["cpu_baseline"] = {"value": n_s * K_PSI / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n_s} samples x {K_PSI} psi of the same workload, {dt:.1f} s "
+                                          "(FFT exact sampler + C statistics/reduction twin of the oracle)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples-per-gpu", type=int, default=12500)
+    ap.add_argument("--chains", type=int, default=0)
+    ap.add_argument("--burn", type=int, default=0)
+    ap.add_argument("--thin", type=int, default=0)
+    ap.add_argument("--stats-only", action="store_true")
+    ap.add_argument("--cpu-samples", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,12 @@ int mclcar_ctx_sync(mclcar_ctx* ctx);
 /* this context is shard `rank` of `world`: samplers draw global chains rank, rank+world,
  * ... so that the union over ranks does not depend on `world`. */
 int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world);
+/* instrumentation: kernel-launch counters per category and, while enabled, CUDA-event time
+ * spans recorded on the context's stream around each group of launches.  Categories:
+ * 0 torus half sweeps, 1 sample emission, 2 statistics (K2), 3 reduction (K3),
+ * 4 shared-memory chain sampler, 5 GLM data terms.  profile(enable) resets both. */
+int mclcar_ctx_profile(mclcar_ctx* ctx, int enable);
+int mclcar_ctx_profile_read(mclcar_ctx* ctx, double ms_out[8], int64_t launches_out[8]);
 /* NCCL (dlopen'ed on first use, libnccl.so.2): rank 0 obtains a 128-byte unique id,
  * hands it to the other ranks by any channel, then every rank calls comm_init.  Once
  * initialised, every *_eval/_grad/_hess call all-gathers its partial tuples with ONE

@@ -60,6 +60,8 @@ SIGNATURES = {
     "mclcar_ctx_set_stream": (_i, [_vp, _vp]),
     "mclcar_ctx_sync": (_i, [_vp]),
     "mclcar_ctx_set_shard": (_i, [_vp, _i, _i]),
+    "mclcar_ctx_profile": (_i, [_vp, _i]),
+    "mclcar_ctx_profile_read": (_i, [_vp, _pd, _pi64]),
     "mclcar_nccl_unique_id": (_i, [_vp, C.c_char_p]),
     "mclcar_nccl_comm_init": (_i, [_vp, C.c_char_p]),
     "mclcar_graph_torus": (_i, [_vp, _i, _i]),

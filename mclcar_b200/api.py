@@ -111,6 +111,23 @@ def make_data(y, X=None, W=None, torus=None, n_trial=None, eigenvalues=None, dev
     return CarData(ctx=ctx, n=n, X=X, y=y, W=Wc, torus=tuple(torus) if torus is not None else None, n_trial=nt)
 
 
+def set_design_obs(data: CarData, X, y, n_trial=None) -> CarData:
+    """Replace design and observations on an existing context (the graph stays uploaded)."""
+    ctx = data.ctx
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if X is not None:
+        Xc = np.asfortranarray(X, dtype=np.float64)
+        check(lib.mclcar_set_design(ctx.h, Xc.ctypes.data_as(C.POINTER(C.c_double)), Xc.shape[1]), ctx.h)
+    else:
+        check(lib.mclcar_set_design(ctx.h, None, 0), ctx.h)
+    nt = None
+    if n_trial is not None:
+        nt = np.ascontiguousarray(np.broadcast_to(np.asarray(n_trial, dtype=np.float64), (data.n,)))
+    check(lib.mclcar_set_obs(ctx.h, dptr(y), dptr(nt)), ctx.h)
+    data.X, data.y, data.n_trial = (None if X is None else np.asarray(X)), y, nt
+    return data
+
+
 class SimData:
     """The reference's `simdata` = list(simY, t10, t20) (R/mcl.dCAR.R:7) as a device handle."""
 

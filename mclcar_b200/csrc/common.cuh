@@ -40,14 +40,13 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4{c0, c1, c2, c3};
 }
 
-// uniform in (0, 1): (k + 0.5) * 2^-32, never 0 or 1
-__device__ __forceinline__ float u01(uint32_t k) { return fmaf((float)k, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+// uniform in (0, 1) from the top 24 bits: (k24 + 0.5) * 2^-24 -- exactly representable in
+// fp32, never 0 or 1 (a 32-bit construction rounds to 0/1 at the ends of the range)
+__device__ __forceinline__ float u01(uint32_t k) { return fmaf((float)(k >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f); }
 
 // two standard normals from two 32-bit words (Box-Muller, fp32 fast intrinsics)
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-    // 1 - u01 is in (0, 1]: argument of the log is never 0
-    const float u = fmaf((float)a, -2.3283064365386963e-10f, 1.0f - 1.1641532182693481e-10f);
-    const float r = sqrtf(-2.0f * __logf(u));
+    const float r = sqrtf(-2.0f * __logf(u01(a)));
     float s, c;
     __sincosf(6.2831853071795865f * u01(b), &s, &c);
     n0 = r * c;

@@ -59,6 +59,22 @@ int ensure_pinned(mclcar_ctx* ctx, size_t bytes) {
     return MCLCAR_OK;
 }
 
+ProfScope::ProfScope(mclcar_ctx* c, int category, int64_t n_launches) : ctx(c), cat(category) {
+    ctx->launches[cat] += n_launches;
+    if (ctx->profiling && cudaEventCreate(&a) == cudaSuccess) cudaEventRecord(a, ctx->stream);
+}
+void ProfScope::close() {
+    if (!a) return;
+    cudaEvent_t b = nullptr;
+    if (cudaEventCreate(&b) == cudaSuccess) {
+        cudaEventRecord(b, ctx->stream);
+        ctx->spans.push_back({cat, a, b});
+    } else {
+        cudaEventDestroy(a);
+    }
+    a = nullptr;
+}
+
 template <class T>
 static int upload(mclcar_ctx* ctx, T*& dptr, const std::vector<T>& h) {
     if (ctx->host_only) return MCLCAR_OK;
@@ -187,6 +203,7 @@ void mclcar_ctx_destroy(mclcar_ctx* ctx) {
         for (void* p : ptrs)
             if (p) cudaFree(p);
         comm_destroy(ctx);
+        for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
         if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
         if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     }
@@ -215,6 +232,35 @@ int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world) {
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, MCLCAR_EINVAL, "bad shard %d of %d", rank, world);
     ctx->rank = rank;
     ctx->world = world;
+    return MCLCAR_OK;
+}
+
+int mclcar_ctx_profile(mclcar_ctx* ctx, int enable) {
+    if (!ctx) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    ctx->spans.clear();
+    for (int c = 0; c < PROF_NCAT; ++c) { ctx->launches[c] = 0; ctx->span_ms[c] = 0.0; }
+    ctx->profiling = enable != 0;
+    return MCLCAR_OK;
+}
+
+int mclcar_ctx_profile_read(mclcar_ctx* ctx, double ms_out[8], int64_t launches_out[8]) {
+    if (!ctx) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& sp : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) ctx->span_ms[sp.cat] += ms;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+    for (int c = 0; c < PROF_NCAT; ++c) {
+        if (ms_out) ms_out[c] = ctx->span_ms[c];
+        if (launches_out) launches_out[c] = ctx->launches[c];
+    }
     return MCLCAR_OK;
 }
 

@@ -17,6 +17,9 @@ enum GraphKind { GRAPH_NONE = 0, GRAPH_TORUS = 1, GRAPH_CSR = 2 };
 // tuple kinds ("what" at the ABI)
 enum { WHAT_LR = 0, WHAT_GRAD = 1, WHAT_HESS = 2 };
 
+// instrumentation categories (mclcar_ctx_profile_read)
+enum { PROF_SWEEP = 0, PROF_EMIT = 1, PROF_STATS = 2, PROF_REDUCE = 3, PROF_CSR_SAMPLER = 4, PROF_GLM = 5, PROF_NCAT = 8 };
+
 struct DeviceBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -74,6 +77,13 @@ struct mclcar_ctx {
     // ---- NCCL (dlopen'ed)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
+
+    // ---- instrumentation: kernel launches per category and (when enabled) CUDA-event spans
+    bool profiling = false;
+    int64_t launches[mclcar::PROF_NCAT] = {0};
+    struct Span { int cat; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double span_ms[mclcar::PROF_NCAT] = {0};
 };
 
 struct mclcar_samples {
@@ -117,6 +127,16 @@ void set_global_error(const char* msg);
         int _s = (expr);                 \
         if (_s != MCLCAR_OK) return _s;  \
     } while (0)
+
+// RAII span: two events on the context's stream around a group of launches of one category
+struct ProfScope {
+    mclcar_ctx* ctx;
+    int cat;
+    cudaEvent_t a = nullptr;
+    ProfScope(mclcar_ctx* c, int category, int64_t n_launches);
+    void close();
+    ~ProfScope() { close(); }
+};
 
 int ensure(mclcar_ctx* ctx, DeviceBuf& b, size_t bytes);
 int ensure_pinned(mclcar_ctx* ctx, size_t bytes);

@@ -398,6 +398,8 @@ int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host) {
     p.sub_idx = d_idx; p.sub_ptr = d_ptr;
     p.partial = (double*)ctx->d_partial.p; p.S = S; p.T = (int)Tr;
 
+    ProfScope prof(ctx, PROF_REDUCE, 2 + (plan.shift_mode == MCLCAR_SHIFT_MAX ? 1 : 0) +
+                                         (plan.what == WHAT_HESS ? (d + 15) / 16 : 0));
     if (plan.shift_mode == MCLCAR_SHIFT_MAX) {
         k3_prepare_max<MCLCAR_MAX_P><<<K, kThreads, (size_t)csr * sizeof(double), st>>>(p, (double*)ctx->d_coef.p, Fr);
     }
@@ -439,6 +441,7 @@ int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host) {
     const int n_copy = plan.what == WHAT_HESS ? 0 : 1 + Fr;
     k3_finalize<<<K, 128, 0, st>>>(p, (const double*)ctx->d_coef.p, (double*)ctx->d_tuples.p, n_copy);
     MCL_CUDA(ctx, cudaGetLastError());
+    prof.close();
 
     // device tuples (padded F) -> host tuples (exact F)
     MCL_TRY(ensure_pinned(ctx, (size_t)K * Tr * sizeof(double)));

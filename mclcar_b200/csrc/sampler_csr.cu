@@ -250,6 +250,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* m
         p.counters = (unsigned long long*)d_cnt;
         const size_t smem = in_smem ? (size_t)n * CB * sizeof(float) : 0;
         cudaError_t e = cudaSuccess;
+        ProfScope prof(ctx, PROF_CSR_SAMPLER, 1);
         if (fam == FAM_GAUSS) {
             e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
             if (e == cudaSuccess) gibbs_csr_kernel<FAM_GAUSS><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(p);

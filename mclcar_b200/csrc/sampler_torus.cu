@@ -137,6 +137,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, uint3
     while ((int)block.x / 2 >= hv && block.x > 1) { block.x /= 2; block.y *= 2; }
     dim3 grid((hv + block.x - 1) / block.x, (p.n1 + block.y - 1) / block.y, (unsigned)t.C);
     if (t.C > 65535) return fail(ctx, MCLCAR_ELIMIT, "more than 65535 chains in one torus sampler launch");
+    ProfScope prof(ctx, PROF_SWEEP, 2);
     for (int col = 0; col < 2; ++col) {
         if (vec4) gibbs_torus_half_sweep<4><<<grid, block, 0, ctx->stream>>>(p, col);
         else gibbs_torus_half_sweep<1><<<grid, block, 0, ctx->stream>>>(p, col);
@@ -150,6 +151,7 @@ int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, i
     const int h = ctx->n2 / 2;
     dim3 block(128);
     dim3 grid((h + 127) / 128, ctx->n1, (unsigned)nch);
+    ProfScope prof(ctx, PROF_EMIT, 1);
     if (dtype == MCLCAR_F32)
         torus_emit_kernel<float><<<grid, block, 0, ctx->stream>>>(t.red, t.black, ctx->n1, h, d_mu, (float*)out, ld, slot0, nch);
     else

@@ -42,6 +42,7 @@ int samples_alloc_stats(mclcar_ctx* ctx, mclcar_samples* s, int d) {
 
 int samples_update_qbar(mclcar_ctx* ctx, mclcar_samples* s) {
     MCL_TRY(ensure(ctx, ctx->d_tuples, (size_t)s->d * sizeof(double)));
+    ProfScope prof(ctx, PROF_STATS, 1);
     rowmean_kernel<<<s->d, 256, 0, ctx->stream>>>(s->d_q, s->N, s->N, (double*)ctx->d_tuples.p);
     MCL_CUDA(ctx, cudaGetLastError());
     s->qbar.assign(s->d, 0.0);

@@ -133,6 +133,7 @@ int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64
     }
     p.out = partial;
     dim3 grid((unsigned)xblocks, (unsigned)chunks);
+    ProfScope prof(ctx, PROF_STATS, chunks > 1 ? 2 : 1);
     if (dtype == MCLCAR_F32) MCL_TRY(launch_typed<float>(ctx, p, grid));
     else MCL_TRY(launch_typed<double>(ctx, p, grid));
     if (chunks > 1) {
@@ -158,6 +159,7 @@ int launch_transpose(mclcar_ctx* ctx, const void* in, int dtype, int64_t rows, i
                      void* out, int64_t ld_out) {
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
     if (grid.y > 65535) return fail(ctx, MCLCAR_ELIMIT, "transpose: too many rows (%lld)", (long long)rows);
+    ProfScope prof(ctx, PROF_STATS, 1);
     if (dtype == MCLCAR_F32)
         transpose_kernel<float, float><<<grid, block, 0, ctx->stream>>>((const float*)in, (float*)out, rows, cols, ld_in, ld_out);
     else

@@ -284,6 +284,7 @@ int launch_stats_torus_fast(mclcar_ctx* ctx, const void* M, int dtype, int64_t N
     const size_t smem = carry_bytes + kStages * stage_bytes + (kStages + 2) * sizeof(uint64_t) +
                         (kThreads / 32) * (3 + 2 * kMaxNC) * sizeof(double) + 128;
     int grid = (int)std::min<int64_t>(prm.items, (int64_t)2 * ctx->n_sm);
+    ProfScope prof(ctx, PROF_STATS, S > 1 ? 2 : 1);
     if (dtype == MCLCAR_F32) MCL_TRY(launch_typed<float>(ctx, prm, grid, smem));
     else MCL_TRY(launch_typed<double>(ctx, prm, grid, smem));
     if (S > 1) {
