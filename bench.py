@@ -238,6 +238,17 @@ def run_ours(args):
         res = step_resident()
     assert np.all(np.isfinite(res)), "non-finite result in warm-up"
 
+    if args.debug and rank == 0:  # wall-clock breakdown of one step, outside the timed region
+        def tick(label, fn):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+            print(f"[debug] {label}: {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)
+            return r
+        tick("set_design_obs", lambda: api.set_design_obs(data, X_pin.numpy(), y_pin.numpy()))
+        sd_ = tick("mcl_prep_dCAR", lambda: api.mcl_prep_dCAR(PSI0, N_gpu, data, control))
+        tick("mcl_dCAR_batch (first: stats + reduce)", lambda: api.mcl_dCAR_batch(psis, data, sd_, rho_cons=None))
+        tick("mcl_dCAR_batch (second: reduce only)", lambda: api.mcl_dCAR_batch(psis, data, sd_, rho_cons=None))
+        tick("close", lambda: sd_.close())
+
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -336,6 +347,7 @@ def main():
     ap.add_argument("--stats-only", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

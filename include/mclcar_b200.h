@@ -114,8 +114,10 @@ typedef struct mclcar_sampler_opts {
     int32_t burn;      /* sweeps discarded at the start of every chain (0: default)         */
     int32_t thin;      /* sweeps between kept states (0: default)                            */
     int32_t keep;      /* 1: keep the sample matrix in HBM; 0: keep sufficient statistics only */
-    int32_t dtype;     /* MCLCAR_F32 (default) or MCLCAR_F64 chain state and stored samples */
-    int32_t reserved[4];
+    int32_t dtype;     /* MCLCAR_F32 (default) or MCLCAR_F64 stored samples (chain state is fp32) */
+    int32_t reserved[2];
+    double omega;      /* over-relaxation factor of the Gaussian Gibbs update in [1, 2); 0: optimal
+                          for the graph's spectrum (SOR); 1: plain Gibbs                        */
 } mclcar_sampler_opts;
 
 /* the reference's own sample matrix (simY / Zy / u.y) copied to the device: parity path.

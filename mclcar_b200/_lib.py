@@ -31,7 +31,7 @@ class MclcarError(RuntimeError):
 
 class SamplerOpts(C.Structure):
     _fields_ = [("n_chains", C.c_int64), ("burn", C.c_int32), ("thin", C.c_int32), ("keep", C.c_int32),
-                ("dtype", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("dtype", C.c_int32), ("reserved", C.c_int32 * 2), ("omega", C.c_double)]
 
 
 def _load() -> C.CDLL:

@@ -305,7 +305,7 @@ def vmle_dCAR(MLE: dict, data: CarData, simdata: SimData) -> np.ndarray:
 def _sampler_opts(control: Optional[dict]) -> L.SamplerOpts:
     """GPU keys appended to the reference's control-list idiom (`con[names(control)] <-
     control`, R/OptimMCL.R:6-11): n.chains, burn, thin, keep, dtype."""
-    con = {"n.chains": 0, "burn": 0, "thin": 0, "keep": True, "dtype": "f32"}
+    con = {"n.chains": 0, "burn": 0, "thin": 0, "keep": True, "dtype": "f32", "omega": 0.0}
     for k, v in (control or {}).items():
         if k not in con:
             raise ValueError(f"unknown sampler control '{k}'")
@@ -316,6 +316,7 @@ def _sampler_opts(control: Optional[dict]) -> L.SamplerOpts:
     o.thin = int(con["thin"])
     o.keep = 1 if con["keep"] else 0
     o.dtype = L.F64 if con["dtype"] in ("f64", np.float64) else L.F32
+    o.omega = float(con["omega"])
     return o
 
 

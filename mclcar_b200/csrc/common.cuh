@@ -40,13 +40,43 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4{c0, c1, c2, c3};
 }
 
-// uniform in (0, 1) from the top 24 bits: (k24 + 0.5) * 2^-24 -- exactly representable in
-// fp32, never 0 or 1 (a 32-bit construction rounds to 0/1 at the ends of the range)
-__device__ __forceinline__ float u01(uint32_t k) { return fmaf((float)(k >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f); }
+// the ten round keys of one seed, computed once on the host and passed in the kernel
+// parameters (constant bank): the per-round key schedule costs no instructions
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+__host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k[2 * r] = k0;
+        K.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return K;
+}
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, K.k[2 * r], K.k[2 * r + 1]);
+    return Philox4{c0, c1, c2, c3};
+}
 
-// two standard normals from two 32-bit words (Box-Muller, fp32 fast intrinsics)
+// uniform in (0, 1) from the top 23 bits, built in the mantissa (no int->float conversion):
+// (k23 * 2^-23) + 2^-24, exactly representable, never 0 or 1
+__device__ __forceinline__ float u01(uint32_t k) {
+    return __uint_as_float(0x3f800000u | (k >> 9)) - 0.99999994039535522461f;  // 1 - 2^-24
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// two standard normals from two 32-bit words (Box-Muller on the MUFU unit: lg2, sqrt, sin, cos)
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-    const float r = sqrtf(-2.0f * __logf(u01(a)));
+    const float r = sqrt_approx(-1.3862943611198906f * __log2f(u01(a)));  // sqrt(-2 ln u)
     float s, c;
     __sincosf(6.2831853071795865f * u01(b), &s, &c);
     n0 = r * c;

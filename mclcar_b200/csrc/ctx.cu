@@ -31,6 +31,58 @@ int require_device(mclcar_ctx* ctx) {
     return MCLCAR_OK;
 }
 
+// best-fit block of the cache (at most 25 % larger than asked), else a fresh cudaMalloc; when
+// that fails every cached free block is returned to the driver and the allocation retried
+int pool_alloc(mclcar_ctx* ctx, void** out, size_t bytes) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 16;
+    int best = -1;
+    for (int i = 0; i < (int)ctx->pool.size(); ++i) {
+        auto& b = ctx->pool[i];
+        if (!b.used && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 + 4096 &&
+            (best < 0 || b.bytes < ctx->pool[best].bytes))
+            best = i;
+    }
+    if (best >= 0) {
+        ctx->pool[best].used = true;
+        *out = ctx->pool[best].p;
+        return MCLCAR_OK;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto it = ctx->pool.begin(); it != ctx->pool.end();) {
+            if (!it->used) { cudaFree(it->p); it = ctx->pool.erase(it); } else ++it;
+        }
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MCLCAR_ENOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->pool.push_back({p, bytes, true});
+    *out = p;
+    return MCLCAR_OK;
+}
+
+// the block becomes reusable by later calls on the same stream (stream order makes that safe)
+void pool_free(mclcar_ctx* ctx, void* p) {
+    if (!p) return;
+    for (auto& b : ctx->pool)
+        if (b.p == p) {
+            b.used = false;
+            return;
+        }
+    cudaFree(p);  // not ours
+}
+
+void pool_release_all(mclcar_ctx* ctx) {
+    for (auto& b : ctx->pool) cudaFree(b.p);
+    ctx->pool.clear();
+}
+
 int ensure(mclcar_ctx* ctx, DeviceBuf& b, size_t bytes) {
     if (bytes <= b.bytes && b.p) return MCLCAR_OK;
     if (b.p) {
@@ -79,14 +131,28 @@ template <class T>
 static int upload(mclcar_ctx* ctx, T*& dptr, const std::vector<T>& h) {
     if (ctx->host_only) return MCLCAR_OK;
     if (dptr) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(dptr);
+        pool_free(ctx, dptr);
         dptr = nullptr;
     }
     if (h.empty()) return MCLCAR_OK;
-    MCL_CUDA(ctx, cudaMalloc((void**)&dptr, h.size() * sizeof(T)));
-    MCL_CUDA(ctx, cudaMemcpy(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    MCL_TRY(pool_alloc(ctx, (void**)&dptr, h.size() * sizeof(T)));
+    MCL_CUDA(ctx, cudaMemcpyAsync(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MCLCAR_OK;
+}
+
+// dot product with four independent accumulators (vectorises; error ~ sqrt(n) eps)
+static double dot4(const double* a, const double* b, int n) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int i = 0;
+    for (; i + 3 < n; i += 4) {
+        s0 += a[i] * b[i];
+        s1 += a[i + 1] * b[i + 1];
+        s2 += a[i + 2] * b[i + 2];
+        s3 += a[i + 3] * b[i + 3];
+    }
+    for (; i < n; ++i) s0 += a[i] * b[i];
+    return (s0 + s1) + (s2 + s3);
 }
 
 // y = W x on the host CSR copy
@@ -197,11 +263,11 @@ void mclcar_ctx_destroy(mclcar_ctx* ctx) {
     if (!ctx->host_only) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
-        void* ptrs[] = {ctx->d_rowptr, ctx->d_colidx, ctx->d_val, ctx->d_order, ctx->d_X, ctx->d_WX, ctx->d_y,
-                        ctx->d_ntrial, ctx->d_coef.p, ctx->d_partial.p, ctx->d_tuples.p, ctx->d_subidx.p,
+        void* ptrs[] = {ctx->d_coef.p, ctx->d_partial.p, ctx->d_tuples.p, ctx->d_subidx.p,
                         ctx->d_gather.p};
         for (void* p : ptrs)
             if (p) cudaFree(p);
+        pool_release_all(ctx);
         comm_destroy(ctx);
         for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
         if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -367,15 +433,10 @@ int mclcar_set_design(mclcar_ctx* ctx, const double* X, int p) {
     ctx->G1.assign((size_t)p * p, 0.0);
     for (int a = 0; a < p; ++a)
         for (int b = 0; b < p; ++b) {
-            long double s0 = 0, s1 = 0;
             const double *xa = ctx->X.data() + (size_t)a * n, *xb = ctx->X.data() + (size_t)b * n,
                          *wb = ctx->WX.data() + (size_t)b * n;
-            for (int i = 0; i < n; ++i) {
-                s0 += (long double)xa[i] * xb[i];
-                s1 += (long double)xa[i] * wb[i];
-            }
-            ctx->G0[(size_t)a * p + b] = (double)s0;
-            ctx->G1[(size_t)a * p + b] = (double)s1;
+            ctx->G0[(size_t)a * p + b] = dot4(xa, xb, n);
+            ctx->G1[(size_t)a * p + b] = dot4(xa, wb, n);
         }
     MCL_TRY(upload(ctx, ctx->d_X, ctx->X));
     MCL_TRY(upload(ctx, ctx->d_WX, ctx->WX));
@@ -398,22 +459,12 @@ int mclcar_set_obs(mclcar_ctx* ctx, const double* y, const double* ntrial) {
     std::vector<double> Wy(n);
     spmv(ctx, ctx->y.data(), Wy.data());
     ctx->qobs.assign(2 + 2 * p, 0.0);
-    long double s0 = 0, s1 = 0;
-    for (int i = 0; i < n; ++i) {
-        s0 += (long double)y[i] * y[i];
-        s1 += (long double)y[i] * Wy[i];
-    }
-    ctx->qobs[0] = (double)s0;
-    ctx->qobs[1] = (double)s1;
+    ctx->qobs[0] = dot4(y, y, n);
+    ctx->qobs[1] = dot4(y, Wy.data(), n);
     for (int a = 0; a < p; ++a) {
-        long double u = 0, v = 0;
         const double* xa = ctx->X.data() + (size_t)a * n;
-        for (int i = 0; i < n; ++i) {
-            u += (long double)xa[i] * y[i];
-            v += (long double)xa[i] * Wy[i];
-        }
-        ctx->qobs[2 + a] = (double)u;
-        ctx->qobs[2 + p + a] = (double)v;
+        ctx->qobs[2 + a] = dot4(xa, y, n);
+        ctx->qobs[2 + p + a] = dot4(xa, Wy.data(), n);
     }
     MCL_TRY(upload(ctx, ctx->d_y, ctx->y));
     MCL_TRY(upload(ctx, ctx->d_ntrial, ctx->ntrial));

@@ -124,11 +124,10 @@ int dcar_ensure_stats(mclcar_ctx* ctx, mclcar_samples* s) {
             // general graph, sample-major: transpose to site-major on the device, then the lane-per-sample kernel
             const size_t es = s->dtype == MCLCAR_F32 ? 4 : 8;
             void* t = nullptr;
-            MCL_CUDA(ctx, cudaMalloc(&t, (size_t)s->sites * s->N * es));
+            MCL_TRY(pool_alloc(ctx, &t, (size_t)s->sites * s->N * es));
             int st = launch_transpose(ctx, s->d_M, s->dtype, s->N, s->sites, s->ld, t, s->N);
             if (st == MCLCAR_OK) st = launch_stats_site_major(ctx, t, s->dtype, s->N, s->N, s->d_q, s->N);
-            cudaStreamSynchronize(ctx->stream);
-            cudaFree(t);
+            pool_free(ctx, t);
             MCL_TRY(st);
         }
     } else {
@@ -307,14 +306,14 @@ int mclcar_dcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, i
     s->psi0.assign(psi0, psi0 + P);
     s->t10 = affine_h(m0, ctx->qobs.data());
     if (s->d_base) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(s->d_base);
+        pool_free(ctx, s->d_base);
         s->d_base = nullptr;
     }
     s->base_mean = 0.0;
     if (t20) {
-        MCL_CUDA(ctx, cudaMalloc((void**)&s->d_base, (size_t)s->N * sizeof(double)));
-        MCL_CUDA(ctx, cudaMemcpy(s->d_base, t20, (size_t)s->N * sizeof(double), cudaMemcpyHostToDevice));
+        MCL_TRY(pool_alloc(ctx, (void**)&s->d_base, (size_t)s->N * sizeof(double)));
+        MCL_CUDA(ctx, cudaMemcpyAsync(s->d_base, t20, (size_t)s->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         long double a = 0;
         for (int64_t i = 0; i < s->N; ++i) a += t20[i];
         s->base_mean = (double)(a / s->N);

@@ -74,6 +74,11 @@ struct mclcar_ctx {
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
 
+    // ---- caching device allocator: big buffers (sample matrices, chain state, statistics) are
+    // recycled across calls so that steady-state steps do no cudaMalloc / cudaFree
+    struct PoolBlock { void* p; size_t bytes; bool used; };
+    std::vector<PoolBlock> pool;
+
     // ---- NCCL (dlopen'ed)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
@@ -138,6 +143,9 @@ struct ProfScope {
     ~ProfScope() { close(); }
 };
 
+int pool_alloc(mclcar_ctx* ctx, void** out, size_t bytes);
+void pool_free(mclcar_ctx* ctx, void* p);
+void pool_release_all(mclcar_ctx* ctx);
 int ensure(mclcar_ctx* ctx, DeviceBuf& b, size_t bytes);
 int ensure_pinned(mclcar_ctx* ctx, size_t bytes);
 int require_device(mclcar_ctx* ctx);
@@ -197,7 +205,7 @@ struct TorusChains {
 };
 int torus_chains_alloc(mclcar_ctx* ctx, int64_t C, TorusChains& t);
 void torus_chains_free(mclcar_ctx* ctx, TorusChains& t);
-int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, uint32_t sweep);
+int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep);
 int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, int dtype, int64_t ld, int64_t slot0,
                int64_t nch);
 
@@ -213,11 +221,11 @@ struct GmrfHost {
     const std::vector<int>* color_ptr = nullptr;  // colouring: positions -> sites
     const std::vector<int>* order = nullptr;
 };
-int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* mu_host, const double* y,
+int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, const double* mu_host, const double* y,
                     const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
                     void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out);
 int check_rho(mclcar_ctx* ctx, double rho);
-void default_schedule(const mclcar_ctx* ctx, double rho, int* burn, int* thin);
+void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* burn, int* thin);
 int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N);
 int dcar_ensure_stats(mclcar_ctx* ctx, mclcar_samples* s);
 

@@ -28,8 +28,12 @@ int check_rho(mclcar_ctx* ctx, double rho) {
     return MCLCAR_OK;
 }
 
-// contraction factor per chromatic Gauss-Seidel sweep ~ (|rho| * spectral radius)^2
-void default_schedule(const mclcar_ctx* ctx, double rho, int* burn, int* thin) {
+// Sweep schedule.  mu = |rho| * spectral radius of W is the Jacobi contraction factor.  Plain
+// chromatic Gibbs (omega = 1) decorrelates at rate mu^2 per sweep; on a two-colourable graph
+// (consistently ordered) the over-relaxed sampler with omega* = 2/(1 + sqrt(1 - mu^2)) does so
+// at rate omega* - 1 (Young's SOR theory; Fox & Parker 2017 for samplers), with a linear
+// polynomial factor at omega* itself.  thin: autocorrelation <= 1 %; burn: start bias <= 1e-6.
+void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* burn, int* thin) {
     double lam = 0;
     if (!ctx->eigs.empty()) lam = std::max(std::fabs(ctx->ew_min), std::fabs(ctx->ew_max));
     else
@@ -38,10 +42,29 @@ void default_schedule(const mclcar_ctx* ctx, double rho, int* burn, int* thin) {
             for (int e = ctx->rowptr[i]; e < ctx->rowptr[i + 1]; ++e) a += ctx->binary ? 1.0 : std::fabs(ctx->val[e]);
             lam = std::max(lam, a);
         }
-    double gam = std::pow(std::fabs(rho) * lam, 2.0);
-    gam = std::min(std::max(gam, 1e-3), 0.9995);
-    if (*thin <= 0) *thin = (int)std::min(4000.0, std::max(1.0, std::ceil(std::log(0.01) / std::log(gam))));
-    if (*burn <= 0) *burn = (int)std::min(40000.0, std::max(8.0, std::ceil(std::log(1e-6) / std::log(gam))));
+    const double mu = std::min(std::max(std::fabs(rho) * lam, 1e-2), 0.9998);
+    const double w_opt = 2.0 / (1.0 + std::sqrt(1.0 - mu * mu));
+    if (!(*omega > 0)) *omega = ctx->ncolors == 2 ? w_opt : 1.0;
+    if (*omega < 1.0) *omega = 1.0;
+    if (*omega > 1.98) *omega = 1.98;
+    const double w = *omega;
+    double rate;
+    bool poly = false;
+    if (w >= w_opt - 1e-12) {
+        rate = w - 1.0;
+        poly = w > 1.0 && w < w_opt + 0.02;
+    } else {
+        const double t = 0.5 * (w * mu + std::sqrt(w * w * mu * mu - 4.0 * (w - 1.0)));
+        rate = t * t;
+    }
+    rate = std::min(std::max(rate, 1e-3), 0.9996);
+    auto sweeps_for = [&](double tol, int lo, int hi) {
+        for (int k = lo; k < hi; ++k)
+            if ((poly ? k : 1.0) * std::pow(rate, k) <= tol) return k;
+        return hi;
+    };
+    if (*thin <= 0) *thin = sweeps_for(0.01, 1, 4000);
+    if (*burn <= 0) *burn = sweeps_for(1e-6, 4, 40000);
 }
 
 int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N) {
@@ -75,7 +98,8 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
     else o.keep = 1;
     if (o.dtype != MCLCAR_F64) o.dtype = MCLCAR_F32;
     int burn = o.burn, thin = o.thin;
-    default_schedule(ctx, rho, &burn, &thin);
+    double omega = o.omega;
+    default_schedule(ctx, rho, &omega, &burn, &thin);
     const int n = ctx->n;
     const size_t es = o.dtype == MCLCAR_F32 ? 4 : 8;
 
@@ -106,19 +130,19 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         TorusChains tc;
         void* staging = nullptr;
         do {
-            cudaError_t e = cudaSuccess;
             if (!mu.empty()) {
-                e = cudaMalloc((void**)&d_mu, (size_t)n * sizeof(double));
-                if (e == cudaSuccess) e = cudaMemcpyAsync(d_mu, mu.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+                if ((st = pool_alloc(ctx, (void**)&d_mu, (size_t)n * sizeof(double)))) break;
+                cudaError_t e = cudaMemcpyAsync(d_mu, mu.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // mu is a local
+                if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ECUDA, "upload of X beta0 failed: %s", cudaGetErrorString(e)); break; }
             }
-            if (e == cudaSuccess) e = cudaMalloc(o.keep ? &s->d_M : &staging, (size_t)(o.keep ? N : C) * ld * es);
-            if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ENOMEM, "cudaMalloc for %lld samples of %d sites failed: %s", (long long)(o.keep ? N : C), n, cudaGetErrorString(e)); break; }
+            if ((st = pool_alloc(ctx, o.keep ? &s->d_M : &staging, (size_t)(o.keep ? N : C) * ld * es))) break;
             if ((st = torus_chains_alloc(ctx, C, tc))) break;
             if (!o.keep && (st = samples_alloc_stats(ctx, s, 2 + 2 * ctx->p))) break;
             uint32_t sweep = 0;
-            for (int b = 0; b < burn && st == MCLCAR_OK; ++b) st = torus_sweep(ctx, tc, rho, sigma, sweep++);
+            for (int b = 0; b < burn && st == MCLCAR_OK; ++b) st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++);
             for (int64_t e_i = 0; e_i < E && st == MCLCAR_OK; ++e_i) {
-                for (int t = 0; t < thin && st == MCLCAR_OK; ++t) st = torus_sweep(ctx, tc, rho, sigma, sweep++);
+                for (int t = 0; t < thin && st == MCLCAR_OK; ++t) st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++);
                 if (st) break;
                 const int64_t nch = std::min<int64_t>(C, N - e_i * C);
                 if (o.keep) {
@@ -137,7 +161,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
             }
         } while (0);
         torus_chains_free(ctx, tc);
-        if (staging) cudaFree(staging);
+        pool_free(ctx, staging);
     } else {
         // ---- generic chromatic sampler with shared-memory-resident chains, site-major output
         s->layout = MCLCAR_ROW_IS_SAMPLE;
@@ -149,19 +173,17 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         g.qdiag.assign(n, 1.0 / sigma);
         g.qoff.resize(ctx->colidx.size());
         for (size_t e = 0; e < g.qoff.size(); ++e) g.qoff[e] = -rho * (ctx->binary ? 1.0 : ctx->val[e]) / sigma;
-        cudaError_t e = cudaMalloc(&s->d_M, (size_t)n * ld * es);
-        if (e != cudaSuccess) st = fail(ctx, MCLCAR_ENOMEM, "cudaMalloc for the sample matrix failed: %s", cudaGetErrorString(e));
+        st = pool_alloc(ctx, &s->d_M, (size_t)n * ld * es);
         const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
         if (st == MCLCAR_OK)
-            st = run_csr_sampler(ctx, g, 0, mu.empty() ? nullptr : mu.data(), nullptr, nullptr, nullptr, N, C, burn, thin,
+            st = run_csr_sampler(ctx, g, FAM_GAUSS, omega, mu.empty() ? nullptr : mu.data(), nullptr, nullptr, nullptr, N, C, burn, thin,
                                  s->d_M, o.dtype == MCLCAR_F64, ld, &s->accept, &s->sweeps);
     }
-    if (d_mu) { cudaStreamSynchronize(ctx->stream); cudaFree(d_mu); }
+    pool_free(ctx, d_mu);
     if (st == MCLCAR_OK) st = mclcar_dcar_attach(ctx, s, psi0, P, nullptr);
     if (st == MCLCAR_OK && !o.keep && s->d_M) {  // statistics only on the generic path: compute, then drop the matrix
         st = dcar_ensure_stats(ctx, s);
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(s->d_M);
+        pool_free(ctx, s->d_M);
         s->d_M = nullptr;
     }
     if (st != MCLCAR_OK) {

@@ -45,7 +45,8 @@ struct CsrSamplerParams {
     int64_t ld;
     int out_f64;
     float* state_g;    // global-memory state [grid][n][CB] when it does not fit in smem, else null
-    uint32_t seed_lo, seed_hi;
+    PhiloxKeys keys;
+    float keep, gain, noise;   // over-relaxation: x' = keep*x + gain*m + noise*sd*z (Gaussian family)
     int64_t pair0, pair_stride;  // global pair id = pair0 + local_pair * pair_stride
     unsigned long long* counters;  // [0] accepted, [1] proposed
 };
@@ -87,13 +88,19 @@ __global__ void __launch_bounds__(kThreads) gibbs_csr_kernel(const CsrSamplerPar
                     m1 = fmaf(c, v.y, m1);
                 }
                 const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)sweep, (uint32_t)gpair,
-                                                (uint32_t)(gpair >> 32) ^ (kTagCsr << 16), p.seed_lo, p.seed_hi);
+                                                (uint32_t)(gpair >> 32) ^ (kTagCsr << 16), p.keys);
                 float z0, z1;
                 box_muller(r.x, r.y, z0, z1);
                 const float sdv = p.sd[s];
                 float2 nv;
-                nv.x = fmaf(sdv, z0, m0);
-                nv.y = fmaf(sdv, z1, m1);
+                if constexpr (FAM == FAM_GAUSS) {
+                    const float2 cur = *reinterpret_cast<const float2*>(x + (size_t)s * CB + 2 * pr);
+                    nv.x = fmaf(p.keep, cur.x, fmaf(p.gain, m0, p.noise * sdv * z0));
+                    nv.y = fmaf(p.keep, cur.y, fmaf(p.gain, m1, p.noise * sdv * z1));
+                } else {
+                    nv.x = fmaf(sdv, z0, m0);
+                    nv.y = fmaf(sdv, z1, m1);
+                }
                 if constexpr (FAM != FAM_GAUSS) {
                     const float2 cur = *reinterpret_cast<const float2*>(x + (size_t)s * CB + 2 * pr);
                     const float ys = p.yv[s], xbs = p.xb[s];
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(kThreads) gibbs_csr_kernel(const CsrSamplerPar
 
 }  // namespace
 
-int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* mu_host, const double* y,
+int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, const double* mu_host, const double* y,
                     const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
                     void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out) {
     MCL_TRY(require_device(ctx));
@@ -193,7 +200,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* m
 
     // ---- upload
     auto up = [&](const void* h, size_t bytes, void** d) -> int {
-        MCL_CUDA(ctx, cudaMalloc(d, bytes ? bytes : 4));
+        MCL_TRY(pool_alloc(ctx, d, bytes ? bytes : 4));
         if (bytes) MCL_CUDA(ctx, cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
         return MCLCAR_OK;
     };
@@ -235,8 +242,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* m
         unsigned long long zero[2] = {0, 0};
         if ((st = upv(zero, sizeof zero, &d_cnt))) break;
         if (!in_smem) {
-            cudaError_t e = cudaMalloc(&d_state, (size_t)grid * n * CB * sizeof(float));
-            if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ENOMEM, "cudaMalloc of the chain state failed"); break; }
+            if ((st = pool_alloc(ctx, &d_state, (size_t)grid * n * CB * sizeof(float)))) break;
             owned.push_back(d_state);
         }
         p.n = n; p.ncolors = ncol;
@@ -245,7 +251,8 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* m
         p.mu = (const double*)d_mu; p.yv = (const float*)d_y; p.nt = (const float*)d_nt; p.xb = (const float*)d_xb;
         p.CB = CB; p.C = C; p.burn = burn; p.thin = thin; p.E = E; p.N = N;
         p.out = d_out; p.ld = ld; p.out_f64 = out_f64; p.state_g = (float*)d_state;
-        p.seed_lo = (uint32_t)ctx->seed; p.seed_hi = (uint32_t)(ctx->seed >> 32);
+        p.keys = philox_keys(ctx->seed);
+        p.keep = (float)(1.0 - omega); p.gain = (float)omega; p.noise = (float)std::sqrt(omega * (2.0 - omega));
         p.pair0 = ctx->rank; p.pair_stride = ctx->world;
         p.counters = (unsigned long long*)d_cnt;
         const size_t smem = in_smem ? (size_t)n * CB * sizeof(float) : 0;
@@ -270,7 +277,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, const double* m
         if (sweeps_out) *sweeps_out = (int64_t)burn + (int64_t)E * thin;
     } while (0);
     cudaStreamSynchronize(ctx->stream);
-    for (void* d : owned) cudaFree(d);
+    for (void* d : owned) pool_free(ctx, d);
     return st;
 }
 

@@ -30,12 +30,11 @@ __global__ void to_f64_kernel(const T* in, double* out, int64_t rows, int64_t co
 int samples_alloc_stats(mclcar_ctx* ctx, mclcar_samples* s, int d) {
     if (s->d_q && s->d == d) return MCLCAR_OK;
     if (s->d_q) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(s->d_q);
+        pool_free(ctx, s->d_q);
         s->d_q = nullptr;
     }
     s->d = d;
-    MCL_CUDA(ctx, cudaMalloc((void**)&s->d_q, (size_t)d * s->N * sizeof(double)));
+    MCL_TRY(pool_alloc(ctx, (void**)&s->d_q, (size_t)d * s->N * sizeof(double)));
     s->stats_ready = false;
     return MCLCAR_OK;
 }
@@ -87,15 +86,14 @@ int mclcar_samples_from_host(mclcar_ctx* ctx, const void* M, int dtype, int layo
     // device copy is packed to a 16-byte aligned leading dimension (bulk-copy requirement)
     const int64_t align = 16 / es;
     const int64_t ldd = (lead + align - 1) / align * align;
-    cudaError_t e = cudaMalloc(&s->d_M, (size_t)outer * ldd * es);
-    if (e != cudaSuccess) {
+    int stp = pool_alloc(ctx, &s->d_M, (size_t)outer * ldd * es);
+    if (stp != MCLCAR_OK) {
         delete s;
-        return fail(ctx, MCLCAR_ENOMEM, "cudaMalloc of %zu bytes for the sample matrix failed: %s", (size_t)outer * ldd * es,
-                    cudaGetErrorString(e));
+        return stp;
     }
     s->owned = true;
     s->ld = ldd;
-    e = cudaMemcpy2DAsync(s->d_M, (size_t)ldd * es, M, (size_t)ld * es, (size_t)lead * es, (size_t)outer,
+    cudaError_t e = cudaMemcpy2DAsync(s->d_M, (size_t)ldd * es, M, (size_t)ld * es, (size_t)lead * es, (size_t)outer,
                           cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
@@ -123,10 +121,9 @@ void mclcar_samples_free(mclcar_samples* s) {
     mclcar_ctx* ctx = s->ctx;
     if (ctx && !ctx->host_only) {
         cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        if (s->owned && s->d_M) cudaFree(s->d_M);
-        if (s->d_q) cudaFree(s->d_q);
-        if (s->d_base) cudaFree(s->d_base);
+        if (s->owned && s->d_M) pool_free(ctx, s->d_M);
+        if (s->d_q) pool_free(ctx, s->d_q);
+        if (s->d_base) pool_free(ctx, s->d_base);
     }
     delete s;
 }
@@ -143,7 +140,7 @@ int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double*
     const int64_t rows = same ? rows_src : cols_src, cols = same ? cols_src : rows_src;
     if (ld < cols) return fail(ctx, MCLCAR_EINVAL, "ld too small");
     double* tmp = nullptr;
-    MCL_CUDA(ctx, cudaMalloc((void**)&tmp, (size_t)rows * cols * sizeof(double)));
+    MCL_TRY(pool_alloc(ctx, (void**)&tmp, (size_t)rows * cols * sizeof(double)));
     cudaStream_t st = ctx->stream;
     int status = MCLCAR_OK;
     if (same) {
@@ -167,10 +164,9 @@ int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double*
         // transpose in the source dtype, then widen
         void* t2 = nullptr;
         const size_t es = s->dtype == MCLCAR_F32 ? 4 : 8;
-        cudaError_t e = cudaMalloc(&t2, (size_t)rows * cols * es);
-        if (e != cudaSuccess) {
-            cudaFree(tmp);
-            return fail(ctx, MCLCAR_ENOMEM, "cudaMalloc failed in samples_fetch");
+        if (pool_alloc(ctx, &t2, (size_t)rows * cols * es) != MCLCAR_OK) {
+            pool_free(ctx, tmp);
+            return MCLCAR_ENOMEM;
         }
         status = launch_transpose(ctx, s->d_M, s->dtype, rows_src, cols_src, s->ld, t2, cols);
         if (status == MCLCAR_OK) {
@@ -183,8 +179,7 @@ int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double*
                     to_f64_kernel<double><<<g, 256, 0, st>>>((const double*)t2 + r0 * cols, tmp + r0 * cols, nr, cols, cols, cols);
             }
         }
-        cudaStreamSynchronize(st);
-        cudaFree(t2);
+        pool_free(ctx, t2);
     }
     if (status == MCLCAR_OK) {
         cudaError_t e = cudaMemcpy2DAsync(out, (size_t)ld * 8, tmp, (size_t)cols * 8, (size_t)cols * 8, (size_t)rows,
@@ -192,7 +187,7 @@ int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double*
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) status = fail(ctx, MCLCAR_ECUDA, "device to host copy failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(tmp);
+    pool_free(ctx, tmp);
     return status;
 }
 
