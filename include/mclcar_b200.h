@@ -166,6 +166,30 @@ int mclcar_dcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int 
 /* MCMLE.var, R/mcl.dCAR.R:156-165 (un-normalised, un-shifted weights); out: K x P x P */
 int mclcar_dcar_mcmle_var(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, double* out);
 
+/* ---- Binomial / Poisson GLM with latent CAR effects (R/mcl.glm.R, R/mcl.bin.R, R/mcl.pois.R) ----
+ * Sample sets are the N x n matrix Zy, ROW = sample (MCLCAR_ROW_IS_SAMPLE).  The eigenvalues of
+ * W must be known (torus: analytic; CSR: mclcar_graph_set_eigenvalues) -- they replace the
+ * per-call chol.spam log-determinant (R/mcl.bin.R:50-52) and eigen(W) (R/mcl.bin.R:176). */
+/* mcl.prep.glm + postZ (R/mcl.glm.R:5-40, R/postZ.R:2-14): N latent fields z | y at psi0 drawn by
+ * the batched Metropolis-within-Gibbs sampler; lHZy.psi is attached implicitly. */
+int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int64_t N,
+                    const mclcar_sampler_opts* opts, mclcar_samples** out);
+/* attach the importance point to the reference's own Zy; lHZy_psi NULL = recompute
+ * log f_psi0(y, Z_i) (R/mcl.glm.R:34-37), else the reference's vector (N). */
+int mclcar_glm_attach(mclcar_ctx* ctx, mclcar_samples* s, int family, const double* psi0, int P,
+                      const double* lHZy_psi);
+int mclcar_glm_lhzy(mclcar_ctx* ctx, mclcar_samples* s, double* out /* N */);
+/* mcl.glm(pars, mcdata, family, Evar) = mcl.bin / mcl.pois (R/mcl.bin.R:33-79) for K candidates;
+ * subsets as in mclcar_dcar_eval (Exp.CAR.glm centre points, R/rsmSub.R:175-181). */
+int mclcar_glm_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P,
+                    const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* lr, double* var);
+/* mcl.grad.glm (R/mcl.bin.R:160-217): grad K x P, gradvar K x P x P when evar != 0 */
+int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
+                    int shift_mode, double* grad, double* gradvar);
+/* mcl.Hessian.glm (R/mcl.bin.R:222-297; Poisson beta block as coded at R/mcl.pois.R:268) */
+int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
+                    double* hess);
+
 /* ---- staged evaluation (what the one-shot calls above are made of) ------------------------
  * stage 1, device: per-candidate partial tuples of this context's samples, to host memory;
  * stage 2, host only: merge the tuples of G shards in shard order (mclcar_tuples_merge);

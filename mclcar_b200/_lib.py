@@ -21,6 +21,7 @@ F64, F32 = 0, 1
 SHIFT_MEAN, SHIFT_MAX = 0, 1
 WHAT_LR, WHAT_GRAD, WHAT_HESS = 0, 1, 2
 MAX_P, MAX_COV = 12, 8
+FAMILY_DCAR, FAMILY_BINOM, FAMILY_POISSON, FAMILY_HCAR = 0, 1, 2, 3
 
 
 class MclcarError(RuntimeError):
@@ -85,6 +86,12 @@ SIGNATURES = {
     "mclcar_dcar_grad": (_i, [_vp, _vp, _pd, _i, _i, _i, _i, _pd, _pd]),
     "mclcar_dcar_hess": (_i, [_vp, _vp, _pd, _i, _i, _i, _pd]),
     "mclcar_dcar_mcmle_var": (_i, [_vp, _vp, _pd, _i, _i, _pd]),
+    "mclcar_glm_prep": (_i, [_vp, _i, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
+    "mclcar_glm_attach": (_i, [_vp, _vp, _i, _pd, _i, _pd]),
+    "mclcar_glm_lhzy": (_i, [_vp, _vp, _pd]),
+    "mclcar_glm_eval": (_i, [_vp, _vp, _pd, _i, _i, _pi64, _pi64, _i, _pd, _pd]),
+    "mclcar_glm_grad": (_i, [_vp, _vp, _pd, _i, _i, _i, _i, _pd, _pd]),
+    "mclcar_glm_hess": (_i, [_vp, _vp, _pd, _i, _i, _i, _pd]),
     "mclcar_tuple_len": (_i64, [_i, _i, _i]),
     "mclcar_dcar_partial": (_i, [_vp, _vp, _pd, _i, _i, _i, _pi64, _pi64, _i, _pd]),
     "mclcar_tuples_merge": (_i, [_i, _i, _i, _i, _i, _pd, _pd]),

@@ -335,3 +335,138 @@ def sampler_diag(data: CarData, simdata) -> dict:
     sw = C.c_int64()
     check(lib.mclcar_samples_diag(data.ctx.h, simdata.h, C.byref(acc), C.byref(sw)), data.ctx.h)
     return {"accept": acc.value, "sweeps": sw.value}
+
+
+# ------------------------------------------------------------------------------------------
+# Binomial / Poisson GLM with latent CAR effects (R/mcl.glm.R)
+# ------------------------------------------------------------------------------------------
+_FAMILY = {"binom": L.FAMILY_BINOM, "poisson": L.FAMILY_POISSON}
+
+
+class McData:
+    """The reference's `mcdata` (data + Zy + lHZy.psi + mcmc.pars, R/mcl.glm.R:36-39) as a
+    device handle."""
+
+    def __init__(self, data: CarData, handle, psi, family: str):
+        self.data, self.h, self.psi, self.family = data, handle, np.asarray(psi, dtype=np.float64), family
+
+    @property
+    def n_samples(self) -> int:
+        return int(lib.mclcar_samples_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.mclcar_samples_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def Zy(self) -> np.ndarray:
+        """N x n matrix, row = sample (R/postZsub.R:427)."""
+        N, n = self.n_samples, self.data.n
+        out = np.empty((N, n), dtype=np.float64)
+        check(lib.mclcar_samples_fetch(self.data.ctx.h, self.h, L.COL_IS_SAMPLE, dptr(out), n), self.data.ctx.h)
+        return out
+
+    @property
+    def lHZy_psi(self) -> np.ndarray:
+        out = np.empty(self.n_samples)
+        check(lib.mclcar_glm_lhzy(self.data.ctx.h, self.h, dptr(out)), self.data.ctx.h)
+        return out
+
+    @property
+    def mcmc_pars(self) -> dict:
+        return sampler_diag(self.data, self)
+
+
+def mcdata_from_matrix(psi, data: CarData, Zy, family: str, lHZy_psi=None, dtype=np.float64) -> McData:
+    """Wrap the reference's own `Zy` (N x n, row = sample) [and `lHZy.psi`]: the parity path."""
+    Zy = np.asarray(Zy)
+    if Zy.shape[1] != data.n:
+        raise ValueError("Zy must be N x n")
+    M = np.ascontiguousarray(Zy.T, dtype=dtype)  # [site][sample] == column-major N x n
+    h = C.c_void_p()
+    ctx = data.ctx
+    check(lib.mclcar_samples_from_host(ctx.h, M.ctypes.data_as(C.c_void_p), L.F64 if dtype == np.float64 else L.F32,
+                                       L.ROW_IS_SAMPLE, data.n, Zy.shape[0], Zy.shape[0], C.byref(h)), ctx.h)
+    md = McData(data, h, psi, family)
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    base = None if lHZy_psi is None else np.ascontiguousarray(lHZy_psi, dtype=np.float64)
+    check(lib.mclcar_glm_attach(ctx.h, h, _FAMILY[family], dptr(psi), psi.size, dptr(base)), ctx.h)
+    return md
+
+
+def mcl_prep_glm(data: CarData, family: str, psi, mcmc_control: Optional[dict] = None) -> McData:
+    """mcl.prep.glm(data, family, psi, mcmc.control), R/mcl.glm.R:5-40.  The reference's
+    single-chain MALA / RWMH kernels (R/postZsub.R) are replaced by the batched
+    Metropolis-within-Gibbs sampler; `mcmc.control` takes the GPU keys of mcl_prep_dCAR plus,
+    for compatibility, N.Zy/thin/burns which set the number of kept samples."""
+    con = dict(mcmc_control or {})
+    N = int(con.pop("n.samples", 0))
+    if not N:
+        N_Zy, thin, burns = con.pop("N.Zy", 10_000), con.pop("thin.ref", 5), con.pop("burns", 5_000)
+        N = int((N_Zy - burns) // thin)   # rows of Z in postZ (R/postZsub.R:427)
+    for k in ("method", "Scale", "scale.fixed", "c.ad"):
+        con.pop(k, None)
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    o = _sampler_opts(con)
+    h = C.c_void_p()
+    check(lib.mclcar_glm_prep(data.ctx.h, _FAMILY[family], dptr(psi), psi.size, N, C.byref(o), C.byref(h)), data.ctx.h)
+    return McData(data, h, psi, family)
+
+
+def mcl_glm_batch(psis, mcdata: McData, family: Optional[str] = None, subsets=None, Evar=True, clamp=False,
+                  shift=L.SHIFT_MEAN) -> np.ndarray:
+    """Row k = mcl.glm(psis[k], mcdata, family, Evar=TRUE).  `clamp` applies the variance clamp of
+    Exp.CAR.glm (R/rsmSub.R:183,188): 0 -> 1e-8, values above 1e8 -> 1e8."""
+    psis = np.ascontiguousarray(np.atleast_2d(psis), dtype=np.float64)
+    K, P = psis.shape
+    lr = np.empty(K)
+    var = np.empty(K) if Evar else None
+    idx, ptr, _keep = _subsets(subsets, K)
+    ctx = mcdata.data.ctx
+    check(lib.mclcar_glm_eval(ctx.h, mcdata.h, dptr(psis), K, P, i64ptr(idx), i64ptr(ptr), shift, dptr(lr), dptr(var)), ctx.h)
+    if not Evar:
+        return lr
+    if clamp:
+        var = np.where(var == 0, 1e-8, np.minimum(1e8, var))
+    return np.stack([lr, var], axis=1)
+
+
+def mcl_glm(pars, mcdata: McData, family: Optional[str] = None, Evar=False):
+    """mcl.glm, R/mcl.glm.R:43-47 -> mcl.bin / mcl.pois (R/mcl.bin.R:33-79)."""
+    r = mcl_glm_batch(np.asarray(pars, dtype=np.float64)[None, :], mcdata, family, Evar=True)[0]
+    return r if Evar else float(r[0])
+
+
+def mcl_grad_glm(pars, mcdata: McData, family: Optional[str] = None, Evar=False, shift=L.SHIFT_MEAN):
+    """mcl.grad.glm, R/mcl.glm.R:78-82 -> mcl.grad.bin / .pois (R/mcl.bin.R:160-217)."""
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    P = pars.size
+    grad = np.empty(P)
+    gv = np.empty((P, P)) if Evar else None
+    ctx = mcdata.data.ctx
+    check(lib.mclcar_glm_grad(ctx.h, mcdata.h, dptr(pars), 1, P, 1 if Evar else 0, shift, dptr(grad), dptr(gv)), ctx.h)
+    return {"grad.lr": grad, "grad.var": gv} if Evar else grad
+
+
+def mcl_Hessian_glm(pars, mcdata: McData, family: Optional[str] = None, shift=L.SHIFT_MEAN) -> np.ndarray:
+    """mcl.Hessian.glm, R/mcl.glm.R:85-89 -> mcl.Hessian.bin / .pois (R/mcl.bin.R:222-297)."""
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    P = pars.size
+    H = np.empty((P, P))
+    ctx = mcdata.data.ctx
+    check(lib.mclcar_glm_hess(ctx.h, mcdata.h, dptr(pars), 1, P, shift, dptr(H)), ctx.h)
+    return H
+
+
+def vmle_glm(MLE: dict, mcdata: McData, family: Optional[str] = None) -> np.ndarray:
+    """vmle.glm, R/mcl.bin.R:302-309."""
+    A = mcl_grad_glm(MLE["estimate"], mcdata, family, Evar=True)["grad.var"]
+    Binv = np.linalg.inv(np.asarray(MLE["hessian"], dtype=np.float64))
+    return Binv @ A @ Binv

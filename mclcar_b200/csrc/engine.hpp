@@ -95,6 +95,7 @@ struct mclcar_samples {
     mclcar_ctx* ctx = nullptr;
     int dtype = MCLCAR_F64;
     int layout = MCLCAR_COL_IS_SAMPLE;
+    int family = 0;  // FAM_* of the attached model (GLM sample sets)
     int64_t sites = 0, N = 0, ld = 0;
     void* d_M = nullptr;  // may be null (statistics-only sample set)
     bool owned = false;

@@ -1,0 +1,577 @@
+// Binomial / Poisson GLM with latent CAR effects: mirrors R/mcl.glm.R, R/mcl.bin.R and
+// R/mcl.pois.R of the reference.
+//
+// For a latent sample z (row of Zy) and a candidate theta = (rho, sigma, beta):
+//   logH(z; theta) = Const(theta) + cterm + D(z; beta) - (z'z - rho z'Wz)/(2 sigma)      (R/mcl.bin.R:54-59)
+//   Const = -n/2 log(2 pi) + 1/2 logdet((I - rho W)/sigma),  cterm = sum lchoose | -sum lfactorial,
+//   D     = y'eta - sum n_j log(1 + e^eta_j)   |   y'eta - sum e^eta_j,          eta = X beta + z
+//   grad.logH = ( z'Wz/(2 sigma) - 1/2 sum lam/(1 - rho lam),  -n/(2 sigma) + z'(I - rho W)z/(2 sigma^2),
+//                 X'(y - mu) )                                                         (R/mcl.bin.R:188-196)
+//   Hessian.logH: (R/mcl.bin.R:260-274; Poisson beta-beta block as coded at R/mcl.pois.R:268)
+// so every per-sample quantity is affine in the statistics
+//   q = ( z'z, z'Wz,  { D_b, g_b[p], H_b[p(p+1)/2] : b = distinct beta of the batch } ).
+// z'z and z'Wz come from the site-major statistics kernel (stats_csr.cu); the beta-dependent
+// data terms from glm_terms_kernel below: ONE pass over the sample matrix per tile of
+// candidate betas, lane = sample, fp64 exp / log1p.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "engine.hpp"
+
+namespace mclcar {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kBT = 2;  // candidate betas per pass
+
+struct GlmTermsParams {
+    const void* M;  // [n][ld] site-major
+    int64_t ld, N;
+    int n, p;
+    const double* X;   // [p][n]
+    const double* y;   // [n]
+    const double* nt;  // [n] or null (== 1)
+    const double* beta;  // [nb][p] this tile's betas
+    int nb;              // betas in this tile (<= kBT)
+    int chunk;           // sites per chunk
+    double* out;         // [chunks][nb * ns][ldq]
+    int64_t ldq;
+    int ns;              // statistics per beta: 1 (+ p (+ p(p+1)/2))
+};
+
+// MODE 0: D only; 1: D + gradient; 2: D + gradient + Hessian block
+template <typename T, int FAM, int PT, int MODE>
+__global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParams prm) {
+    constexpr int NH = PT * (PT + 1) / 2;
+    constexpr int NS = 1 + (MODE >= 1 ? PT : 0) + (MODE >= 2 ? NH : 0);
+    __shared__ double sbeta[kBT * PT];
+    if (threadIdx.x < kBT * PT) {
+        const int b = threadIdx.x / PT, a = threadIdx.x % PT;
+        sbeta[threadIdx.x] = (b < prm.nb && a < prm.p) ? prm.beta[b * prm.p + a] : 0.0;
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= prm.N) return;
+    const T* M = reinterpret_cast<const T*>(prm.M);
+    const int s0 = blockIdx.y * prm.chunk, s1 = min(prm.n, s0 + prm.chunk);
+    double acc[kBT][NS];
+#pragma unroll
+    for (int b = 0; b < kBT; ++b)
+#pragma unroll
+        for (int t = 0; t < NS; ++t) acc[b][t] = 0.0;
+    for (int s = s0; s < s1; ++s) {
+        const double z = (double)ld_stream(M + (size_t)s * prm.ld + i);
+        const double ys = __ldg(prm.y + s);
+        const double ns = prm.nt ? __ldg(prm.nt + s) : 1.0;
+        double xr[PT];
+#pragma unroll
+        for (int a = 0; a < PT; ++a) xr[a] = a < prm.p ? __ldg(prm.X + (size_t)a * prm.n + s) : 0.0;
+#pragma unroll
+        for (int b = 0; b < kBT; ++b) {
+            if (b >= prm.nb) break;
+            double eta = z;
+#pragma unroll
+            for (int a = 0; a < PT; ++a) eta = fma(xr[a], sbeta[b * PT + a], eta);
+            double mu, v;
+            if (FAM == FAM_BINOM) {
+                // log(1 + e^eta) without overflow; p = e^eta / (1 + e^eta)
+                const double t = exp(-fabs(eta));
+                const double l1p = log1p(t);
+                const double inv = 1.0 / (1.0 + t);
+                const double pz = eta >= 0.0 ? inv : t * inv;
+                acc[b][0] += ys * eta - ns * (fmax(eta, 0.0) + l1p);
+                mu = ns * pz;
+                v = -ns * pz * (1.0 - pz);   // -n p (1 - p): R/mcl.bin.R:262,268
+            } else {
+                const double ex = exp(eta);
+                acc[b][0] += ys * eta - ex;
+                mu = ex;
+                v = ex * ex;                 // +exp(eta)^2, as coded at R/mcl.pois.R:268
+            }
+            if (MODE >= 1) {
+                const double r = ys - mu;
+#pragma unroll
+                for (int a = 0; a < PT; ++a) acc[b][1 + a] = fma(xr[a], r, acc[b][1 + a]);
+            }
+            if (MODE >= 2) {
+                int t = 1 + PT;
+#pragma unroll
+                for (int a = 0; a < PT; ++a) {
+                    const double va = v * xr[a];
+#pragma unroll
+                    for (int c = a; c < PT; ++c) {
+                        acc[b][t] = fma(va, xr[c], acc[b][t]);
+                        ++t;
+                    }
+                }
+            }
+        }
+    }
+    // compact (exact p) output order: D, g[0..p), H packed upper over p
+    const int p = prm.p;
+    double* o = prm.out + (size_t)blockIdx.y * prm.nb * prm.ns * prm.ldq + i;
+#pragma unroll
+    for (int b = 0; b < kBT; ++b) {
+        if (b >= prm.nb) break;
+        double* ob = o + (size_t)b * prm.ns * prm.ldq;
+        ob[0] = acc[b][0];
+        if (MODE >= 1) {
+#pragma unroll
+            for (int a = 0; a < PT; ++a)
+                if (a < p) ob[(size_t)(1 + a) * prm.ldq] = acc[b][1 + a];
+        }
+        if (MODE >= 2) {
+            int t = 1 + PT, tc = 1 + p;
+#pragma unroll
+            for (int a = 0; a < PT; ++a)
+#pragma unroll
+                for (int c = a; c < PT; ++c) {
+                    if (a < p && c < p) ob[(size_t)(tc++) * prm.ldq] = acc[b][t];
+                    ++t;
+                }
+        }
+    }
+}
+
+__global__ void glm_chunk_sum_kernel(const double* partial, double* q, int S, int d, int64_t ldq, int64_t N) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (int j = 0; j < d; ++j) {
+        double a = 0.0;
+        for (int s = 0; s < S; ++s) a += partial[((size_t)s * d + j) * ldq + i];
+        q[(size_t)j * ldq + i] = a;
+    }
+}
+
+template <typename T, int FAM, int PT>
+void launch_mode(const GlmTermsParams& p, int mode, dim3 grid, cudaStream_t st) {
+    if (mode == 0) glm_terms_kernel<T, FAM, PT, 0><<<grid, kThreads, 0, st>>>(p);
+    else if (mode == 1) glm_terms_kernel<T, FAM, PT, 1><<<grid, kThreads, 0, st>>>(p);
+    else glm_terms_kernel<T, FAM, PT, 2><<<grid, kThreads, 0, st>>>(p);
+}
+template <typename T, int FAM>
+void launch_p(const GlmTermsParams& p, int mode, dim3 grid, cudaStream_t st) {
+    if (p.p <= 1) launch_mode<T, FAM, 1>(p, mode, grid, st);
+    else if (p.p <= 2) launch_mode<T, FAM, 2>(p, mode, grid, st);
+    else if (p.p <= 4) launch_mode<T, FAM, 4>(p, mode, grid, st);
+    else launch_mode<T, FAM, 8>(p, mode, grid, st);
+}
+
+// data terms of `nb_total` distinct betas -> rows [row0 + b*ns, ...) of q [.][ldq]
+int glm_data_terms(mclcar_ctx* ctx, const mclcar_samples* s, int fam, const std::vector<double>& betas, int nb_total,
+                   int mode, double* d_q, int64_t ldq, int row0) {
+    const int p = ctx->p, n = ctx->n;
+    const int ns = 1 + (mode >= 1 ? p : 0) + (mode >= 2 ? p * (p + 1) / 2 : 0);
+    const int64_t N = s->N;
+    const int64_t xblocks = (N + kThreads - 1) / kThreads;
+    int chunks = (int)std::max<int64_t>(1, ((int64_t)4 * ctx->n_sm + xblocks - 1) / xblocks);
+    chunks = std::min(chunks, std::max(1, n / 32));
+    const int chunk = (n + chunks - 1) / chunks;
+    chunks = (n + chunk - 1) / chunk;
+    double* d_beta = nullptr;
+    MCL_TRY(pool_alloc(ctx, (void**)&d_beta, betas.size() * sizeof(double)));
+    MCL_CUDA(ctx, cudaMemcpyAsync(d_beta, betas.data(), betas.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double* partial = nullptr;
+    if (chunks > 1) MCL_TRY(pool_alloc(ctx, (void**)&partial, (size_t)chunks * kBT * ns * ldq * sizeof(double)));
+    int st = MCLCAR_OK;
+    for (int b0 = 0; b0 < nb_total && st == MCLCAR_OK; b0 += kBT) {
+        GlmTermsParams prm{};
+        prm.M = s->d_M; prm.ld = s->ld; prm.N = N; prm.n = n; prm.p = p;
+        prm.X = ctx->d_X; prm.y = ctx->d_y; prm.nt = ctx->d_ntrial;
+        prm.beta = d_beta + (size_t)b0 * p; prm.nb = std::min(kBT, nb_total - b0);
+        prm.chunk = chunk; prm.ldq = ldq; prm.ns = ns;
+        double* dst = d_q + (size_t)(row0 + b0 * ns) * ldq;
+        prm.out = chunks > 1 ? partial : dst;
+        dim3 grid((unsigned)xblocks, (unsigned)chunks);
+        ProfScope prof(ctx, PROF_GLM, chunks > 1 ? 2 : 1);
+        const bool f32 = s->dtype == MCLCAR_F32;
+        if (fam == FAM_BINOM) {
+            if (f32) launch_p<float, FAM_BINOM>(prm, mode, grid, ctx->stream);
+            else launch_p<double, FAM_BINOM>(prm, mode, grid, ctx->stream);
+        } else {
+            if (f32) launch_p<float, FAM_POIS>(prm, mode, grid, ctx->stream);
+            else launch_p<double, FAM_POIS>(prm, mode, grid, ctx->stream);
+        }
+        if (chunks > 1)
+            glm_chunk_sum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(partial, dst, chunks, prm.nb * ns, ldq, N);
+        if (cudaGetLastError() != cudaSuccess) st = fail(ctx, MCLCAR_ECUDA, "GLM data-term kernel launch failed");
+    }
+    pool_free(ctx, partial);
+    pool_free(ctx, d_beta);
+    return st;
+}
+
+// ---- host-side scalars -----------------------------------------------------------------
+int need_eigs(mclcar_ctx* ctx) {
+    if (ctx->eigs.empty())
+        return fail(ctx, MCLCAR_ESTATE, "the GLM functions need the eigenvalues of W (mclcar_graph_set_eigenvalues): "
+                                       "log-determinant and the gradient / Hessian terms of R/mcl.bin.R:176-177,192,265");
+    return MCLCAR_OK;
+}
+double half_logdet_Q(const mclcar_ctx* ctx, double rho, double sigma) {
+    long double a = 0;
+    for (double l : ctx->eigs) a += std::log1p(-rho * l);
+    return (double)(0.5L * (a - (long double)ctx->n * std::log(sigma)));
+}
+double sum_lam_ratio(const mclcar_ctx* ctx, double rho, int power) {
+    long double a = 0;
+    for (double l : ctx->eigs) {
+        const double r = l / (1.0 - rho * l);
+        a += power == 1 ? r : r * r;
+    }
+    return (double)a;
+}
+// psi-independent data constant: sum(sapply(y, lchoose, n = n.trial)) | -sum(lfactorial(y))
+double glm_cterm(const mclcar_ctx* ctx, int fam) {
+    const int n = ctx->n;
+    long double a = 0;
+    if (fam == FAM_POIS) {
+        for (int j = 0; j < n; ++j) a -= std::lgamma(ctx->y[j] + 1.0);
+        return (double)a;
+    }
+    auto lch = [](double nn, double k) { return std::lgamma(nn + 1.0) - std::lgamma(k + 1.0) - std::lgamma(nn - k + 1.0); };
+    bool scalar = true;
+    for (int j = 1; j < n && scalar; ++j) scalar = ctx->ntrial.empty() || ctx->ntrial[j] == ctx->ntrial[0];
+    if (scalar) {
+        const double nn = ctx->ntrial.empty() ? 1.0 : ctx->ntrial[0];
+        for (int j = 0; j < n; ++j) a += lch(nn, ctx->y[j]);
+    } else {  // vector n.trial: the reference's sapply sums the whole n x n table (R/mcl.bin.R:26)
+        for (int j = 0; j < n; ++j)
+            for (int l = 0; l < n; ++l) a += lch(ctx->ntrial[l], ctx->y[j]);
+    }
+    return (double)a;
+}
+
+struct GlmBatch {
+    int fam = FAM_BINOM, p = 0, P = 0, K = 0;
+    int nb = 0;                  // distinct betas (index 0 = the importance beta when the base is internal)
+    std::vector<double> betas;   // nb x p
+    std::vector<int> bidx;       // K: beta index of each candidate
+    int mode = 0, ns = 1, d = 2; // statistics per beta, total rows
+    double* d_q = nullptr;       // [d][N]: z'z, z'Wz, then per beta: D, g, H
+    std::vector<double> qbar;
+};
+
+int glm_check(mclcar_ctx* ctx, mclcar_samples* s, int P) {
+    if (!ctx || !s) return MCLCAR_EINVAL;
+    if (s->ctx != ctx) return fail(ctx, MCLCAR_EINVAL, "sample set belongs to another context");
+    if (ctx->kind == GRAPH_NONE || !ctx->has_obs) return fail(ctx, MCLCAR_ESTATE, "set graph, design and observations first");
+    if (ctx->p < 1) return fail(ctx, MCLCAR_ESTATE, "the GLM needs a design matrix covX");
+    if (P != 2 + ctx->p) return fail(ctx, MCLCAR_EINVAL, "parameter vector of length %d; expected %d", P, 2 + ctx->p);
+    if (s->sites != ctx->n) return fail(ctx, MCLCAR_EINVAL, "sample matrix has %lld sites, graph has %d", (long long)s->sites, ctx->n);
+    if (s->layout != MCLCAR_ROW_IS_SAMPLE) return fail(ctx, MCLCAR_EINVAL, "GLM sample sets are N x n with row = sample (Zy)");
+    if (!s->d_M) return fail(ctx, MCLCAR_ESTATE, "GLM sample sets must keep the sample matrix");
+    return need_eigs(ctx);
+}
+
+// z'z and z'Wz of every sample -> rows 0, 1 of s->d_q (kept with the sample set)
+int glm_static_stats(mclcar_ctx* ctx, mclcar_samples* s) {
+    if (s->stats_ready && s->d == 2) return MCLCAR_OK;
+    MCL_TRY(samples_alloc_stats(ctx, s, 2));
+    MCL_TRY(launch_quadforms_site_major(ctx, s->d_M, s->dtype, s->N, s->ld, ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_val,
+                                        0, nullptr, s->d_q, s->N));
+    s->stats_ready = true;
+    return MCLCAR_OK;
+}
+
+int glm_build_batch(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int mode, GlmBatch& gb) {
+    const int p = ctx->p;
+    gb.fam = s->family; gb.p = p; gb.P = P; gb.K = K; gb.mode = mode;
+    gb.ns = 1 + (mode >= 1 ? p : 0) + (mode >= 2 ? p * (p + 1) / 2 : 0);
+    gb.betas.clear(); gb.bidx.assign(K, 0); gb.nb = 0;
+    auto find_or_add = [&](const double* b) {
+        for (int t = 0; t < gb.nb; ++t)
+            if (std::memcmp(gb.betas.data() + (size_t)t * p, b, p * sizeof(double)) == 0) return t;
+        gb.betas.insert(gb.betas.end(), b, b + p);
+        return gb.nb++;
+    };
+    if (!s->d_base) find_or_add(s->psi0.data() + 2);  // index 0: importance beta
+    for (int k = 0; k < K; ++k) gb.bidx[k] = find_or_add(psi + (size_t)k * P + 2);
+    gb.d = 2 + gb.nb * gb.ns;
+    MCL_TRY(glm_static_stats(ctx, s));
+    MCL_TRY(pool_alloc(ctx, (void**)&gb.d_q, (size_t)gb.d * s->N * sizeof(double)));
+    MCL_CUDA(ctx, cudaMemcpyAsync(gb.d_q, s->d_q, (size_t)2 * s->N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    MCL_TRY(glm_data_terms(ctx, s, gb.fam, gb.betas, gb.nb, mode, gb.d_q, s->N, 2));
+    // column means (shift and centres)
+    mclcar_samples tmp;
+    tmp.N = s->N; tmp.d = gb.d; tmp.d_q = gb.d_q;
+    MCL_TRY(samples_update_qbar(ctx, &tmp));
+    gb.qbar = tmp.qbar;
+    tmp.d_q = nullptr;
+    return MCLCAR_OK;
+}
+
+// affine maps of candidate k over the batch statistics
+struct GlmAffine {
+    double c0 = 0;
+    std::vector<double> c;      // d
+    std::vector<double> a0, A;  // P, P x d  (gradient of logH)
+    double rho = 0, sigma = 1;
+};
+
+void glm_affine(const mclcar_ctx* ctx, const GlmBatch& gb, const double* pars, int b, double cterm, GlmAffine& m) {
+    const int d = gb.d, P = gb.P, p = gb.p, n = ctx->n;
+    const double rho = pars[0], sigma = pars[1];
+    m.rho = rho; m.sigma = sigma;
+    m.c.assign(d, 0.0);
+    m.c0 = -0.5 * n * std::log(2.0 * M_PI) + half_logdet_Q(ctx, rho, sigma) + cterm;
+    m.c[0] = -1.0 / (2 * sigma);
+    m.c[1] = rho / (2 * sigma);
+    const int rb = 2 + b * gb.ns;  // first row of this beta's statistics
+    m.c[rb] = 1.0;
+    m.a0.assign(P, 0.0);
+    m.A.assign((size_t)P * d, 0.0);
+    if (gb.mode >= 1) {
+        m.a0[0] = -0.5 * sum_lam_ratio(ctx, rho, 1);
+        m.A[1] = 0.5 / sigma;
+        m.a0[1] = -n / (2 * sigma);
+        m.A[(size_t)d + 0] = 1.0 / (2 * sigma * sigma);
+        m.A[(size_t)d + 1] = -rho / (2 * sigma * sigma);
+        for (int a = 0; a < p; ++a) m.A[(size_t)(2 + a) * d + rb + 1 + a] = 1.0;
+    }
+}
+
+int glm_partial(mclcar_ctx* ctx, mclcar_samples* s, GlmBatch& gb, const double* psi, int what, int shift_mode,
+                const int64_t* subset_idx, const int64_t* subset_ptr, double* tuples) {
+    const int d = gb.d, K = gb.K, P = gb.P;
+    const int F = what == WHAT_LR ? 0 : P;
+    ReducePlan plan;
+    plan.d_q = gb.d_q; plan.ldq = s->N; plan.d = d; plan.N = s->N; plan.K = K; plan.F = F; plan.what = what;
+    plan.shift_mode = shift_mode; plan.d_base = s->d_base;
+    plan.subset_idx = subset_idx; plan.subset_ptr = subset_ptr;
+    const int cs = coef_stride_of(d, F);
+    plan.coef_stride = cs;
+    plan.coef.assign((size_t)K * cs, 0.0);
+    const double cterm = s->d_base ? glm_cterm(ctx, gb.fam) : 0.0;
+    GlmAffine m0, m;
+    if (!s->d_base) glm_affine(ctx, gb, s->psi0.data(), 0, 0.0, m0);
+    for (int k = 0; k < K; ++k) {
+        glm_affine(ctx, gb, psi + (size_t)k * P, gb.bidx[k], cterm, m);
+        double* cf = plan.coef.data() + (size_t)k * cs;
+        cf[0] = m.c0;
+        for (int j = 0; j < d; ++j) cf[1 + j] = m.c[j];
+        if (!s->d_base) {  // r = logH(z; theta) - logH(z; psi0), coefficients differenced first
+            cf[0] -= m0.c0;
+            for (int j = 0; j < d; ++j) cf[1 + j] -= m0.c[j];
+        }
+        double shift = cf[0];
+        for (int j = 0; j < d; ++j) shift += cf[1 + j] * gb.qbar[j];
+        if (s->d_base) shift -= s->base_mean;
+        cf[coef_off_shift(d)] = shift;
+        int64_t nsub = s->N;
+        if (subset_ptr && subset_ptr[k + 1] > subset_ptr[k]) nsub = subset_ptr[k + 1] - subset_ptr[k];
+        cf[coef_off_n(d)] = (double)nsub;
+        cf[coef_off_centre(d)] = 1.0;
+        for (int a = 0; a < F; ++a) {
+            double* fa = cf + coef_off_feat(d, F) + (size_t)a * (1 + d);
+            fa[0] = m.a0[a];
+            double fbar = m.a0[a];
+            for (int j = 0; j < d; ++j) {
+                fa[1 + j] = m.A[(size_t)a * d + j];
+                fbar += fa[1 + j] * gb.qbar[j];
+            }
+            cf[coef_off_centre(d) + 1 + a] = fbar;
+        }
+    }
+    MCL_TRY(run_reduce(ctx, plan, tuples));
+    return gather_and_merge(ctx, what, F, d, K, tuples);
+}
+
+}  // namespace
+}  // namespace mclcar
+
+using namespace mclcar;
+
+extern "C" {
+
+int mclcar_glm_attach(mclcar_ctx* ctx, mclcar_samples* s, int family, const double* psi0, int P, const double* lHZy_psi) {
+    if (!psi0) return MCLCAR_EINVAL;
+    if (family != MCLCAR_FAMILY_BINOM && family != MCLCAR_FAMILY_POISSON) return fail(ctx, MCLCAR_EINVAL, "family must be binomial or Poisson");
+    MCL_TRY(glm_check(ctx, s, P));
+    MCL_TRY(require_device(ctx));
+    if (!(psi0[1] > 0)) return fail(ctx, MCLCAR_EINVAL, "sigma must be positive");
+    s->family = family == MCLCAR_FAMILY_BINOM ? FAM_BINOM : FAM_POIS;
+    s->psi0.assign(psi0, psi0 + P);
+    if (s->d_base) { pool_free(ctx, s->d_base); s->d_base = nullptr; }
+    s->base_mean = 0.0;
+    if (lHZy_psi) {
+        MCL_TRY(pool_alloc(ctx, (void**)&s->d_base, (size_t)s->N * sizeof(double)));
+        MCL_CUDA(ctx, cudaMemcpyAsync(s->d_base, lHZy_psi, (size_t)s->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        long double a = 0;
+        for (int64_t i = 0; i < s->N; ++i) a += lHZy_psi[i];
+        s->base_mean = (double)(a / s->N);
+    }
+    s->attached = true;
+    return MCLCAR_OK;
+}
+
+/* lHZy.psi_i = log f_psi0(y, Z_i), R/mcl.glm.R:34-37 */
+int mclcar_glm_lhzy(mclcar_ctx* ctx, mclcar_samples* s, double* out) {
+    if (!out || !s || !s->attached) return MCLCAR_EINVAL;
+    MCL_TRY(glm_check(ctx, s, (int)s->psi0.size()));
+    MCL_TRY(require_device(ctx));
+    if (s->d_base) {
+        MCL_CUDA(ctx, cudaMemcpy(out, s->d_base, (size_t)s->N * sizeof(double), cudaMemcpyDeviceToHost));
+        return MCLCAR_OK;
+    }
+    // the batch holds one "candidate" = psi0 itself: its beta is the importance beta (index 0)
+    GlmBatch gb;
+    const int P = (int)s->psi0.size();
+    std::vector<double> psi(s->psi0);
+    int st = glm_build_batch(ctx, s, psi.data(), 1, P, 0, gb);
+    if (st != MCLCAR_OK) { pool_free(ctx, gb.d_q); return st; }
+    std::vector<double> q((size_t)gb.d * s->N);
+    cudaError_t e = cudaMemcpyAsync(q.data(), gb.d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    pool_free(ctx, gb.d_q);
+    if (e != cudaSuccess) return fail(ctx, MCLCAR_ECUDA, "copy of the statistics failed: %s", cudaGetErrorString(e));
+    GlmAffine m;
+    glm_affine(ctx, gb, psi.data(), gb.bidx[0], glm_cterm(ctx, gb.fam), m);
+    for (int64_t i = 0; i < s->N; ++i) {
+        double h = m.c0;
+        for (int j = 0; j < gb.d; ++j) h += m.c[j] * q[(size_t)j * s->N + i];
+        out[i] = h;
+    }
+    return MCLCAR_OK;
+}
+
+static int glm_run(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int what, int evar,
+                   const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* out0, double* out1) {
+    if (!s || !psi || K < 1 || !out0) return MCLCAR_EINVAL;
+    MCL_TRY(glm_check(ctx, s, P));
+    MCL_TRY(require_device(ctx));
+    if (!s->attached) return fail(ctx, MCLCAR_ESTATE, "call mclcar_glm_attach (or _prep) first");
+    if (P > MCLCAR_MAX_P) return fail(ctx, MCLCAR_ELIMIT, "P = %d exceeds MCLCAR_MAX_P", P);
+    for (int k = 0; k < K; ++k)
+        if (!(psi[(size_t)k * P + 1] > 0)) return fail(ctx, MCLCAR_EINVAL, "sigma must be positive (candidate %d)", k);
+    GlmBatch gb;
+    const int mode = what == WHAT_LR ? 0 : (what == WHAT_GRAD ? 1 : 2);
+    int st = glm_build_batch(ctx, s, psi, K, P, mode, gb);
+    const int d = gb.d, F = what == WHAT_LR ? 0 : P, p = ctx->p, n = ctx->n;
+    const int64_t T = tuple_len(what, F, d);
+    std::vector<double> tuples((size_t)K * (T > 0 ? T : 1));
+    if (st == MCLCAR_OK) st = glm_partial(ctx, s, gb, psi, what, shift_mode, subset_idx, subset_ptr, tuples.data());
+    pool_free(ctx, gb.d_q);
+    MCL_TRY(st);
+    std::vector<double> vbar(1 + F), C((size_t)(1 + F) * (1 + F));
+    for (int k = 0; k < K; ++k) {
+        const double* tup = tuples.data() + (size_t)k * T;
+        const double* pars = psi + (size_t)k * P;
+        const double nn = tup[0], shift = tup[1];
+        if (what == WHAT_LR) {  // R/mcl.bin.R:61-78
+            centred_moments(tup, 1, vbar.data(), C.data());
+            out0[k] = std::log(vbar[0]) + shift;
+            if (out1) out1[k] = C[0] / (nn - 1.0) / (vbar[0] * vbar[0]) / nn;
+        } else if (what == WHAT_GRAD) {  // R/mcl.bin.R:198-216
+            const int V = 1 + P;
+            centred_moments(tup, V, vbar.data(), C.data());
+            const double eb = vbar[0];
+            for (int a = 0; a < P; ++a) out0[(size_t)k * P + a] = vbar[1 + a] / eb;
+            if (out1 && evar)
+                for (int a = 0; a < P; ++a)
+                    for (int b = 0; b < P; ++b)
+                        out1[(size_t)k * P * P + a * P + b] = C[(size_t)(1 + a) * V + 1 + b] / (nn - 1.0) / (eb * eb) / nn;
+        } else {  // R/mcl.bin.R:276-296
+            const double rho = pars[0], sigma = pars[1];
+            const double Se = tup[2];
+            const double* Sf = tup + 3;
+            const double* Sff = tup + 3 + P;
+            const double* R1 = tup + 3 + P + P * (P + 1) / 2;
+            const int rb = 2 + gb.bidx[k] * gb.ns;
+            const double zz = R1[0] / Se, zWz = R1[1] / Se;  // weighted means of the statistics
+            double* o = out0 + (size_t)k * P * P;
+            for (int t = 0; t < P * P; ++t) o[t] = 0.0;
+            // mean(w Hessian.logH)
+            o[0] = -0.5 * sum_lam_ratio(ctx, rho, 2);
+            o[1] = o[P] = -0.5 * zWz / (sigma * sigma);
+            o[P + 1] = -((zz - rho * zWz) / sigma) / (sigma * sigma) + 0.5 * n / (sigma * sigma);
+            int t = rb + 1 + p;
+            for (int a = 0; a < p; ++a)
+                for (int b = a; b < p; ++b, ++t) o[(2 + a) * P + 2 + b] = o[(2 + b) * P + 2 + a] = R1[t] / Se;
+            // + mean(w g g') - (mean w g)(mean w g)'
+            int sidx = 0;
+            for (int a = 0; a < P; ++a)
+                for (int b = a; b < P; ++b, ++sidx) {
+                    const double v = Sff[sidx] / Se - (Sf[a] / Se) * (Sf[b] / Se);
+                    o[a * P + b] += v;
+                    if (a != b) o[b * P + a] += v;
+                }
+        }
+    }
+    return MCLCAR_OK;
+}
+
+int mclcar_glm_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, const int64_t* subset_idx,
+                    const int64_t* subset_ptr, int shift_mode, double* lr, double* var) {
+    return glm_run(ctx, s, psi, K, P, WHAT_LR, 0, subset_idx, subset_ptr, shift_mode, lr, var);
+}
+int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar, int shift_mode,
+                    double* grad, double* gradvar) {
+    return glm_run(ctx, s, psi, K, P, WHAT_GRAD, evar, nullptr, nullptr, shift_mode, grad, gradvar);
+}
+int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode, double* hess) {
+    return glm_run(ctx, s, psi, K, P, WHAT_HESS, 0, nullptr, nullptr, shift_mode, hess, nullptr);
+}
+
+/* mcl.prep.glm(data, family, psi, ...) with postZ, R/mcl.glm.R:5-40: draws N latent fields
+ * z | y at psi0 with the batched Metropolis-within-Gibbs sampler and attaches psi0. */
+int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
+                    mclcar_samples** out) {
+    if (!ctx || !psi0 || !out) return MCLCAR_EINVAL;
+    *out = nullptr;
+    MCL_TRY(require_device(ctx));
+    if (family != MCLCAR_FAMILY_BINOM && family != MCLCAR_FAMILY_POISSON) return fail(ctx, MCLCAR_EINVAL, "family must be binomial or Poisson");
+    if (ctx->kind == GRAPH_NONE || !ctx->has_obs || ctx->p < 1) return fail(ctx, MCLCAR_ESTATE, "set graph, design (covX) and observations first");
+    if (P != 2 + ctx->p) return fail(ctx, MCLCAR_EINVAL, "psi0 has length %d; expected %d", P, 2 + ctx->p);
+    if (N < 1 || N >= ((int64_t)1 << 31)) return fail(ctx, MCLCAR_EINVAL, "bad sample count");
+    MCL_TRY(need_eigs(ctx));
+    const double rho = psi0[0], sigma = psi0[1];
+    if (!(sigma > 0)) return fail(ctx, MCLCAR_EINVAL, "sigma must be positive");
+    MCL_TRY(check_rho(ctx, rho));
+    mclcar_sampler_opts o{};
+    if (opts) o = *opts;
+    o.keep = 1;
+    if (o.dtype != MCLCAR_F64) o.dtype = MCLCAR_F32;
+    int burn = o.burn, thin = o.thin;
+    double omega = 1.0;  // Metropolis-within-Gibbs: no over-relaxation
+    default_schedule(ctx, rho, &omega, &burn, &thin);
+    // the likelihood sharpens the conditionals and the accept step slows the chain: be generous
+    if (o.burn <= 0) burn = std::max(4 * burn, 200);
+    if (o.thin <= 0) thin = std::max(2 * thin, 10);
+    const int n = ctx->n;
+    const size_t es = o.dtype == MCLCAR_F32 ? 4 : 8;
+    std::vector<double> xb(n, 0.0);
+    for (int l = 0; l < ctx->p; ++l)
+        for (int i = 0; i < n; ++i) xb[i] += ctx->X[(size_t)l * n + i] * psi0[2 + l];
+    mclcar_samples* s = new (std::nothrow) mclcar_samples();
+    if (!s) return fail(ctx, MCLCAR_ENOMEM, "out of host memory");
+    s->ctx = ctx; s->dtype = o.dtype; s->sites = n; s->N = N; s->owned = true; s->layout = MCLCAR_ROW_IS_SAMPLE;
+    const int64_t align = 16 / es;
+    s->ld = (N + align - 1) / align * align;
+    GmrfHost g;
+    g.n = n; g.rowptr = &ctx->rowptr; g.colidx = &ctx->colidx; g.color_ptr = &ctx->color_ptr; g.order = &ctx->order;
+    g.qdiag.assign(n, 1.0 / sigma);
+    g.qoff.resize(ctx->colidx.size());
+    for (size_t e = 0; e < g.qoff.size(); ++e) g.qoff[e] = -rho * (ctx->binary ? 1.0 : ctx->val[e]) / sigma;
+    int st = pool_alloc(ctx, &s->d_M, (size_t)n * s->ld * es);
+    const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
+    if (st == MCLCAR_OK)
+        st = run_csr_sampler(ctx, g, family == MCLCAR_FAMILY_BINOM ? FAM_BINOM : FAM_POIS, 1.0, nullptr, ctx->y.data(),
+                             ctx->ntrial.empty() ? nullptr : ctx->ntrial.data(), xb.data(), N, C, burn, thin, s->d_M,
+                             o.dtype == MCLCAR_F64, s->ld, &s->accept, &s->sweeps);
+    if (st == MCLCAR_OK) st = mclcar_glm_attach(ctx, s, family, psi0, P, nullptr);
+    if (st != MCLCAR_OK) {
+        std::string keep_err = ctx->err;
+        mclcar_samples_free(s);
+        ctx->err = keep_err;
+        return st;
+    }
+    *out = s;
+    return MCLCAR_OK;
+}
+
+}  // extern "C"

@@ -263,7 +263,7 @@ def sim_glm_data(family, W, pars, Xs, n_trial, rng) -> dict:
     z = graphs.car_sim_wmat(float(pars[0]), 1.0 / float(pars[1]), W, rng)
     eta = Xs @ np.asarray(pars[2:], dtype=np.float64) + z
     if family == "binom":
-        y = rng.binomial(n_trial, 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
+        y = rng.binomial(np.asarray(n_trial).astype(np.int64), 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
     else:
         y = rng.poisson(np.exp(eta)).astype(np.float64)
     return {"y": y, "covX": Xs, "W": W, "n.trial": n_trial, "Z.true": z}
