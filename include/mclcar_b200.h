@@ -190,6 +190,32 @@ int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
 int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
                     double* hess);
 
+/* ---- hierarchical CAR, Gaussian response (R/HCAR.sim.R, R/mcl.HCAR.R) ---------------------
+ * y = X beta + Z u + e, e ~ N(0, sigma.e (I - rho W)^-1), u ~ N(0, sigma.u (I - lambda M)^-1).
+ * The context's graph is the individual-level W (upload an empty CSR graph and pass has_W = 0
+ * for the reference's W = NULL variant); design and observations as usual.  M (K x K,
+ * symmetric) and Z (n x K) come in CSR; eig_M = data$bb, the eigenvalues of W = data$aa go
+ * through mclcar_graph_set_eigenvalues.  A sample set is u.y (K x N, column = sample). */
+int mclcar_hcar_set_model(mclcar_ctx* ctx, int K, const int* M_rowptr, const int* M_colidx, const double* M_val,
+                          const int* Z_rowptr, const int* Z_colidx, const double* Z_val, const double* eig_M,
+                          int has_W);
+/* sim.HCAR(psi, data, n.samples), R/HCAR.sim.R:3-87: N draws of u | y at psi0 (chromatic Gibbs on
+ * Q* = Z'Qe Z + Qu instead of one Cholesky and N backsolves) with lpsi and const.psi attached */
+int mclcar_hcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
+                     mclcar_samples** out);
+int mclcar_hcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* lpsi);
+int mclcar_hcar_lpsi(mclcar_ctx* ctx, mclcar_samples* s, double* lpsi /* N or NULL */, double* const_psi);
+/* mcl.HCAR(pars, mcdata, data, Evar), R/mcl.HCAR.R:4-97, for K candidates.  The reference takes
+ * exp() unshifted and clamps +-Inf to +-1e5 with a warning (:81-84): candidates where that would
+ * have happened get +-1e5 and are counted in *n_clamped. */
+int mclcar_hcar_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, double* lr, double* var,
+                     int* n_clamped);
+/* mcl.grad.HCAR (R/mcl.HCAR.R:101-213) and mcl.Hessian.HCAR (:216-391, H.rho.beta as coded at :356) */
+int mclcar_hcar_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
+                     int shift_mode, double* grad, double* gradvar);
+int mclcar_hcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
+                     double* hess);
+
 /* ---- staged evaluation (what the one-shot calls above are made of) ------------------------
  * stage 1, device: per-candidate partial tuples of this context's samples, to host memory;
  * stage 2, host only: merge the tuples of G shards in shard order (mclcar_tuples_merge);

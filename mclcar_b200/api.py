@@ -470,3 +470,156 @@ def vmle_glm(MLE: dict, mcdata: McData, family: Optional[str] = None) -> np.ndar
     A = mcl_grad_glm(MLE["estimate"], mcdata, family, Evar=True)["grad.var"]
     Binv = np.linalg.inv(np.asarray(MLE["hessian"], dtype=np.float64))
     return Binv @ A @ Binv
+
+
+# ------------------------------------------------------------------------------------------
+# Hierarchical CAR, Gaussian response (R/HCAR.sim.R, R/mcl.HCAR.R)
+# ------------------------------------------------------------------------------------------
+def make_hcar_data(y, X, M, Z, W=None, aa=None, bb=None, device: int = 0, seed: int = 0,
+                   ctx: Optional[Context] = None) -> CarData:
+    """The reference's HCAR `data` list(y, X, W, M, Z, In, Ik[, aa, bb]) (R/mcl.HCAR.R:16-26).
+    `W` may be None (the reference's 3+p parameter variant); aa / bb are the eigenvalues of W
+    and M (computed densely here when missing, as R/mcl.HCAR.R:166-173 does per call)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n = y.shape[0]
+    Mc = sp.csr_matrix(M, dtype=np.float64)
+    Mc.sort_indices()
+    Zc = sp.csr_matrix(Z, dtype=np.float64)
+    Zc.sort_indices()
+    K = Mc.shape[0]
+    if Zc.shape != (n, K):
+        raise ValueError("Z must be n x K")
+    if bb is None:
+        bb = np.linalg.eigvalsh(Mc.toarray())
+    has_W = W is not None
+    if has_W:
+        if aa is None:
+            aa = np.linalg.eigvalsh(sp.csr_matrix(W).toarray())
+        data = make_data(y, X=X, W=W, eigenvalues=aa, device=device, seed=seed, ctx=ctx)
+    else:
+        data = make_data(y, X=X, W=sp.csr_matrix((n, n), dtype=np.float64), device=device, seed=seed, ctx=ctx)
+    bbc = np.ascontiguousarray(bb, dtype=np.float64)
+    arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (Mc.indptr, Mc.indices, Zc.indptr, Zc.indices)]
+    mv, zv = np.ascontiguousarray(Mc.data), np.ascontiguousarray(Zc.data)
+    check(lib.mclcar_hcar_set_model(data.ctx.h, K, iptr(arrs[0]), iptr(arrs[1]), dptr(mv), iptr(arrs[2]), iptr(arrs[3]),
+                                    dptr(zv), dptr(bbc), 1 if has_W else 0), data.ctx.h)
+    data.extra.update({"K": K, "has_W": has_W, "M": Mc, "Z": Zc})
+    return data
+
+
+class HcarMc:
+    """sim.HCAR's return list(psi, n.samples, u.y, lpsi, const.psi) (R/HCAR.sim.R:85) as a handle."""
+
+    def __init__(self, data: CarData, handle, psi):
+        self.data, self.h, self.psi = data, handle, np.asarray(psi, dtype=np.float64)
+
+    @property
+    def n_samples(self) -> int:
+        return int(lib.mclcar_samples_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.mclcar_samples_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def u_y(self) -> np.ndarray:
+        """K x N, column = sample (R/HCAR.sim.R:68-69)."""
+        N, K = self.n_samples, self.data.extra["K"]
+        out = np.empty((N, K), dtype=np.float64)
+        check(lib.mclcar_samples_fetch(self.data.ctx.h, self.h, L.COL_IS_SAMPLE, dptr(out), K), self.data.ctx.h)
+        return out.T
+
+    @property
+    def lpsi(self) -> np.ndarray:
+        out = np.empty(self.n_samples)
+        check(lib.mclcar_hcar_lpsi(self.data.ctx.h, self.h, dptr(out), None), self.data.ctx.h)
+        return out
+
+    @property
+    def const_psi(self) -> float:
+        v = C.c_double()
+        check(lib.mclcar_hcar_lpsi(self.data.ctx.h, self.h, None, C.byref(v)), self.data.ctx.h)
+        return v.value
+
+
+def sim_HCAR(psi, data: CarData, n_samples: int, control: Optional[dict] = None) -> HcarMc:
+    """sim.HCAR(psi, data, n.samples), R/HCAR.sim.R:3-87."""
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    h = C.c_void_p()
+    o = _sampler_opts(control)
+    check(lib.mclcar_hcar_prep(data.ctx.h, dptr(psi), psi.size, int(n_samples), C.byref(o), C.byref(h)), data.ctx.h)
+    return HcarMc(data, h, psi)
+
+
+def hcar_mc_from_matrix(psi, data: CarData, u_y, lpsi=None, dtype=np.float64) -> HcarMc:
+    """Wrap the reference's own `u.y` (K x N, column = sample) [and `lpsi`]: the parity path."""
+    u_y = np.asarray(u_y)
+    K = data.extra["K"]
+    if u_y.shape[0] != K:
+        raise ValueError("u.y must be K x N")
+    Mx = np.ascontiguousarray(u_y.T, dtype=dtype)
+    h = C.c_void_p()
+    ctx = data.ctx
+    check(lib.mclcar_samples_from_host(ctx.h, Mx.ctypes.data_as(C.c_void_p), L.F64 if dtype == np.float64 else L.F32,
+                                       L.COL_IS_SAMPLE, K, Mx.shape[0], K, C.byref(h)), ctx.h)
+    mc = HcarMc(data, h, psi)
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    base = None if lpsi is None else np.ascontiguousarray(lpsi, dtype=np.float64)
+    check(lib.mclcar_hcar_attach(ctx.h, h, dptr(psi), psi.size, dptr(base)), ctx.h)
+    return mc
+
+
+def mcl_HCAR_batch(psis, mcdata: HcarMc, data: Optional[CarData] = None, Evar=True):
+    """Row k = mcl.HCAR(psis[k], mcdata, data, Evar=TRUE); warns like the reference when a
+    candidate overflowed (R/mcl.HCAR.R:81-84)."""
+    import warnings
+    psis = np.ascontiguousarray(np.atleast_2d(psis), dtype=np.float64)
+    K, P = psis.shape
+    lr, var = np.empty(K), (np.empty(K) if Evar else None)
+    ncl = C.c_int(0)
+    ctx = mcdata.data.ctx
+    check(lib.mclcar_hcar_eval(ctx.h, mcdata.h, dptr(psis), K, P, dptr(lr), dptr(var), C.byref(ncl)), ctx.h)
+    if ncl.value:
+        warnings.warn("Design area too large: Inf produced! Choose a parameter closer to psi.")
+    return np.stack([lr, var], axis=1) if Evar else lr
+
+
+def mcl_HCAR(pars, mcdata: HcarMc, data: Optional[CarData] = None, Evar=False):
+    """mcl.HCAR, R/mcl.HCAR.R:4-97."""
+    r = mcl_HCAR_batch(np.asarray(pars, dtype=np.float64)[None, :], mcdata, data, Evar=True)[0]
+    return r if Evar else float(r[0])
+
+
+def mcl_grad_HCAR(pars, mcdata: HcarMc, data: Optional[CarData] = None, Evar=False, shift=L.SHIFT_MEAN):
+    """mcl.grad.HCAR, R/mcl.HCAR.R:101-213."""
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    P = pars.size
+    grad = np.empty(P)
+    gv = np.empty((P, P)) if Evar else None
+    ctx = mcdata.data.ctx
+    check(lib.mclcar_hcar_grad(ctx.h, mcdata.h, dptr(pars), 1, P, 1 if Evar else 0, shift, dptr(grad), dptr(gv)), ctx.h)
+    return {"grad.lr": grad, "grad.var": gv} if Evar else grad
+
+
+def mcl_Hessian_HCAR(pars, mcdata: HcarMc, data: Optional[CarData] = None, shift=L.SHIFT_MEAN) -> np.ndarray:
+    """mcl.Hessian.HCAR, R/mcl.HCAR.R:216-391."""
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    P = pars.size
+    H = np.empty((P, P))
+    ctx = mcdata.data.ctx
+    check(lib.mclcar_hcar_hess(ctx.h, mcdata.h, dptr(pars), 1, P, shift, dptr(H)), ctx.h)
+    return H
+
+
+def vmle_HCAR(MLE: dict, mcdata: HcarMc, data: Optional[CarData] = None) -> np.ndarray:
+    """vmle.HCAR, R/mcl.HCAR.R:410-416."""
+    A = mcl_grad_HCAR(MLE["estimate"], mcdata, data, Evar=True)["grad.var"]
+    Binv = np.linalg.inv(np.asarray(MLE["hessian"], dtype=np.float64))
+    return Binv @ A @ Binv

@@ -260,6 +260,7 @@ int mclcar_ctx_create(int device, uint64_t seed, mclcar_ctx** out) {
 
 void mclcar_ctx_destroy(mclcar_ctx* ctx) {
     if (!ctx) return;
+    hcar_forget(ctx);
     if (!ctx->host_only) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);

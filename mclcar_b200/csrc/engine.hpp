@@ -168,6 +168,7 @@ int merge_tuples(int what, int F, int d, int G, int K, const double* in, double*
 void centred_moments(const double* tup, int V, double* vbar, double* C);
 int gather_and_merge(mclcar_ctx* ctx, int what, int F, int d, int K, double* tuples);
 void comm_destroy(mclcar_ctx* ctx);
+void hcar_forget(mclcar_ctx* ctx);
 
 // ---- reduction kernels (reduce.cu) ----------------------------------------------------------
 struct ReducePlan {
