@@ -193,13 +193,16 @@ def run_ours(args):
             idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
         dist.broadcast(idbuf, 0)
         L.check(L.lib.mclcar_nccl_comm_init(ctx.h, bytes(idbuf.cpu().numpy().tobytes())), ctx.h)
-    control = {"n.chains": args.chains, "burn": args.burn, "thin": args.thin, "keep": not args.stats_only}
+    control = {"n.chains": args.chains, "burn": args.burn, "thin": args.thin, "keep": not args.stats_only, "omega": args.omega}
 
     data = api.make_data(y_pin.numpy(), X=X_pin.numpy(), torus=(N1, N2), ctx=ctx)
+
+    diag = {"sweeps": 0}
 
     def step_resident():
         sd = api.mcl_prep_dCAR(PSI0, N_gpu, data, control)
         res = api.mcl_dCAR_batch(psis, data, sd, rho_cons=None)
+        diag["sweeps"] = api.sampler_diag(data, sd)["sweeps"]
         sd.close()
         return res
 
@@ -276,12 +279,18 @@ def run_ours(args):
     # per-kernel numbers from the CUDA-event spans recorded inside the library (this rank)
     sweep_launches = int(launches[0])
     sweep_ms = float(ms_cat[0])
-    sd_diag_sweeps = sweep_launches // 2 // max(args.steps, 1)
+    sweeps_step = int(diag["sweeps"])
     chains = args.chains if args.chains > 0 else max(1, (32 << 20) // n)
     chains = min(chains, N_gpu)
-    bytes_per_half_sweep = chains * (n // 2) * 8.0  # read other colour + write own colour, fp32
-    sweep_gbs = bytes_per_half_sweep * sweep_launches / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
-    site_updates_per_s = chains * (n / 2) * sweep_launches / (sweep_ms * 1e-3) * world if sweep_ms > 0 else None
+    omega = args.omega if args.omega > 0 else 2.0 / (1.0 + np.sqrt(1.0 - (4 * PSI0[0]) ** 2))
+    # algorithmic bytes per site update: read the other colour + write own colour (fp32), plus the
+    # read of the current value for the over-relaxed update
+    bytes_per_update = 8.0 if omega == 1.0 else 12.0
+    updates_step = float(chains) * n * sweeps_step
+    sweep_gbs = bytes_per_update * updates_step * args.steps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
+    site_updates_per_s = updates_step * args.steps / (sweep_ms * 1e-3) * world if sweep_ms > 0 else None
+    launches_per_sweep = sweep_launches / max(sweeps_step * args.steps, 1)
+    bytes_per_launch = bytes_per_update * chains * n / max(launches_per_sweep, 1e-9)
     like_ms = float(ms_cat[2] + ms_cat[3])
     like_bytes = N_gpu * n * 4.0 * args.steps
     like_gbs = like_bytes / (like_ms * 1e-3) / 1e9 if like_ms > 0 and not args.stats_only else None
@@ -292,7 +301,7 @@ def run_ours(args):
         "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(), "samples_per_gpu": N_gpu, "psi_points": K_PSI, "chains_per_gpu": chains,
-                   "sweeps_per_step": sd_diag_sweeps, "sample_storage": "fp32 in HBM" if not args.stats_only else "statistics only",
+                   "sweeps_per_step": sweeps_step, "omega": omega, "sample_storage": "fp32 in HBM" if not args.stats_only else "statistics only",
                    "arithmetic": "fp32 chain state and normals; fp64 statistics, weights and reductions",
                    "l2": "inputs larger than L2 (chain state %.0f MB, sample matrix %.1f GB per GPU)" % (chains * n * 4 / 1e6, N_gpu * n * 4 / 1e9),
                    "parallelism": f"chains sharded over {world} GPU(s), one NCCL all-gather of partial tuples per psi batch"},
@@ -300,14 +309,17 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(y.nbytes + X.nbytes + psis.nbytes + PSI0.nbytes),
                 "d2h_bytes_per_step": int(K_PSI * 5 * 8 + 2 * 8)},
         "gpu_launches": int(launches.sum()),
-        "roofline": {"kernel": "gibbs_torus_half_sweep<4>", "bound": "hbm", "achieved": sweep_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "gibbs_torus_sweep_fused" if launches_per_sweep < 1.5 else "gibbs_torus_half_sweep_v4",
+                     "bound": "hbm", "achieved": sweep_gbs, "peak": peak, "unit": "GB/s",
                      "frac": (sweep_gbs / peak) if sweep_gbs else None, "traffic": None,
-                     "algorithmic_bytes_per_launch": bytes_per_half_sweep, "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "algorithmic_bytes_per_site_update": bytes_per_update,
+                     "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
                      "launches": sweep_launches, "peak_source": peak_src,
                      "share_of_step": sweep_ms / (1e3 * t_res) if t_res > 0 else None},
         "phases": {
             "sampler": {"metric": "gibbs_site_updates_per_s", "value": site_updates_per_s, "ms_per_step": sweep_ms / args.steps,
-                        "bytes_per_site_update": 8, "roofline_site_updates_per_s": peak * 1e9 / 8 * world},
+                        "bytes_per_site_update": bytes_per_update,
+                        "roofline_site_updates_per_s": peak * 1e9 / bytes_per_update * world},
             "emit": {"ms_per_step": float(ms_cat[1]) / args.steps},
             "likelihood": {"metric": METRIC, "value": (N_tot * K_PSI * args.steps / (like_ms * 1e-3)) if like_ms > 0 else None,
                            "ms_per_step": like_ms / args.steps, "achieved_GBps": like_gbs,
@@ -344,6 +356,7 @@ def main():
     ap.add_argument("--chains", type=int, default=0)
     ap.add_argument("--burn", type=int, default=0)
     ap.add_argument("--thin", type=int, default=0)
+    ap.add_argument("--omega", type=float, default=0.0)
     ap.add_argument("--stats-only", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -201,13 +201,23 @@ int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples);
 
 // ---- samplers (sampler_torus.cu / sampler_csr.cu) ---------------------------------------------
 struct TorusChains {
-    float* red = nullptr;
+    float* red = nullptr;    // current state
     float* black = nullptr;
+    float* red2 = nullptr;   // ping-pong partner used by the fused sweep
+    float* black2 = nullptr;
     int64_t C = 0;
 };
 int torus_chains_alloc(mclcar_ctx* ctx, int64_t C, TorusChains& t);
 void torus_chains_free(mclcar_ctx* ctx, TorusChains& t);
-int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep);
+struct TorusEmit {   // where the black half sweep of an emitting sweep writes the samples
+    void* out = nullptr;
+    int dtype = MCLCAR_F32;
+    int64_t ld = 0, slot0 = 0, nch = 0;
+    const double* d_mu = nullptr;  // per-site mean (device) or null => mu_const
+    double mu_const = 0.0;
+};
+int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep,
+                const TorusEmit* emit = nullptr);
 int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, int dtype, int64_t ld, int64_t slot0,
                int64_t nch);
 

@@ -139,18 +139,25 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
             if ((st = pool_alloc(ctx, o.keep ? &s->d_M : &staging, (size_t)(o.keep ? N : C) * ld * es))) break;
             if ((st = torus_chains_alloc(ctx, C, tc))) break;
             if (!o.keep && (st = samples_alloc_stats(ctx, s, 2 + 2 * ctx->p))) break;
+            // constant mean (intercept-only design): no per-site mean traffic in the emitting sweep
+            bool mu_is_const = true;
+            for (size_t i = 1; i < mu.size() && mu_is_const; ++i) mu_is_const = mu[i] == mu[0];
+            const bool fused = (ctx->n2 / 2) % 4 == 0;   // emission fused into the last black half sweep
             uint32_t sweep = 0;
             for (int b = 0; b < burn && st == MCLCAR_OK; ++b) st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++);
             for (int64_t e_i = 0; e_i < E && st == MCLCAR_OK; ++e_i) {
-                for (int t = 0; t < thin && st == MCLCAR_OK; ++t) st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++);
-                if (st) break;
                 const int64_t nch = std::min<int64_t>(C, N - e_i * C);
-                if (o.keep) {
-                    st = torus_emit(ctx, tc, d_mu, s->d_M, o.dtype, ld, e_i * C, nch);
-                } else {
-                    st = torus_emit(ctx, tc, d_mu, staging, o.dtype, ld, 0, nch);
+                TorusEmit em;
+                em.out = o.keep ? s->d_M : staging; em.dtype = o.dtype; em.ld = ld; em.slot0 = o.keep ? e_i * C : 0; em.nch = nch;
+                em.d_mu = (mu.empty() || mu_is_const) ? nullptr : d_mu;
+                em.mu_const = mu.empty() ? 0.0 : mu[0];
+                for (int t = 0; t < thin && st == MCLCAR_OK; ++t)
+                    st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++, (fused && t == thin - 1) ? &em : nullptr);
+                if (st) break;
+                if (!fused) st = torus_emit(ctx, tc, d_mu, em.out, o.dtype, ld, em.slot0, nch);
+                if (st == MCLCAR_OK && !o.keep) {
                     bool handled = false;
-                    if (st == MCLCAR_OK) st = launch_stats_torus_fast(ctx, staging, o.dtype, nch, ld, s->d_q + e_i * C, N, &handled);
+                    st = launch_stats_torus_fast(ctx, staging, o.dtype, nch, ld, s->d_q + e_i * C, N, &handled);
                     if (st == MCLCAR_OK && !handled) st = fail(ctx, MCLCAR_ELIMIT, "statistics-only sampling needs n2 %% 4 == 0 and rows <= 24 KB");
                 }
             }

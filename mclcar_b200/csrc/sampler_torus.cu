@@ -10,7 +10,7 @@
 // HBM traffic per site update.  Site (i, j) of colour col sits at half-column c with
 // j = 2c + ((i & 1) ^ col); its four neighbours are other[i-1][c], other[i+1][c], other[i][c]
 // and other[i][c + s], s = +1 if ((i & 1) ^ col) else -1 (cyclic).
-// One thread updates 4 consecutive half-columns of 2 consecutive rows, each 4-vector from ONE
+// One thread updates 4 consecutive half-columns of 8 consecutive rows, each 4-vector from ONE
 // Philox4x32-10 call keyed by (seed; half-lattice vector index, sweep*2+colour, global chain
 // id) -- results do not depend on the launch geometry nor on how chains are sharded over GPUs.
 //
@@ -19,6 +19,9 @@
 // for every omega in (0, 2); with the red-black ordering and omega = 2/(1 + sqrt(1 - mu^2)),
 // mu = |rho| lambda_max(W), the chain decorrelates at rate omega - 1 per sweep instead of
 // mu^2 (0.25 instead of 0.64 at rho = 0.2).  omega = 1 is the plain Gibbs sampler.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "engine.hpp"
 
@@ -26,11 +29,12 @@ namespace mclcar {
 namespace {
 
 constexpr uint32_t kTagTorus = 0x7052u;
-constexpr int kRows = 2;  // lattice rows per thread
 
 struct TorusSweepParams {
     float* red;    // [C][n1][h]
     float* black;  // [C][n1][h]
+    float* red_out;    // fused sweep only: the other buffer of the ping-pong pair
+    float* black_out;
     int n1, h;     // h = n2 / 2
     int64_t C;
     // over-relaxed Gibbs update  x' = keep*x + gain*(sum of neighbours) + noise*z  with
@@ -39,15 +43,24 @@ struct TorusSweepParams {
     uint32_t sweep;
     int64_t chain0, chain_stride;  // global chain id = chain0 + local * chain_stride
     PhiloxKeys keys;
+    // emission (black half sweep of the last sweep of a thinning block): sample = mu + state,
+    // written in the reference's site order to out[(slot0 + chain) * ld + site]
+    void* out;
+    int64_t ld, slot0, nch;
+    const double* mu;   // [n] or null
+    double mu_const;    // used when mu is null
 };
 
-// VEC = 4: h % 4 == 0, 16-byte path.  VEC = 1: any h.  SOR: read the current value too.
-template <int VEC, bool SOR>
-__global__ void __launch_bounds__(256) gibbs_torus_half_sweep(const TorusSweepParams p, const int col) {
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// 16-byte path (h % 4 == 0).  SOR: the update reads the current value too.  EMIT: the black
+// half sweep also stores the finished sample row segment (both colours are in registers).
+template <bool SOR, bool EMIT, typename TO, int kRows>
+__global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSweepParams p, const int col) {
     const int h = p.h, n1 = p.n1;
-    const int hv = h / VEC;
-    const int cv = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i0 = (blockIdx.y * blockDim.y + threadIdx.y) * kRows;
+    const int hv = h >> 2;
+    const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int i0 = (blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kRows;
     const int64_t ch = blockIdx.z;
     if (cv >= hv || i0 >= n1) return;
     const size_t plane = (size_t)n1 * h;
@@ -55,65 +68,255 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep(const TorusSweepPa
     const float* __restrict__ oth = (col == 0 ? p.black : p.red) + ch * plane;
     const uint64_t gch = (uint64_t)(p.chain0 + ch * p.chain_stride);
     const uint32_t c2 = (uint32_t)gch, c3 = (uint32_t)(gch >> 32) ^ (kTagTorus << 16), c1 = p.sweep * 2u + (uint32_t)col;
-    const int c0 = cv * VEC;
+    const int c0 = cv << 2;
+    const int cl = c0 == 0 ? h - 1 : c0 - 1, cr = c0 + 4 == h ? 0 : c0 + 4;
+    const int iend = min(i0 + kRows, n1);
 
-    if constexpr (VEC == 4) {
-        const int cl = c0 == 0 ? h - 1 : c0 - 1, cr = c0 + 4 == h ? 0 : c0 + 4;
-        int ip = i0 == 0 ? n1 - 1 : i0 - 1;
-        float4 up = *reinterpret_cast<const float4*>(oth + (unsigned)(ip * h + c0));
-        float4 o = *reinterpret_cast<const float4*>(oth + (unsigned)(i0 * h + c0));
+    int row = i0 * h;                                  // offset of row i (floats)
+    float4 up = ld4(oth + (i0 == 0 ? (n1 - 1) * h : row - h) + c0);
+    float4 o = ld4(oth + row + c0);
+    uint32_t ctr = (uint32_t)(i0 * hv + cv);
+    // loads of row i are issued one iteration ahead (software prefetch in registers)
+    int rown = i0 + 1 == n1 ? 0 : row + h;
+    float4 d = ld4(oth + rown + c0);
+    float e = oth[row + ((((i0 & 1) ^ col) != 0) ? cr : cl)];
+    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (SOR) cur = ld4(own + row + c0);
 #pragma unroll
-        for (int k = 0; k < kRows; ++k) {
-            const int i = i0 + k;
-            if (i >= n1) break;
-            const int in = i + 1 == n1 ? 0 : i + 1;
-            const float4 d = *reinterpret_cast<const float4*>(oth + (unsigned)(in * h + c0));
-            const bool fwd = ((i & 1) ^ col) != 0;  // same-row neighbour sits at c + 1, else at c - 1
-            const float e = oth[(unsigned)(i * h + (fwd ? cr : cl))];
-            const Philox4 r = philox4x32_10((uint32_t)(i * hv + cv), c1, c2, c3, p.keys);
+    for (int k = 0; k < kRows; ++k) {
+        const int i = i0 + k;
+        if (i >= iend) break;
+        const bool fwd = ((i & 1) ^ col) != 0;          // same-row neighbour sits at c + 1, else at c - 1
+        // prefetch row i + 1
+        const int row2 = i + 2 >= n1 ? (i + 2 - n1) * h : rown + h;
+        float4 dn = d, curn = cur;
+        float en = e;
+        if (k + 1 < kRows && i + 1 < iend) {
+            dn = ld4(oth + row2 + c0);
+            en = oth[rown + (fwd ? cl : cr)];           // row i + 1 has the opposite parity
+            if (SOR) curn = ld4(own + rown + c0);
+        }
+        const Philox4 r = philox4x32_10(ctr, c1, c2, c3, p.keys);
+        float z0, z1, z2, z3;
+        box_muller(r.x, r.y, z0, z1);
+        box_muller(r.z, r.w, z2, z3);
+        float4 s;
+        if (fwd) {
+            s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e;
+        } else {
+            s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w;
+        }
+        float4 v;
+        v.x = fmaf(p.gain, s.x + (up.x + d.x), p.noise * z0);
+        v.y = fmaf(p.gain, s.y + (up.y + d.y), p.noise * z1);
+        v.z = fmaf(p.gain, s.z + (up.z + d.z), p.noise * z2);
+        v.w = fmaf(p.gain, s.w + (up.w + d.w), p.noise * z3);
+        if (SOR) {
+            v.x = fmaf(p.keep, cur.x, v.x);
+            v.y = fmaf(p.keep, cur.y, v.y);
+            v.z = fmaf(p.keep, cur.z, v.z);
+            v.w = fmaf(p.keep, cur.w, v.w);
+        }
+        *reinterpret_cast<float4*>(own + row + c0) = v;
+        if (EMIT) {
+            if (ch < p.nch) {
+                // black half sweep (col == 1): o = finished red values, v = new black values of the same
+                // half-columns; red sits at column 2c + par, black at 2c + 1 - par (par = i & 1)
+                const bool par = (i & 1) != 0;
+                const size_t site = (size_t)i * 2 * h + 2 * c0;
+                float a[8];
+                a[0] = par ? v.x : o.x; a[1] = par ? o.x : v.x; a[2] = par ? v.y : o.y; a[3] = par ? o.y : v.y;
+                a[4] = par ? v.z : o.z; a[5] = par ? o.z : v.z; a[6] = par ? v.w : o.w; a[7] = par ? o.w : v.w;
+                TO* dst = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld + site;
+                if (p.mu != nullptr) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + __ldg(p.mu + site + t));
+                } else if (sizeof(TO) == 4) {
+                    const float m = (float)p.mu_const;
+                    float4* d4 = reinterpret_cast<float4*>(dst);
+                    d4[0] = make_float4(a[0] + m, a[1] + m, a[2] + m, a[3] + m);
+                    d4[1] = make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + p.mu_const);
+                }
+            }
+        }
+        up = o;
+        o = d;
+        d = dn;
+        e = en;
+        cur = curn;
+        row = rown;
+        rown = row2;
+        ctr += (uint32_t)hv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused full sweep: ONE pass over HBM per sweep instead of two.  A CTA owns TR lattice rows of
+// one chain at full width.  Black rows r0-2 .. r0+TR+1 and red rows r0-1 .. r0+TR are staged into
+// shared memory by the bulk-async copy engine (cp.async.bulk, one mbarrier); phase 1 updates red
+// for the TR rows AND the two halo rows (recomputing what the neighbouring tiles compute -- same
+// Philox counters, hence the same numbers), phase 2 updates black for the TR rows from the new
+// red values in shared memory.  Traffic: (2TR+6)/(2TR) reads + 1 write of the state per sweep,
+// about 9 B per site update instead of 12 (over-relaxed) for the two-launch form; results are
+// bit-identical to it.
+// ---------------------------------------------------------------------------------------------
+template <bool SOR, bool EMIT, typename TO>
+__global__ void __launch_bounds__(256) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
+    extern __shared__ __align__(128) unsigned char fsm[];
+    const int h = p.h, n1 = p.n1, hv = h >> 2;
+    const int r0 = blockIdx.x * TR;
+    const int rows = min(TR, n1 - r0);
+    const int64_t ch = blockIdx.y;
+    const size_t plane = (size_t)n1 * h;
+    const float* __restrict__ gred = p.red + ch * plane;      // read from the current buffers,
+    const float* __restrict__ gblk = p.black + ch * plane;
+    float* __restrict__ ored = p.red_out + ch * plane;        // write to the other pair: tiles of the
+    float* __restrict__ oblk = p.black_out + ch * plane;      // same launch never see each other's output
+    float* sB = reinterpret_cast<float*>(fsm);             // [rows + 4][h]: black rows r0-2 ..
+    float* sR = sB + (size_t)(TR + 4) * h;                 // [rows + 2][h]: red rows r0-1 ..
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sR + (size_t)(TR + 2) * h);
+    const uint32_t row_bytes = (uint32_t)h * 4u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, row_bytes * (uint32_t)(2 * rows + 6));
+        for (int l = 0; l < rows + 4; ++l) {
+            int i = r0 - 2 + l;
+            i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
+            bulk_g2s(sB + (size_t)l * h, gblk + (size_t)i * h, row_bytes, bar);
+        }
+        for (int l = 0; l < rows + 2; ++l) {
+            int i = r0 - 1 + l;
+            i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
+            bulk_g2s(sR + (size_t)l * h, gred + (size_t)i * h, row_bytes, bar);
+        }
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const uint64_t gch = (uint64_t)(p.chain0 + ch * p.chain_stride);
+    const uint32_t c2 = (uint32_t)gch, c3 = (uint32_t)(gch >> 32) ^ (kTagTorus << 16);
+    // warp ty owns rows ty, ty + 8, ...; its lanes stride the column vectors of the row
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+
+    // ---- phase 1: red rows r0-1 .. r0+rows (local 0 .. rows+1), black neighbours from sB
+    for (int lr = ty; lr < rows + 2; lr += 8) {
+        int i = r0 - 1 + lr;
+        i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
+        const bool fwd = (i & 1) != 0;
+        const float* bu = sB + (size_t)lr * h;
+        const float* bo = bu + h;
+        const float* bd = bo + h;
+        float* rr = sR + (size_t)lr * h;
+        const bool interior = lr >= 1 && lr <= rows;
+        for (int cv = tx; cv < hv; cv += 32) {
+            const int c0 = cv << 2;
+            const float4 o = ld4(bo + c0), up = ld4(bu + c0), d = ld4(bd + c0);
+            const float e = bo[fwd ? (c0 + 4 == h ? 0 : c0 + 4) : (c0 == 0 ? h - 1 : c0 - 1)];
+            const Philox4 r = philox4x32_10((uint32_t)(i * hv + cv), p.sweep * 2u, c2, c3, p.keys);
             float z0, z1, z2, z3;
             box_muller(r.x, r.y, z0, z1);
             box_muller(r.z, r.w, z2, z3);
             float4 s;
-            if (fwd) {
-                s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e;
-            } else {
-                s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w;
-            }
+            if (fwd) { s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e; }
+            else { s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w; }
             float4 v;
             v.x = fmaf(p.gain, s.x + (up.x + d.x), p.noise * z0);
             v.y = fmaf(p.gain, s.y + (up.y + d.y), p.noise * z1);
             v.z = fmaf(p.gain, s.z + (up.z + d.z), p.noise * z2);
             v.w = fmaf(p.gain, s.w + (up.w + d.w), p.noise * z3);
-            float4* dst = reinterpret_cast<float4*>(own + (unsigned)(i * h + c0));
-            if constexpr (SOR) {
-                const float4 cur = *dst;
-                v.x = fmaf(p.keep, cur.x, v.x);
-                v.y = fmaf(p.keep, cur.y, v.y);
-                v.z = fmaf(p.keep, cur.z, v.z);
-                v.w = fmaf(p.keep, cur.w, v.w);
+            if (SOR) {
+                const float4 cur = ld4(rr + c0);
+                v.x = fmaf(p.keep, cur.x, v.x); v.y = fmaf(p.keep, cur.y, v.y);
+                v.z = fmaf(p.keep, cur.z, v.z); v.w = fmaf(p.keep, cur.w, v.w);
             }
-            *dst = v;
-            up = o;
-            o = d;
-        }
-    } else {
-        for (int k = 0; k < kRows; ++k) {
-            const int i = i0 + k;
-            if (i >= n1) break;
-            const int iu = i == 0 ? n1 - 1 : i - 1, id = i + 1 == n1 ? 0 : i + 1;
-            const bool fwd = ((i & 1) ^ col) != 0;
-            const int c = c0;
-            const int cn = fwd ? (c + 1 == h ? 0 : c + 1) : (c == 0 ? h - 1 : c - 1);
-            const Philox4 r = philox4x32_10((uint32_t)(i * hv + cv), c1, c2, c3, p.keys);
-            float z0, z1;
-            box_muller(r.x, r.y, z0, z1);
-            const float s = oth[(size_t)i * h + c] + oth[(size_t)i * h + cn] + oth[(size_t)iu * h + c] + oth[(size_t)id * h + c];
-            float v = fmaf(p.gain, s, p.noise * z0);
-            if constexpr (SOR) v = fmaf(p.keep, own[(size_t)i * h + c], v);
-            own[(size_t)i * h + c] = v;
+            *reinterpret_cast<float4*>(rr + c0) = v;
+            if (interior) *reinterpret_cast<float4*>(ored + (size_t)i * h + c0) = v;
         }
     }
+    __syncthreads();
+    // ---- phase 2: black rows r0 .. r0+rows-1 from the new red rows in sR
+    for (int t = ty; t < rows; t += 8) {
+        const int i = r0 + t;
+        const bool fwd = (i & 1) == 0;   // ((i & 1) ^ 1)
+        const float* ru = sR + (size_t)t * h;
+        const float* ro = ru + h;
+        const float* rd = ro + h;
+        const float* bc = sB + (size_t)(t + 2) * h;
+        for (int cv = tx; cv < hv; cv += 32) {
+            const int c0 = cv << 2;
+            const float4 o = ld4(ro + c0), up = ld4(ru + c0), d = ld4(rd + c0);
+            const float e = ro[fwd ? (c0 + 4 == h ? 0 : c0 + 4) : (c0 == 0 ? h - 1 : c0 - 1)];
+            const Philox4 r = philox4x32_10((uint32_t)(i * hv + cv), p.sweep * 2u + 1u, c2, c3, p.keys);
+            float z0, z1, z2, z3;
+            box_muller(r.x, r.y, z0, z1);
+            box_muller(r.z, r.w, z2, z3);
+            float4 s;
+            if (fwd) { s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e; }
+            else { s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w; }
+            float4 v;
+            v.x = fmaf(p.gain, s.x + (up.x + d.x), p.noise * z0);
+            v.y = fmaf(p.gain, s.y + (up.y + d.y), p.noise * z1);
+            v.z = fmaf(p.gain, s.z + (up.z + d.z), p.noise * z2);
+            v.w = fmaf(p.gain, s.w + (up.w + d.w), p.noise * z3);
+            if (SOR) {
+                const float4 cur = ld4(bc + c0);
+                v.x = fmaf(p.keep, cur.x, v.x); v.y = fmaf(p.keep, cur.y, v.y);
+                v.z = fmaf(p.keep, cur.z, v.z); v.w = fmaf(p.keep, cur.w, v.w);
+            }
+            *reinterpret_cast<float4*>(oblk + (size_t)i * h + c0) = v;
+            if (EMIT) {
+                if (ch < p.nch) {
+                    const bool par = (i & 1) != 0;
+                    const size_t site = (size_t)i * 2 * h + 2 * c0;
+                    float a[8];
+                    a[0] = par ? v.x : o.x; a[1] = par ? o.x : v.x; a[2] = par ? v.y : o.y; a[3] = par ? o.y : v.y;
+                    a[4] = par ? v.z : o.z; a[5] = par ? o.z : v.z; a[6] = par ? v.w : o.w; a[7] = par ? o.w : v.w;
+                    TO* dst = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld + site;
+                    if (p.mu != nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = (TO)((double)a[q] + __ldg(p.mu + site + q));
+                    } else if (sizeof(TO) == 4) {
+                        const float m = (float)p.mu_const;
+                        float4* d4 = reinterpret_cast<float4*>(dst);
+                        d4[0] = make_float4(a[0] + m, a[1] + m, a[2] + m, a[3] + m);
+                        d4[1] = make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = (TO)((double)a[q] + p.mu_const);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// generic path: any h, one site per thread
+template <bool SOR>
+__global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v1(const TorusSweepParams p, const int col) {
+    const int h = p.h, n1 = p.n1;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int64_t ch = blockIdx.z;
+    if (c >= h || i >= n1) return;
+    const size_t plane = (size_t)n1 * h;
+    float* own = (col == 0 ? p.red : p.black) + ch * plane;
+    const float* oth = (col == 0 ? p.black : p.red) + ch * plane;
+    const uint64_t gch = (uint64_t)(p.chain0 + ch * p.chain_stride);
+    const int iu = i == 0 ? n1 - 1 : i - 1, id = i + 1 == n1 ? 0 : i + 1;
+    const bool fwd = ((i & 1) ^ col) != 0;
+    const int cn = fwd ? (c + 1 == h ? 0 : c + 1) : (c == 0 ? h - 1 : c - 1);
+    const Philox4 r = philox4x32_10((uint32_t)(i * h + c), p.sweep * 2u + (uint32_t)col, (uint32_t)gch,
+                                    (uint32_t)(gch >> 32) ^ (kTagTorus << 16), p.keys);
+    float z0, z1;
+    box_muller(r.x, r.y, z0, z1);
+    const float s = oth[(size_t)i * h + c] + oth[(size_t)i * h + cn] + oth[(size_t)iu * h + c] + oth[(size_t)id * h + c];
+    float v = fmaf(p.gain, s, p.noise * z0);
+    if (SOR) v = fmaf(p.keep, own[(size_t)i * h + c], v);
+    own[(size_t)i * h + c] = v;
 }
 
 // write the current state of chains [0, nch) as samples: out[(slot0 + ch)*ld + site] = mu[site] + z
@@ -138,14 +341,35 @@ __global__ void __launch_bounds__(256) torus_emit_kernel(const float* red, const
     o[1] = (TO)v1;
 }
 
+template <int R>
+void launch_v4(const TorusSweepParams& p, bool sor, bool emit, bool f32, int64_t C, cudaStream_t st) {
+    const int hv = p.h / 4;
+    const int strips = (p.n1 + R - 1) / R;
+    dim3 block(256);  // 32 column vectors x 8 row strips
+    dim3 grid((hv + 31) / 32, (strips + 7) / 8, (unsigned)C);
+    if (sor) gibbs_torus_half_sweep_v4<true, false, float, R><<<grid, block, 0, st>>>(p, 0);
+    else gibbs_torus_half_sweep_v4<false, false, float, R><<<grid, block, 0, st>>>(p, 0);
+    if (emit) {
+        if (sor && f32) gibbs_torus_half_sweep_v4<true, true, float, R><<<grid, block, 0, st>>>(p, 1);
+        else if (sor) gibbs_torus_half_sweep_v4<true, true, double, R><<<grid, block, 0, st>>>(p, 1);
+        else if (f32) gibbs_torus_half_sweep_v4<false, true, float, R><<<grid, block, 0, st>>>(p, 1);
+        else gibbs_torus_half_sweep_v4<false, true, double, R><<<grid, block, 0, st>>>(p, 1);
+    } else {
+        if (sor) gibbs_torus_half_sweep_v4<true, false, float, R><<<grid, block, 0, st>>>(p, 1);
+        else gibbs_torus_half_sweep_v4<false, false, float, R><<<grid, block, 0, st>>>(p, 1);
+    }
+}
+
 }  // namespace
 
 int torus_chains_alloc(mclcar_ctx* ctx, int64_t C, TorusChains& t) {
-    const size_t plane = (size_t)ctx->n1 * (ctx->n2 / 2);
-    MCL_TRY(pool_alloc(ctx, (void**)&t.red, (size_t)C * plane * sizeof(float)));
-    MCL_TRY(pool_alloc(ctx, (void**)&t.black, (size_t)C * plane * sizeof(float)));
-    MCL_CUDA(ctx, cudaMemsetAsync(t.red, 0, (size_t)C * plane * sizeof(float), ctx->stream));
-    MCL_CUDA(ctx, cudaMemsetAsync(t.black, 0, (size_t)C * plane * sizeof(float), ctx->stream));
+    const size_t bytes = (size_t)C * ctx->n1 * (ctx->n2 / 2) * sizeof(float);
+    MCL_TRY(pool_alloc(ctx, (void**)&t.red, bytes));
+    MCL_TRY(pool_alloc(ctx, (void**)&t.black, bytes));
+    MCL_TRY(pool_alloc(ctx, (void**)&t.red2, bytes));
+    MCL_TRY(pool_alloc(ctx, (void**)&t.black2, bytes));
+    MCL_CUDA(ctx, cudaMemsetAsync(t.red, 0, bytes, ctx->stream));
+    MCL_CUDA(ctx, cudaMemsetAsync(t.black, 0, bytes, ctx->stream));
     t.C = C;
     return MCLCAR_OK;
 }
@@ -153,11 +377,15 @@ int torus_chains_alloc(mclcar_ctx* ctx, int64_t C, TorusChains& t) {
 void torus_chains_free(mclcar_ctx* ctx, TorusChains& t) {
     pool_free(ctx, t.red);
     pool_free(ctx, t.black);
-    t.red = t.black = nullptr;
+    pool_free(ctx, t.red2);
+    pool_free(ctx, t.black2);
+    t.red = t.black = t.red2 = t.black2 = nullptr;
 }
 
-// one full sweep (both colours) of all chains; omega in [1, 2): over-relaxation factor
-int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep) {
+// one full sweep (both colours) of all chains; omega in [1, 2): over-relaxation factor.  When
+// `emit` is given (16-byte path only) the black half sweep also writes the samples.
+int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep,
+                const TorusEmit* emit) {
     TorusSweepParams p{};
     p.red = t.red; p.black = t.black; p.n1 = ctx->n1; p.h = ctx->n2 / 2; p.C = t.C;
     p.keep = (float)(1.0 - omega);
@@ -168,19 +396,59 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
     p.chain0 = ctx->rank; p.chain_stride = ctx->world;
     const bool vec4 = (p.h % 4) == 0;
     const bool sor = omega != 1.0;
-    const int hv = vec4 ? p.h / 4 : p.h;
-    dim3 block(32, 8);
-    while ((int)block.x / 2 >= hv && block.x > 1) { block.x /= 2; block.y *= 2; }
-    const int rows_t = (p.n1 + kRows - 1) / kRows;
-    dim3 grid((hv + block.x - 1) / block.x, (rows_t + block.y - 1) / block.y, (unsigned)t.C);
     if (t.C > 65535) return fail(ctx, MCLCAR_ELIMIT, "more than 65535 chains in one torus sampler launch");
     if ((int64_t)p.n1 * p.h >= ((int64_t)1 << 31)) return fail(ctx, MCLCAR_ELIMIT, "lattice too large for 32-bit indexing");
-    ProfScope prof(ctx, PROF_SWEEP, 2);
-    for (int col = 0; col < 2; ++col) {
-        if (vec4 && sor) gibbs_torus_half_sweep<4, true><<<grid, block, 0, ctx->stream>>>(p, col);
-        else if (vec4) gibbs_torus_half_sweep<4, false><<<grid, block, 0, ctx->stream>>>(p, col);
-        else if (sor) gibbs_torus_half_sweep<1, true><<<grid, block, 0, ctx->stream>>>(p, col);
-        else gibbs_torus_half_sweep<1, false><<<grid, block, 0, ctx->stream>>>(p, col);
+    if (emit && !vec4) return fail(ctx, MCLCAR_EINVAL, "fused emission needs n2 % 8 == 0");
+    if (vec4) {
+        static int rows_cfg = [] { const char* e = getenv("MCLCAR_SWEEP_ROWS"); return e ? atoi(e) : 4; }();
+        if (emit) {
+            p.out = emit->out; p.ld = emit->ld; p.slot0 = emit->slot0; p.nch = emit->nch;
+            p.mu = emit->d_mu; p.mu_const = emit->mu_const;
+        }
+        const bool f32 = !emit || emit->dtype == MCLCAR_F32;
+        const char* fe = getenv("MCLCAR_SWEEP_FUSED");  // read per call: tests toggle it
+        const int fused_cfg = fe ? atoi(fe) : 1;
+        static int tr_cfg = [] { const char* e = getenv("MCLCAR_SWEEP_TR"); return e ? atoi(e) : 0; }();
+        const size_t row_b = (size_t)p.h * 4;
+        int TR = tr_cfg > 0 ? tr_cfg : (int)((72 * 1024 / row_b - 6) / 2);
+        TR = std::min(TR, 64);
+        if (fused_cfg && TR >= 4 && p.n1 >= TR + 4) {
+            ProfScope prof(ctx, PROF_SWEEP, 1);
+            p.red_out = t.red2; p.black_out = t.black2;
+            std::swap(t.red, t.red2);        // the output pair is the current state from now on
+            std::swap(t.black, t.black2);
+            const size_t smem = (size_t)(2 * TR + 6) * row_b + 64;
+            dim3 grid((p.n1 + TR - 1) / TR, (unsigned)t.C);
+#define LAUNCH_FUSED(S, E, TO_)                                                                                  \
+    do {                                                                                                         \
+        cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        gibbs_torus_sweep_fused<S, E, TO_><<<grid, 256, smem, ctx->stream>>>(p, TR);                            \
+    } while (0)
+            if (emit) {
+                if (sor && f32) LAUNCH_FUSED(true, true, float);
+                else if (sor) LAUNCH_FUSED(true, true, double);
+                else if (f32) LAUNCH_FUSED(false, true, float);
+                else LAUNCH_FUSED(false, true, double);
+            } else {
+                if (sor) LAUNCH_FUSED(true, false, float);
+                else LAUNCH_FUSED(false, false, float);
+            }
+#undef LAUNCH_FUSED
+            MCL_CUDA(ctx, cudaGetLastError());
+            return MCLCAR_OK;
+        }
+        ProfScope prof(ctx, PROF_SWEEP, 2);
+        if (rows_cfg == 2) launch_v4<2>(p, sor, emit != nullptr, f32, t.C, ctx->stream);
+        else if (rows_cfg == 8) launch_v4<8>(p, sor, emit != nullptr, f32, t.C, ctx->stream);
+        else launch_v4<4>(p, sor, emit != nullptr, f32, t.C, ctx->stream);
+    } else {
+        ProfScope prof(ctx, PROF_SWEEP, 2);
+        dim3 block(32, 8);
+        dim3 grid((p.h + 31) / 32, (p.n1 + 7) / 8, (unsigned)t.C);
+        for (int col = 0; col < 2; ++col) {
+            if (sor) gibbs_torus_half_sweep_v1<true><<<grid, block, 0, ctx->stream>>>(p, col);
+            else gibbs_torus_half_sweep_v1<false><<<grid, block, 0, ctx->stream>>>(p, col);
+        }
     }
     MCL_CUDA(ctx, cudaGetLastError());
     return MCLCAR_OK;

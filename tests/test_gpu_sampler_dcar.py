@@ -151,3 +151,24 @@ def test_mcl_estimate_matches_exact_likelihood_ratio():
         av = dcar.Avar_lik_dCAR(th, psi0, eig, N)
         assert np.isfinite(av) and r[1] == pytest.approx(av, rel=0.3)
     assert np.abs(zs).max() < 4.5
+
+
+def test_fused_sweep_is_bit_identical_to_two_half_sweeps(monkeypatch):
+    """The shared-memory fused sweep recomputes halo rows from the same Philox counters: its
+    samples equal those of the two-launch red/black form bit for bit."""
+    n1, n2 = 96, 128   # 6 tiles of 16-ish rows, wrap-around at both ends
+    rng = np.random.default_rng(3)
+    n = n1 * n2
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    y = rng.standard_normal(n)
+    psi = [0.21, 1.2, 0.3, -0.2]
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MCLCAR_SWEEP_FUSED", fused)
+        for omega in (0.0, 1.0):
+            d = api.make_data(y, X=X, torus=(n1, n2), seed=5)
+            sd = api.mcl_prep_dCAR(psi, 12, d, {"n.chains": 4, "burn": 3, "thin": 2, "omega": omega})
+            out[(fused, omega)] = sd.simY
+    for omega in (0.0, 1.0):
+        np.testing.assert_array_equal(out[("1", omega)], out[("0", omega)])
+    assert np.abs(out[("1", 0.0)] - out[("1", 1.0)]).max() > 0.1
