@@ -172,3 +172,21 @@ def test_fused_sweep_is_bit_identical_to_two_half_sweeps(monkeypatch):
     for omega in (0.0, 1.0):
         np.testing.assert_array_equal(out[("1", omega)], out[("0", omega)])
     assert np.abs(out[("1", 0.0)] - out[("1", 1.0)]).max() > 0.1
+
+
+@pytest.mark.parametrize("omega", [0.0, 1.0])
+def test_default_thinning_decorrelates_kept_states(omega):
+    """The default schedule promises <= ~1 % autocorrelation between consecutive kept states
+    of a chain (both for the over-relaxed default and for plain Gibbs): check the lag-1
+    autocorrelation of the sufficient statistics along each chain."""
+    n1 = n2 = 256
+    C, E = 64, 40
+    data = api.make_data(np.zeros(n1 * n2), X=None, torus=(n1, n2), seed=101)
+    sd = api.mcl_prep_dCAR([0.2, 1.0], C * E, data, {"n.chains": C, "omega": omega, "keep": False})
+    q = sd.stats().reshape(E, C, 2)          # sample index = e * C + chain
+    d = q - q.mean(axis=0, keepdims=True)
+    acf = (d[1:] * d[:-1]).sum(axis=0) / (d * d).sum(axis=0)      # per chain, per statistic
+    # mean over 64 chains of a lag-1 estimate from 40 points: s.e. ~ 1/sqrt(64*40) = 0.02 (+ O(1/E) bias)
+    assert np.abs(acf.mean(axis=0) + 1.0 / E).max() < 0.07
+    sweeps = api.sampler_diag(data, sd)["sweeps"]
+    assert sweeps < (300 if omega == 0.0 else 600)
