@@ -30,6 +30,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define MCLCAR_API __attribute__((visibility("default")))
+#else
+#define MCLCAR_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -69,44 +75,44 @@ typedef struct mclcar_samples mclcar_samples;
  * observation bookkeeping, tuple merge and finish stages work; compute calls fail with
  * MCLCAR_ENODEV).  `seed` is the Philox key; in R the glue draws it from R's RNG so that
  * set.seed() still makes runs reproducible. */
-int mclcar_ctx_create(int device, uint64_t seed, mclcar_ctx** out);
-void mclcar_ctx_destroy(mclcar_ctx* ctx);
-const char* mclcar_last_error(const mclcar_ctx* ctx); /* ctx may be NULL: last create error */
+MCLCAR_API int mclcar_ctx_create(int device, uint64_t seed, mclcar_ctx** out);
+MCLCAR_API void mclcar_ctx_destroy(mclcar_ctx* ctx);
+MCLCAR_API const char* mclcar_last_error(const mclcar_ctx* ctx); /* ctx may be NULL: last create error */
 /* run all work on the given cudaStream_t (NULL: the context's own stream) */
-int mclcar_ctx_set_stream(mclcar_ctx* ctx, void* cuda_stream);
-int mclcar_ctx_sync(mclcar_ctx* ctx);
+MCLCAR_API int mclcar_ctx_set_stream(mclcar_ctx* ctx, void* cuda_stream);
+MCLCAR_API int mclcar_ctx_sync(mclcar_ctx* ctx);
 /* this context is shard `rank` of `world`: samplers draw global chains rank, rank+world,
  * ... so that the union over ranks does not depend on `world`. */
-int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world);
+MCLCAR_API int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world);
 /* instrumentation: kernel-launch counters per category and, while enabled, CUDA-event time
  * spans recorded on the context's stream around each group of launches.  Categories:
  * 0 torus half sweeps, 1 sample emission, 2 statistics (K2), 3 reduction (K3),
  * 4 shared-memory chain sampler, 5 GLM data terms.  profile(enable) resets both. */
-int mclcar_ctx_profile(mclcar_ctx* ctx, int enable);
-int mclcar_ctx_profile_read(mclcar_ctx* ctx, double ms_out[8], int64_t launches_out[8]);
+MCLCAR_API int mclcar_ctx_profile(mclcar_ctx* ctx, int enable);
+MCLCAR_API int mclcar_ctx_profile_read(mclcar_ctx* ctx, double ms_out[8], int64_t launches_out[8]);
 /* NCCL (dlopen'ed on first use, libnccl.so.2): rank 0 obtains a 128-byte unique id,
  * hands it to the other ranks by any channel, then every rank calls comm_init.  Once
  * initialised, every *_eval/_grad/_hess call all-gathers its partial tuples with ONE
  * ncclAllGather per candidate batch and merges them in rank order on every rank. */
-int mclcar_nccl_unique_id(mclcar_ctx* ctx, unsigned char id_out[128]);
-int mclcar_nccl_comm_init(mclcar_ctx* ctx, const unsigned char id[128]);
+MCLCAR_API int mclcar_nccl_unique_id(mclcar_ctx* ctx, unsigned char id_out[128]);
+MCLCAR_API int mclcar_nccl_comm_init(mclcar_ctx* ctx, const unsigned char id[128]);
 
 /* ---- model: graph, design, observations ------------------------------------------ */
 /* rook-neighbour n1 x n2 torus, site (i, j) at index i*n2 + j; equals the W built by
  * CAR.simTorus (R/CAR.simLM.R:4-7) when n1 == n2.  Eigenvalues are analytic. */
-int mclcar_graph_torus(mclcar_ctx* ctx, int n1, int n2);
+MCLCAR_API int mclcar_graph_torus(mclcar_ctx* ctx, int n1, int n2);
 /* general neighbourhood matrix W in CSR (0-based, symmetric, zero diagonal; val NULL =
  * binary).  Replaces `data$W` (dense n x n in the reference).  Validated on upload. */
-int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val);
+MCLCAR_API int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val);
 /* eigenvalues of W (`data$lambda`, eigen(W) at R/mcl.bin.R:176): needed by the GLM
  * gradient / Hessian and for the rho range check on CSR graphs.  Optional. */
-int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, int n);
+MCLCAR_API int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, int n);
 /* design matrix X = model.matrix(y ~ ., data.vec) / covX, n x p column-major; p may be 0 */
-int mclcar_set_design(mclcar_ctx* ctx, const double* X, int p);
+MCLCAR_API int mclcar_set_design(mclcar_ctx* ctx, const double* X, int p);
 /* observed response y (n) and, for the binomial family, n.trial (n, or NULL) */
-int mclcar_set_obs(mclcar_ctx* ctx, const double* y, const double* ntrial);
-int mclcar_graph_n(const mclcar_ctx* ctx);
-int mclcar_graph_ncolors(const mclcar_ctx* ctx);
+MCLCAR_API int mclcar_set_obs(mclcar_ctx* ctx, const double* y, const double* ntrial);
+MCLCAR_API int mclcar_graph_n(const mclcar_ctx* ctx);
+MCLCAR_API int mclcar_graph_ncolors(const mclcar_ctx* ctx);
 
 /* ---- sample sets ------------------------------------------------------------------- */
 typedef struct mclcar_sampler_opts {
@@ -122,49 +128,49 @@ typedef struct mclcar_sampler_opts {
 
 /* the reference's own sample matrix (simY / Zy / u.y) copied to the device: parity path.
  * `sites` is n for dCAR / GLM and K (districts) for HCAR. */
-int mclcar_samples_from_host(mclcar_ctx* ctx, const void* M, int dtype, int layout, int64_t sites,
+MCLCAR_API int mclcar_samples_from_host(mclcar_ctx* ctx, const void* M, int dtype, int layout, int64_t sites,
                              int64_t N, int64_t ld, mclcar_samples** out);
 /* same, for a matrix already resident in device memory (not copied, not owned) */
-int mclcar_samples_from_device(mclcar_ctx* ctx, const void* M_dev, int dtype, int layout, int64_t sites,
+MCLCAR_API int mclcar_samples_from_device(mclcar_ctx* ctx, const void* M_dev, int dtype, int layout, int64_t sites,
                                int64_t N, int64_t ld, mclcar_samples** out);
-void mclcar_samples_free(mclcar_samples* s);
-int64_t mclcar_samples_count(const mclcar_samples* s);
+MCLCAR_API void mclcar_samples_free(mclcar_samples* s);
+MCLCAR_API int64_t mclcar_samples_count(const mclcar_samples* s);
 /* copy the sample matrix back as fp64 in the given layout (ld >= leading extent) */
-int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double* out, int64_t ld);
+MCLCAR_API int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double* out, int64_t ld);
 /* sampler diagnostics: mean acceptance rate (1 for pure Gibbs) and sweeps actually run */
-int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate, int64_t* sweeps);
+MCLCAR_API int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate, int64_t* sweeps);
 
 /* ---- direct CAR (R/mcl.dCAR.R) --------------------------------------------------------- */
 /* per-sample sufficient statistics q_i = (Y'Y, Y'WY, X'Y[p], X'WY[p]) in one pass over the
  * samples; replaces the per-sample dense products of logunnorm / D.log.unorm
  * (R/mcl.dCAR.R:168-210).  q_out: N x (2+2p) column-major, may be NULL. */
-int mclcar_dcar_stats(mclcar_ctx* ctx, mclcar_samples* s, double* q_out);
+MCLCAR_API int mclcar_dcar_stats(mclcar_ctx* ctx, mclcar_samples* s, double* q_out);
 /* mcl.prep.dCAR(psi, n.samples, data), R/mcl.dCAR.R:2-8: draws N samples at psi0 with the
  * chromatic Gibbs sampler and attaches t10 = h(y; psi0), t20_i = h(Y_i; psi0). */
-int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
+MCLCAR_API int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
                      mclcar_samples** out);
 /* attach the importance point to a sample set built with samples_from_*: t20 NULL means
  * "compute h(Y_i; psi0) from the statistics", otherwise the reference's own t20 (N). */
-int mclcar_dcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* t20);
-int mclcar_dcar_t10_t20(mclcar_ctx* ctx, mclcar_samples* s, double* t10, double* t20 /* N or NULL */);
+MCLCAR_API int mclcar_dcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* t20);
+MCLCAR_API int mclcar_dcar_t10_t20(mclcar_ctx* ctx, mclcar_samples* s, double* t10, double* t20 /* N or NULL */);
 /* mcl.dCAR(pars, data, simdata, rho.cons, Evar=TRUE) for K candidates at once
  * (R/mcl.dCAR.R:11-50; batch call sites R/rsmSub.R:78-95,110).  rho_cons NULL disables the
  * guard (R: rho.cons = NULL), else candidates outside get (-1e8, 1e8).  A candidate k uses
  * the sample subset subset_idx[subset_ptr[k] .. subset_ptr[k+1]) (0-based) when subset_ptr
  * is not NULL and the range is non-empty -- the centre-point subsampling of
  * R/rsmSub.R:81-86 -- else all samples.  var may be NULL (Evar = FALSE). */
-int mclcar_dcar_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, const double* rho_cons,
+MCLCAR_API int mclcar_dcar_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, const double* rho_cons,
                      const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* lr,
                      double* var);
 /* mc.gradlik.dCAR(pars, data, simdata, Evar), R/mcl.dCAR.R:213-283; evar in {0, 1, 2};
  * grad: K x P; gradvar: K x P x P or NULL. */
-int mclcar_dcar_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
+MCLCAR_API int mclcar_dcar_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
                      int shift_mode, double* grad, double* gradvar);
 /* mc.Hesslik.dCAR, R/mcl.dCAR.R:287-394; hess: K x P x P */
-int mclcar_dcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
+MCLCAR_API int mclcar_dcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
                      double* hess);
 /* MCMLE.var, R/mcl.dCAR.R:156-165 (un-normalised, un-shifted weights); out: K x P x P */
-int mclcar_dcar_mcmle_var(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, double* out);
+MCLCAR_API int mclcar_dcar_mcmle_var(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, double* out);
 
 /* ---- Binomial / Poisson GLM with latent CAR effects (R/mcl.glm.R, R/mcl.bin.R, R/mcl.pois.R) ----
  * Sample sets are the N x n matrix Zy, ROW = sample (MCLCAR_ROW_IS_SAMPLE).  The eigenvalues of
@@ -172,22 +178,22 @@ int mclcar_dcar_mcmle_var(mclcar_ctx* ctx, mclcar_samples* s, const double* psi,
  * per-call chol.spam log-determinant (R/mcl.bin.R:50-52) and eigen(W) (R/mcl.bin.R:176). */
 /* mcl.prep.glm + postZ (R/mcl.glm.R:5-40, R/postZ.R:2-14): N latent fields z | y at psi0 drawn by
  * the batched Metropolis-within-Gibbs sampler; lHZy.psi is attached implicitly. */
-int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int64_t N,
+MCLCAR_API int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int64_t N,
                     const mclcar_sampler_opts* opts, mclcar_samples** out);
 /* attach the importance point to the reference's own Zy; lHZy_psi NULL = recompute
  * log f_psi0(y, Z_i) (R/mcl.glm.R:34-37), else the reference's vector (N). */
-int mclcar_glm_attach(mclcar_ctx* ctx, mclcar_samples* s, int family, const double* psi0, int P,
+MCLCAR_API int mclcar_glm_attach(mclcar_ctx* ctx, mclcar_samples* s, int family, const double* psi0, int P,
                       const double* lHZy_psi);
-int mclcar_glm_lhzy(mclcar_ctx* ctx, mclcar_samples* s, double* out /* N */);
+MCLCAR_API int mclcar_glm_lhzy(mclcar_ctx* ctx, mclcar_samples* s, double* out /* N */);
 /* mcl.glm(pars, mcdata, family, Evar) = mcl.bin / mcl.pois (R/mcl.bin.R:33-79) for K candidates;
  * subsets as in mclcar_dcar_eval (Exp.CAR.glm centre points, R/rsmSub.R:175-181). */
-int mclcar_glm_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P,
+MCLCAR_API int mclcar_glm_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P,
                     const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* lr, double* var);
 /* mcl.grad.glm (R/mcl.bin.R:160-217): grad K x P, gradvar K x P x P when evar != 0 */
-int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
+MCLCAR_API int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
                     int shift_mode, double* grad, double* gradvar);
 /* mcl.Hessian.glm (R/mcl.bin.R:222-297; Poisson beta block as coded at R/mcl.pois.R:268) */
-int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
+MCLCAR_API int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
                     double* hess);
 
 /* ---- hierarchical CAR, Gaussian response (R/HCAR.sim.R, R/mcl.HCAR.R) ---------------------
@@ -196,24 +202,24 @@ int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
  * for the reference's W = NULL variant); design and observations as usual.  M (K x K,
  * symmetric) and Z (n x K) come in CSR; eig_M = data$bb, the eigenvalues of W = data$aa go
  * through mclcar_graph_set_eigenvalues.  A sample set is u.y (K x N, column = sample). */
-int mclcar_hcar_set_model(mclcar_ctx* ctx, int K, const int* M_rowptr, const int* M_colidx, const double* M_val,
+MCLCAR_API int mclcar_hcar_set_model(mclcar_ctx* ctx, int K, const int* M_rowptr, const int* M_colidx, const double* M_val,
                           const int* Z_rowptr, const int* Z_colidx, const double* Z_val, const double* eig_M,
                           int has_W);
 /* sim.HCAR(psi, data, n.samples), R/HCAR.sim.R:3-87: N draws of u | y at psi0 (chromatic Gibbs on
  * Q* = Z'Qe Z + Qu instead of one Cholesky and N backsolves) with lpsi and const.psi attached */
-int mclcar_hcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
+MCLCAR_API int mclcar_hcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
                      mclcar_samples** out);
-int mclcar_hcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* lpsi);
-int mclcar_hcar_lpsi(mclcar_ctx* ctx, mclcar_samples* s, double* lpsi /* N or NULL */, double* const_psi);
+MCLCAR_API int mclcar_hcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* lpsi);
+MCLCAR_API int mclcar_hcar_lpsi(mclcar_ctx* ctx, mclcar_samples* s, double* lpsi /* N or NULL */, double* const_psi);
 /* mcl.HCAR(pars, mcdata, data, Evar), R/mcl.HCAR.R:4-97, for K candidates.  The reference takes
  * exp() unshifted and clamps +-Inf to +-1e5 with a warning (:81-84): candidates where that would
  * have happened get +-1e5 and are counted in *n_clamped. */
-int mclcar_hcar_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, double* lr, double* var,
+MCLCAR_API int mclcar_hcar_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, double* lr, double* var,
                      int* n_clamped);
 /* mcl.grad.HCAR (R/mcl.HCAR.R:101-213) and mcl.Hessian.HCAR (:216-391, H.rho.beta as coded at :356) */
-int mclcar_hcar_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
+MCLCAR_API int mclcar_hcar_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int evar,
                      int shift_mode, double* grad, double* gradvar);
-int mclcar_hcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
+MCLCAR_API int mclcar_hcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
                      double* hess);
 
 /* ---- staged evaluation (what the one-shot calls above are made of) ------------------------
@@ -223,15 +229,15 @@ int mclcar_hcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int 
  * `what`: 0 = lr/var, 1 = gradient (+ variance forms), 2 = Hessian.  A tuple is
  * mclcar_tuple_len(what, F, d) doubles with F = P gradient features and d = 2 + 2p
  * statistics for the direct CAR model (layouts: mclcar_b200/csrc/tuples.cu). */
-int64_t mclcar_tuple_len(int what, int F, int d);
-int mclcar_dcar_partial(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int what,
+MCLCAR_API int64_t mclcar_tuple_len(int what, int F, int d);
+MCLCAR_API int mclcar_dcar_partial(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int what,
                         const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* tuples);
 /* tuples_in: [G][K][T], tuples_out: [K][T] */
-int mclcar_tuples_merge(int what, int F, int d, int G, int K, const double* tuples_in, double* tuples_out);
+MCLCAR_API int mclcar_tuples_merge(int what, int F, int d, int G, int K, const double* tuples_in, double* tuples_out);
 /* what = 0: out0 = lr[K], out1 = var[K] or NULL.  what = 1: out0 = grad[K*P], out1 =
  * gradvar[K*P*P] or NULL with evar 1 | 2 as in mc.gradlik.dCAR, 3 = MCMLE.var.
  * what = 2: out0 = hess[K*P*P].  Works on a host-only context. */
-int mclcar_dcar_finish(mclcar_ctx* ctx, const double* psi0, int P0, const double* psi, int K, int P, int what,
+MCLCAR_API int mclcar_dcar_finish(mclcar_ctx* ctx, const double* psi0, int P0, const double* psi, int K, int P, int what,
                        int evar, const double* rho_cons, const double* tuples, double* out0, double* out1);
 
 #ifdef __cplusplus

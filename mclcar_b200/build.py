@@ -16,7 +16,7 @@ LIB = ROOT / "lib" / "libmclcar_b200.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas,-fvisibility=hidden", "--expt-relaxed-constexpr",
 ]
 
 

@@ -75,10 +75,21 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 // two standard normals from two 32-bit words (Box-Muller on the MUFU unit: lg2, sqrt, sin, cos)
+// .ftz forms: the arguments are never denormal (u >= 2^-24), so the denormal fix-up code of the
+// default intrinsics is dead weight
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void sincos_approx(float x, float& s, float& c) {
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
+}
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-    const float r = sqrt_approx(-1.3862943611198906f * __log2f(u01(a)));  // sqrt(-2 ln u)
+    const float r = sqrt_approx(-1.3862943611198906f * lg2_approx(u01(a)));  // sqrt(-2 ln u)
     float s, c;
-    __sincosf(6.2831853071795865f * u01(b), &s, &c);
+    sincos_approx(6.2831853071795865f * u01(b), s, c);
     n0 = r * c;
     n1 = r * s;
 }

@@ -183,16 +183,19 @@ __global__ void __launch_bounds__(256) gibbs_torus_sweep_fused(const TorusSweepP
         mbar_init(bar, 1);
         mbar_fence_init();
         mbar_expect_tx(bar, row_bytes * (uint32_t)(2 * rows + 6));
-        for (int l = 0; l < rows + 4; ++l) {
-            int i = r0 - 2 + l;
-            i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
-            bulk_g2s(sB + (size_t)l * h, gblk + (size_t)i * h, row_bytes, bar);
-        }
-        for (int l = 0; l < rows + 2; ++l) {
-            int i = r0 - 1 + l;
-            i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
-            bulk_g2s(sR + (size_t)l * h, gred + (size_t)i * h, row_bytes, bar);
-        }
+        // rows are contiguous in HBM except at the torus wrap: at most three bulk copies per colour
+        auto copy_rows = [&](float* dst, const float* src, int first, int cnt) {
+            int done = 0;
+            while (done < cnt) {
+                int i = first + done;
+                i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
+                const int run = min(cnt - done, n1 - i);
+                bulk_g2s(dst + (size_t)done * h, src + (size_t)i * h, row_bytes * (uint32_t)run, bar);
+                done += run;
+            }
+        };
+        copy_rows(sB, gblk, r0 - 2, rows + 4);
+        copy_rows(sR, gred, r0 - 1, rows + 2);
     }
     __syncthreads();
     mbar_wait(bar, 0);
