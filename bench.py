@@ -267,6 +267,33 @@ def run_ours(args):
         step_e2e()
     t_e2e, res2 = timed(step_e2e, args.steps)
 
+    # the fp64 likelihood pass over a resident sample matrix (the shape the reference's own simY
+    # has): K2<double> + K3 for all candidates, timed with the library's CUDA-event spans
+    fp64 = None
+    if not args.no_fp64 and rank == 0:
+        n64 = args.fp64_samples
+        g = torch.Generator(device="cuda").manual_seed(1)
+        Y64 = torch.randn((n64, n), dtype=torch.float64, device="cuda", generator=g) + 1.0
+        sd64 = api.simdata_from_device(PSI0, data, Y64.data_ptr(), n64, n)
+        api.mcl_dCAR_batch(psis, data, sd64, rho_cons=None)      # warm-up (also computes the statistics)
+        sd64.close()
+        L.check(L.lib.mclcar_ctx_profile(ctx.h, 1), ctx.h)
+        reps = 5
+        for _ in range(reps):
+            sd64 = api.simdata_from_device(PSI0, data, Y64.data_ptr(), n64, n)
+            r64 = api.mcl_dCAR_batch(psis, data, sd64, rho_cons=None)
+            sd64.close()
+        ms64 = np.zeros(8)
+        l64 = np.zeros(8, dtype=np.int64)
+        L.check(L.lib.mclcar_ctx_profile_read(ctx.h, L.dptr(ms64), L.i64ptr(l64)), ctx.h)
+        L.check(L.lib.mclcar_ctx_profile(ctx.h, 0), ctx.h)
+        b64 = n64 * n * 8.0 * reps
+        fp64 = {"samples": n64, "bytes_per_sample": n * 8, "stats_ms": float(ms64[2]) / reps, "reduce_ms": float(ms64[3]) / reps,
+                "stats_kernel_GBps": b64 / (float(ms64[2]) * 1e-3) / 1e9,
+                "pass_GBps": b64 / (float(ms64[2] + ms64[3]) * 1e-3) / 1e9,
+                "evals_per_s": n64 * K_PSI * reps / (float(ms64[2] + ms64[3]) * 1e-3), "finite": bool(np.all(np.isfinite(r64[:, 0])))}
+        del Y64
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -296,6 +323,14 @@ def run_ours(args):
     like_gbs = like_bytes / (like_ms * 1e-3) / 1e9 if like_ms > 0 and not args.stats_only else None
     stats_gbs = like_bytes / (float(ms_cat[2]) * 1e-3) / 1e9 if ms_cat[2] > 0 and not args.stats_only else None
 
+    traffic = None
+    try:  # measured DRAM traffic of the dominant kernel (one ncu --set full capture, profiles/)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)["gibbs_torus_sweep_fused"]
+        if launches_per_sweep < 1.5:
+            traffic = tr["dram_bytes_per_launch"] * chains / tr["chains"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -311,7 +346,7 @@ def run_ours(args):
         "gpu_launches": int(launches.sum()),
         "roofline": {"kernel": "gibbs_torus_sweep_fused" if launches_per_sweep < 1.5 else "gibbs_torus_half_sweep_v4",
                      "bound": "hbm", "achieved": sweep_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": (sweep_gbs / peak) if sweep_gbs else None, "traffic": None,
+                     "frac": (sweep_gbs / peak) if sweep_gbs else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "algorithmic_bytes_per_site_update": bytes_per_update,
                      "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
                      "launches": sweep_launches, "peak_source": peak_src,
@@ -328,6 +363,8 @@ def run_ours(args):
                            "reduce_ms_per_step": float(ms_cat[3]) / args.steps,
                            "algorithmic_bytes_per_sample": n * 4},
         },
+        "likelihood_fp64_resident": None if fp64 is None else dict(fp64, frac_of_hbm_peak=fp64["pass_GBps"] / peak,
+                                                                    stats_kernel_frac=fp64["stats_kernel_GBps"] / peak),
         "clocks": clk,
         "result_check": {"lr_min": float(res[:, 0].min()), "lr_max": float(res[:, 0].max()),
                          "var_max": float(res[:, 1].max()), "e2e_equal": bool(np.allclose(res, res2, rtol=1e-9, atol=1e-12))},
@@ -361,6 +398,8 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--debug", action="store_true")
+    ap.add_argument("--no-fp64", action="store_true")
+    ap.add_argument("--fp64-samples", type=int, default=1500)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -199,6 +199,19 @@ def simdata_from_matrix(psi, data: CarData, simY, t20=None, dtype=np.float64) ->
     return sd
 
 
+def simdata_from_device(psi, data: CarData, dev_ptr: int, n_samples: int, ld: int, dtype=np.float64) -> SimData:
+    """Wrap a sample matrix ALREADY RESIDENT in device memory (sample-major: sample i at
+    dev_ptr + i*ld elements); not copied, not owned."""
+    h = C.c_void_p()
+    ctx = data.ctx
+    check(lib.mclcar_samples_from_device(ctx.h, C.c_void_p(dev_ptr), L.F64 if dtype == np.float64 else L.F32,
+                                         L.COL_IS_SAMPLE, data.n, int(n_samples), int(ld), C.byref(h)), ctx.h)
+    sd = SimData(data, h, psi)
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    check(lib.mclcar_dcar_attach(ctx.h, h, dptr(psi), psi.size, None), ctx.h)
+    return sd
+
+
 def _subsets(subsets, K):
     if subsets is None:
         return None, None, None
