@@ -172,6 +172,18 @@ MCLCAR_API int mclcar_dcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double
 /* MCMLE.var, R/mcl.dCAR.R:156-165 (un-normalised, un-shifted weights); out: K x P x P */
 MCLCAR_API int mclcar_dcar_mcmle_var(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, double* out);
 
+/* ---- "next" rows of the scope: profile / GLS step and exact likelihood in batches,
+ * from the p x p design constants and the spectrum of W instead of dense n x n products */
+/* sigmabeta(rho, data), R/loglik.dCAR.R:72-86, for K values of rho; out: K x (1 + p) = (sigma, beta) */
+MCLCAR_API int mclcar_dcar_sigmabeta(mclcar_ctx* ctx, const double* rho, int K, double* out);
+/* mcl.profile.dCAR(rho, data, simdata, rho.cons, Evar), R/mcl.dCAR.R:53-96, for K values of rho at once */
+MCLCAR_API int mclcar_dcar_profile_eval(mclcar_ctx* ctx, mclcar_samples* s, const double* rho, int K, const double* rho_cons,
+                             int shift_mode, double* lr, double* var);
+/* loglik.dCAR(pars, data, rho.cons), R/loglik.dCAR.R:7-42 (needs the eigenvalues of W), K candidates */
+MCLCAR_API int mclcar_dcar_loglik(mclcar_ctx* ctx, const double* psi, int K, int P, const double* rho_cons, double* out);
+/* ploglik.dCAR(rho, data), R/loglik.dCAR.R:45-69, K values of rho */
+MCLCAR_API int mclcar_dcar_ploglik(mclcar_ctx* ctx, const double* rho, int K, double* out);
+
 /* ---- Binomial / Poisson GLM with latent CAR effects (R/mcl.glm.R, R/mcl.bin.R, R/mcl.pois.R) ----
  * Sample sets are the N x n matrix Zy, ROW = sample (MCLCAR_ROW_IS_SAMPLE).  The eigenvalues of
  * W must be known (torus: analytic; CSR: mclcar_graph_set_eigenvalues) -- they replace the

@@ -86,6 +86,10 @@ SIGNATURES = {
     "mclcar_dcar_grad": (_i, [_vp, _vp, _pd, _i, _i, _i, _i, _pd, _pd]),
     "mclcar_dcar_hess": (_i, [_vp, _vp, _pd, _i, _i, _i, _pd]),
     "mclcar_dcar_mcmle_var": (_i, [_vp, _vp, _pd, _i, _i, _pd]),
+    "mclcar_dcar_sigmabeta": (_i, [_vp, _pd, _i, _pd]),
+    "mclcar_dcar_profile_eval": (_i, [_vp, _vp, _pd, _i, _pd, _i, _pd, _pd]),
+    "mclcar_dcar_loglik": (_i, [_vp, _pd, _i, _i, _pd, _pd]),
+    "mclcar_dcar_ploglik": (_i, [_vp, _pd, _i, _pd]),
     "mclcar_glm_prep": (_i, [_vp, _i, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
     "mclcar_glm_attach": (_i, [_vp, _vp, _i, _pd, _i, _pd]),
     "mclcar_glm_lhzy": (_i, [_vp, _vp, _pd]),

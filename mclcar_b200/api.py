@@ -251,27 +251,44 @@ def mcl_dCAR(pars, data: CarData, simdata: SimData, rho_cons=(-0.249, 0.249), Ev
 
 
 def sigmabeta(rho, data: CarData) -> np.ndarray:
-    """GLS (sigma, beta) given rho, R/loglik.dCAR.R:72-86 (host; depends on the observed
-    data only)."""
-    W = _host_W(data)
-    X, y = data.X, data.y
-    Q1X = X - rho * (W @ X)
-    Q1y = y - rho * (W @ y)
-    beta = np.linalg.solve(X.T @ Q1X, X.T @ Q1y)
-    res = y - X @ beta
-    return np.concatenate([[res @ (res - rho * (W @ res)) / data.n], beta])
+    """sigmabeta(rho, data), R/loglik.dCAR.R:72-86: GLS (sigma, beta) given rho, from the p x p
+    design constants (the reference forms dense n x n products)."""
+    r = np.ascontiguousarray(np.atleast_1d(rho), dtype=np.float64)
+    out = np.empty((r.size, 1 + data.p))
+    check(lib.mclcar_dcar_sigmabeta(data.ctx.h, dptr(r), r.size, dptr(out)), data.ctx.h)
+    return out[0] if np.ndim(rho) == 0 else out
 
 
-def _host_W(data: CarData):
-    if data.W is not None:
-        return data.W
-    if "W" not in data.extra:
-        n1, n2 = data.torus
-        idx = np.arange(n1 * n2).reshape(n1, n2)
-        rows = np.repeat(idx.ravel(), 4)
-        cols = np.stack([np.roll(idx, 1, 0), np.roll(idx, -1, 0), np.roll(idx, 1, 1), np.roll(idx, -1, 1)], -1).ravel()
-        data.extra["W"] = sp.csr_matrix((np.ones(rows.size), (rows, cols)), shape=(n1 * n2, n1 * n2))
-    return data.extra["W"]
+def get_beta_lm(rho, data: CarData) -> np.ndarray:
+    """get.beta.lm(rho, data), R/loglik.dCAR.R:89-101."""
+    return sigmabeta(rho, data)[..., 1:]
+
+
+def loglik_dCAR(pars, data: CarData, rho_cons=(-0.249, 0.249)):
+    """loglik.dCAR(pars, data, rho.cons), R/loglik.dCAR.R:7-42; `pars` may be a K x P batch (the
+    100 x 100 exact surface of R/rsmMCL.R:95-102 is one call)."""
+    ps = np.ascontiguousarray(np.atleast_2d(pars), dtype=np.float64)
+    out = np.empty(ps.shape[0])
+    rc = None if rho_cons is None else np.ascontiguousarray(rho_cons, dtype=np.float64)
+    check(lib.mclcar_dcar_loglik(data.ctx.h, dptr(ps), ps.shape[0], ps.shape[1], dptr(rc), dptr(out)), data.ctx.h)
+    return float(out[0]) if np.ndim(pars) == 1 else out
+
+
+def ploglik_dCAR(rho, data: CarData):
+    """ploglik.dCAR(rho, data), R/loglik.dCAR.R:45-69."""
+    r = np.ascontiguousarray(np.atleast_1d(rho), dtype=np.float64)
+    out = np.empty(r.size)
+    check(lib.mclcar_dcar_ploglik(data.ctx.h, dptr(r), r.size, dptr(out)), data.ctx.h)
+    return float(out[0]) if np.ndim(rho) == 0 else out
+
+
+def mcl_profile_dCAR_batch(rhos, data: CarData, simdata: "SimData", rho_cons=(-0.249, 0.249), shift=L.SHIFT_MEAN) -> np.ndarray:
+    """mcl.profile.dCAR over a whole grid of rho in one call -> (K, 2)."""
+    r = np.ascontiguousarray(np.atleast_1d(rhos), dtype=np.float64)
+    lr, var = np.empty(r.size), np.empty(r.size)
+    rc = None if rho_cons is None else np.ascontiguousarray(rho_cons, dtype=np.float64)
+    check(lib.mclcar_dcar_profile_eval(data.ctx.h, simdata.h, dptr(r), r.size, dptr(rc), shift, dptr(lr), dptr(var)), data.ctx.h)
+    return np.stack([lr, var], axis=1)
 
 
 def mcl_profile_dCAR(rho, data: CarData, simdata: SimData, rho_cons=(-0.249, 0.249), Evar=False):

@@ -128,3 +128,27 @@ def test_rho_cons_sentinels():
                                     L.dptr(lr), L.dptr(var)) == 0
     assert lr[1] == -1e8 and var[1] == 1e8          # R/mcl.dCAR.R:39-42
     assert abs(lr[0]) < 1e-12 and abs(var[0]) < 1e-20  # psi == psi0: ratio 1, weights constant
+
+
+def test_profile_and_exact_likelihood_on_host_context():
+    """sigmabeta / loglik.dCAR / ploglik.dCAR (R/loglik.dCAR.R) from the design constants and the
+    analytic torus spectrum: pure host algebra, checked against the oracle's dense forms."""
+    from oracle import graphs
+    odata, psi0, simdata, rng = helpers.torus_case(9, 9, 20, seed=14)
+    ctx = api.Context(device=-1)
+    data = api.make_data(odata["y"], X=odata["X"], torus=(9, 9), ctx=ctx)
+    eig = graphs.torus_eigenvalues(9, 9)
+    rhos = np.array([-0.2, -0.05, 0.0, 0.11, 0.23])
+    sb = api.sigmabeta(rhos, data)
+    for k, r in enumerate(rhos):
+        np.testing.assert_allclose(sb[k], dcar.sigmabeta(r, odata), rtol=1e-11)
+        assert api.ploglik_dCAR(r, data) == pytest.approx(dcar.ploglik_dCAR(r, odata, eig), rel=1e-12)
+    np.testing.assert_allclose(api.get_beta_lm(0.1, data), dcar.sigmabeta(0.1, odata)[1:], rtol=1e-11)
+    psis = psi0[None, :] * (1 + 0.05 * rng.standard_normal((6, 4)))
+    psis[5, 0] = 0.2495
+    got = api.loglik_dCAR(psis, data)
+    ref = [dcar.loglik_dCAR(p, odata, eig) for p in psis]
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    assert got[5] == -1e8                                        # R/loglik.dCAR.R:36-40
+    assert api.loglik_dCAR(psis[5], data, rho_cons=None) == pytest.approx(dcar.loglik_dCAR(psis[5], odata, eig, rho_cons=None), rel=1e-12)
+    assert api.loglik_dCAR(psis[0][:2], data) == pytest.approx(dcar.loglik_dCAR(psis[0][:2], odata, eig), rel=1e-12)

@@ -169,3 +169,22 @@ def test_identity_at_psi0_and_exact_ratio():
     exact = dcar.loglik_dCAR(th, odata, eig) - dcar.loglik_dCAR(psi0, odata, eig)
     assert abs(r[0] - exact) < 4 * np.sqrt(r[1])
     assert r[1] == pytest.approx(dcar.Avar_lik_dCAR(th, psi0, eig, 4000), rel=0.35)
+
+
+def test_profile_batch_and_exact_surface_on_device():
+    """mcl.profile.dCAR over a rho grid in one call, and the exact likelihood surface with the
+    log-determinant sums reduced on the device (n * K large enough to take that path)."""
+    n1 = n2 = 64
+    odata, psi0, simdata, rng = helpers.torus_case(n1, n2, 200, seed=31)
+    data = _mk(odata, torus=(n1, n2))
+    sd = api.simdata_from_matrix(psi0, data, simdata["simY"])
+    rhos = np.linspace(psi0[0] - 0.01, psi0[0] + 0.01, 9)
+    got = api.mcl_profile_dCAR_batch(rhos, data, sd)
+    ref = np.stack([dcar.mcl_profile_dCAR(r, odata, simdata, Evar=True) for r in rhos])
+    # the grid's centre is (almost) psi0 itself: the ratio there is ~1e-10 by cancellation of O(1e3) terms
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-10)
+    eig = graphs.torus_eigenvalues(n1, n2)
+    grid = np.array([[r, s, psi0[2], psi0[3]] for r in np.linspace(-0.24, 0.24, 10) for s in np.linspace(0.5, 1.5, 10)])
+    np.testing.assert_allclose(api.loglik_dCAR(grid, data), [dcar.loglik_dCAR(p, odata, eig) for p in grid], rtol=1e-12)
+    np.testing.assert_allclose(api.ploglik_dCAR(np.linspace(-0.2, 0.2, 60), data),
+                               [dcar.ploglik_dCAR(r, odata, eig) for r in np.linspace(-0.2, 0.2, 60)], rtol=1e-12)
