@@ -18,6 +18,9 @@
 // and two uniforms come from ONE Philox4x32-10 call keyed by (seed; site, sweep, global pair
 // id).  Kept states are written site-major ("row = sample" of the R matrix Zy): for every
 // site the CB chains of a CTA form one contiguous run.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "engine.hpp"
 
@@ -54,12 +57,13 @@ struct CsrSamplerParams {
 namespace {
 
 constexpr uint32_t kTagCsr = 0x4373u;
-constexpr int kThreads = 256;
+constexpr int kMaxThreads = 1024;
 
 __device__ __forceinline__ float softplusf(float t) { return t > 15.f ? t : __logf(1.f + __expf(t)); }
 
 template <int FAM>
-__global__ void __launch_bounds__(kThreads) gibbs_csr_kernel(const CsrSamplerParams p) {
+__global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSamplerParams p) {
+    const int kThreads = blockDim.x;
     extern __shared__ float sm_state[];
     const int CB = p.CB, hp = CB / 2;           // pairs per site row
     const int pr = threadIdx.x % hp;            // chain pair within the CTA
@@ -256,17 +260,23 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
         p.pair0 = ctx->rank; p.pair_stride = ctx->world;
         p.counters = (unsigned long long*)d_cnt;
         const size_t smem = in_smem ? (size_t)n * CB * sizeof(float) : 0;
+        // all warps of the CTA share the resident state: as many as the largest colour class can feed
+        int max_class = 1;
+        for (int c = 0; c < ncol; ++c) max_class = std::max(max_class, (*g.color_ptr)[c + 1] - (*g.color_ptr)[c]);
+        int threads = 256;
+        while (threads < kMaxThreads && (threads / (CB / 2)) < max_class) threads *= 2;
+        if (const char* te = getenv("MCLCAR_CSR_THREADS")) threads = atoi(te);
         cudaError_t e = cudaSuccess;
         ProfScope prof(ctx, PROF_CSR_SAMPLER, 1);
         if (fam == FAM_GAUSS) {
             e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
-            if (e == cudaSuccess) gibbs_csr_kernel<FAM_GAUSS><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(p);
+            if (e == cudaSuccess) gibbs_csr_kernel<FAM_GAUSS><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
         } else if (fam == FAM_BINOM) {
             e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_BINOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
-            if (e == cudaSuccess) gibbs_csr_kernel<FAM_BINOM><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(p);
+            if (e == cudaSuccess) gibbs_csr_kernel<FAM_BINOM><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
         } else {
             e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_POIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
-            if (e == cudaSuccess) gibbs_csr_kernel<FAM_POIS><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(p);
+            if (e == cudaSuccess) gibbs_csr_kernel<FAM_POIS><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
         }
         if (e == cudaSuccess) e = cudaGetLastError();
         unsigned long long cnt[2] = {0, 0};
