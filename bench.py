@@ -143,7 +143,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _print_json(line)
 
 
 def workload_name():
@@ -378,9 +378,39 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": n_s * K_PSI / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{n_s} samples x {K_PSI} psi of the same workload, {dt:.1f} s "
                                           "(FFT exact sampler + C statistics/reduction twin of the oracle)"}
-    print(json.dumps(line), flush=True)
+    _print_json(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+class _CleanStdout:
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE JSON
+    line is written to the real stdout at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+    def emit(self, text: str):
+        os.write(self.saved, (text + "\n").encode())
+
+
+_OUT = None
+
+
+def _print_json(line: dict):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
@@ -401,10 +431,14 @@ def main():
     ap.add_argument("--no-fp64", action="store_true")
     ap.add_argument("--fp64-samples", type=int, default=1500)
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    global _OUT
+    with _CleanStdout() as out:
+        _OUT = out
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    _OUT = None
 
 
 if __name__ == "__main__":
