@@ -234,6 +234,17 @@ MCLCAR_API int mclcar_hcar_grad(mclcar_ctx* ctx, mclcar_samples* s, const double
 MCLCAR_API int mclcar_hcar_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
                      double* hess);
 
+/* ---- one process, several GPUs (what an R session uses): one context per device, each holding the
+ * same graph / design / observations; the devices are driven concurrently by host threads and the
+ * partial tuples are merged on the host in shard order (same result as the NCCL path). */
+/* mcl.prep.dCAR with the N_total samples split over G contexts (shard g draws global chains g, g+G, ...) */
+MCLCAR_API int mclcar_multi_dcar_prep(mclcar_ctx** ctxs, int G, const double* psi0, int P, int64_t N_total,
+                           const mclcar_sampler_opts* opts, mclcar_samples** out /* G handles */);
+/* mcl.dCAR / mc.gradlik.dCAR / mc.Hesslik.dCAR / MCMLE.var over all shards; what, evar, out0, out1 as in
+ * mclcar_dcar_finish */
+MCLCAR_API int mclcar_multi_dcar_run(mclcar_ctx** ctxs, mclcar_samples** samples, int G, const double* psi, int K, int P, int what,
+                          int evar, const double* rho_cons, int shift_mode, double* out0, double* out1);
+
 /* ---- staged evaluation (what the one-shot calls above are made of) ------------------------
  * stage 1, device: per-candidate partial tuples of this context's samples, to host memory;
  * stage 2, host only: merge the tuples of G shards in shard order (mclcar_tuples_merge);

@@ -103,6 +103,8 @@ SIGNATURES = {
     "mclcar_hcar_eval": (_i, [_vp, _vp, _pd, _i, _i, _pd, _pd, _pi]),
     "mclcar_hcar_grad": (_i, [_vp, _vp, _pd, _i, _i, _i, _i, _pd, _pd]),
     "mclcar_hcar_hess": (_i, [_vp, _vp, _pd, _i, _i, _i, _pd]),
+    "mclcar_multi_dcar_prep": (_i, [C.POINTER(_vp), _i, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
+    "mclcar_multi_dcar_run": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _pd, _i, _i, _i, _i, _pd, _i, _pd, _pd]),
     "mclcar_tuple_len": (_i64, [_i, _i, _i]),
     "mclcar_dcar_partial": (_i, [_vp, _vp, _pd, _i, _i, _i, _pi64, _pi64, _i, _pd]),
     "mclcar_tuples_merge": (_i, [_i, _i, _i, _i, _i, _pd, _pd]),

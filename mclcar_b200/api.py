@@ -653,3 +653,69 @@ def vmle_HCAR(MLE: dict, mcdata: HcarMc, data: Optional[CarData] = None) -> np.n
     A = mcl_grad_HCAR(MLE["estimate"], mcdata, data, Evar=True)["grad.var"]
     Binv = np.linalg.inv(np.asarray(MLE["hessian"], dtype=np.float64))
     return Binv @ A @ Binv
+
+
+# ------------------------------------------------------------------------------------------
+# one process, several GPUs (the R session's situation on a multi-GPU box)
+# ------------------------------------------------------------------------------------------
+class MultiData:
+    """The same model uploaded to one context per device."""
+
+    def __init__(self, datas: Sequence[CarData]):
+        self.datas = list(datas)
+        self.G = len(self.datas)
+        self._ctx_arr = (C.c_void_p * self.G)(*[d.ctx.h for d in self.datas])
+
+    @property
+    def p(self):
+        return self.datas[0].p
+
+
+def make_data_multi(y, X=None, W=None, torus=None, devices: Sequence[int] = (0,), seed: int = 0) -> MultiData:
+    return MultiData([make_data(y, X=X, W=W, torus=torus, device=dev, seed=seed) for dev in devices])
+
+
+class MultiSimData:
+    def __init__(self, md: MultiData, handles, psi):
+        self.md, self.psi = md, np.asarray(psi, dtype=np.float64)
+        self.parts = [SimData(d, C.c_void_p(h), psi) for d, h in zip(md.datas, handles)]
+        self._arr = (C.c_void_p * md.G)(*[p.h for p in self.parts])
+
+    @property
+    def n_samples(self):
+        return sum(p.n_samples for p in self.parts)
+
+
+def mcl_prep_dCAR_multi(psi, n_samples: int, md: MultiData, control: Optional[dict] = None) -> MultiSimData:
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    o = _sampler_opts(control)
+    out = (C.c_void_p * md.G)()
+    check(lib.mclcar_multi_dcar_prep(md._ctx_arr, md.G, dptr(psi), psi.size, int(n_samples), C.byref(o), out), md.datas[0].ctx.h)
+    return MultiSimData(md, list(out), psi)
+
+
+def _multi_run(md: MultiData, sd: MultiSimData, psis, what, evar, rho_cons, shift, n0, n1):
+    psis = np.ascontiguousarray(np.atleast_2d(psis), dtype=np.float64)
+    K, P = psis.shape
+    out0, out1 = np.empty(n0(K, P)), np.zeros(n1(K, P))
+    rc = None if rho_cons is None else np.ascontiguousarray(rho_cons, dtype=np.float64)
+    check(lib.mclcar_multi_dcar_run(md._ctx_arr, sd._arr, md.G, dptr(psis), K, P, what, evar, dptr(rc), shift, dptr(out0), dptr(out1)),
+          md.datas[0].ctx.h)
+    return out0, out1
+
+
+def mcl_dCAR_batch_multi(psis, md: MultiData, sd: MultiSimData, rho_cons=None, shift=L.SHIFT_MEAN) -> np.ndarray:
+    lr, var = _multi_run(md, sd, psis, L.WHAT_LR, 0, rho_cons, shift, lambda K, P: K, lambda K, P: K)
+    return np.stack([lr, var], axis=1)
+
+
+def mc_gradlik_dCAR_multi(pars, md: MultiData, sd: MultiSimData, Evar=0, shift=L.SHIFT_MEAN):
+    P = len(pars)
+    g, v = _multi_run(md, sd, np.asarray(pars)[None, :], L.WHAT_GRAD, int(Evar), None, shift, lambda K, P: K * P, lambda K, P: K * P * P)
+    return {"grad": g, "grad.var": v.reshape(P, P)} if Evar else g
+
+
+def mc_Hesslik_dCAR_multi(pars, md: MultiData, sd: MultiSimData, shift=L.SHIFT_MEAN) -> np.ndarray:
+    P = len(pars)
+    H, _ = _multi_run(md, sd, np.asarray(pars)[None, :], L.WHAT_HESS, 0, None, shift, lambda K, P: K * P * P, lambda K, P: K * P * P)
+    return H.reshape(P, P)

@@ -187,6 +187,7 @@ static int build_plan(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int
 int dcar_partial(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int what,
                  const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* tuples) {
     MCL_TRY(check_ready(ctx, s, true));
+    MCL_TRY(require_device(ctx));   // binds this host thread to the context's device
     if (K < 1 || !psi || !tuples) return fail(ctx, MCLCAR_EINVAL, "empty candidate batch");
     if (P > MCLCAR_MAX_P) return fail(ctx, MCLCAR_ELIMIT, "P = %d exceeds MCLCAR_MAX_P", P);
     if (what < WHAT_LR || what > WHAT_HESS) return fail(ctx, MCLCAR_EINVAL, "bad 'what' %d", what);
