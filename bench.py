@@ -312,8 +312,11 @@ def run_ours(args):
     omega = args.omega if args.omega > 0 else 2.0 / (1.0 + np.sqrt(1.0 - (4 * PSI0[0]) ** 2))
     # algorithmic bytes per site update: read the other colour + write own colour (fp32), plus the
     # read of the current value for the over-relaxed update
-    bytes_per_update = 8.0 if omega == 1.0 else 12.0
     updates_step = float(chains) * n * sweeps_step
+    launches_per_sweep_ = int(launches[0]) / max(sweeps_step * args.steps, 1)
+    # fused sweep (one launch): both colours read once + written once per sweep = 8 B per site update;
+    # two-launch half sweeps: 8 B plain Gibbs, 12 B over-relaxed (the own colour is read as well)
+    bytes_per_update = 8.0 if (launches_per_sweep_ < 1.5 or omega == 1.0) else 12.0
     sweep_gbs = bytes_per_update * updates_step * args.steps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
     site_updates_per_s = updates_step * args.steps / (sweep_ms * 1e-3) * world if sweep_ms > 0 else None
     launches_per_sweep = sweep_launches / max(sweeps_step * args.steps, 1)

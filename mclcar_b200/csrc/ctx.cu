@@ -2,7 +2,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <map>
 
 #include "engine.hpp"
 
@@ -379,20 +378,22 @@ int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colid
         if (rowptr[i + 1] < rowptr[i]) return fail(ctx, MCLCAR_EINVAL, "rowptr not monotone at row %d", i);
     // validate: indices in range, zero diagonal, symmetric (W is used as a symmetric matrix by
     // the reference without checking: eigen(W, symmetric = TRUE), R/loglik.dCAR.R:25)
-    std::map<std::pair<int, int>, double> ent;
     for (int i = 0; i < n; ++i)
         for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
             const int j = colidx[e];
             if (j < 0 || j >= n) return fail(ctx, MCLCAR_EINVAL, "column index %d out of range in row %d", j, i);
             if (j == i) return fail(ctx, MCLCAR_EINVAL, "W must have a zero diagonal (row %d)", i);
-            if (!ent.emplace(std::make_pair(i, j), val ? val[e] : 1.0).second)
-                return fail(ctx, MCLCAR_EINVAL, "duplicate entry (%d, %d)", i, j);
+            for (int e2 = rowptr[i]; e2 < e; ++e2)
+                if (colidx[e2] == j) return fail(ctx, MCLCAR_EINVAL, "duplicate entry (%d, %d)", i, j);
         }
-    for (auto& kv : ent) {
-        auto it = ent.find(std::make_pair(kv.first.second, kv.first.first));
-        if (it == ent.end() || it->second != kv.second)
-            return fail(ctx, MCLCAR_EINVAL, "W is not symmetric at (%d, %d)", kv.first.first, kv.first.second);
-    }
+    for (int i = 0; i < n; ++i)
+        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {   // the mirror entry (j, i) must exist with the same value
+            const int j = colidx[e];
+            bool found = false;
+            for (int e2 = rowptr[j]; e2 < rowptr[j + 1] && !found; ++e2)
+                found = colidx[e2] == i && (val ? val[e2] == val[e] : true);
+            if (!found) return fail(ctx, MCLCAR_EINVAL, "W is not symmetric at (%d, %d)", i, j);
+        }
     invalidate_model(ctx);
     ctx->kind = GRAPH_CSR;
     ctx->n = n; ctx->n1 = ctx->n2 = 0;

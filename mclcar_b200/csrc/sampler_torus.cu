@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
 // bit-identical to it.
 // ---------------------------------------------------------------------------------------------
 template <bool SOR, bool EMIT, typename TO>
-__global__ void __launch_bounds__(256) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
+__global__ void __launch_bounds__(512) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
     extern __shared__ __align__(128) unsigned char fsm[];
     const int h = p.h, n1 = p.n1, hv = h >> 2;
     const int r0 = blockIdx.x * TR;
@@ -203,10 +203,10 @@ __global__ void __launch_bounds__(256) gibbs_torus_sweep_fused(const TorusSweepP
     const uint64_t gch = (uint64_t)(p.chain0 + ch * p.chain_stride);
     const uint32_t c2 = (uint32_t)gch, c3 = (uint32_t)(gch >> 32) ^ (kTagTorus << 16);
     // warp ty owns rows ty, ty + 8, ...; its lanes stride the column vectors of the row
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
     // ---- phase 1: red rows r0-1 .. r0+rows (local 0 .. rows+1), black neighbours from sB
-    for (int lr = ty; lr < rows + 2; lr += 8) {
+    for (int lr = ty; lr < rows + 2; lr += nw) {
         int i = r0 - 1 + lr;
         i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
         const bool fwd = (i & 1) != 0;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) gibbs_torus_sweep_fused(const TorusSweepP
     }
     __syncthreads();
     // ---- phase 2: black rows r0 .. r0+rows-1 from the new red rows in sR
-    for (int t = ty; t < rows; t += 8) {
+    for (int t = ty; t < rows; t += nw) {
         const int i = r0 + t;
         const bool fwd = (i & 1) == 0;   // ((i & 1) ^ 1)
         const float* ru = sR + (size_t)t * h;
@@ -403,7 +403,6 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
     if ((int64_t)p.n1 * p.h >= ((int64_t)1 << 31)) return fail(ctx, MCLCAR_ELIMIT, "lattice too large for 32-bit indexing");
     if (emit && !vec4) return fail(ctx, MCLCAR_EINVAL, "fused emission needs n2 % 8 == 0");
     if (vec4) {
-        static int rows_cfg = [] { const char* e = getenv("MCLCAR_SWEEP_ROWS"); return e ? atoi(e) : 4; }();
         if (emit) {
             p.out = emit->out; p.ld = emit->ld; p.slot0 = emit->slot0; p.nch = emit->nch;
             p.mu = emit->d_mu; p.mu_const = emit->mu_const;
@@ -421,11 +420,12 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
             std::swap(t.red, t.red2);        // the output pair is the current state from now on
             std::swap(t.black, t.black2);
             const size_t smem = (size_t)(2 * TR + 6) * row_b + 64;
+            const int fthreads = 256;   // 384 / 512 threads and other tile heights measured within 1 %
             dim3 grid((p.n1 + TR - 1) / TR, (unsigned)t.C);
 #define LAUNCH_FUSED(S, E, TO_)                                                                                  \
     do {                                                                                                         \
         cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        gibbs_torus_sweep_fused<S, E, TO_><<<grid, 256, smem, ctx->stream>>>(p, TR);                            \
+        gibbs_torus_sweep_fused<S, E, TO_><<<grid, fthreads, smem, ctx->stream>>>(p, TR);                            \
     } while (0)
             if (emit) {
                 if (sor && f32) LAUNCH_FUSED(true, true, float);
@@ -441,9 +441,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
             return MCLCAR_OK;
         }
         ProfScope prof(ctx, PROF_SWEEP, 2);
-        if (rows_cfg == 2) launch_v4<2>(p, sor, emit != nullptr, f32, t.C, ctx->stream);
-        else if (rows_cfg == 8) launch_v4<8>(p, sor, emit != nullptr, f32, t.C, ctx->stream);
-        else launch_v4<4>(p, sor, emit != nullptr, f32, t.C, ctx->stream);
+        launch_v4<4>(p, sor, emit != nullptr, f32, t.C, ctx->stream);
     } else {
         ProfScope prof(ctx, PROF_SWEEP, 2);
         dim3 block(32, 8);
