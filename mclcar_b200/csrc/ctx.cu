@@ -27,6 +27,9 @@ int require_device(mclcar_ctx* ctx) {
     if (ctx->host_only) return fail(ctx, MCLCAR_ENODEV, "compute call on a host-only context: there is no CPU fallback");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return fail(ctx, MCLCAR_ECUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    // a non-sticky error left behind by an earlier, unrelated runtime call (ours or another library's in
+    // this process) must not be blamed on this call's first launch check
+    cudaGetLastError();
     return MCLCAR_OK;
 }
 

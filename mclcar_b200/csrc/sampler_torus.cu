@@ -424,7 +424,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
             dim3 grid((p.n1 + TR - 1) / TR, (unsigned)t.C);
 #define LAUNCH_FUSED(S, E, TO_)                                                                                  \
     do {                                                                                                         \
-        cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         gibbs_torus_sweep_fused<S, E, TO_><<<grid, fthreads, smem, ctx->stream>>>(p, TR);                            \
     } while (0)
             if (emit) {
