@@ -125,7 +125,7 @@ def run_reference(args):
     psis = psi_grid()
     from oracle import cpu_path
     cores = cpu_path.host_threads()
-    n_s = args.cpu_samples or 8 * cores
+    n_s = args.cpu_samples or 16 * cores
     for _ in range(args.warmup):
         cpu_hot_path(min(n_s, cores), y, psis)
     t = 0.0
@@ -375,7 +375,7 @@ def run_ours(args):
     if not args.no_cpu_baseline:
         from oracle import cpu_path
         cores = cpu_path.host_threads()
-        n_s = args.cpu_samples or 8 * cores
+        n_s = args.cpu_samples or 32 * cores     # ~5-10 s of host work
         cpu_hot_path(min(n_s, cores), y, psis)
         dt, _ = cpu_hot_path(n_s, y, psis)
         line["cpu_baseline"] = {"value": n_s * K_PSI / dt, "unit": UNIT, "cores": cores, "kind": "port",

@@ -163,6 +163,62 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
 // about 9 B per site update instead of 12 (over-relaxed) for the two-launch form; results are
 // bit-identical to it.
 // ---------------------------------------------------------------------------------------------
+// one lattice row of one colour inside the fused sweep: lanes stride the column vectors.  FWD (the
+// same-row neighbour sits at c + 1, else c - 1) is uniform over the row, so it is a template argument
+// and the per-item selects vanish; all row pointers are formed once per row.
+template <bool SOR, bool FWD, bool EMIT, typename TO>
+__device__ __forceinline__ void fused_row(const TorusSweepParams& p, const float* __restrict__ nu, const float* __restrict__ nm,
+                                          const float* __restrict__ nd, float* __restrict__ own_s, const float* __restrict__ cur_s,
+                                          float* __restrict__ gout, TO* __restrict__ emit_row, const double* __restrict__ mu_row,
+                                          bool par, int tx, int hv, int h, uint32_t ctr0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    for (int cv = tx; cv < hv; cv += 32) {
+        const int c0 = cv << 2;
+        const float4 o = ld4(nm + c0), up = ld4(nu + c0), d = ld4(nd + c0);
+        const float e = FWD ? nm[c0 + 4 == h ? 0 : c0 + 4] : nm[c0 == 0 ? h - 1 : c0 - 1];
+        const Philox4 r = philox4x32_10(ctr0 + (uint32_t)cv, c1, c2, c3, p.keys);
+        float z0, z1, z2, z3;
+        box_muller(r.x, r.y, z0, z1);
+        box_muller(r.z, r.w, z2, z3);
+        float4 s;
+        if (FWD) { s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e; }
+        else { s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w; }
+        float4 v;
+        v.x = fmaf(p.gain, s.x + (up.x + d.x), p.noise * z0);
+        v.y = fmaf(p.gain, s.y + (up.y + d.y), p.noise * z1);
+        v.z = fmaf(p.gain, s.z + (up.z + d.z), p.noise * z2);
+        v.w = fmaf(p.gain, s.w + (up.w + d.w), p.noise * z3);
+        if (SOR) {
+            const float4 cur = ld4(cur_s + c0);
+            v.x = fmaf(p.keep, cur.x, v.x); v.y = fmaf(p.keep, cur.y, v.y);
+            v.z = fmaf(p.keep, cur.z, v.z); v.w = fmaf(p.keep, cur.w, v.w);
+        }
+        if (own_s) *reinterpret_cast<float4*>(own_s + c0) = v;
+        if (gout) *reinterpret_cast<float4*>(gout + c0) = v;
+        if (EMIT) {
+            if (emit_row) {
+                // o = finished values of the other colour at the same half-columns; the emitting (black) colour sits at
+                // column 2c + 1 - par, the other at 2c + par
+                float a[8];
+                a[0] = par ? v.x : o.x; a[1] = par ? o.x : v.x; a[2] = par ? v.y : o.y; a[3] = par ? o.y : v.y;
+                a[4] = par ? v.z : o.z; a[5] = par ? o.z : v.z; a[6] = par ? v.w : o.w; a[7] = par ? o.w : v.w;
+                TO* dst = emit_row + 2 * c0;
+                if (mu_row != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dst[q] = (TO)((double)a[q] + __ldg(mu_row + 2 * c0 + q));
+                } else if (sizeof(TO) == 4) {
+                    const float m = (float)p.mu_const;
+                    float4* d4 = reinterpret_cast<float4*>(dst);
+                    d4[0] = make_float4(a[0] + m, a[1] + m, a[2] + m, a[3] + m);
+                    d4[1] = make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dst[q] = (TO)((double)a[q] + p.mu_const);
+                }
+            }
+        }
+    }
+}
+
 template <bool SOR, bool EMIT, typename TO>
 __global__ void __launch_bounds__(512) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
     extern __shared__ __align__(128) unsigned char fsm[];
@@ -202,98 +258,39 @@ __global__ void __launch_bounds__(512) gibbs_torus_sweep_fused(const TorusSweepP
 
     const uint64_t gch = (uint64_t)(p.chain0 + ch * p.chain_stride);
     const uint32_t c2 = (uint32_t)gch, c3 = (uint32_t)(gch >> 32) ^ (kTagTorus << 16);
-    // warp ty owns rows ty, ty + 8, ...; its lanes stride the column vectors of the row
+    // warp ty owns rows ty, ty + nw, ...; its lanes stride the column vectors of the row
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
     // ---- phase 1: red rows r0-1 .. r0+rows (local 0 .. rows+1), black neighbours from sB
     for (int lr = ty; lr < rows + 2; lr += nw) {
         int i = r0 - 1 + lr;
         i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
-        const bool fwd = (i & 1) != 0;
-        const float* bu = sB + (size_t)lr * h;
-        const float* bo = bu + h;
-        const float* bd = bo + h;
+        const float* bo = sB + (size_t)(lr + 1) * h;
         float* rr = sR + (size_t)lr * h;
-        const bool interior = lr >= 1 && lr <= rows;
-        for (int cv = tx; cv < hv; cv += 32) {
-            const int c0 = cv << 2;
-            const float4 o = ld4(bo + c0), up = ld4(bu + c0), d = ld4(bd + c0);
-            const float e = bo[fwd ? (c0 + 4 == h ? 0 : c0 + 4) : (c0 == 0 ? h - 1 : c0 - 1)];
-            const Philox4 r = philox4x32_10((uint32_t)(i * hv + cv), p.sweep * 2u, c2, c3, p.keys);
-            float z0, z1, z2, z3;
-            box_muller(r.x, r.y, z0, z1);
-            box_muller(r.z, r.w, z2, z3);
-            float4 s;
-            if (fwd) { s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e; }
-            else { s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w; }
-            float4 v;
-            v.x = fmaf(p.gain, s.x + (up.x + d.x), p.noise * z0);
-            v.y = fmaf(p.gain, s.y + (up.y + d.y), p.noise * z1);
-            v.z = fmaf(p.gain, s.z + (up.z + d.z), p.noise * z2);
-            v.w = fmaf(p.gain, s.w + (up.w + d.w), p.noise * z3);
-            if (SOR) {
-                const float4 cur = ld4(rr + c0);
-                v.x = fmaf(p.keep, cur.x, v.x); v.y = fmaf(p.keep, cur.y, v.y);
-                v.z = fmaf(p.keep, cur.z, v.z); v.w = fmaf(p.keep, cur.w, v.w);
-            }
-            *reinterpret_cast<float4*>(rr + c0) = v;
-            if (interior) *reinterpret_cast<float4*>(ored + (size_t)i * h + c0) = v;
-        }
+        float* gout = (lr >= 1 && lr <= rows) ? ored + (size_t)i * h : nullptr;
+        const uint32_t ctr0 = (uint32_t)(i * hv);
+        if (i & 1) fused_row<SOR, true, false, TO>(p, bo - h, bo, bo + h, rr, rr, gout, nullptr, nullptr, false, tx, hv, h, ctr0, p.sweep * 2u, c2, c3);
+        else fused_row<SOR, false, false, TO>(p, bo - h, bo, bo + h, rr, rr, gout, nullptr, nullptr, false, tx, hv, h, ctr0, p.sweep * 2u, c2, c3);
     }
     __syncthreads();
     // ---- phase 2: black rows r0 .. r0+rows-1 from the new red rows in sR
     for (int t = ty; t < rows; t += nw) {
         const int i = r0 + t;
-        const bool fwd = (i & 1) == 0;   // ((i & 1) ^ 1)
-        const float* ru = sR + (size_t)t * h;
-        const float* ro = ru + h;
-        const float* rd = ro + h;
+        const float* ro = sR + (size_t)(t + 1) * h;
         const float* bc = sB + (size_t)(t + 2) * h;
-        for (int cv = tx; cv < hv; cv += 32) {
-            const int c0 = cv << 2;
-            const float4 o = ld4(ro + c0), up = ld4(ru + c0), d = ld4(rd + c0);
-            const float e = ro[fwd ? (c0 + 4 == h ? 0 : c0 + 4) : (c0 == 0 ? h - 1 : c0 - 1)];
-            const Philox4 r = philox4x32_10((uint32_t)(i * hv + cv), p.sweep * 2u + 1u, c2, c3, p.keys);
-            float z0, z1, z2, z3;
-            box_muller(r.x, r.y, z0, z1);
-            box_muller(r.z, r.w, z2, z3);
-            float4 s;
-            if (fwd) { s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e; }
-            else { s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w; }
-            float4 v;
-            v.x = fmaf(p.gain, s.x + (up.x + d.x), p.noise * z0);
-            v.y = fmaf(p.gain, s.y + (up.y + d.y), p.noise * z1);
-            v.z = fmaf(p.gain, s.z + (up.z + d.z), p.noise * z2);
-            v.w = fmaf(p.gain, s.w + (up.w + d.w), p.noise * z3);
-            if (SOR) {
-                const float4 cur = ld4(bc + c0);
-                v.x = fmaf(p.keep, cur.x, v.x); v.y = fmaf(p.keep, cur.y, v.y);
-                v.z = fmaf(p.keep, cur.z, v.z); v.w = fmaf(p.keep, cur.w, v.w);
-            }
-            *reinterpret_cast<float4*>(oblk + (size_t)i * h + c0) = v;
-            if (EMIT) {
-                if (ch < p.nch) {
-                    const bool par = (i & 1) != 0;
-                    const size_t site = (size_t)i * 2 * h + 2 * c0;
-                    float a[8];
-                    a[0] = par ? v.x : o.x; a[1] = par ? o.x : v.x; a[2] = par ? v.y : o.y; a[3] = par ? o.y : v.y;
-                    a[4] = par ? v.z : o.z; a[5] = par ? o.z : v.z; a[6] = par ? v.w : o.w; a[7] = par ? o.w : v.w;
-                    TO* dst = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld + site;
-                    if (p.mu != nullptr) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) dst[q] = (TO)((double)a[q] + __ldg(p.mu + site + q));
-                    } else if (sizeof(TO) == 4) {
-                        const float m = (float)p.mu_const;
-                        float4* d4 = reinterpret_cast<float4*>(dst);
-                        d4[0] = make_float4(a[0] + m, a[1] + m, a[2] + m, a[3] + m);
-                        d4[1] = make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) dst[q] = (TO)((double)a[q] + p.mu_const);
-                    }
-                }
+        float* gout = oblk + (size_t)i * h;
+        TO* erow = nullptr;
+        const double* mrow = nullptr;
+        if (EMIT) {
+            if (ch < p.nch) {
+                erow = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld + (size_t)i * 2 * h;
+                if (p.mu != nullptr) mrow = p.mu + (size_t)i * 2 * h;
             }
         }
+        const uint32_t ctr0 = (uint32_t)(i * hv);
+        const bool par = (i & 1) != 0;
+        if (!par) fused_row<SOR, true, EMIT, TO>(p, ro - h, ro, ro + h, nullptr, bc, gout, erow, mrow, par, tx, hv, h, ctr0, p.sweep * 2u + 1u, c2, c3);
+        else fused_row<SOR, false, EMIT, TO>(p, ro - h, ro, ro + h, nullptr, bc, gout, erow, mrow, par, tx, hv, h, ctr0, p.sweep * 2u + 1u, c2, c3);
     }
 }
 

@@ -190,3 +190,26 @@ def test_default_thinning_decorrelates_kept_states(omega):
     assert np.abs(acf.mean(axis=0) + 1.0 / E).max() < 0.07
     sweeps = api.sampler_diag(data, sd)["sweeps"]
     assert sweeps < (300 if omega == 0.0 else 600)
+
+
+def test_large_general_graph_uses_global_state_fallback():
+    """48,400-site lattice (no wrap) given as CSR: too large for the shared-memory chain state, so
+    the sampler keeps the state in global memory.  Quadratic-form moments vs the closed form
+    (the rook lattice's spectrum is the sum of two path-graph spectra)."""
+    m = 220
+    W = graphs.lattice_W(m, m)
+    a = 2 * np.cos(np.pi * np.arange(1, m + 1) / (m + 1))
+    ew = (a[:, None] + a[None, :]).ravel()
+    rho, sigma = 0.2, 1.1
+    n = m * m
+    data = api.make_data(np.zeros(n), X=None, W=W, eigenvalues=ew, seed=31)
+    assert api.lib.mclcar_graph_ncolors(data.ctx.h) == 2
+    N = 512
+    sd = api.mcl_prep_dCAR([rho, sigma], N, data)
+    q = sd.stats()
+    mom = graphs.car_moments(ew, rho, sigma)
+    assert abs(q[:, 0].mean() - mom["E_xx"]) < 5 * np.sqrt(mom["V_xx"] / N)
+    assert abs(q[:, 1].mean() - mom["E_xWx"]) < 5 * np.sqrt(mom["V_xWx"] / N)
+    assert np.var(q[:, 0]) == pytest.approx(mom["V_xx"], rel=0.3)
+    Y = sd.simY
+    np.testing.assert_allclose(q, dcar.suffstats(W, None, Y), rtol=1e-12)
