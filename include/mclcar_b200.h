@@ -81,6 +81,9 @@ MCLCAR_API const char* mclcar_last_error(const mclcar_ctx* ctx); /* ctx may be N
 /* run all work on the given cudaStream_t (NULL: the context's own stream) */
 MCLCAR_API int mclcar_ctx_set_stream(mclcar_ctx* ctx, void* cuda_stream);
 MCLCAR_API int mclcar_ctx_sync(mclcar_ctx* ctx);
+/* device buffers (sample matrices, chain state, scratch) are recycled by a caching allocator that keeps at most
+ * half of the device memory cached; trim returns every cached free block to the driver now */
+MCLCAR_API int mclcar_ctx_trim(mclcar_ctx* ctx);
 /* this context is shard `rank` of `world`: samplers draw global chains rank, rank+world,
  * ... so that the union over ranks does not depend on `world`. */
 MCLCAR_API int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "mclcar_last_error": (C.c_char_p, [_vp]),
     "mclcar_ctx_set_stream": (_i, [_vp, _vp]),
     "mclcar_ctx_sync": (_i, [_vp]),
+    "mclcar_ctx_trim": (_i, [_vp]),
     "mclcar_ctx_set_shard": (_i, [_vp, _i, _i]),
     "mclcar_ctx_profile": (_i, [_vp, _i]),
     "mclcar_ctx_profile_read": (_i, [_vp, _pd, _pi64]),

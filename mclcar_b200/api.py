@@ -49,6 +49,10 @@ class Context:
     def sync(self):
         check(lib.mclcar_ctx_sync(self.h), self.h)
 
+    def trim(self):
+        """Return every cached free device buffer to the driver."""
+        check(lib.mclcar_ctx_trim(self.h), self.h)
+
     def set_shard(self, rank: int, world: int):
         check(lib.mclcar_ctx_set_shard(self.h, rank, world), self.h)
 

@@ -75,9 +75,30 @@ void pool_free(mclcar_ctx* ctx, void* p) {
     for (auto& b : ctx->pool)
         if (b.p == p) {
             b.used = false;
+            // never sit on more than half of the device: a session that changes problem sizes would
+            // otherwise accumulate blocks of every size it has ever used
+            pool_trim(ctx, ctx->pool_cap);
             return;
         }
     cudaFree(p);  // not ours
+}
+
+// return cached FREE blocks to the driver, largest first, until at most keep_bytes stay cached
+void pool_trim(mclcar_ctx* ctx, size_t keep_bytes) {
+    size_t cached = 0;
+    for (auto& b : ctx->pool)
+        if (!b.used) cached += b.bytes;
+    if (cached <= keep_bytes) return;
+    cudaStreamSynchronize(ctx->stream);
+    while (cached > keep_bytes) {
+        int big = -1;
+        for (int i = 0; i < (int)ctx->pool.size(); ++i)
+            if (!ctx->pool[i].used && (big < 0 || ctx->pool[i].bytes > ctx->pool[big].bytes)) big = i;
+        if (big < 0) break;
+        cached -= ctx->pool[big].bytes;
+        cudaFree(ctx->pool[big].p);
+        ctx->pool.erase(ctx->pool.begin() + big);
+    }
 }
 
 void pool_release_all(mclcar_ctx* ctx) {
@@ -254,6 +275,7 @@ int mclcar_ctx_create(int device, uint64_t seed, mclcar_ctx** out) {
             return MCLCAR_ENODEV;
         }
         ctx->n_sm = prop.multiProcessorCount;
+        ctx->pool_cap = prop.totalGlobalMem / 2;
         ctx->stream = ctx->own_stream;
     }
     *out = ctx;
@@ -286,6 +308,13 @@ int mclcar_ctx_set_stream(mclcar_ctx* ctx, void* cuda_stream) {
     MCL_TRY(require_device(ctx));
     cudaStreamSynchronize(ctx->stream);
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return MCLCAR_OK;
+}
+
+int mclcar_ctx_trim(mclcar_ctx* ctx) {
+    if (!ctx) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    pool_trim(ctx, 0);
     return MCLCAR_OK;
 }
 

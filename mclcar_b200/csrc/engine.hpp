@@ -78,6 +78,10 @@ struct mclcar_ctx {
     // recycled across calls so that steady-state steps do no cudaMalloc / cudaFree
     struct PoolBlock { void* p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
+    size_t pool_cap = (size_t)64 << 30;  // cached free bytes allowed to linger (half the device memory)
+
+    // ---- hierarchical model (hcar.cu owns the type)
+    void* hcar = nullptr;
 
     // ---- NCCL (dlopen'ed)
     void* nccl_lib = nullptr;
@@ -147,6 +151,7 @@ struct ProfScope {
 int pool_alloc(mclcar_ctx* ctx, void** out, size_t bytes);
 void pool_free(mclcar_ctx* ctx, void* p);
 void pool_release_all(mclcar_ctx* ctx);
+void pool_trim(mclcar_ctx* ctx, size_t keep_bytes);
 int ensure(mclcar_ctx* ctx, DeviceBuf& b, size_t bytes);
 int ensure_pinned(mclcar_ctx* ctx, size_t bytes);
 int require_device(mclcar_ctx* ctx);

@@ -42,7 +42,6 @@ struct HcarModel {
 
 namespace {
 
-std::map<mclcar_ctx*, HcarModel> g_models;  // one hierarchical model per context
 
 HostCsr transpose_times(const HostCsr& A, const HostCsr& B) {  // A'B, A and B with the same number of rows
     std::vector<std::map<int, double>> acc(A.cols);
@@ -217,10 +216,7 @@ void hcar_affine(const mclcar_ctx* ctx, const HcarModel& hm, const HcarPars& t, 
     }
 }
 
-HcarModel* model_of(mclcar_ctx* ctx) {
-    auto it = g_models.find(ctx);
-    return it == g_models.end() ? nullptr : &it->second;
-}
+HcarModel* model_of(mclcar_ctx* ctx) { return static_cast<HcarModel*>(ctx->hcar); }
 
 int hcar_check(mclcar_ctx* ctx, mclcar_samples* s, HcarModel** hm) {
     if (!ctx || !s) return MCLCAR_EINVAL;
@@ -282,7 +278,16 @@ int hcar_stats(mclcar_ctx* ctx, HcarModel& hm, mclcar_samples* s) {
 
 }  // namespace
 
-void hcar_forget(mclcar_ctx* ctx) { g_models.erase(ctx); }
+void hcar_forget(mclcar_ctx* ctx) {
+    HcarModel* hm = static_cast<HcarModel*>(ctx->hcar);
+    if (!hm) return;
+    if (!ctx->host_only) {
+        void* dev[] = {hm->dM_rp, hm->dM_ci, hm->dA_rp, hm->dA_ci, hm->dB_rp, hm->dB_ci, hm->dM_v, hm->dA_v, hm->dB_v, hm->d_lin};
+        for (void* d : dev) pool_free(ctx, d);
+    }
+    delete hm;
+    ctx->hcar = nullptr;
+}
 
 }  // namespace mclcar
 
@@ -346,7 +351,8 @@ int mclcar_hcar_set_model(mclcar_ctx* ctx, int K, const int* M_rowptr, const int
         std::copy(hm.ZtWX.begin(), hm.ZtWX.end(), lin.begin() + (size_t)(2 + p) * K);
         MCL_TRY(up(ctx, hm.d_lin, lin));
     }
-    g_models[ctx] = std::move(hm);
+    hcar_forget(ctx);
+    ctx->hcar = new HcarModel(std::move(hm));
     return MCLCAR_OK;
 }
 
