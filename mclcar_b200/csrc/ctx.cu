@@ -226,7 +226,17 @@ static void colour_graph(mclcar_ctx* c) {
     for (int i = 0; i < n; ++i) c->order[pos[c->color_of[i]]++] = i;
 }
 
+void edge_cache_clear(mclcar_ctx* ctx) {
+    for (auto& c : ctx->edge_cache) {
+        void* dev[] = {c.d_eptr, c.d_ei, c.d_ej, c.d_ew, c.d_diag};
+        for (void* d : dev)
+            if (d && !ctx->host_only) pool_free(ctx, d);
+    }
+    ctx->edge_cache.clear();
+}
+
 static int finish_graph(mclcar_ctx* ctx) {
+    edge_cache_clear(ctx);   // cached edge lists are keyed by the host CSR arrays that just changed
     ctx->max_deg = 0;
     for (int i = 0; i < ctx->n; ++i) ctx->max_deg = std::max(ctx->max_deg, ctx->rowptr[i + 1] - ctx->rowptr[i]);
     colour_graph(ctx);

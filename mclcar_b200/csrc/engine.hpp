@@ -20,6 +20,15 @@ enum { WHAT_LR = 0, WHAT_GRAD = 1, WHAT_HESS = 2 };
 // instrumentation categories (mclcar_ctx_profile_read)
 enum { PROF_SWEEP = 0, PROF_EMIT = 1, PROF_STATS = 2, PROF_REDUCE = 3, PROF_CSR_SAMPLER = 4, PROF_GLM = 5, PROF_NCAT = 8 };
 
+// upper-triangle edge list of a symmetric CSR matrix, on the device (stats_csr.cu), cached per matrix
+struct EdgeCache {
+    const int* key_rowptr = nullptr;
+    const int* key_colidx = nullptr;
+    int n = 0, nnz = 0;
+    int *d_eptr = nullptr, *d_ei = nullptr, *d_ej = nullptr;
+    double *d_ew = nullptr, *d_diag = nullptr;
+};
+
 struct DeviceBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -79,6 +88,8 @@ struct mclcar_ctx {
     struct PoolBlock { void* p; size_t bytes; bool used; };
     std::vector<PoolBlock> pool;
     size_t pool_cap = (size_t)64 << 30;  // cached free bytes allowed to linger (half the device memory)
+
+    std::vector<mclcar::EdgeCache> edge_cache;
 
     // ---- hierarchical model (hcar.cu owns the type)
     void* hcar = nullptr;
@@ -165,8 +176,9 @@ int launch_transpose(mclcar_ctx* ctx, const void* in, int dtype, int64_t rows, i
 int launch_stats_torus_fast(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, double* d_q,
                             int64_t ldq, bool* handled);
 int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, int n,
-                                const int* d_rowptr, const int* d_colidx, const double* d_val, int L,
-                                const double* const* d_vecs, double* d_out, int64_t ldq);
+                                const std::vector<int>& rowptr, const std::vector<int>& colidx,
+                                const std::vector<double>& val, int L, const double* const* d_vecs, double* d_out,
+                                int64_t ldq);
 int samples_alloc_stats(mclcar_ctx* ctx, mclcar_samples* s, int d);
 int samples_update_qbar(mclcar_ctx* ctx, mclcar_samples* s);
 int merge_tuples(int what, int F, int d, int G, int K, const double* in, double* out);
@@ -174,6 +186,7 @@ void centred_moments(const double* tup, int V, double* vbar, double* C);
 int gather_and_merge(mclcar_ctx* ctx, int what, int F, int d, int K, double* tuples);
 void comm_destroy(mclcar_ctx* ctx);
 void hcar_forget(mclcar_ctx* ctx);
+void edge_cache_clear(mclcar_ctx* ctx);
 
 // ---- reduction kernels (reduce.cu) ----------------------------------------------------------
 struct ReducePlan {

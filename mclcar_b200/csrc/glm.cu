@@ -271,8 +271,8 @@ int glm_check(mclcar_ctx* ctx, mclcar_samples* s, int P) {
 int glm_static_stats(mclcar_ctx* ctx, mclcar_samples* s) {
     if (s->stats_ready && s->d == 2) return MCLCAR_OK;
     MCL_TRY(samples_alloc_stats(ctx, s, 2));
-    MCL_TRY(launch_quadforms_site_major(ctx, s->d_M, s->dtype, s->N, s->ld, ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_val,
-                                        0, nullptr, s->d_q, s->N));
+    MCL_TRY(launch_quadforms_site_major(ctx, s->d_M, s->dtype, s->N, s->ld, ctx->n, ctx->rowptr, ctx->colidx, ctx->val, 0, nullptr,
+                                        s->d_q, s->N));
     s->stats_ready = true;
     return MCLCAR_OK;
 }

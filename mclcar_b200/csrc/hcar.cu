@@ -253,10 +253,10 @@ int hcar_stats(mclcar_ctx* ctx, HcarModel& hm, mclcar_samples* s) {
     if (!st) {
         std::vector<const double*> vecs(L);
         for (int l = 0; l < L; ++l) vecs[l] = hm.d_lin + (size_t)l * K;
-        st = launch_quadforms_site_major(ctx, U, s->dtype, N, ld, K, hm.dM_rp, hm.dM_ci, hm.dM_v, L, vecs.data(), f1, N);
+        st = launch_quadforms_site_major(ctx, U, s->dtype, N, ld, K, hm.M.rowptr, hm.M.colidx, hm.M.val, L, vecs.data(), f1, N);
     }
-    if (!st) st = launch_quadforms_site_major(ctx, U, s->dtype, N, ld, K, hm.dA_rp, hm.dA_ci, hm.dA_v, 0, nullptr, fA, N);
-    if (!st && hm.has_W) st = launch_quadforms_site_major(ctx, U, s->dtype, N, ld, K, hm.dB_rp, hm.dB_ci, hm.dB_v, 0, nullptr, fB, N);
+    if (!st) st = launch_quadforms_site_major(ctx, U, s->dtype, N, ld, K, hm.ZtZ.rowptr, hm.ZtZ.colidx, hm.ZtZ.val, 0, nullptr, fA, N);
+    if (!st && hm.has_W) st = launch_quadforms_site_major(ctx, U, s->dtype, N, ld, K, hm.ZtWZ.rowptr, hm.ZtWZ.colidx, hm.ZtWZ.val, 0, nullptr, fB, N);
     if (!st) {
         std::vector<double> cst(2 * p + 1, 0.0);
         for (int l = 0; l < p; ++l) { cst[l] = hm.Xty[l]; cst[p + l] = hm.XtWy[l]; }
@@ -281,6 +281,7 @@ int hcar_stats(mclcar_ctx* ctx, HcarModel& hm, mclcar_samples* s) {
 void hcar_forget(mclcar_ctx* ctx) {
     HcarModel* hm = static_cast<HcarModel*>(ctx->hcar);
     if (!hm) return;
+    edge_cache_clear(ctx);   // edge lists of M, Z'Z, Z'WZ are keyed by this model's arrays
     if (!ctx->host_only) {
         void* dev[] = {hm->dM_rp, hm->dM_ci, hm->dA_rp, hm->dA_ci, hm->dB_rp, hm->dB_ci, hm->dM_v, hm->dA_v, hm->dB_v, hm->d_lin};
         for (void* d : dev) pool_free(ctx, d);

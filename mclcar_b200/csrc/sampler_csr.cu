@@ -33,6 +33,8 @@ struct CsrSamplerParams {
     const int* rowptr;     // [n + 1] by position
     const int* colidx;     // neighbour SITE ids
     const float* coef;     // -Q_sj / Q_ss per entry
+    int coef_uniform;      // all entries equal (binary W, constant diagonal): use coef_value, skip the loads
+    float coef_value;
     const float* hm;       // b_s / Q_ss per site
     const float* sd;       // 1/sqrt(Q_ss) per site
     const double* mu;      // added to kept states (site order) or null
@@ -85,11 +87,23 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                 const int s = p.site_of[t];
                 float m0 = p.hm[s], m1 = m0;
                 const int e1 = p.rowptr[t + 1];
-                for (int e = p.rowptr[t]; e < e1; ++e) {
-                    const float2 v = *reinterpret_cast<const float2*>(x + (size_t)p.colidx[e] * CB + 2 * pr);
-                    const float c = p.coef[e];
-                    m0 = fmaf(c, v.x, m0);
-                    m1 = fmaf(c, v.y, m1);
+                // neighbour gathers four at a time: the index loads are independent, so the dependent
+                // index -> shared-memory chains overlap instead of serialising
+                for (int e = p.rowptr[t]; e < e1; e += 4) {
+                    int j[4];
+                    float c[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool ok = e + k < e1;
+                        j[k] = ok ? p.colidx[e + k] : s;
+                        c[k] = ok ? (p.coef_uniform ? p.coef_value : p.coef[e + k]) : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 v = *reinterpret_cast<const float2*>(x + (size_t)j[k] * CB + 2 * pr);
+                        m0 = fmaf(c[k], v.x, m0);
+                        m1 = fmaf(c[k], v.y, m1);
+                    }
                 }
                 const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)sweep, (uint32_t)gpair,
                                                 (uint32_t)(gpair >> 32) ^ (kTagCsr << 16), p.keys);
@@ -251,7 +265,10 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
         }
         p.n = n; p.ncolors = ncol;
         p.color_ptr = (const int*)d_cp; p.site_of = (const int*)d_so; p.rowptr = (const int*)d_rp;
-        p.colidx = (const int*)d_ci; p.coef = (const float*)d_coef; p.hm = (const float*)d_hm; p.sd = (const float*)d_sd;
+        p.colidx = (const int*)d_ci; p.coef = (const float*)d_coef;
+        p.coef_uniform = 1;
+        for (size_t e = 1; e < coef.size() && p.coef_uniform; ++e) p.coef_uniform = coef[e] == coef[0];
+        p.coef_value = coef.empty() ? 0.f : coef[0]; p.hm = (const float*)d_hm; p.sd = (const float*)d_sd;
         p.mu = (const double*)d_mu; p.yv = (const float*)d_y; p.nt = (const float*)d_nt; p.xb = (const float*)d_xb;
         p.CB = CB; p.C = C; p.burn = burn; p.thin = thin; p.E = E; p.N = N;
         p.out = d_out; p.ld = ld; p.out_f64 = out_f64; p.state_g = (float*)d_state;

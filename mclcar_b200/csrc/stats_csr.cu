@@ -23,9 +23,12 @@ struct SiteMajorParams {
     const void* M;
     int64_t ld, N;
     int n;
-    const int* rowptr;
-    const int* colidx;
-    const double* val;  // null = binary
+    // upper triangle (j > s) of the symmetric matrix as a flat edge list sorted by s, plus the diagonal
+    const int* eptr;    // [n + 1] first edge of every site
+    const int* ei;      // [nedge] s
+    const int* ej;      // [nedge] j
+    const double* ew;   // [nedge] A_sj, null = 1
+    const double* diag; // [n] A_ss, null = 0
     int L;
     const double* vec[2 * MCLCAR_MAX_COV];
     int chunk;     // sites per chunk
@@ -37,28 +40,30 @@ template <typename T, int LT>
 __global__ void __launch_bounds__(kThreads) stats_site_major_kernel(const SiteMajorParams p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.N) return;
-    const T* M = reinterpret_cast<const T*>(p.M);
+    const T* M = reinterpret_cast<const T*>(p.M) + i;
     const int s0 = blockIdx.y * p.chunk;
     const int s1 = min(p.n, s0 + p.chunk);
     double xx = 0.0, xax = 0.0, lin[LT > 0 ? LT : 1];
 #pragma unroll
     for (int l = 0; l < LT; ++l) lin[l] = 0.0;
+    // (1) x'x, diagonal part of x'Ax and the linear forms: a streaming pass over the chunk's sites
+#pragma unroll 4
     for (int s = s0; s < s1; ++s) {
-        const double x = (double)ld_stream(M + (size_t)s * p.ld + i);
+        const double x = (double)ld_stream(M + (size_t)s * p.ld);
         xx = fma(x, x, xx);
-        double nb = 0.0;
-        const int e1 = p.rowptr[s + 1];
-        for (int e = p.rowptr[s]; e < e1; ++e) {
-            const int j = p.colidx[e];
-            if (j < s) continue;
-            const double w = p.val ? p.val[e] : 1.0;
-            if (j == s) nb = fma(0.5 * w, x, nb);
-            else nb = fma(w, (double)__ldg(M + (size_t)j * p.ld + i), nb);
-        }
-        xax = fma(x, nb, xax);
+        if (p.diag) xax = fma(0.5 * __ldg(p.diag + s) * x, x, xax);
 #pragma unroll
         for (int l = 0; l < LT; ++l)
             if (l < p.L) lin[l] = fma(__ldg(p.vec[l] + s), x, lin[l]);
+    }
+    // (2) off-diagonal part: the chunk's edges, independent iterations => many gathers in flight
+    const int e0 = p.eptr[s0], e1 = p.eptr[s1];
+#pragma unroll 4
+    for (int e = e0; e < e1; ++e) {
+        const double a = (double)__ldg(M + (size_t)__ldg(p.ei + e) * p.ld);
+        const double b = (double)__ldg(M + (size_t)__ldg(p.ej + e) * p.ld);
+        const double w = p.ew ? __ldg(p.ew + e) : 1.0;
+        xax = fma(w * a, b, xax);
     }
     double* o = p.out + (size_t)blockIdx.y * (2 + p.L) * p.ldq + i;
     o[0] = xx;
@@ -107,14 +112,51 @@ int launch_typed(mclcar_ctx* ctx, const SiteMajorParams& p, dim3 grid) {
 
 }  // namespace
 
-// generic form: any symmetric CSR matrix on the device, any list of dense vectors
+// generic form: any symmetric CSR matrix (host copy given), any list of dense device vectors.  The
+// upper-triangle edge list is built on the host and cached on the context keyed by the CSR arrays.
 int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, int n,
-                                const int* d_rowptr, const int* d_colidx, const double* d_val, int L,
-                                const double* const* d_vecs, double* d_out, int64_t ldq) {
+                                const std::vector<int>& rowptr, const std::vector<int>& colidx,
+                                const std::vector<double>& val, int L, const double* const* d_vecs, double* d_out,
+                                int64_t ldq) {
     if (L > 2 * MCLCAR_MAX_COV) return fail(ctx, MCLCAR_ELIMIT, "too many linear forms (%d)", L);
+    // ---- edge list (cached)
+    EdgeCache* ec = nullptr;
+    for (auto& c : ctx->edge_cache)
+        if (c.key_rowptr == rowptr.data() && c.key_colidx == colidx.data() && c.n == n && c.nnz == (int)colidx.size()) ec = &c;
+    if (!ec) {
+        std::vector<int> eptr(n + 1, 0), ei, ej;
+        std::vector<double> ew, diag(n, 0.0);
+        bool any_diag = false, weighted = !val.empty();
+        for (int s = 0; s < n; ++s) {
+            eptr[s] = (int)ei.size();
+            for (int e = rowptr[s]; e < rowptr[s + 1]; ++e) {
+                const int j = colidx[e];
+                const double w = weighted ? val[e] : 1.0;
+                if (j == s) { diag[s] += w; any_diag = true; }
+                else if (j > s) { ei.push_back(s); ej.push_back(j); ew.push_back(w); }
+            }
+        }
+        eptr[n] = (int)ei.size();
+        bool unit = true;
+        for (double w : ew) unit = unit && w == 1.0;
+        ctx->edge_cache.emplace_back();
+        ec = &ctx->edge_cache.back();
+        ec->key_rowptr = rowptr.data(); ec->key_colidx = colidx.data(); ec->n = n; ec->nnz = (int)colidx.size();
+        auto up = [&](const void* h, size_t bytes, void** d) -> int {
+            MCL_TRY(pool_alloc(ctx, d, bytes ? bytes : 16));
+            if (bytes) MCL_CUDA(ctx, cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            return MCLCAR_OK;
+        };
+        MCL_TRY(up(eptr.data(), eptr.size() * sizeof(int), (void**)&ec->d_eptr));
+        MCL_TRY(up(ei.data(), ei.size() * sizeof(int), (void**)&ec->d_ei));
+        MCL_TRY(up(ej.data(), ej.size() * sizeof(int), (void**)&ec->d_ej));
+        if (!unit) MCL_TRY(up(ew.data(), ew.size() * sizeof(double), (void**)&ec->d_ew));
+        if (any_diag) MCL_TRY(up(diag.data(), diag.size() * sizeof(double), (void**)&ec->d_diag));
+        MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors are locals
+    }
     SiteMajorParams p{};
     p.M = M; p.ld = ld; p.N = N; p.n = n;
-    p.rowptr = d_rowptr; p.colidx = d_colidx; p.val = d_val;
+    p.eptr = ec->d_eptr; p.ei = ec->d_ei; p.ej = ec->d_ej; p.ew = ec->d_ew; p.diag = ec->d_diag;
     p.L = L;
     for (int l = 0; l < L; ++l) p.vec[l] = d_vecs[l];
     p.ldq = ldq;
@@ -151,8 +193,7 @@ int launch_stats_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N
         vecs[l] = ctx->d_X + (size_t)l * ctx->n;
         vecs[p + l] = ctx->d_WX + (size_t)l * ctx->n;
     }
-    return launch_quadforms_site_major(ctx, M, dtype, N, ld, ctx->n, ctx->d_rowptr, ctx->d_colidx, ctx->d_val, 2 * p,
-                                       vecs, d_q, ldq);
+    return launch_quadforms_site_major(ctx, M, dtype, N, ld, ctx->n, ctx->rowptr, ctx->colidx, ctx->val, 2 * p, vecs, d_q, ldq);
 }
 
 int launch_transpose(mclcar_ctx* ctx, const void* in, int dtype, int64_t rows, int64_t cols, int64_t ld_in,
