@@ -197,12 +197,13 @@ def run_ours(args):
 
     data = api.make_data(y_pin.numpy(), X=X_pin.numpy(), torus=(N1, N2), ctx=ctx)
 
-    diag = {"sweeps": 0}
+    diag = {"sweeps": 0, "chains": 0}
 
     def step_resident():
         sd = api.mcl_prep_dCAR(PSI0, N_gpu, data, control)
         res = api.mcl_dCAR_batch(psis, data, sd, rho_cons=None)
-        diag["sweeps"] = api.sampler_diag(data, sd)["sweeps"]
+        dg = api.sampler_diag(data, sd)
+        diag["sweeps"], diag["chains"] = dg["sweeps"], dg["chains"]
         sd.close()
         return res
 
@@ -307,8 +308,7 @@ def run_ours(args):
     sweep_launches = int(launches[0])
     sweep_ms = float(ms_cat[0])
     sweeps_step = int(diag["sweeps"])
-    chains = args.chains if args.chains > 0 else max(1, (32 << 20) // n)
-    chains = min(chains, N_gpu)
+    chains = int(diag["chains"])      # the library's own choice unless --chains is given
     omega = args.omega if args.omega > 0 else 2.0 / (1.0 + np.sqrt(1.0 - (4 * PSI0[0]) ** 2))
     # algorithmic bytes per site update: read the other colour + write own colour (fp32), plus the
     # read of the current value for the over-relaxed update

@@ -367,8 +367,10 @@ def mcl_prep_dCAR(psi, n_samples: int, data: CarData, control: Optional[dict] = 
 def sampler_diag(data: CarData, simdata) -> dict:
     acc = C.c_double()
     sw = C.c_int64()
+    ch = C.c_int64()
     check(lib.mclcar_samples_diag(data.ctx.h, simdata.h, C.byref(acc), C.byref(sw)), data.ctx.h)
-    return {"accept": acc.value, "sweeps": sw.value}
+    check(lib.mclcar_samples_chains(data.ctx.h, simdata.h, C.byref(ch)), data.ctx.h)
+    return {"accept": acc.value, "sweeps": sw.value, "chains": ch.value}
 
 
 # ------------------------------------------------------------------------------------------

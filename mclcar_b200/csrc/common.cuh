@@ -167,6 +167,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// orders earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // streaming (read-once) global loads: do not allocate in L1
 __device__ __forceinline__ double ld_stream(const double* p) {
     double v;

@@ -128,6 +128,7 @@ struct mclcar_samples {
     // sampler diagnostics
     double accept = 1.0;
     int64_t sweeps = 0;
+    int64_t chains = 0;   // parallel chains the sampler ran (0: matrix supplied by the caller)
 };
 
 namespace mclcar {

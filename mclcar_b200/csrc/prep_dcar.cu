@@ -3,6 +3,7 @@
 // sparse Cholesky per sample); here N/C kept states of C parallel Gibbs chains.
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 
 #include "engine.hpp"
 
@@ -67,6 +68,28 @@ void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* bur
     if (*burn <= 0) *burn = sweeps_for(1e-6, 4, 40000);
 }
 
+// Chains of the tiled torus sampler.  One sweep is one launch over all chains: its ramp-up (every
+// CTA of the first wave waits for its tile) and tail cost about 9 us, so launches should carry
+// >= 10^8 site updates (measured on B200: 33 chains of 10^6 sites reach 0.58 of the HBM roofline,
+// 111+ chains 0.72).  More chains mean fewer kept states per chain, i.e. relatively more burn-in:
+// keep burn-in below 1/8 of the kept sweeps, then pick the count in the upper fifth of the range
+// with the smallest modelled time: launches (burn + ceil(N / C) thin) x (C + the launch overhead
+// expressed in chains).
+int64_t default_torus_chains(int n, int64_t N, int burn, int thin) {
+    int64_t c_hi = std::max<int64_t>(1, ((int64_t)160 << 20) / n);
+    c_hi = std::min<int64_t>(c_hi, std::max<int64_t>(1, N * thin / (8 * (int64_t)std::max(burn, 1))));
+    c_hi = std::min<int64_t>(std::min<int64_t>(c_hi, N), 65535);
+    const int64_t c_lo = std::max<int64_t>(1, c_hi - c_hi / 5);
+    const double overhead = 5.4e6 / n;   // ~9 us of ramp-up and tail at ~6e11 site updates/s
+    int64_t best = c_hi;
+    double best_cost = 1e300;
+    for (int64_t c = c_hi; c >= c_lo; --c) {
+        const double cost = (double)(burn + (N + c - 1) / c * thin) * ((double)c + overhead);
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
 int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N) {
     const size_t cap = 200 * 1024;
     int cbmax = 0;
@@ -120,7 +143,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
     double* d_mu = nullptr;
     if (use_torus) {
         // ---- spatially tiled red-black sampler, sample-major output
-        int64_t C = o.n_chains > 0 ? o.n_chains : std::max<int64_t>(1, ((int64_t)32 << 20) / n);
+        int64_t C = o.n_chains > 0 ? o.n_chains : default_torus_chains(n, N, burn, thin);
         C = std::min<int64_t>(std::min<int64_t>(C, N), 65535);
         const int64_t E = (N + C - 1) / C;
         const int64_t align = 16 / es;
@@ -162,6 +185,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
                 }
             }
             s->sweeps = sweep;
+            s->chains = C;
             if (st == MCLCAR_OK && !o.keep) {
                 if ((st = samples_update_qbar(ctx, s))) break;
                 s->stats_ready = true;
@@ -185,6 +209,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         if (st == MCLCAR_OK)
             st = run_csr_sampler(ctx, g, FAM_GAUSS, omega, mu.empty() ? nullptr : mu.data(), nullptr, nullptr, nullptr, N, C, burn, thin,
                                  s->d_M, o.dtype == MCLCAR_F64, ld, &s->accept, &s->sweeps);
+        s->chains = C;
     }
     pool_free(ctx, d_mu);
     if (st == MCLCAR_OK) st = mclcar_dcar_attach(ctx, s, psi0, P, nullptr);

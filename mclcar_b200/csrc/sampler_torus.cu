@@ -40,6 +40,7 @@ struct TorusSweepParams {
     // over-relaxed Gibbs update  x' = keep*x + gain*(sum of neighbours) + noise*z  with
     // keep = 1 - omega, gain = omega*rho, noise = sqrt(omega (2 - omega) sigma); omega = 1 is plain Gibbs
     float keep, gain, noise;
+    float rad2;    // -2 ln2 * noise^2: radius of the scaled Box-Muller pair = sqrt(rad2 * lg2(u))
     uint32_t sweep;
     int64_t chain0, chain_stride;  // global chain id = chain0 + local * chain_stride
     PhiloxKeys keys;
@@ -52,6 +53,45 @@ struct TorusSweepParams {
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// The update of four consecutive half-columns of one row (ONE Philox4x32-10 block), shared by the
+// two-launch and the fused kernels so that both produce the same bits:
+//     x' = keep * x + gain * (sum of the four neighbours) + noise * z,   z ~ N(0, 1).
+// o/up/d: the other colour at the same half-columns in this row / the row above / below; e: the
+// same-row neighbour beyond the vector (c + 4 when FWD, c - 1 otherwise).  The noise scale is folded
+// into the Box-Muller radius (sqrt(rad2 * lg2 u), rad2 = -2 ln2 noise^2) and the product
+// radius * cos/sin into the final FMA: 6 FP32 instructions per site besides the RNG.
+template <bool SOR, bool FWD>
+__device__ __forceinline__ float4 gibbs_update4(const float4 o, const float4 up, const float4 d, const float e,
+                                                const float4 cur, const Philox4 r, const float keep, const float gain,
+                                                const float rad2) {
+    const float ra = sqrt_approx(rad2 * lg2_approx(u01(r.x)));
+    const float rb = sqrt_approx(rad2 * lg2_approx(u01(r.z)));
+    float sa, ca, sb, cb;
+    sincos_approx(6.2831853071795865f * u01(r.y), sa, ca);
+    sincos_approx(6.2831853071795865f * u01(r.w), sb, cb);
+    float4 s;
+    if (FWD) { s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e; }
+    else { s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w; }
+    s.x = __fadd_rn(s.x, __fadd_rn(up.x, d.x));
+    s.y = __fadd_rn(s.y, __fadd_rn(up.y, d.y));
+    s.z = __fadd_rn(s.z, __fadd_rn(up.z, d.z));
+    s.w = __fadd_rn(s.w, __fadd_rn(up.w, d.w));
+    float4 v;
+    if (SOR) {
+        v.x = __fmaf_rn(ra, ca, __fmul_rn(keep, cur.x));
+        v.y = __fmaf_rn(ra, sa, __fmul_rn(keep, cur.y));
+        v.z = __fmaf_rn(rb, cb, __fmul_rn(keep, cur.z));
+        v.w = __fmaf_rn(rb, sb, __fmul_rn(keep, cur.w));
+    } else {
+        v.x = __fmul_rn(ra, ca); v.y = __fmul_rn(ra, sa); v.z = __fmul_rn(rb, cb); v.w = __fmul_rn(rb, sb);
+    }
+    v.x = __fmaf_rn(gain, s.x, v.x);
+    v.y = __fmaf_rn(gain, s.y, v.y);
+    v.z = __fmaf_rn(gain, s.z, v.z);
+    v.w = __fmaf_rn(gain, s.w, v.w);
+    return v;
+}
 
 // 16-byte path (h % 4 == 0).  SOR: the update reads the current value too.  EMIT: the black
 // half sweep also stores the finished sample row segment (both colours are in registers).
@@ -97,26 +137,8 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
             if (SOR) curn = ld4(own + rown + c0);
         }
         const Philox4 r = philox4x32_10(ctr, c1, c2, c3, p.keys);
-        float z0, z1, z2, z3;
-        box_muller(r.x, r.y, z0, z1);
-        box_muller(r.z, r.w, z2, z3);
-        float4 s;
-        if (fwd) {
-            s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e;
-        } else {
-            s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w;
-        }
-        float4 v;
-        v.x = fmaf(p.gain, s.x + (up.x + d.x), p.noise * z0);
-        v.y = fmaf(p.gain, s.y + (up.y + d.y), p.noise * z1);
-        v.z = fmaf(p.gain, s.z + (up.z + d.z), p.noise * z2);
-        v.w = fmaf(p.gain, s.w + (up.w + d.w), p.noise * z3);
-        if (SOR) {
-            v.x = fmaf(p.keep, cur.x, v.x);
-            v.y = fmaf(p.keep, cur.y, v.y);
-            v.z = fmaf(p.keep, cur.z, v.z);
-            v.w = fmaf(p.keep, cur.w, v.w);
-        }
+        const float4 v = fwd ? gibbs_update4<SOR, true>(o, up, d, e, cur, r, p.keep, p.gain, p.rad2)
+                             : gibbs_update4<SOR, false>(o, up, d, e, cur, r, p.keep, p.gain, p.rad2);
         *reinterpret_cast<float4*>(own + row + c0) = v;
         if (EMIT) {
             if (ch < p.nch) {
@@ -163,38 +185,28 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
 // about 9 B per site update instead of 12 (over-relaxed) for the two-launch form; results are
 // bit-identical to it.
 // ---------------------------------------------------------------------------------------------
-// one lattice row of one colour inside the fused sweep: lanes stride the column vectors.  FWD (the
-// same-row neighbour sits at c + 1, else c - 1) is uniform over the row, so it is a template argument
-// and the per-item selects vanish; all row pointers are formed once per row.
-template <bool SOR, bool FWD, bool EMIT, typename TO>
-__device__ __forceinline__ void fused_row(const TorusSweepParams& p, const float* __restrict__ nu, const float* __restrict__ nm,
-                                          const float* __restrict__ nd, float* __restrict__ own_s, const float* __restrict__ cur_s,
+// One lattice row of one colour inside the fused sweep: lanes stride the column vectors.  FWD (the
+// same-row neighbour sits at c + 1, else c - 1) is uniform over the row, so it is a template
+// argument.  PH2 = black phase: the own colour is only read (current value), the new row goes to
+// global memory (and to the sample matrix when EMIT).  The loop body is kept small on purpose: a
+// four-way unrolled straight-line variant (more instruction-level parallelism, 4x the code) measured
+// 5 % slower -- the 24 resident warps already cover the latencies, instruction fetch does not.
+template <bool SOR, bool FWD, bool PH2, bool EMIT, typename TO>
+__device__ __forceinline__ void fused_row(const TorusSweepParams& p, const float* __restrict__ nm, float* __restrict__ own,
                                           float* __restrict__ gout, TO* __restrict__ emit_row, const double* __restrict__ mu_row,
-                                          bool par, int tx, int hv, int h, uint32_t ctr0, uint32_t c1, uint32_t c2, uint32_t c3) {
+                                          const bool par, const int tx, const int hv, const int h, const uint32_t ctr0,
+                                          const uint32_t c1, const uint32_t c2, const uint32_t c3) {
     for (int cv = tx; cv < hv; cv += 32) {
         const int c0 = cv << 2;
-        const float4 o = ld4(nm + c0), up = ld4(nu + c0), d = ld4(nd + c0);
+        const float4 o = ld4(nm + c0), up = ld4(nm - h + c0), d = ld4(nm + h + c0);
         const float e = FWD ? nm[c0 + 4 == h ? 0 : c0 + 4] : nm[c0 == 0 ? h - 1 : c0 - 1];
+        float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (SOR) cur = ld4(own + c0);
         const Philox4 r = philox4x32_10(ctr0 + (uint32_t)cv, c1, c2, c3, p.keys);
-        float z0, z1, z2, z3;
-        box_muller(r.x, r.y, z0, z1);
-        box_muller(r.z, r.w, z2, z3);
-        float4 s;
-        if (FWD) { s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e; }
-        else { s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w; }
-        float4 v;
-        v.x = fmaf(p.gain, s.x + (up.x + d.x), p.noise * z0);
-        v.y = fmaf(p.gain, s.y + (up.y + d.y), p.noise * z1);
-        v.z = fmaf(p.gain, s.z + (up.z + d.z), p.noise * z2);
-        v.w = fmaf(p.gain, s.w + (up.w + d.w), p.noise * z3);
-        if (SOR) {
-            const float4 cur = ld4(cur_s + c0);
-            v.x = fmaf(p.keep, cur.x, v.x); v.y = fmaf(p.keep, cur.y, v.y);
-            v.z = fmaf(p.keep, cur.z, v.z); v.w = fmaf(p.keep, cur.w, v.w);
-        }
-        if (own_s) *reinterpret_cast<float4*>(own_s + c0) = v;
+        const float4 v = gibbs_update4<SOR, FWD>(o, up, d, e, cur, r, p.keep, p.gain, p.rad2);
+        if (!PH2) *reinterpret_cast<float4*>(own + c0) = v;
         if (gout) *reinterpret_cast<float4*>(gout + c0) = v;
-        if (EMIT) {
+        if (EMIT && PH2) {
             if (emit_row) {
                 // o = finished values of the other colour at the same half-columns; the emitting (black) colour sits at
                 // column 2c + 1 - par, the other at 2c + par
@@ -204,7 +216,7 @@ __device__ __forceinline__ void fused_row(const TorusSweepParams& p, const float
                 TO* dst = emit_row + 2 * c0;
                 if (mu_row != nullptr) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) dst[q] = (TO)((double)a[q] + __ldg(mu_row + 2 * c0 + q));
+                    for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + __ldg(mu_row + 2 * c0 + t));
                 } else if (sizeof(TO) == 4) {
                     const float m = (float)p.mu_const;
                     float4* d4 = reinterpret_cast<float4*>(dst);
@@ -212,7 +224,7 @@ __device__ __forceinline__ void fused_row(const TorusSweepParams& p, const float
                     d4[1] = make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m);
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) dst[q] = (TO)((double)a[q] + p.mu_const);
+                    for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + p.mu_const);
                 }
             }
         }
@@ -220,8 +232,8 @@ __device__ __forceinline__ void fused_row(const TorusSweepParams& p, const float
 }
 
 template <bool SOR, bool EMIT, typename TO>
-__global__ void __launch_bounds__(512) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
-    extern __shared__ __align__(128) unsigned char fsm[];
+__global__ void __launch_bounds__(256, 3) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
+    extern __shared__ __align__(128) float fsm[];
     const int h = p.h, n1 = p.n1, hv = h >> 2;
     const int r0 = blockIdx.x * TR;
     const int rows = min(TR, n1 - r0);
@@ -231,9 +243,9 @@ __global__ void __launch_bounds__(512) gibbs_torus_sweep_fused(const TorusSweepP
     const float* __restrict__ gblk = p.black + ch * plane;
     float* __restrict__ ored = p.red_out + ch * plane;        // write to the other pair: tiles of the
     float* __restrict__ oblk = p.black_out + ch * plane;      // same launch never see each other's output
-    float* sB = reinterpret_cast<float*>(fsm);             // [rows + 4][h]: black rows r0-2 ..
-    float* sR = sB + (size_t)(TR + 4) * h;                 // [rows + 2][h]: red rows r0-1 ..
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sR + (size_t)(TR + 2) * h);
+    float* sB = fsm;                                       // [TR + 4][h]: black rows r0-2 ..
+    float* sR = fsm + (size_t)(TR + 4) * h;                // [TR + 2][h]: red rows r0-1 ..
+    uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + (size_t)(2 * TR + 6) * h);
     const uint32_t row_bytes = (uint32_t)h * 4u;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -269,15 +281,15 @@ __global__ void __launch_bounds__(512) gibbs_torus_sweep_fused(const TorusSweepP
         float* rr = sR + (size_t)lr * h;
         float* gout = (lr >= 1 && lr <= rows) ? ored + (size_t)i * h : nullptr;
         const uint32_t ctr0 = (uint32_t)(i * hv);
-        if (i & 1) fused_row<SOR, true, false, TO>(p, bo - h, bo, bo + h, rr, rr, gout, nullptr, nullptr, false, tx, hv, h, ctr0, p.sweep * 2u, c2, c3);
-        else fused_row<SOR, false, false, TO>(p, bo - h, bo, bo + h, rr, rr, gout, nullptr, nullptr, false, tx, hv, h, ctr0, p.sweep * 2u, c2, c3);
+        if (i & 1) fused_row<SOR, true, false, false, TO>(p, bo, rr, gout, nullptr, nullptr, false, tx, hv, h, ctr0, p.sweep * 2u, c2, c3);
+        else fused_row<SOR, false, false, false, TO>(p, bo, rr, gout, nullptr, nullptr, false, tx, hv, h, ctr0, p.sweep * 2u, c2, c3);
     }
     __syncthreads();
     // ---- phase 2: black rows r0 .. r0+rows-1 from the new red rows in sR
     for (int t = ty; t < rows; t += nw) {
         const int i = r0 + t;
         const float* ro = sR + (size_t)(t + 1) * h;
-        const float* bc = sB + (size_t)(t + 2) * h;
+        float* bc = sB + (size_t)(t + 2) * h;
         float* gout = oblk + (size_t)i * h;
         TO* erow = nullptr;
         const double* mrow = nullptr;
@@ -289,8 +301,8 @@ __global__ void __launch_bounds__(512) gibbs_torus_sweep_fused(const TorusSweepP
         }
         const uint32_t ctr0 = (uint32_t)(i * hv);
         const bool par = (i & 1) != 0;
-        if (!par) fused_row<SOR, true, EMIT, TO>(p, ro - h, ro, ro + h, nullptr, bc, gout, erow, mrow, par, tx, hv, h, ctr0, p.sweep * 2u + 1u, c2, c3);
-        else fused_row<SOR, false, EMIT, TO>(p, ro - h, ro, ro + h, nullptr, bc, gout, erow, mrow, par, tx, hv, h, ctr0, p.sweep * 2u + 1u, c2, c3);
+        if (!par) fused_row<SOR, true, true, EMIT, TO>(p, ro, bc, gout, erow, mrow, par, tx, hv, h, ctr0, p.sweep * 2u + 1u, c2, c3);
+        else fused_row<SOR, false, true, EMIT, TO>(p, ro, bc, gout, erow, mrow, par, tx, hv, h, ctr0, p.sweep * 2u + 1u, c2, c3);
     }
 }
 
@@ -391,6 +403,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
     p.keep = (float)(1.0 - omega);
     p.gain = (float)(omega * rho);
     p.noise = (float)std::sqrt(omega * (2.0 - omega) * sigma);
+    p.rad2 = (float)(-2.0 * std::log(2.0) * omega * (2.0 - omega) * sigma);
     p.keys = philox_keys(ctx->seed);
     p.sweep = sweep;
     p.chain0 = ctx->rank; p.chain_stride = ctx->world;
@@ -405,19 +418,23 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
             p.mu = emit->d_mu; p.mu_const = emit->mu_const;
         }
         const bool f32 = !emit || emit->dtype == MCLCAR_F32;
-        const char* fe = getenv("MCLCAR_SWEEP_FUSED");  // read per call: tests toggle it
+        const char* fe = getenv("MCLCAR_SWEEP_FUSED");  // read per call: tests toggle it (0 = two half-sweep launches)
         const int fused_cfg = fe ? atoi(fe) : 1;
         static int tr_cfg = [] { const char* e = getenv("MCLCAR_SWEEP_TR"); return e ? atoi(e) : 0; }();
         const size_t row_b = (size_t)p.h * 4;
-        int TR = tr_cfg > 0 ? tr_cfg : (int)((72 * 1024 / row_b - 6) / 2);
+        const int fthreads = 256, nw = fthreads / 32;
+        // tile height: three CTAs of <= 72 KB per SM; the red phase covers TR + 2 rows, so TR + 2 a multiple
+        // of the warp count keeps the warps of a CTA level at the phase barrier (14 rows for 1000 x 1000)
+        int TR = (int)((72 * 1024 / row_b - 6) / 2);
         TR = std::min(TR, 64);
+        if (TR + 2 > nw && (TR + 2) % nw != 0) TR -= (TR + 2) % nw;
+        if (tr_cfg > 0) TR = tr_cfg;
         if (fused_cfg && TR >= 4 && p.n1 >= TR + 4) {
             ProfScope prof(ctx, PROF_SWEEP, 1);
             p.red_out = t.red2; p.black_out = t.black2;
             std::swap(t.red, t.red2);        // the output pair is the current state from now on
             std::swap(t.black, t.black2);
             const size_t smem = (size_t)(2 * TR + 6) * row_b + 64;
-            const int fthreads = 256;   // 384 / 512 threads and other tile heights measured within 1 %
             dim3 grid((p.n1 + TR - 1) / TR, (unsigned)t.C);
 #define LAUNCH_FUSED(S, E, TO_)                                                                                  \
     do {                                                                                                         \

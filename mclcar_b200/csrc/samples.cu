@@ -198,4 +198,10 @@ int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate,
     return MCLCAR_OK;
 }
 
+int mclcar_samples_chains(mclcar_ctx* ctx, mclcar_samples* s, int64_t* chains) {
+    if (!ctx || !s || !chains) return MCLCAR_EINVAL;
+    *chains = s->chains;
+    return MCLCAR_OK;
+}
+
 }  // extern "C"

@@ -156,22 +156,39 @@ def test_mcl_estimate_matches_exact_likelihood_ratio():
 def test_fused_sweep_is_bit_identical_to_two_half_sweeps(monkeypatch):
     """The shared-memory fused sweep recomputes halo rows from the same Philox counters: its
     samples equal those of the two-launch red/black form bit for bit."""
-    n1, n2 = 96, 128   # 6 tiles of 16-ish rows, wrap-around at both ends
+    n1, n2 = 96, 128   # several row strips, wrap-around at both ends
     rng = np.random.default_rng(3)
     n = n1 * n2
     X = np.column_stack([np.ones(n), rng.standard_normal(n)])
     y = rng.standard_normal(n)
     psi = [0.21, 1.2, 0.3, -0.2]
     out = {}
-    for fused in ("1", "0"):
-        monkeypatch.setenv("MCLCAR_SWEEP_FUSED", fused)
+    for mode in ("1", "0"):   # fused (one launch per sweep), two launches
+        monkeypatch.setenv("MCLCAR_SWEEP_FUSED", mode)
         for omega in (0.0, 1.0):
             d = api.make_data(y, X=X, torus=(n1, n2), seed=5)
             sd = api.mcl_prep_dCAR(psi, 12, d, {"n.chains": 4, "burn": 3, "thin": 2, "omega": omega})
-            out[(fused, omega)] = sd.simY
+            out[(mode, omega)] = sd.simY
     for omega in (0.0, 1.0):
         np.testing.assert_array_equal(out[("1", omega)], out[("0", omega)])
     assert np.abs(out[("1", 0.0)] - out[("1", 1.0)]).max() > 0.1
+
+
+def test_fused_sweep_fp64_samples_with_site_mean(monkeypatch):
+    """Many chains, a fp64 sample matrix and a non-constant mean X beta0: the fused sweep's emission
+    path is still bit-identical to the two-launch form."""
+    n1, n2 = 200, 64
+    n = n1 * n2
+    rng = np.random.default_rng(8)
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    y = rng.standard_normal(n)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MCLCAR_SWEEP_FUSED", mode)
+        d = api.make_data(y, X=X, torus=(n1, n2), seed=11)
+        sd = api.mcl_prep_dCAR([0.2, 0.9, 0.1, 0.4], 160, d, {"n.chains": 80, "burn": 2, "thin": 3, "dtype": "f64"})
+        out[mode] = sd.simY
+    np.testing.assert_array_equal(out["1"], out["0"])
 
 
 @pytest.mark.parametrize("omega", [0.0, 1.0])
