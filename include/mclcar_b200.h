@@ -213,6 +213,15 @@ MCLCAR_API int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double*
 MCLCAR_API int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
                     double* hess);
 
+/* get.beta.glm(beta0, rho.sig, mcdata, family) (R/mcl.glm.R:50-54 -> get.beta.bin, R/mcl.bin.R:83-95)
+ * and the beta solve of mcl.profile.glm (R/mcl.bin.R:111-123): root of the beta block of
+ * mcl.grad.glm at fixed (rho, sigma) by Newton steps on a batched forward-difference Jacobian
+ * (nleqslv restated: stop when max|g| <= ftol or after maxit steps; the reference uses ftol = 1,
+ * maxit = 2 / 3).  beta_out, fvec_out: p doubles (nleqslv's $x, $fvec); termcd as nleqslv's. */
+MCLCAR_API int mclcar_glm_get_beta(mclcar_ctx* ctx, mclcar_samples* s, const double* rho_sig, const double* beta0,
+                        int maxit, double ftol, double* beta_out, double* fvec_out, int* iters_out,
+                        int* termcd_out);
+
 /* ---- hierarchical CAR, Gaussian response (R/HCAR.sim.R, R/mcl.HCAR.R) ---------------------
  * y = X beta + Z u + e, e ~ N(0, sigma.e (I - rho W)^-1), u ~ N(0, sigma.u (I - lambda M)^-1).
  * The context's graph is the individual-level W (upload an empty CSR graph and pass has_W = 0

@@ -254,6 +254,41 @@ def mcl_dCAR(pars, data: CarData, simdata: SimData, rho_cons=(-0.249, 0.249), Ev
     return r if Evar else float(r[0])
 
 
+def _centre_subsets(std_order, n_samples: int, n0: int, rng, subsets):
+    """Sample subsets of the centre points (std.order > 4): `sample(n.samples, floor(n.samples/n0))`
+    per centre row (R/rsmSub.R:81,175).  R's RNG stream is not reproducible here: indices come
+    from `rng` (numpy Generator) unless the caller supplies `subsets`."""
+    if subsets is not None:
+        return subsets
+    nb = n_samples // int(n0)
+    rng = rng if rng is not None else np.random.default_rng()
+    return [rng.choice(n_samples, nb, replace=False) if so > 4 else None for so in std_order]
+
+
+def Exp_dCAR(exp_design, data: CarData, psi, n0: int, mc_data: SimData, rng=None, subsets=None) -> np.ndarray:
+    """Exp.dCAR(exp.design, data, psi, n0, mc.data), R/rsmSub.R:65-97, as ONE batched device call
+    instead of a loop of mcl.dCAR calls.  `exp_design`: rows (rho, sigma, std.order), decoded.
+    Returns the design's mc.lr and mc.var columns, shape (rows, 2)."""
+    if mc_data is None:
+        raise ValueError("Please provide the Monte Carlo samples by specifying mc.data!")
+    D = np.atleast_2d(np.asarray(exp_design, dtype=np.float64))
+    beta0 = np.asarray(psi, dtype=np.float64)[2:]
+    psis = np.column_stack([D[:, :2], np.tile(beta0, (D.shape[0], 1))])
+    subs = _centre_subsets(D[:, 2], mc_data.n_samples, n0, rng, subsets)
+    return mcl_dCAR_batch(psis, data, mc_data, rho_cons=None, subsets=subs, Evar=True)
+
+
+def ExpPath_dCAR(exp_design, data: CarData, psi, mc_data: SimData) -> np.ndarray:
+    """ExpPath.dCAR, R/rsmSub.R:102-115.  The reference writes `rho.cons = NULL` inside `c(...)`
+    (:110), so mcl.dCAR's default guard (-0.249, 0.249) stays active: kept."""
+    if mc_data is None:
+        raise ValueError("Please provide the Monte Carlo samples by specifying mc.data!")
+    D = np.atleast_2d(np.asarray(exp_design, dtype=np.float64))
+    beta0 = np.asarray(psi, dtype=np.float64)[2:]
+    psis = np.column_stack([D[:, :2], np.tile(beta0, (D.shape[0], 1))])
+    return mcl_dCAR_batch(psis, data, mc_data, rho_cons=(-0.249, 0.249), Evar=True)
+
+
 def sigmabeta(rho, data: CarData) -> np.ndarray:
     """sigmabeta(rho, data), R/loglik.dCAR.R:72-86: GLS (sigma, beta) given rho, from the p x p
     design constants (the reference forms dense n x n products)."""
@@ -499,6 +534,78 @@ def mcl_Hessian_glm(pars, mcdata: McData, family: Optional[str] = None, shift=L.
     ctx = mcdata.data.ctx
     check(lib.mclcar_glm_hess(ctx.h, mcdata.h, dptr(pars), 1, P, shift, dptr(H)), ctx.h)
     return H
+
+
+def Exp_CAR_glm(exp_design, mcdata: McData, family: Optional[str], psi, n0: int, rng=None, subsets=None) -> np.ndarray:
+    """Exp.CAR.glm(exp.design, data, family, psi, n0, mc.data), R/rsmSub.R:159-192, as ONE batched
+    device call.  `exp_design`: rows (rho, sigma, std.order), decoded.  Variance clamp as
+    R/rsmSub.R:183,188.  Returns the columns (mc.lr, mc.var)."""
+    if mcdata is None:
+        raise ValueError("Please provide the Monte Carlo samples by specifying mc.data!")
+    D = np.atleast_2d(np.asarray(exp_design, dtype=np.float64))
+    beta0 = np.asarray(psi, dtype=np.float64)[2:]
+    psis = np.column_stack([D[:, :2], np.tile(beta0, (D.shape[0], 1))])
+    subs = _centre_subsets(D[:, 2], mcdata.n_samples, n0, rng, subsets)
+    return mcl_glm_batch(psis, mcdata, family, subsets=subs, Evar=True, clamp=True)
+
+
+def ExpPath_CAR_glm(exp_design, mcdata: McData, family: Optional[str], psi) -> np.ndarray:
+    """ExpPath.CAR.glm, R/rsmSub.R:197-212.  The reference's clamp reads the single element
+    mc.res[2] (:210): every row gets the clamped variance of the FIRST path point -- kept."""
+    if mcdata is None:
+        raise ValueError("Please provide the Monte Carlo samples by specifying mc.data!")
+    D = np.atleast_2d(np.asarray(exp_design, dtype=np.float64))
+    beta0 = np.asarray(psi, dtype=np.float64)[2:]
+    psis = np.column_stack([D[:, :2], np.tile(beta0, (D.shape[0], 1))])
+    r = mcl_glm_batch(psis, mcdata, family, Evar=True)
+    v = 1e-8 if r[0, 1] == 0 else min(1e8, r[0, 1])
+    return np.column_stack([r[:, 0], np.full(D.shape[0], v)])
+
+
+def get_beta_glm(beta0, rho_sig, mcdata: McData, family: Optional[str] = None, maxit: int = 2, ftol: float = 1.0) -> dict:
+    """get.beta.glm(beta0, rho.sig, mcdata, family), R/mcl.glm.R:50-54 -> get.beta.bin
+    (R/mcl.bin.R:83-95): nleqslv(beta0, grad.beta, method="Newton", control=list(ftol=1, maxit=2)).
+    Returns nleqslv's list fields x, fvec, termcd, iter."""
+    beta0 = np.ascontiguousarray(beta0, dtype=np.float64)
+    rs = np.ascontiguousarray(rho_sig, dtype=np.float64)
+    p = beta0.size
+    x, fvec = np.empty(p), np.empty(p)
+    it, tc = C.c_int(), C.c_int()
+    ctx = mcdata.data.ctx
+    check(lib.mclcar_glm_get_beta(ctx.h, mcdata.h, dptr(rs), dptr(beta0), int(maxit), float(ftol), dptr(x), dptr(fvec),
+                                  C.byref(it), C.byref(tc)), ctx.h)
+    return {"x": x, "fvec": fvec, "termcd": tc.value, "iter": it.value}
+
+
+def mcl_profile_glm(pars, beta0, mcdata: McData, family: Optional[str] = None, Evar=False) -> np.ndarray:
+    """mcl.profile.glm(pars, beta0, mcdata, family, Evar), R/mcl.glm.R:57-61 -> mcl.bin.profile
+    (R/mcl.bin.R:99-156): beta by nleqslv(..., control=list(ftol=1, maxit=3)), then the ratio at
+    (rho, sigma, beta): c(mc.lr, [v.lr,] beta, grad.beta)."""
+    pars = np.asarray(pars, dtype=np.float64)
+    sol = get_beta_glm(beta0, pars[:2], mcdata, family, maxit=3, ftol=1.0)
+    r = mcl_glm(np.concatenate([pars[:2], sol["x"]]), mcdata, family, Evar=True)
+    head = r if Evar else r[:1]
+    return np.concatenate([head, sol["x"], sol["fvec"]])
+
+
+def postZ(data: CarData, family: str, psi, Z_start=None, mcmc_control: Optional[dict] = None) -> dict:
+    """postZ(data, family, psi, Z.start, mcmc.control), R/postZ.R:2-14: latent fields z | y at psi.
+    The reference runs ONE Metropolis chain over the whole field (MALA / random walk variants,
+    R/postZsub.R) and keeps (N.Zy - burns)/thin states; here the batched Metropolis-within-Gibbs
+    sampler draws the same number of states from many parallel chains.  `method`, `Scale`,
+    `scale.fixed` and `c.ad` are accepted and have no effect (there is no proposal scale to tune),
+    `Z.start` likewise (chains start at zero and burn in).  Returns list(Z, AC.r) like the
+    fixed-scale branches (R/postZsub.R:489-490): Z is N x n (row = sample), AC.r the mean
+    acceptance rate."""
+    con = dict(mcmc_control or {})
+    ctl = {"N.Zy": con.pop("N.Zy", 10_000), "thin.ref": con.pop("thin", 5), "burns": con.pop("burns", 5_000)}
+    if (int(ctl["N.Zy"]) - int(ctl["burns"])) // int(ctl["thin.ref"]) < 1:
+        raise ValueError("mcmc.control leaves no samples: (N.Zy - burns) / thin < 1")
+    if "gpu.thin" in con:
+        ctl["thin"] = con.pop("gpu.thin")
+    ctl.update(con)     # method / Scale / scale.fixed / c.ad (ignored) and the GPU keys n.chains, burn, dtype
+    md = mcl_prep_glm(data, family, psi, ctl)
+    return {"Z": md.Zy, "AC.r": md.mcmc_pars["accept"], "mcdata": md}
 
 
 def vmle_glm(MLE: dict, mcdata: McData, family: Optional[str] = None) -> np.ndarray:

@@ -517,6 +517,95 @@ int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
     return glm_run(ctx, s, psi, K, P, WHAT_HESS, 0, nullptr, nullptr, shift_mode, hess, nullptr);
 }
 
+/* get.beta.glm (R/mcl.bin.R:83-95, R/mcl.glm.R:50-54) and the beta solve inside mcl.*.profile
+ * (R/mcl.bin.R:111-123): root of the beta block of mcl.grad.glm at fixed (rho, sigma), with the
+ * reference's penalty (sign(g) 1e5 once any |beta - beta0| > 2).  The reference hands the function
+ * to nleqslv (CRAN, version unpinned, not vendored) with ftol = 1 and maxit = 2 or 3.  Restated
+ * here: Newton iterations on a forward-difference Jacobian (step sqrt(eps) max(|beta_j|, 1)), stop as
+ * soon as max|g| <= ftol, step halving (<= 4) when |g|^2 does not decrease.  The p + 1 gradient
+ * evaluations of one Jacobian go through ONE batched mclcar_glm_grad call: the candidate betas
+ * share the passes over the sample matrix. */
+int mclcar_glm_get_beta(mclcar_ctx* ctx, mclcar_samples* s, const double* rho_sig, const double* beta0, int maxit,
+                        double ftol, double* beta_out, double* fvec_out, int* iters_out, int* termcd_out) {
+    if (!ctx || !s || !rho_sig || !beta0 || !beta_out) return MCLCAR_EINVAL;
+    const int p = ctx->p, P = 2 + p;
+    MCL_TRY(glm_check(ctx, s, P));
+    if (maxit < 0) return fail(ctx, MCLCAR_EINVAL, "maxit must be >= 0");
+    std::vector<double> x(beta0, beta0 + p), f(p), psi((size_t)(p + 1) * P), g((size_t)(p + 1) * P), J((size_t)p * p), dx(p);
+    // the reference's grad.beta closure for a batch of betas (rows of B): F rows of length p
+    auto F = [&](const double* B, int nb, double* out) -> int {
+        for (int k = 0; k < nb; ++k) {
+            psi[(size_t)k * P] = rho_sig[0];
+            psi[(size_t)k * P + 1] = rho_sig[1];
+            for (int a = 0; a < p; ++a) psi[(size_t)k * P + 2 + a] = B[(size_t)k * p + a];
+        }
+        MCL_TRY(glm_run(ctx, s, psi.data(), nb, P, WHAT_GRAD, 0, nullptr, nullptr, MCLCAR_SHIFT_MEAN, g.data(), nullptr));
+        for (int k = 0; k < nb; ++k) {
+            bool far = false;
+            for (int a = 0; a < p; ++a) far = far || std::fabs(beta0[a] - B[(size_t)k * p + a]) > 2.0;
+            for (int a = 0; a < p; ++a) {
+                const double v = g[(size_t)k * P + 2 + a];
+                out[(size_t)k * p + a] = far ? ((v > 0) - (v < 0)) * 1e5 : v;
+            }
+        }
+        return MCLCAR_OK;
+    };
+    auto maxabs = [&](const std::vector<double>& v) { double m = 0; for (double t : v) m = std::max(m, std::fabs(t)); return m; };
+    auto sumsq = [&](const std::vector<double>& v) { double m = 0; for (double t : v) m += t * t; return m; };
+    MCL_TRY(F(x.data(), 1, f.data()));
+    int it = 0, termcd = 4;   // nleqslv codes: 1 = function criterion met, 4 = iteration limit, 3 = no better point
+    std::vector<double> B((size_t)(p + 1) * p), Fb((size_t)(p + 1) * p), xn(p), fn(p);
+    while (true) {
+        if (maxabs(f) <= ftol) { termcd = 1; break; }
+        if (it >= maxit) { termcd = 4; break; }
+        // forward-difference Jacobian: one batched gradient call for x + h_j e_j, j = 1..p
+        std::vector<double> h(p);
+        for (int j = 0; j < p; ++j) {
+            h[j] = std::sqrt(2.220446049250313e-16) * std::max(std::fabs(x[j]), 1.0);
+            for (int a = 0; a < p; ++a) B[(size_t)j * p + a] = x[a] + (a == j ? h[j] : 0.0);
+        }
+        MCL_TRY(F(B.data(), p, Fb.data()));
+        for (int j = 0; j < p; ++j)
+            for (int a = 0; a < p; ++a) J[(size_t)a * p + j] = (Fb[(size_t)j * p + a] - f[a]) / h[j];
+        // solve J dx = -f (Gaussian elimination with partial pivoting; p <= MCLCAR_MAX_COV)
+        std::vector<double> A(J);
+        for (int a = 0; a < p; ++a) dx[a] = -f[a];
+        bool singular = false;
+        for (int c = 0; c < p && !singular; ++c) {
+            int piv = c;
+            for (int r = c + 1; r < p; ++r) if (std::fabs(A[(size_t)r * p + c]) > std::fabs(A[(size_t)piv * p + c])) piv = r;
+            if (!(std::fabs(A[(size_t)piv * p + c]) > 0)) { singular = true; break; }
+            if (piv != c) { for (int k = 0; k < p; ++k) std::swap(A[(size_t)c * p + k], A[(size_t)piv * p + k]); std::swap(dx[c], dx[piv]); }
+            for (int r = c + 1; r < p; ++r) {
+                const double m = A[(size_t)r * p + c] / A[(size_t)c * p + c];
+                for (int k = c; k < p; ++k) A[(size_t)r * p + k] -= m * A[(size_t)c * p + k];
+                dx[r] -= m * dx[c];
+            }
+        }
+        if (singular) { termcd = 6; break; }   // nleqslv: Jacobian singular
+        for (int c = p - 1; c >= 0; --c) {
+            for (int k = c + 1; k < p; ++k) dx[c] -= A[(size_t)c * p + k] * dx[k];
+            dx[c] /= A[(size_t)c * p + c];
+        }
+        const double f0 = sumsq(f);
+        double t = 1.0;
+        bool ok = false;
+        for (int half = 0; half <= 4; ++half, t *= 0.5) {
+            for (int a = 0; a < p; ++a) xn[a] = x[a] + t * dx[a];
+            MCL_TRY(F(xn.data(), 1, fn.data()));
+            if (sumsq(fn) < f0) { ok = true; break; }
+        }
+        ++it;
+        if (!ok) { termcd = 3; break; }
+        x = xn; f = fn;
+    }
+    for (int a = 0; a < p; ++a) beta_out[a] = x[a];
+    if (fvec_out) for (int a = 0; a < p; ++a) fvec_out[a] = f[a];
+    if (iters_out) *iters_out = it;
+    if (termcd_out) *termcd_out = termcd;
+    return MCLCAR_OK;
+}
+
 /* mcl.prep.glm(data, family, psi, ...) with postZ, R/mcl.glm.R:5-40: draws N latent fields
  * z | y at psi0 with the batched Metropolis-within-Gibbs sampler and attaches psi0. */
 int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,

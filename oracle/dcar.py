@@ -235,6 +235,35 @@ def eval_batch_dCAR(psis, data, simdata, rho_cons=None, subsets=None) -> np.ndar
     return out
 
 
+def Exp_dCAR(design, data, psi, n0, simdata, subsets) -> np.ndarray:
+    """``Exp.dCAR`` (R/rsmSub.R:65-97).  ``design``: rows (rho, sigma, std.order)
+    already decoded; rows with std.order > 4 (centre points) use the 0-based
+    sample subset ``subsets[k]`` (``sample(n.samples, floor(n.samples / n0))``,
+    :81); beta is held at ``psi[-c(1,2)]``; ``rho.cons = NULL`` (:86,91).  Returns
+    the columns (mc.lr, mc.var)."""
+    design = np.asarray(design, dtype=np.float64)
+    beta0 = np.asarray(psi, dtype=np.float64)[2:]
+    out = np.zeros((design.shape[0], 2))
+    for k, row in enumerate(design):
+        pars = np.concatenate([row[:2], beta0])
+        sd = simdata
+        if row[2] > 4:
+            idx = np.asarray(subsets[k])
+            sd = {"simY": simdata["simY"][:, idx], "t10": simdata["t10"], "t20": np.asarray(simdata["t20"])[idx]}
+        out[k] = mcl_dCAR(pars, data, sd, rho_cons=None, Evar=True)
+    return out
+
+
+def ExpPath_dCAR(design, data, psi, simdata) -> np.ndarray:
+    """``ExpPath.dCAR`` (R/rsmSub.R:102-115).  Quirk kept: ``rho.cons = NULL`` is
+    written INSIDE ``c(x, psi[-c(1,2)], rho.cons = NULL)`` (:110), where it
+    vanishes, so ``mcl.dCAR`` runs with its default guard (-0.249, 0.249) and
+    path points outside it return the sentinels (-1e8, 1e8)."""
+    design = np.asarray(design, dtype=np.float64)
+    beta0 = np.asarray(psi, dtype=np.float64)[2:]
+    return np.array([mcl_dCAR(np.concatenate([row[:2], beta0]), data, simdata, Evar=True) for row in design])
+
+
 # --------------------------------------------------------------------------
 # exact likelihood (known answers), R/loglik.dCAR.R
 # --------------------------------------------------------------------------

@@ -190,6 +190,110 @@ def vmle_glm(MLE, mcdata, family, ew=None) -> np.ndarray:
     return Binv @ A @ Binv
 
 
+def get_beta_glm(beta0, rho_sig, mcdata, family, ew=None, maxit=2, ftol=1.0) -> dict:
+    """``get.beta.bin`` / ``.pois`` (R/mcl.bin.R:83-95): root of the beta block of
+    ``mcl.grad.*`` at fixed (rho, sigma), penalised by sign(g) 1e5 once any
+    abs(beta0 - beta) > 2.  The reference calls ``nleqslv`` (CRAN, version
+    unpinned, not under /root/reference) with ``ftol = 1, maxit = 2``; its
+    published algorithm is restated as: Newton steps on a forward-difference
+    Jacobian (step sqrt(eps) max(abs(beta_j), 1)), stop once max abs(g) <= ftol
+    (termcd 1) or after ``maxit`` steps (termcd 4), halving the step (<= 4 times)
+    while the sum of squares does not decrease (termcd 3 if it never does)."""
+    beta0 = np.asarray(beta0, dtype=np.float64)
+    p = beta0.size
+    if ew is None:
+        ew = np.linalg.eigvalsh(_dense(mcdata["W"]))
+
+    def F(beta):
+        g = mcl_grad_glm(np.concatenate([np.asarray(rho_sig, dtype=np.float64), beta]), mcdata, family, ew=ew)[2:]
+        if np.any(np.abs(beta0 - beta) > 2):
+            return np.sign(g) * 1e5
+        return g
+
+    x = beta0.copy()
+    f = F(x)
+    it, termcd = 0, 4
+    while True:
+        if np.max(np.abs(f)) <= ftol:
+            termcd = 1
+            break
+        if it >= maxit:
+            termcd = 4
+            break
+        J = np.zeros((p, p))
+        for j in range(p):
+            h = np.sqrt(np.finfo(np.float64).eps) * max(abs(x[j]), 1.0)
+            xj = x.copy()
+            xj[j] += h
+            J[:, j] = (F(xj) - f) / h
+        try:
+            dx = np.linalg.solve(J, -f)
+        except np.linalg.LinAlgError:
+            termcd = 6
+            break
+        f0 = float(f @ f)
+        t, ok = 1.0, False
+        for _ in range(5):
+            xn = x + t * dx
+            fn = F(xn)
+            if float(fn @ fn) < f0:
+                ok = True
+                break
+            t *= 0.5
+        it += 1
+        if not ok:
+            termcd = 3
+            break
+        x, f = xn, fn
+    return {"x": x, "fvec": f, "termcd": termcd, "iter": it}
+
+
+def mcl_profile_glm(pars, beta0, mcdata, family, Evar=False, ew=None) -> np.ndarray:
+    """``mcl.bin.profile`` / ``mcl.pois.profile`` (R/mcl.bin.R:99-156): beta from
+    the solve above with ``maxit = 3``, then the ratio at (rho, sigma, beta):
+    ``c(mc.lr, [v.lr,] beta, grad.beta)``."""
+    sol = get_beta_glm(beta0, pars[:2], mcdata, family, ew=ew, maxit=3, ftol=1.0)
+    th = np.concatenate([np.asarray(pars[:2], dtype=np.float64), sol["x"]])
+    r = mcl_glm(th, mcdata, family, Evar=True)
+    head = r if Evar else r[:1]
+    return np.concatenate([head, sol["x"], sol["fvec"]])
+
+
+def Exp_CAR_glm(design, mcdata, family, psi, n0, subsets) -> np.ndarray:
+    """``Exp.CAR.glm`` (R/rsmSub.R:159-192).  ``design``: rows (rho, sigma,
+    std.order) already decoded; rows with std.order > 4 (centre points) use the
+    0-based sample subset ``subsets[k]`` (the reference draws
+    ``sample(n.samples, floor(n.samples / n0))``, :175); beta is held at
+    ``psi[-c(1,2)]``; variance 0 -> 1e-8, capped at 1e8 (:183,188).  Returns the
+    columns (mc.lr, mc.var)."""
+    design = np.asarray(design, dtype=np.float64)
+    beta0 = np.asarray(psi, dtype=np.float64)[2:]
+    out = np.zeros((design.shape[0], 2))
+    for k, row in enumerate(design):
+        pars = np.concatenate([row[:2], beta0])
+        md = mcdata
+        if row[2] > 4:
+            idx = np.asarray(subsets[k])
+            md = dict(mcdata)
+            md["Zy"] = mcdata["Zy"][idx]
+            md["lHZy.psi"] = np.asarray(mcdata["lHZy.psi"])[idx]
+        res = mcl_glm(pars, md, family, Evar=True)
+        out[k] = (res[0], 1e-8 if res[1] == 0 else min(1e8, res[1]))
+    return out
+
+
+def ExpPath_CAR_glm(design, mcdata, family, psi) -> np.ndarray:
+    """``ExpPath.CAR.glm`` (R/rsmSub.R:197-212): all samples at every path point.
+    Quirk kept: the clamp ``ifelse(mc.res[2]==0, 1e-8, min(1e8, mc.res[2]))``
+    (:210) reads the single element ``mc.res[2]`` -- the variance of the FIRST
+    point -- so every row receives that one clamped value."""
+    design = np.asarray(design, dtype=np.float64)
+    beta0 = np.asarray(psi, dtype=np.float64)[2:]
+    res = np.array([mcl_glm(np.concatenate([row[:2], beta0]), mcdata, family, Evar=True) for row in design])
+    v = 1e-8 if res[0, 1] == 0 else min(1e8, res[0, 1])
+    return np.column_stack([res[:, 0], np.full(design.shape[0], v)])
+
+
 def eval_batch_glm(psis, mcdata, family, subsets=None, clamp=True) -> np.ndarray:
     """``Exp.CAR.glm`` call pattern (R/rsmSub.R:159-192): rows (mc.lr, mc.var),
     variance clamped to [1e-8 if exactly 0, <= 1e8]."""

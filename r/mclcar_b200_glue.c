@@ -187,13 +187,22 @@ SEXP C_mclb_samples_glm(SEXP ctx, SEXP Zy, SEXP family, SEXP psi, SEXP lHZy) { /
     if (st != MCLCAR_OK) { mclcar_samples_free(s); Rf_error("%s", mclcar_last_error(c)); }
     return wrap_samples(s);
 }
-SEXP C_mclb_mcl_glm(SEXP ctx, SEXP samples, SEXP pars) { /* pars: K x P -> K x 2 */
+/* pars: K x P -> K x 2; sub_idx / sub_ptr (doubles, 0-based, or NULL): sample subsets of the centre
+ * points of Exp.CAR.glm [R/rsmSub.R:175-181] */
+SEXP C_mclb_mcl_glm(SEXP ctx, SEXP samples, SEXP pars, SEXP sub_idx, SEXP sub_ptr) {
     mclcar_ctx* c = ctx_of(ctx);
     int K = Rf_nrows(pars), P = Rf_ncols(pars);
     double* psi = (double*)R_alloc((size_t)K * P, sizeof(double));
     for (int k = 0; k < K; ++k) for (int j = 0; j < P; ++j) psi[k * P + j] = REAL(pars)[k + (size_t)j * K];
+    int64_t *idx = NULL, *ptr = NULL;
+    if (!Rf_isNull(sub_ptr)) {
+        ptr = (int64_t*)R_alloc((size_t)K + 1, sizeof(int64_t));
+        for (int k = 0; k <= K; ++k) ptr[k] = (int64_t)REAL(sub_ptr)[k];
+        idx = (int64_t*)R_alloc((size_t)LENGTH(sub_idx) + 1, sizeof(int64_t));
+        for (R_xlen_t t = 0; t < XLENGTH(sub_idx); ++t) idx[t] = (int64_t)REAL(sub_idx)[t];
+    }
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, K, 2));
-    int st = mclcar_glm_eval(c, samples_of(samples), psi, K, P, NULL, NULL, MCLCAR_SHIFT_MEAN, REAL(out), REAL(out) + K);
+    int st = mclcar_glm_eval(c, samples_of(samples), psi, K, P, idx, ptr, MCLCAR_SHIFT_MEAN, REAL(out), REAL(out) + K);
     UNPROTECT(1);
     if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
     return out;
@@ -219,6 +228,24 @@ SEXP C_mclb_hess_glm(SEXP ctx, SEXP samples, SEXP pars) {
     UNPROTECT(1);
     if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
     return H;
+}
+
+/* get.beta.glm / the beta solve of mcl.profile.glm [R/mcl.bin.R:83-95, 111-123] -> list(x, fvec, termcd, iter) */
+SEXP C_mclb_get_beta_glm(SEXP ctx, SEXP samples, SEXP rho_sig, SEXP beta0, SEXP maxit, SEXP ftol) {
+    mclcar_ctx* c = ctx_of(ctx);
+    int p = LENGTH(beta0), it = 0, tc = 0;
+    SEXP x = PROTECT(Rf_allocVector(REALSXP, p));
+    SEXP f = PROTECT(Rf_allocVector(REALSXP, p));
+    int st = mclcar_glm_get_beta(c, samples_of(samples), REAL(rho_sig), REAL(beta0), Rf_asInteger(maxit), Rf_asReal(ftol),
+                                 REAL(x), REAL(f), &it, &tc);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+    SET_VECTOR_ELT(out, 0, x);
+    SET_VECTOR_ELT(out, 1, f);
+    SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(tc));
+    SET_VECTOR_ELT(out, 3, Rf_ScalarInteger(it));
+    UNPROTECT(3);
+    if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
+    return out;
 }
 
 /* HCAR: sim.HCAR / mcl.HCAR / mcl.grad.HCAR / mcl.Hessian.HCAR  [R/HCAR.sim.R, R/mcl.HCAR.R] */

@@ -60,6 +60,16 @@ Exp.dCAR <- function(exp.design, data, psi, n0, mc.data) {
     exp.design
 }
 
+ExpPath.dCAR <- function(exp.design, data, psi, mc.data) {              # R/rsmSub.R:102-115
+    if (is.null(mc.data)) stop("Please provide the Monte Carlo samples by specifying mc.data!")
+    K <- nrow(exp.design)
+    pars <- cbind(exp.design$rho, exp.design$sigma, matrix(as.numeric(psi[-c(1, 2)]), K, length(psi) - 2, byrow = TRUE))
+    ## the reference's `rho.cons = NULL` sits inside c(...) (:110) and is lost: the default guard applies
+    r <- .Call(C_mclb_mcl_dcar, attr(mc.data, "ctx"), mc.data$simY, pars, c(-0.249, 0.249), NULL, NULL)
+    exp.design$mc.lr <- r[, 1]; exp.design$mc.var <- r[, 2]
+    exp.design
+}
+
 mcl.prep.glm <- function(data, family, psi, Z.start = NULL, mcmc.control = list(), pilot.run = TRUE,
                          pilot.plot = FALSE, plot.diag = FALSE) {       # R/mcl.glm.R:5-40
     con <- list(N.Zy = 1e4, thin = 5, burns = 5e3); con[names(mcmc.control)] <- mcmc.control
@@ -70,8 +80,44 @@ mcl.prep.glm <- function(data, family, psi, Z.start = NULL, mcmc.control = list(
     structure(data, class = "mclb_mcdata", ctx = ctx)
 }
 mcl.glm <- function(pars, mcdata, family, Evar = FALSE) {               # R/mcl.glm.R:43-47
-    r <- .Call(C_mclb_mcl_glm, attr(mcdata, "ctx"), mcdata$Zy, matrix(as.numeric(pars), nrow = 1))
+    r <- .Call(C_mclb_mcl_glm, attr(mcdata, "ctx"), mcdata$Zy, matrix(as.numeric(pars), nrow = 1), NULL, NULL)
     if (Evar) as.numeric(r) else r[1, 1]
+}
+postZ <- function(data, family, psi, Z.start, mcmc.control = list(), plots = FALSE) {    # R/postZ.R:2-14
+    md <- mcl.prep.glm(data, family, psi, Z.start, mcmc.control, pilot.run = FALSE)
+    N <- (md$mcmc.pars$N.Zy - md$mcmc.pars$burns) %/% md$mcmc.pars$thin
+    list(Z = .Call(C_mclb_fetch, attr(md, "ctx"), md$Zy, N, 2L), AC.r = attr(md$Zy, "accept"))
+}
+get.beta.glm <- function(beta0, rho.sig, mcdata, family) {              # R/mcl.glm.R:50-54, R/mcl.bin.R:83-95
+    r <- .Call(C_mclb_get_beta_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(rho.sig), as.numeric(beta0), 2L, 1)
+    list(x = r[[1]], fvec = r[[2]], termcd = r[[3]], iter = r[[4]])
+}
+mcl.profile.glm <- function(pars, beta0, mcdata, family, Evar = FALSE) {   # R/mcl.glm.R:57-61, R/mcl.bin.R:99-156
+    r <- .Call(C_mclb_get_beta_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(pars[1:2]), as.numeric(beta0), 3L, 1)
+    lr <- mcl.glm(c(pars[1:2], r[[1]]), mcdata, family, Evar = TRUE)
+    c(if (Evar) lr else lr[1], r[[1]], r[[2]])
+}
+## batched design-point evaluation replacing the loops of Exp.CAR.glm / ExpPath.CAR.glm (R/rsmSub.R:159-212)
+Exp.CAR.glm <- function(exp.design, data, family, psi, n0, mc.data) {
+    if (is.null(mc.data)) stop("Please provide the Monte Carlo samples by specifying mc.data!")
+    n.samples <- (mc.data$mcmc.pars$N.Zy - mc.data$mcmc.pars$burns) %/% mc.data$mcmc.pars$thin
+    nb.sim <- floor(n.samples / n0)
+    dd <- rsm::decode.data(exp.design); K <- nrow(exp.design)
+    pars <- cbind(dd$rho, dd$sigma, matrix(as.numeric(psi[-c(1, 2)]), K, length(psi) - 2, byrow = TRUE))
+    subs <- lapply(seq_len(K), function(k) if (exp.design$std.order[k] > 4) sample(n.samples, nb.sim) - 1 else numeric(0))
+    r <- .Call(C_mclb_mcl_glm, attr(mc.data, "ctx"), mc.data$Zy, pars, as.numeric(unlist(subs)), as.numeric(c(0, cumsum(lengths(subs)))))
+    exp.design$mc.lr <- r[, 1]
+    exp.design$mc.var <- ifelse(r[, 2] == 0, 1e-8, pmin(1e8, r[, 2]))    # per row, as R/rsmSub.R:183,188
+    exp.design
+}
+ExpPath.CAR.glm <- function(exp.design, data, family, psi, mc.data) {
+    if (is.null(mc.data)) stop("Please provide the Monte Carlo samples by specifying mc.data!")
+    K <- nrow(exp.design)
+    pars <- cbind(exp.design$rho, exp.design$sigma, matrix(as.numeric(psi[-c(1, 2)]), K, length(psi) - 2, byrow = TRUE))
+    r <- .Call(C_mclb_mcl_glm, attr(mc.data, "ctx"), mc.data$Zy, pars, NULL, NULL)
+    exp.design$mc.lr <- r[, 1]
+    exp.design$mc.var <- ifelse(r[1, 2] == 0, 1e-8, min(1e8, r[1, 2]))   # single element, as coded at R/rsmSub.R:210
+    exp.design
 }
 mcl.grad.glm <- function(pars, mcdata, family, Evar = FALSE) {          # R/mcl.glm.R:78-82
     r <- .Call(C_mclb_grad_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(pars), Evar)

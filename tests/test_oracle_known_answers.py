@@ -92,6 +92,55 @@ def test_glm_gradient_is_derivative_and_poisson_quirk_is_reproduced(family):
     assert D.shape == (300,) and gb.shape == (300, 2) and Hb.shape == (300, 2, 2)
 
 
+@pytest.mark.parametrize("family", ["binom", "poisson"])
+def test_get_beta_glm_finds_the_root_scipy_finds(family):
+    """The restated nleqslv step (oracle.glm.get_beta_glm) against an independent solver: with a
+    tight tolerance both end at the same root of the beta block of the MC gradient; with the
+    reference's own ftol = 1 it stops as soon as max|g| <= 1 (R/mcl.bin.R:94)."""
+    from scipy.optimize import root
+    rng = np.random.default_rng(3)
+    W = graphs.torus_W(5, 5)
+    ew = np.linalg.eigvalsh(W.toarray())
+    X = np.column_stack([np.ones(25), rng.standard_normal(25) * 0.5])
+    psi = np.array([0.15, 1.1, 0.4, -0.3])
+    data = glm.sim_glm_data(family, W, psi, X, 8, rng)
+    Zy = data["Z.true"][None, :] + 0.3 * rng.standard_normal((300, 25))
+    mc = glm.add_prep(psi, data, Zy, family)
+    beta0 = psi[2:] + 0.3
+    gb = lambda b: glm.mcl_grad_glm(np.concatenate([psi[:2], b]), mc, family, ew=ew)[2:]
+    tight = glm.get_beta_glm(beta0, psi[:2], mc, family, ew=ew, maxit=30, ftol=1e-9)
+    ref = root(gb, beta0, tol=1e-12)
+    if family == "binom":
+        assert tight["termcd"] == 1 and ref.success
+    if ref.success:    # (the Poisson weights of this small case degenerate: no root for either solver)
+        np.testing.assert_allclose(tight["x"], ref.x, rtol=1e-7, atol=1e-8)
+    else:
+        assert tight["termcd"] == 3 and np.linalg.norm(tight["fvec"]) <= np.linalg.norm(ref.fun) * 1.5
+    loose = glm.get_beta_glm(beta0, psi[:2], mc, family, ew=ew, maxit=2, ftol=1.0)
+    assert loose["iter"] <= 2 and (loose["termcd"] == 4 or np.max(np.abs(loose["fvec"])) <= 1.0)
+    np.testing.assert_allclose(loose["fvec"], gb(loose["x"]), rtol=1e-12)
+    # profile: c(mc.lr, v.lr, beta, grad.beta) evaluated at the solved beta
+    pr = glm.mcl_profile_glm(psi[:2], beta0, mc, family, Evar=True, ew=ew)
+    sol = glm.get_beta_glm(beta0, psi[:2], mc, family, ew=ew, maxit=3)
+    np.testing.assert_allclose(pr[2:4], sol["x"])
+    np.testing.assert_allclose(pr[:2], glm.mcl_glm(np.concatenate([psi[:2], sol["x"]]), mc, family, Evar=True))
+
+
+def test_exp_wrappers_equal_the_plain_batch_loops():
+    """Exp.dCAR / ExpPath.dCAR (R/rsmSub.R:65-115) are loops over mcl.dCAR: centre points on
+    subsets, path points under the default rho guard."""
+    odata, psi0, sd, rng = helpers.torus_case(8, 8, 200, seed=9)
+    design = np.array([[psi0[0] - 0.01, psi0[1] - 0.05, 1], [psi0[0] + 0.01, psi0[1] + 0.05, 4], [psi0[0], psi0[1], 5], [psi0[0], psi0[1], 6]])
+    subsets = [None, None, rng.choice(200, 50, replace=False), rng.choice(200, 50, replace=False)]
+    got = dcar.Exp_dCAR(design, odata, psi0, 4, sd, subsets)
+    psis = np.column_stack([design[:, :2], np.tile(psi0[2:], (4, 1))])
+    np.testing.assert_array_equal(got, dcar.eval_batch_dCAR(psis, odata, sd, rho_cons=None, subsets=subsets))
+    assert got[2, 0] != got[3, 0]          # different subsets, same psi
+    path = np.array([[psi0[0], psi0[1], 0], [0.2495, psi0[1], 0]])
+    pp = dcar.ExpPath_dCAR(path, odata, psi0, sd)
+    assert pp[1, 0] == -1e8 and pp[1, 1] == 1e8 and np.isfinite(pp[0]).all()
+
+
 @pytest.mark.parametrize("with_W", [True, False])
 def test_hcar_gradient_is_derivative(with_W):
     rng = np.random.default_rng(4)
