@@ -130,7 +130,7 @@ def test_exp_wrappers_equal_the_plain_batch_loops():
     """Exp.dCAR / ExpPath.dCAR (R/rsmSub.R:65-115) are loops over mcl.dCAR: centre points on
     subsets, path points under the default rho guard."""
     odata, psi0, sd, rng = helpers.torus_case(8, 8, 200, seed=9)
-    design = np.array([[psi0[0] - 0.01, psi0[1] - 0.05, 1], [psi0[0] + 0.01, psi0[1] + 0.05, 4], [psi0[0], psi0[1], 5], [psi0[0], psi0[1], 6]])
+    design = np.array([[psi0[0] - 0.01, psi0[1] - 0.05, 1], [psi0[0] + 0.01, psi0[1] + 0.05, 4], [psi0[0] * 1.02, psi0[1] * 1.01, 5], [psi0[0] * 1.02, psi0[1] * 1.01, 6]])
     subsets = [None, None, rng.choice(200, 50, replace=False), rng.choice(200, 50, replace=False)]
     got = dcar.Exp_dCAR(design, odata, psi0, 4, sd, subsets)
     psis = np.column_stack([design[:, :2], np.tile(psi0[2:], (4, 1))])
