@@ -197,13 +197,13 @@ def run_ours(args):
 
     data = api.make_data(y_pin.numpy(), X=X_pin.numpy(), torus=(N1, N2), ctx=ctx)
 
-    diag = {"sweeps": 0, "chains": 0}
+    diag = {"sweeps": 0, "chains": 0, "omega": 1.0, "thin": 0, "burn": 0}
 
     def step_resident():
         sd = api.mcl_prep_dCAR(PSI0, N_gpu, data, control)
         res = api.mcl_dCAR_batch(psis, data, sd, rho_cons=None)
         dg = api.sampler_diag(data, sd)
-        diag["sweeps"], diag["chains"] = dg["sweeps"], dg["chains"]
+        diag.update({k: dg[k] for k in ("sweeps", "chains", "omega", "thin", "burn")})
         sd.close()
         return res
 
@@ -309,7 +309,7 @@ def run_ours(args):
     sweep_ms = float(ms_cat[0])
     sweeps_step = int(diag["sweeps"])
     chains = int(diag["chains"])      # the library's own choice unless --chains is given
-    omega = args.omega if args.omega > 0 else 2.0 / (1.0 + np.sqrt(1.0 - (4 * PSI0[0]) ** 2))
+    omega = float(diag["omega"])      # the library's schedule (over-relaxation factor, thin, burn)
     # algorithmic bytes per site update: read the other colour + write own colour (fp32), plus the
     # read of the current value for the over-relaxed update
     updates_step = float(chains) * n * sweeps_step
@@ -339,7 +339,7 @@ def run_ours(args):
         "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(), "samples_per_gpu": N_gpu, "psi_points": K_PSI, "chains_per_gpu": chains,
-                   "sweeps_per_step": sweeps_step, "omega": omega, "sample_storage": "fp32 in HBM" if not args.stats_only else "statistics only",
+                   "sweeps_per_step": sweeps_step, "omega": omega, "thin": int(diag["thin"]), "burn": int(diag["burn"]), "sample_storage": "fp32 in HBM" if not args.stats_only else "statistics only",
                    "arithmetic": "fp32 chain state and normals; fp64 statistics, weights and reductions",
                    "l2": "inputs larger than L2 (chain state %.0f MB, sample matrix %.1f GB per GPU)" % (chains * n * 4 / 1e6, N_gpu * n * 4 / 1e9),
                    "parallelism": f"chains sharded over {world} GPU(s), one NCCL all-gather of partial tuples per psi batch"},

@@ -142,8 +142,10 @@ MCLCAR_API int64_t mclcar_samples_count(const mclcar_samples* s);
 MCLCAR_API int mclcar_samples_fetch(mclcar_ctx* ctx, mclcar_samples* s, int layout, double* out, int64_t ld);
 /* sampler diagnostics: mean acceptance rate (1 for pure Gibbs) and sweeps actually run */
 MCLCAR_API int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate, int64_t* sweeps);
-/* parallel chains the sampler ran for this sample set (0 when the matrix came from the caller) */
-MCLCAR_API int mclcar_samples_chains(mclcar_ctx* ctx, mclcar_samples* s, int64_t* chains);
+/* the schedule the sampler ran for this sample set: parallel chains, burn-in sweeps, sweeps per kept
+ * state, over-relaxation factor (all 0 when the matrix came from the caller); any pointer may be NULL */
+MCLCAR_API int mclcar_samples_schedule(mclcar_ctx* ctx, mclcar_samples* s, int64_t* chains, int* burn, int* thin,
+                            double* omega);
 
 /* ---- direct CAR (R/mcl.dCAR.R) --------------------------------------------------------- */
 /* per-sample sufficient statistics q_i = (Y'Y, Y'WY, X'Y[p], X'WY[p]) in one pass over the

@@ -79,7 +79,7 @@ SIGNATURES = {
     "mclcar_samples_count": (_i64, [_vp]),
     "mclcar_samples_fetch": (_i, [_vp, _vp, _i, _pd, _i64]),
     "mclcar_samples_diag": (_i, [_vp, _vp, _pd, _pi64]),
-    "mclcar_samples_chains": (_i, [_vp, _vp, _pi64]),
+    "mclcar_samples_schedule": (_i, [_vp, _vp, _pi64, _pi, _pi, _pd]),
     "mclcar_dcar_stats": (_i, [_vp, _vp, _pd]),
     "mclcar_dcar_prep": (_i, [_vp, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
     "mclcar_dcar_attach": (_i, [_vp, _vp, _pd, _i, _pd]),

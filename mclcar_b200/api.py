@@ -404,8 +404,9 @@ def sampler_diag(data: CarData, simdata) -> dict:
     sw = C.c_int64()
     ch = C.c_int64()
     check(lib.mclcar_samples_diag(data.ctx.h, simdata.h, C.byref(acc), C.byref(sw)), data.ctx.h)
-    check(lib.mclcar_samples_chains(data.ctx.h, simdata.h, C.byref(ch)), data.ctx.h)
-    return {"accept": acc.value, "sweeps": sw.value, "chains": ch.value}
+    bu, th, om = C.c_int(), C.c_int(), C.c_double()
+    check(lib.mclcar_samples_schedule(data.ctx.h, simdata.h, C.byref(ch), C.byref(bu), C.byref(th), C.byref(om)), data.ctx.h)
+    return {"accept": acc.value, "sweeps": sw.value, "chains": ch.value, "burn": bu.value, "thin": th.value, "omega": om.value}
 
 
 # ------------------------------------------------------------------------------------------

@@ -129,6 +129,8 @@ struct mclcar_samples {
     double accept = 1.0;
     int64_t sweeps = 0;
     int64_t chains = 0;   // parallel chains the sampler ran (0: matrix supplied by the caller)
+    int burn = 0, thin = 0;
+    double omega = 0.0;
 };
 
 namespace mclcar {

@@ -652,7 +652,7 @@ int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int6
         st = run_csr_sampler(ctx, g, family == MCLCAR_FAMILY_BINOM ? FAM_BINOM : FAM_POIS, 1.0, nullptr, ctx->y.data(),
                              ctx->ntrial.empty() ? nullptr : ctx->ntrial.data(), xb.data(), N, C, burn, thin, s->d_M,
                              o.dtype == MCLCAR_F64, s->ld, &s->accept, &s->sweeps);
-    s->chains = C;
+    s->chains = C; s->burn = burn; s->thin = thin; s->omega = 1.0;
     if (st == MCLCAR_OK) st = mclcar_glm_attach(ctx, s, family, psi0, P, nullptr);
     if (st != MCLCAR_OK) {
         std::string keep_err = ctx->err;

@@ -636,7 +636,7 @@ int mclcar_hcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, cons
     if (st == MCLCAR_OK)
         st = run_csr_sampler(ctx, g, FAM_GAUSS, omega, nullptr, nullptr, nullptr, nullptr, N, C, burn, thin, s->d_M,
                              o.dtype == MCLCAR_F64, s->ld, &s->accept, &s->sweeps);
-    s->chains = C;
+    s->chains = C; s->burn = burn; s->thin = thin; s->omega = omega;
     if (st == MCLCAR_OK) st = mclcar_hcar_attach(ctx, s, psi0, P, nullptr);
     if (st != MCLCAR_OK) {
         std::string keep_err = ctx->err;

@@ -33,7 +33,13 @@ int check_rho(mclcar_ctx* ctx, double rho) {
 // chromatic Gibbs (omega = 1) decorrelates at rate mu^2 per sweep; on a two-colourable graph
 // (consistently ordered) the over-relaxed sampler with omega* = 2/(1 + sqrt(1 - mu^2)) does so
 // at rate omega* - 1 (Young's SOR theory; Fox & Parker 2017 for samplers), with a linear
-// polynomial factor at omega* itself.  thin: autocorrelation <= 1 %; burn: start bias <= 1e-6.
+// polynomial factor at omega* itself (a Jordan block: k rate^k).  Slightly above omega* every
+// eigenvalue of the sweep operator has modulus exactly omega - 1 and the factor is gone; what
+// remains is the beat of the complex eigenvalue pair, measured on the torus at rho = 0.2 as a
+// prefactor of <= 2.7 on the autocorrelation of the two slowest modes (constant field and
+// checkerboard; scripts/acf_modes.py): lag 4 1.6 %, lag 5 0.3 % at omega* + 0.025 against 2.9 % and
+// 0.8 % at omega*.  Default omega* + 0.025, prefactor 3 in the rule.
+// thin: autocorrelation <= 1 %; burn: start bias <= 1e-6.
 void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* burn, int* thin) {
     double lam = 0;
     if (!ctx->eigs.empty()) lam = std::max(std::fabs(ctx->ew_min), std::fabs(ctx->ew_max));
@@ -45,7 +51,7 @@ void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* bur
         }
     const double mu = std::min(std::max(std::fabs(rho) * lam, 1e-2), 0.9998);
     const double w_opt = 2.0 / (1.0 + std::sqrt(1.0 - mu * mu));
-    if (!(*omega > 0)) *omega = ctx->ncolors == 2 ? w_opt : 1.0;
+    if (!(*omega > 0)) *omega = ctx->ncolors == 2 ? w_opt + 0.025 : 1.0;
     if (*omega < 1.0) *omega = 1.0;
     if (*omega > 1.98) *omega = 1.98;
     const double w = *omega;
@@ -61,7 +67,7 @@ void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* bur
     rate = std::min(std::max(rate, 1e-3), 0.9996);
     auto sweeps_for = [&](double tol, int lo, int hi) {
         for (int k = lo; k < hi; ++k)
-            if ((poly ? k : 1.0) * std::pow(rate, k) <= tol) return k;
+            if ((poly ? k : (w > 1.0 ? 3.0 : 1.0)) * std::pow(rate, k) <= tol) return k;
         return hi;
     };
     if (*thin <= 0) *thin = sweeps_for(0.01, 1, 4000);
@@ -212,6 +218,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         s->chains = C;
     }
     pool_free(ctx, d_mu);
+    s->burn = burn; s->thin = thin; s->omega = omega;
     if (st == MCLCAR_OK) st = mclcar_dcar_attach(ctx, s, psi0, P, nullptr);
     if (st == MCLCAR_OK && !o.keep && s->d_M) {  // statistics only on the generic path: compute, then drop the matrix
         st = dcar_ensure_stats(ctx, s);

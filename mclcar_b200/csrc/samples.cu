@@ -198,9 +198,12 @@ int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate,
     return MCLCAR_OK;
 }
 
-int mclcar_samples_chains(mclcar_ctx* ctx, mclcar_samples* s, int64_t* chains) {
-    if (!ctx || !s || !chains) return MCLCAR_EINVAL;
-    *chains = s->chains;
+int mclcar_samples_schedule(mclcar_ctx* ctx, mclcar_samples* s, int64_t* chains, int* burn, int* thin, double* omega) {
+    if (!ctx || !s) return MCLCAR_EINVAL;
+    if (chains) *chains = s->chains;
+    if (burn) *burn = s->burn;
+    if (thin) *thin = s->thin;
+    if (omega) *omega = s->omega;
     return MCLCAR_OK;
 }
 

@@ -1,0 +1,179 @@
+// Microbenchmark: where do the cycles of one torus site-update item (4 sites, one Philox block) go?
+// Stages are cumulative: A Philox4x32-10 only, B + scaled Box-Muller, C + neighbour sums and FMAs (registers),
+// D + shared-memory loads/stores of a resident tile.  Launch geometry of the fused sweep: 256 threads,
+// 3 CTAs per SM (72 KB dynamic shared memory each).  Prints cycles per warp-item per SM sub-partition.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../mclcar_b200/csrc update_parts.cu -o update_parts
+#include <cstdio>
+#include <cstdlib>
+#include "common.cuh"
+using namespace mclcar;
+
+template <int STAGE>
+__global__ void __launch_bounds__(256, 3) k(PhiloxKeys keys, int iters, float keep, float gain, float rad2, float* out, int h) {
+    extern __shared__ __align__(128) float sm[];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int rows = 34;   // 72 KB / 2000 B
+    if (STAGE >= 3) {
+        for (int i = threadIdx.x; i < rows * h; i += blockDim.x) sm[i] = 0.001f * (float)(i & 1023);
+        __syncthreads();
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t xacc = 0;
+    const uint32_t c2 = blockIdx.x, c3 = 0x70520000u;
+    float4 o = make_float4(0.1f * tx, 0.2f, 0.3f, 0.4f), up = o, d = o, cur = o;
+    float e = 0.5f;
+    for (int it = 0; it < iters; ++it) {
+        const int row = 1 + (ty + it) % (rows - 2);
+        const float* nm = sm + row * h;
+        for (int cv = tx; cv < (h >> 2); cv += 32) {
+            const int c0 = cv << 2;
+            const Philox4 r = philox4x32_10((uint32_t)(it * 4096 + cv), 7u, c2, c3, keys);
+            if (STAGE == 0) { xacc ^= r.x ^ r.y ^ r.z ^ r.w; continue; }
+            const float ra = sqrt_approx(rad2 * lg2_approx(u01(r.x)));
+            const float rb = sqrt_approx(rad2 * lg2_approx(u01(r.z)));
+            float sa, ca, sb, cb;
+            sincos_approx(6.2831853071795865f * u01(r.y), sa, ca);
+            sincos_approx(6.2831853071795865f * u01(r.w), sb, cb);
+            if (STAGE == 1) { acc.x += ra * ca; acc.y += ra * sa; acc.z += rb * cb; acc.w += rb * sb; continue; }
+            if (STAGE >= 3) {
+                o = *reinterpret_cast<const float4*>(nm + c0);
+                up = *reinterpret_cast<const float4*>(nm - h + c0);
+                d = *reinterpret_cast<const float4*>(nm + h + c0);
+                e = nm[c0 + 4 == h ? 0 : c0 + 4];
+                cur = *reinterpret_cast<const float4*>(sm + ((row + 5) % rows) * h + c0);
+            }
+            float4 s;
+            s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e;
+            s.x += up.x + d.x; s.y += up.y + d.y; s.z += up.z + d.z; s.w += up.w + d.w;
+            float4 v;
+            v.x = fmaf(gain, s.x, fmaf(ra, ca, keep * cur.x));
+            v.y = fmaf(gain, s.y, fmaf(ra, sa, keep * cur.y));
+            v.z = fmaf(gain, s.z, fmaf(rb, cb, keep * cur.z));
+            v.w = fmaf(gain, s.w, fmaf(rb, sb, keep * cur.w));
+            if (STAGE >= 3) {
+                *reinterpret_cast<float4*>(sm + ((row + 5) % rows) * h + c0) = v;
+            } else {
+                o = v; cur.x = v.y; cur.y = v.z; e = v.w;   // keep a dependency so nothing is hoisted
+            }
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f || xacc == 0x12345u) out[0] = acc.x + (float)xacc;
+}
+
+// T: the "triple" scheme -- 12 sites (three float4 vectors) from TWO Philox blocks: 24-bit radius + 16-bit angle
+// per Box-Muller pair (6 pairs from 256 bits... 240 used), shared-memory loads/stores as in D
+__device__ __forceinline__ void pair24_16(uint32_t wr, uint32_t ang16, float rad2, float& r, float& s, float& c) {
+    const float u = __uint_as_float(0x3f800000u | (wr >> 9)) - 0.99999994039535522461f;
+    r = sqrt_approx(rad2 * lg2_approx(u));
+    const float a = (float)ang16 * (6.2831853071795865f / 65536.0f);
+    sincos_approx(a, s, c);
+}
+__global__ void __launch_bounds__(256, 3) kT(PhiloxKeys keys, int iters, float keep, float gain, float rad2, float* out, int h) {
+    extern __shared__ __align__(128) float sm[];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int rows = 34;
+    for (int i = threadIdx.x; i < rows * h; i += blockDim.x) sm[i] = 0.001f * (float)(i & 1023);
+    __syncthreads();
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t c2 = blockIdx.x, c3 = 0x70520000u;
+    const int hv = h >> 2, nt = (hv + 2) / 3;
+    for (int it = 0; it < iters; ++it) {
+        const int row = 1 + (ty + it) % (rows - 2);
+        const float* nm = sm + row * h;
+        float* own = sm + ((row + 5) % rows) * h;
+        for (int t = tx; t < nt; t += 32) {
+            const Philox4 r1 = philox4x32_10((uint32_t)(it * 4096 + 2 * t), 7u, c2, c3, keys);
+            const Philox4 r2 = philox4x32_10((uint32_t)(it * 4096 + 2 * t + 1), 7u, c2, c3, keys);
+            float rr[6], ss[6], cc[6];
+            pair24_16(r1.x, ((r1.x & 0xffu) << 8) | (r1.w & 0xffu), rad2, rr[0], ss[0], cc[0]);
+            pair24_16(r1.y, ((r1.y & 0xffu) << 8) | ((r1.w >> 8) & 0xffu), rad2, rr[1], ss[1], cc[1]);
+            pair24_16(r1.z, ((r1.z & 0xffu) << 8) | ((r1.w >> 16) & 0xffu), rad2, rr[2], ss[2], cc[2]);
+            pair24_16(r2.x, ((r2.x & 0xffu) << 8) | (r2.w & 0xffu), rad2, rr[3], ss[3], cc[3]);
+            pair24_16(r2.y, ((r2.y & 0xffu) << 8) | ((r2.w >> 8) & 0xffu), rad2, rr[4], ss[4], cc[4]);
+            pair24_16(r2.z, ((r2.z & 0xffu) << 8) | ((r2.w >> 16) & 0xffu), rad2, rr[5], ss[5], cc[5]);
+            const int cb = 12 * t;
+            const int last = min(3, hv - 3 * t);
+            float4 o[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) o[j] = *reinterpret_cast<const float4*>(nm + min(cb + 4 * j, h - 4));
+            const int ce = cb + 4 * last;
+            const float e = nm[ce == h ? 0 : ce];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (j >= last) break;
+                const int c0 = cb + 4 * j;
+                const float4 up = *reinterpret_cast<const float4*>(nm - h + c0), d = *reinterpret_cast<const float4*>(nm + h + c0);
+                const float4 cur = *reinterpret_cast<const float4*>(own + c0);
+                const float nx = (j + 1 < last) ? o[j + 1 < 3 ? j + 1 : 2].x : e;
+                float4 s;
+                s.x = o[j].x + o[j].y; s.y = o[j].y + o[j].z; s.z = o[j].z + o[j].w; s.w = o[j].w + nx;
+                s.x += up.x + d.x; s.y += up.y + d.y; s.z += up.z + d.z; s.w += up.w + d.w;
+                float4 v;
+                v.x = fmaf(gain, s.x, fmaf(rr[2 * j], cc[2 * j], keep * cur.x));
+                v.y = fmaf(gain, s.y, fmaf(rr[2 * j], ss[2 * j], keep * cur.y));
+                v.z = fmaf(gain, s.z, fmaf(rr[2 * j + 1], cc[2 * j + 1], keep * cur.z));
+                v.w = fmaf(gain, s.w, fmaf(rr[2 * j + 1], ss[2 * j + 1], keep * cur.w));
+                *reinterpret_cast<float4*>(own + c0) = v;
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) out[0] = acc.x;
+}
+void runT(int iters, int sms) {
+    PhiloxKeys keys = philox_keys(42);
+    float* out; cudaMalloc(&out, 4);
+    const int h = 500;
+    const size_t smem = 72 * 1024;
+    cudaFuncSetAttribute(kT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = sms * 3;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    kT<<<grid, 256, smem>>>(keys, 4, 0.25f, 0.25f, -1.2f, out, h);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        kT<<<grid, 256, smem>>>(keys, iters, 0.25f, 0.25f, -1.2f, out, h);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
+    }
+    const double updates = (double)grid * 8 * iters * 125 * 4;
+    printf("%-28s %8.3f ms  %.3e site-updates/s  err=%s\n", "T triples (24+16 bit pairs)", best, updates / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
+}
+
+template <int STAGE>
+void run(const char* name, int iters, int sms) {
+    PhiloxKeys keys = philox_keys(42);
+    float* out; cudaMalloc(&out, 4);
+    const int h = 500;
+    const size_t smem = 72 * 1024;
+    cudaFuncSetAttribute(k<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = sms * 3;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    k<STAGE><<<grid, 256, smem>>>(keys, 4, 0.25f, 0.25f, -1.2f, out, h);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        k<STAGE><<<grid, 256, smem>>>(keys, iters, 0.25f, 0.25f, -1.2f, out, h);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
+    }
+    // warp-items: per CTA 8 warps x iters rows x 4 groups (125 vectors / 32 lanes, last partial)
+    const double items_per_smsp = 3.0 * 8 * iters * 4 / 4.0;
+    const double updates = (double)grid * 8 * iters * 125 * 4;
+    printf("%-28s %8.3f ms  %.1f ns per warp-item per SMSP (= %.0f cycles at 1.9 GHz)  %.3e site-updates/s  err=%s\n", name, best,
+           best * 1e6 / items_per_smsp, best * 1e6 / items_per_smsp * 1.9, updates / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    const int sms = p.multiProcessorCount, iters = 2000;
+    run<0>("A philox", iters, sms);
+    run<1>("B + box-muller", iters, sms);
+    run<2>("C + sums/fma (registers)", iters, sms);
+    run<3>("D + shared memory ld/st", iters, sms);
+    runT(iters, sms);
+    return 0;
+}

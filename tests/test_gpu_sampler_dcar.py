@@ -209,6 +209,40 @@ def test_default_thinning_decorrelates_kept_states(omega):
     assert sweeps < (300 if omega == 0.0 else 600)
 
 
+def test_default_schedule_decorrelates_the_slowest_modes():
+    """The slowest modes of the sweep operator on the torus are the constant field and the
+    checkerboard (Jacobi eigenvalues +-4 rho).  With X = [1, checkerboard] the statistics X'Y are
+    exactly those projections: their autocorrelation between consecutive kept states must meet
+    the schedule's promise (<= 1 %), and with thin = 1 it must decay like c (omega - 1)^k with the
+    prefactor c <= 3 the schedule assumes (no polynomial factor: the default omega sits just above
+    the optimal SOR factor)."""
+    n1 = n2 = 96
+    n = n1 * n2
+    ii, jj = np.divmod(np.arange(n), n2)
+    X = np.column_stack([np.ones(n), np.where((ii + jj) % 2 == 0, 1.0, -1.0)])
+    data = api.make_data(np.zeros(n), X=X, torus=(n1, n2), seed=77)
+    C = 256
+
+    def mode_acf(E, control, lags):
+        sd = api.mcl_prep_dCAR([0.2, 1.0, 0.0, 0.0], C * E, data, dict(control, **{"n.chains": C, "keep": False}))
+        diag = api.sampler_diag(data, sd)
+        m = sd.stats()[:, 2:4].reshape(E, C, 2)          # sample index = e * C + chain
+        m = m - m.mean(axis=(0, 1), keepdims=True)
+        v = (m * m).mean(axis=(0, 1))
+        return diag, np.array([(m[k:] * m[:E - k]).mean(axis=(0, 1)) / v for k in lags])
+
+    diag, acf = mode_acf(200, {}, [1])
+    assert diag["thin"] == 5 and 1.27 < diag["omega"] < 1.28 and diag["burn"] <= 12
+    se = 1.0 / np.sqrt(C * 200)
+    assert np.abs(acf).max() < 0.01 + 4 * se, acf
+    diag1, acf1 = mode_acf(400, {"thin": 1}, [1, 2, 3, 4, 5])
+    rate = diag1["omega"] - 1.0
+    se1 = 1.0 / np.sqrt(C * 400)
+    for k in range(5):      # |acf_k| <= c (omega - 1)^k; c = 3 covers the complex-pair beat
+        assert np.abs(acf1[k]).max() < 3.0 * rate ** (k + 1) + 4 * se1, (k, acf1[k])
+    assert np.abs(acf1[0]).max() > 0.05      # and the check is not vacuous: lag 1 is clearly correlated
+
+
 def test_large_general_graph_uses_global_state_fallback():
     """48,400-site lattice (no wrap) given as CSR: too large for the shared-memory chain state, so
     the sampler keeps the state in global memory.  Quadratic-form moments vs the closed form
