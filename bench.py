@@ -117,6 +117,12 @@ def cpu_hot_path(n_samples: int, y, psis):
     return dt, cpu_path.host_threads()
 
 
+def cpu_sample_size(cores: int) -> int:
+    """Bounded sample of the 12,500-sample shard for the CPU legs: about 32 samples per host thread, at
+    most 1024 (8 GB of fp64 fields), so the leg takes seconds to tens of seconds on any box."""
+    return int(min(32 * cores, 1024))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -125,7 +131,9 @@ def run_reference(args):
     psis = psi_grid()
     from oracle import cpu_path
     cores = cpu_path.host_threads()
-    n_s = args.cpu_samples or 16 * cores
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm is meant to use every host thread it can
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    n_s = args.cpu_samples or cpu_sample_size(cores) // 2
     for _ in range(args.warmup):
         cpu_hot_path(min(n_s, cores), y, psis)
     t = 0.0
@@ -271,7 +279,8 @@ def run_ours(args):
     # the fp64 likelihood pass over a resident sample matrix (the shape the reference's own simY
     # has): K2<double> + K3 for all candidates, timed with the library's CUDA-event spans
     fp64 = None
-    if not args.no_fp64 and rank == 0:
+    # (single-GPU leg: under torchrun the library's evaluators end in a collective, which rank 0 alone must not enter)
+    if not args.no_fp64 and world == 1:
         n64 = args.fp64_samples
         g = torch.Generator(device="cuda").manual_seed(1)
         Y64 = torch.randn((n64, n), dtype=torch.float64, device="cuda", generator=g) + 1.0
@@ -372,10 +381,10 @@ def run_ours(args):
         "result_check": {"lr_min": float(res[:, 0].min()), "lr_max": float(res[:, 0].max()),
                          "var_max": float(res[:, 1].max()), "e2e_equal": bool(np.allclose(res, res2, rtol=1e-9, atol=1e-12))},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (the reference arm times it at every N)
         from oracle import cpu_path
         cores = cpu_path.host_threads()
-        n_s = args.cpu_samples or 32 * cores     # ~5-10 s of host work
+        n_s = args.cpu_samples or cpu_sample_size(cores)
         cpu_hot_path(min(n_s, cores), y, psis)
         dt, _ = cpu_hot_path(n_s, y, psis)
         line["cpu_baseline"] = {"value": n_s * K_PSI / dt, "unit": UNIT, "cores": cores, "kind": "port",
@@ -416,6 +425,21 @@ def _print_json(line: dict):
         print(text, flush=True)
 
 
+def _watchdog(seconds: float):
+    """A hung collective must not hold a GPU box until the driver's limit: dump the stacks and exit non-zero."""
+    import faulthandler
+
+    def fire():
+        sys.stderr.write(f"bench.py: no result after {seconds:.0f} s -- aborting\n")
+        faulthandler.dump_traceback(file=sys.stderr)
+        os._exit(3)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -433,7 +457,10 @@ def main():
     ap.add_argument("--debug", action="store_true")
     ap.add_argument("--no-fp64", action="store_true")
     ap.add_argument("--fp64-samples", type=int, default=1500)
+    ap.add_argument("--watchdog", type=float, default=1500.0, help="abort after this many seconds (0 = never)")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        _watchdog(args.watchdog)
     global _OUT
     with _CleanStdout() as out:
         _OUT = out

@@ -22,6 +22,15 @@ int cpath_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline is meant to use the host's threads */
+void cpath_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* q[i*d + j], d = 2 + 2p: (Y'Y, Y'WY, X'Y[p], (WX)'Y[p]) for N sample-major rows of Y (N x n),
  * rook torus n1 x n2; X, WX column-major n x p. */
 void cpath_stats_torus(const double* Y, int64_t N, int n1, int n2, const double* X, const double* WX, int p,

@@ -33,6 +33,7 @@ def _lib():
     build_c_twin()
     lib = C.CDLL(str(_LIB))
     lib.cpath_num_threads.restype = C.c_int
+    lib.cpath_set_num_threads(C.c_int(host_threads()))
     return lib
 
 
