@@ -1,6 +1,7 @@
 """CPU tests: the C-ABI library loads, exports every symbol the header declares, and its
 host-only stages (model bookkeeping, tuple merge, finish) reproduce the oracle."""
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
@@ -152,3 +153,64 @@ def test_profile_and_exact_likelihood_on_host_context():
     assert got[5] == -1e8                                        # R/loglik.dCAR.R:36-40
     assert api.loglik_dCAR(psis[5], data, rho_cons=None) == pytest.approx(dcar.loglik_dCAR(psis[5], odata, eig, rho_cons=None), rel=1e-12)
     assert api.loglik_dCAR(psis[0][:2], data) == pytest.approx(dcar.loglik_dCAR(psis[0][:2], odata, eig), rel=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# R side of the boundary (R is not installed): the .Call glue must at least type-check against the
+# C-ABI header, and every .Call in r/overrides.R must name a glue entry with the right arity.
+# ---------------------------------------------------------------------------------------------
+def test_r_glue_type_checks_against_the_header():
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-fsyntax-only",
+                        "-I" + os.path.join(root, "tests", "r_stub"), "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "r", "mclcar_b200_glue.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def _call_sites(text):
+    """(.Call symbol, number of arguments after the symbol) for every .Call( in an R source."""
+    out = []
+    i = 0
+    while True:
+        i = text.find(".Call(", i)
+        if i < 0:
+            return out
+        j = i + len(".Call(")
+        depth, args, cur = 1, [], ""
+        while depth:
+            ch = text[j]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    break
+            if ch == "," and depth == 1:
+                args.append(cur)
+                cur = ""
+            else:
+                cur += ch
+            j += 1
+        args.append(cur)
+        out.append((args[0].strip(), len(args) - 1))
+        i = j
+
+
+def test_r_overrides_call_existing_glue_entries_with_matching_arity():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    glue = open(os.path.join(root, "r", "mclcar_b200_glue.c")).read()
+    entries = {m.group(1): (0 if not m.group(2).strip() else m.group(2).count("SEXP"))
+               for m in re.finditer(r"^SEXP (C_mclb_\w+)\(([^)]*)\)", glue, flags=re.M)}
+    assert len(entries) >= 15
+    src = "\n".join(line.split("#", 1)[0] for line in open(os.path.join(root, "r", "overrides.R")).read().splitlines())
+    sites = _call_sites(src)
+    assert len(sites) >= 15
+    for sym, nargs in sites:
+        assert sym in entries, f".Call({sym}, ...) has no glue entry"
+        assert entries[sym] == nargs, f".Call({sym}) passes {nargs} arguments, the glue takes {entries[sym]}"
