@@ -156,6 +156,12 @@ MCLCAR_API int mclcar_dcar_stats(mclcar_ctx* ctx, mclcar_samples* s, double* q_o
  * chromatic Gibbs sampler and attaches t10 = h(y; psi0), t20_i = h(Y_i; psi0). */
 MCLCAR_API int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
                      mclcar_samples** out);
+/* what mclcar_dcar_prep would run for (rho, N, opts) on this context's graph, without running it:
+ * kind 1 = tiled red-black torus kernels, 2 = general chromatic kernel with the chains in shared
+ * memory, 3 = same with the chains in global memory; chains, burn-in sweeps, sweeps per kept state,
+ * over-relaxation factor.  Host logic only (also answers on a host-only context); any output may be NULL. */
+MCLCAR_API int mclcar_dcar_plan(mclcar_ctx* ctx, double rho, int64_t N, const mclcar_sampler_opts* opts, int* kind,
+                     int64_t* chains, int* burn, int* thin, double* omega);
 /* attach the importance point to a sample set built with samples_from_*: t20 NULL means
  * "compute h(Y_i; psi0) from the statistics", otherwise the reference's own t20 (N). */
 MCLCAR_API int mclcar_dcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* t20);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mclcar_samples_schedule": (_i, [_vp, _vp, _pi64, _pi, _pi, _pd]),
     "mclcar_dcar_stats": (_i, [_vp, _vp, _pd]),
     "mclcar_dcar_prep": (_i, [_vp, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
+    "mclcar_dcar_plan": (_i, [_vp, _d, _i64, C.POINTER(SamplerOpts), _pi, _pi64, _pi, _pi, _pd]),
     "mclcar_dcar_attach": (_i, [_vp, _vp, _pd, _i, _pd]),
     "mclcar_dcar_t10_t20": (_i, [_vp, _vp, _pd, _pd]),
     "mclcar_dcar_eval": (_i, [_vp, _vp, _pd, _i, _i, _pd, _pi64, _pi64, _i, _pd, _pd]),

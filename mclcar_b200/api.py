@@ -399,6 +399,17 @@ def mcl_prep_dCAR(psi, n_samples: int, data: CarData, control: Optional[dict] = 
     return SimData(data, h, psi)
 
 
+def plan_dCAR(psi, n_samples: int, data: CarData, control: Optional[dict] = None) -> dict:
+    """What mcl_prep_dCAR(psi, n_samples, data, control) would run, without running it (host logic,
+    works on a host-only context): sampler kind, chains, burn-in, thinning, over-relaxation factor."""
+    o = _sampler_opts(control)
+    kind, ch, bu, th, om = C.c_int(), C.c_int64(), C.c_int(), C.c_int(), C.c_double()
+    check(lib.mclcar_dcar_plan(data.ctx.h, float(np.asarray(psi, dtype=np.float64)[0]), int(n_samples), C.byref(o), C.byref(kind),
+                               C.byref(ch), C.byref(bu), C.byref(th), C.byref(om)), data.ctx.h)
+    names = {1: "torus tiles", 2: "chromatic, chains in shared memory", 3: "chromatic, chains in global memory"}
+    return {"sampler": names[kind.value], "chains": ch.value, "burn": bu.value, "thin": th.value, "omega": om.value}
+
+
 def sampler_diag(data: CarData, simdata) -> dict:
     acc = C.c_double()
     sw = C.c_int64()

@@ -260,6 +260,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
 int check_rho(mclcar_ctx* ctx, double rho);
 void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* burn, int* thin);
 int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N);
+int64_t default_torus_chains(int n, int64_t N, int burn, int thin);
 int dcar_ensure_stats(mclcar_ctx* ctx, mclcar_samples* s);
 
 }  // namespace mclcar

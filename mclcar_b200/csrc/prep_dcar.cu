@@ -234,3 +234,39 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
     *out = s;
     return MCLCAR_OK;
 }
+
+/* What mclcar_dcar_prep would run for (rho, N, opts) on this context's graph, without running it:
+ * sampler kind (1 = tiled red-black torus kernels, 2 = general chromatic kernel with the chains in
+ * shared memory, 3 = same with the chains in global memory), parallel chains, burn-in sweeps, sweeps
+ * per kept state, over-relaxation factor.  Pure host logic: also answers on a host-only context. */
+extern "C" int mclcar_dcar_plan(mclcar_ctx* ctx, double rho, int64_t N, const mclcar_sampler_opts* opts, int* kind,
+                                int64_t* chains, int* burn_out, int* thin_out, double* omega_out) {
+    if (!ctx) return MCLCAR_EINVAL;
+    if (ctx->kind == GRAPH_NONE) return fail(ctx, MCLCAR_ESTATE, "set the graph first");
+    if (N < 1 || N >= ((int64_t)1 << 31)) return fail(ctx, MCLCAR_EINVAL, "bad sample count %lld", (long long)N);
+    MCL_TRY(check_rho(ctx, rho));
+    mclcar_sampler_opts o{};
+    if (opts) o = *opts;
+    int burn = o.burn, thin = o.thin;
+    double omega = o.omega;
+    default_schedule(ctx, rho, &omega, &burn, &thin);
+    const int n = ctx->n;
+    const bool use_torus = ctx->kind == GRAPH_TORUS && ctx->n1 % 2 == 0 && ctx->n2 % 2 == 0 &&
+                           (size_t)n * 8 * sizeof(float) > 200 * 1024;
+    int64_t C;
+    int k;
+    if (use_torus) {
+        C = o.n_chains > 0 ? o.n_chains : default_torus_chains(n, N, burn, thin);
+        C = std::min<int64_t>(std::min<int64_t>(C, N), 65535);
+        k = 1;
+    } else {
+        C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
+        k = (size_t)n * 2 * sizeof(float) <= 200 * 1024 ? 2 : 3;
+    }
+    if (kind) *kind = k;
+    if (chains) *chains = C;
+    if (burn_out) *burn_out = burn;
+    if (thin_out) *thin_out = thin;
+    if (omega_out) *omega_out = omega;
+    return MCLCAR_OK;
+}

@@ -64,6 +64,38 @@ def test_argument_validation():
     assert L.lib.mclcar_ctx_set_shard(ctx.h, 3, 2) == L.EINVAL
 
 
+def test_sampler_plan_rules_on_a_host_only_context():
+    """The schedule and chain-count rules of mcl.prep.dCAR are host logic (prep_dcar.cu):
+    * rho = 0.2 on the even torus: omega = omega* + 0.025 (omega* = 2 / (1 + sqrt(1 - 0.8^2)) = 1.25), 5 sweeps per kept state,
+      12 burn-in sweeps; plain Gibbs needs 11 / 31;
+    * launches carry >= 1e8 site updates: 149 chains for the 12,500-sample shard of the 1000 x 1000 torus, burn-in below
+      1/8 of the kept sweeps for small N; explicit controls are honoured;
+    * small lattices use the shared-memory chromatic kernel."""
+    ctx = api.Context(device=-1)
+    d = api.make_data(np.zeros(10**6), X=None, torus=(1000, 1000), ctx=ctx)
+    pl = api.plan_dCAR([0.2, 1.0], 12500, d)
+    assert pl["sampler"] == "torus tiles"
+    assert pl["omega"] == pytest.approx(1.275, abs=1e-12) and pl["thin"] == 5 and pl["burn"] == 12
+    assert pl["chains"] == 149
+    sweeps = pl["burn"] + -(-12500 // pl["chains"]) * pl["thin"]
+    assert sweeps == 432
+    plain = api.plan_dCAR([0.2, 1.0], 12500, d, {"omega": 1.0})
+    assert plain["omega"] == 1.0 and plain["thin"] == 11 and plain["burn"] == 31
+    small = api.plan_dCAR([0.2, 1.0], 64, d)
+    assert 1 <= small["chains"] <= 64 and small["burn"] * 8 <= -(-64 // small["chains"]) * small["thin"] * small["chains"] + 8 * small["burn"]
+    assert small["chains"] == max(1, 64 * small["thin"] // (8 * small["burn"]))
+    fixed = api.plan_dCAR([0.2, 1.0], 5000, d, {"n.chains": 40, "burn": 7, "thin": 3})
+    assert (fixed["chains"], fixed["burn"], fixed["thin"]) == (40, 7, 3)
+    # weaker dependence -> fewer sweeps; stronger -> more
+    assert api.plan_dCAR([0.05, 1.0], 12500, d)["thin"] < 5 < api.plan_dCAR([0.245, 1.0], 12500, d)["thin"]
+    with pytest.raises(api.MclcarError, match="rho should be within"):
+        api.plan_dCAR([0.26, 1.0], 100, d)
+    ctx2 = api.Context(device=-1)
+    d2 = api.make_data(np.zeros(400), X=None, torus=(20, 20), ctx=ctx2)
+    p2 = api.plan_dCAR([0.2, 1.0], 1000, d2)
+    assert p2["sampler"] == "chromatic, chains in shared memory" and p2["chains"] % 2 == 0 and p2["thin"] == 5
+
+
 def test_colouring():
     ctx = api.Context(device=-1)
     assert L.lib.mclcar_graph_torus(ctx.h, 6, 8) == 0
