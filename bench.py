@@ -250,7 +250,7 @@ def run_ours(args):
         res = step_resident()
     assert np.all(np.isfinite(res)), "non-finite result in warm-up"
 
-    if args.debug and rank == 0:  # wall-clock breakdown of one step, outside the timed region
+    if args.debug and world == 1:  # wall-clock breakdown of one step, outside the timed region (single process only)
         def tick(label, fn):
             torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
             print(f"[debug] {label}: {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)

@@ -77,3 +77,29 @@ def test_two_rank_merge_over_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_bench_never_calls_a_collective_bearing_entry_from_one_rank_only():
+    """Every `mcl_*` evaluator of the library ends in an all-gather once the NCCL communicator is up, so in
+    bench.py such a call must be reached by ALL ranks: none may sit under a condition on `rank` (the fp64 leg
+    once did and hung the 8-GPU run).  Blocks guarded by `world == 1` are single-process and fine."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+    collective = {"mcl_dCAR_batch", "mcl_dCAR", "mcl_profile_dCAR", "mcl_profile_dCAR_batch", "mc_gradlik_dCAR", "mc_Hesslik_dCAR",
+                  "MCMLE_var", "mcl_glm_batch", "mcl_glm", "mcl_grad_glm", "mcl_Hessian_glm", "mcl_HCAR_batch", "mcl_HCAR"}
+
+    def mentions_rank(node):
+        return any(isinstance(n, ast.Name) and n.id == "rank" for n in ast.walk(node))
+
+    offenders = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and mentions_rank(node.test):
+            for sub in node.body:
+                for n in ast.walk(sub):
+                    if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr in collective:
+                        offenders.append((node.lineno, n.func.attr))
+    assert not offenders, f"rank-conditional calls into collective-bearing evaluators: {offenders}"
+    # and the single-GPU legs are guarded by the world size
+    assert "if not args.no_fp64 and world == 1" in src and "if not args.no_cpu_baseline and world == 1" in src
