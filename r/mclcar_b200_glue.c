@@ -170,6 +170,22 @@ SEXP C_mclb_fetch(SEXP ctx, SEXP samples, SEXP nrow, SEXP layout) {
     return out;
 }
 
+/* sampler diagnostics of a sample set: c(accept, sweeps, chains, burn, thin, omega) */
+SEXP C_mclb_samples_diag(SEXP ctx, SEXP samples) {
+    mclcar_ctx* c = ctx_of(ctx);
+    mclcar_samples* s = samples_of(samples);
+    double acc = 0.0, omega = 0.0;
+    int64_t sweeps = 0, chains = 0;
+    int burn = 0, thin = 0;
+    CHECK(c, mclcar_samples_diag(c, s, &acc, &sweeps));
+    CHECK(c, mclcar_samples_schedule(c, s, &chains, &burn, &thin, &omega));
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, 6));
+    REAL(out)[0] = acc; REAL(out)[1] = (double)sweeps; REAL(out)[2] = (double)chains;
+    REAL(out)[3] = burn; REAL(out)[4] = thin; REAL(out)[5] = omega;
+    UNPROTECT(1);
+    return out;
+}
+
 /* GLM: mcl.prep.glm / mcl.glm / mcl.grad.glm / mcl.Hessian.glm  [R/mcl.glm.R, R/mcl.bin.R, R/mcl.pois.R] */
 SEXP C_mclb_prep_glm(SEXP ctx, SEXP family, SEXP psi, SEXP nsamp, SEXP control) {
     mclcar_ctx* c = ctx_of(ctx);

@@ -8,6 +8,8 @@
 
 .mclb <- new.env()
 .mclb$control <- list(n.chains = 0, burn = 0L, thin = 0L, keep = TRUE, dtype = 1L, omega = 0)
+.mclb$COL_IS_SAMPLE <- 0L   # MCLCAR_COL_IS_SAMPLE: simY (n x N), u.y (K x N)
+.mclb$ROW_IS_SAMPLE <- 1L   # MCLCAR_ROW_IS_SAMPLE: Zy (N x n)
 
 .mclb_ctx <- function(data, glm = FALSE) {
     key <- if (glm) "glm" else "lm"
@@ -85,8 +87,9 @@ mcl.glm <- function(pars, mcdata, family, Evar = FALSE) {               # R/mcl.
 }
 postZ <- function(data, family, psi, Z.start, mcmc.control = list(), plots = FALSE) {    # R/postZ.R:2-14
     md <- mcl.prep.glm(data, family, psi, Z.start, mcmc.control, pilot.run = FALSE)
-    N <- (md$mcmc.pars$N.Zy - md$mcmc.pars$burns) %/% md$mcmc.pars$thin
-    list(Z = .Call(C_mclb_fetch, attr(md, "ctx"), md$Zy, N, 2L), AC.r = attr(md$Zy, "accept"))
+    ## Z: N x n, row = sample (R/postZsub.R:427); AC.r: mean acceptance rate of the Metropolis-within-Gibbs chains
+    list(Z = .Call(C_mclb_fetch, attr(md, "ctx"), md$Zy, length(data$y), .mclb$ROW_IS_SAMPLE),
+         AC.r = .Call(C_mclb_samples_diag, attr(md, "ctx"), md$Zy)[1])
 }
 get.beta.glm <- function(beta0, rho.sig, mcdata, family) {              # R/mcl.glm.R:50-54, R/mcl.bin.R:83-95
     r <- .Call(C_mclb_get_beta_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(rho.sig), as.numeric(beta0), 2L, 1)
