@@ -291,3 +291,26 @@ SEXP C_mclb_mcl_hcar(SEXP ctx, SEXP samples, SEXP pars) { /* pars: K x P -> list
     if (ncl) Rf_warning("Design area too large: Inf produced! Choose a parameter closer to psi."); /* R/mcl.HCAR.R:82 */
     return out;
 }
+SEXP C_mclb_grad_hcar(SEXP ctx, SEXP samples, SEXP pars, SEXP evar) { /* -> list(grad.lr, grad.var | NULL)  [R/mcl.HCAR.R:101-213] */
+    mclcar_ctx* c = ctx_of(ctx);
+    int P = LENGTH(pars), ev = Rf_asLogical(evar);
+    SEXP g = PROTECT(Rf_allocVector(REALSXP, P));
+    SEXP v = PROTECT(Rf_allocMatrix(REALSXP, P, P));
+    int st = mclcar_hcar_grad(c, samples_of(samples), REAL(pars), 1, P, ev, MCLCAR_SHIFT_MEAN, REAL(g), ev ? REAL(v) : NULL);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, g);
+    SET_VECTOR_ELT(out, 1, ev ? v : R_NilValue);
+    UNPROTECT(3);
+    if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
+    return out;
+}
+SEXP C_mclb_hess_hcar(SEXP ctx, SEXP samples, SEXP pars) { /* P x P  [R/mcl.HCAR.R:216-391] */
+    mclcar_ctx* c = ctx_of(ctx);
+    int P = LENGTH(pars);
+    SEXP H = PROTECT(Rf_allocMatrix(REALSXP, P, P));
+    int st = mclcar_hcar_hess(c, samples_of(samples), REAL(pars), 1, P, MCLCAR_SHIFT_MEAN, REAL(H));
+    UNPROTECT(1);
+    if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
+    return H;
+}
+

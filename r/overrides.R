@@ -1,57 +1,83 @@
-## Drop-in overrides of the hot-path functions of mclcar (R/mcl.dCAR.R, R/mcl.glm.R, R/HCAR.sim.R,
-## R/mcl.HCAR.R) behind UNCHANGED signatures: source() after library(mclcar), or put in the
-## package's R/ directory together with useDynLib(mclcar).  NOT RUN IN THIS REPOSITORY (no R in
-## the image); the same call sequences are exercised through ctypes in tests/.
+## Drop-in overrides of the hot-path functions of mclcar (R/mcl.dCAR.R, R/mcl.glm.R, R/postZ.R,
+## R/rsmSub.R, R/HCAR.sim.R, R/mcl.HCAR.R) behind UNCHANGED signatures: source() after
+## library(mclcar), or put in the package's R/ directory together with useDynLib(mclcar).
+## NOT RUN IN THIS REPOSITORY (no R in the image).  What is checked here: every .Call below names an
+## entry of r/mclcar_b200_glue.c with the right number of arguments, the glue type-checks against
+## include/mclcar_b200.h (tests/test_abi_host.py), and the same call sequences are exercised
+## through ctypes (mclcar_b200/api.py) by the parity tests.
 ##
-## `data` keeps its reference shape; the engine context is cached in an attribute so that the
-## outer drivers (OptimMCL, rsmMCL -- R/OptimMCL.R, R/rsmMCL.R) run unmodified.
+## `data` keeps its reference shape.  Engine contexts (graph + design + observations on the device)
+## are cached in the package-level environment .mclb, keyed by a fingerprint of the data, so that
+## the outer drivers (OptimMCL, rsmMCL, OptimMCL.HCAR -- R/OptimMCL.R, R/rsmMCL.R) run unmodified.
 
 .mclb <- new.env()
-.mclb$control <- list(n.chains = 0, burn = 0L, thin = 0L, keep = TRUE, dtype = 1L, omega = 0)
+.mclb$control <- list(n.chains = 0, burn = 0L, thin = 0L, keep = TRUE, dtype = 1L, omega = 0)  # dtype 1 = fp32 samples
 .mclb$COL_IS_SAMPLE <- 0L   # MCLCAR_COL_IS_SAMPLE: simY (n x N), u.y (K x N)
 .mclb$ROW_IS_SAMPLE <- 1L   # MCLCAR_ROW_IS_SAMPLE: Zy (N x n)
+.mclb$cache <- new.env()
 
+.mclb_csr <- function(A) {   # symmetric matrix -> 0-based CSR slots (p, j, x)
+    methods::as(methods::as(Matrix::Matrix(as.matrix(A), sparse = TRUE), "generalMatrix"), "RsparseMatrix")
+}
+.mclb_key <- function(...) paste(vapply(list(...), function(v) format(sum(as.numeric(v)), digits = 17), ""), collapse = "|")
+
+## context for the direct CAR model (data$data.vec, data$W) or the GLM (data$y, data$covX, data$W, data$n.trial)
 .mclb_ctx <- function(data, glm = FALSE) {
-    key <- if (glm) "glm" else "lm"
-    if (!is.null(attr(data, "mclb"))) return(attr(data, "mclb"))
+    y <- if (glm) data$y else data$data.vec$y
+    X <- if (glm) data$covX else stats::model.matrix(y ~ ., data = data$data.vec)
+    key <- paste(if (glm) "glm" else "lm", .mclb_key(y, X, data$W, length(y)))
+    if (!is.null(.mclb$cache[[key]])) return(.mclb$cache[[key]])
     ctx <- .Call(C_mclb_ctx, 0L)
-    W <- data$W
-    Wt <- methods::as(Matrix::Matrix(W, sparse = TRUE), "RsparseMatrix")   # CSR, 0-based
-    lambda <- if (is.null(data$lambda)) eigen(as.matrix(W), symmetric = TRUE, only.values = TRUE)$values else data$lambda
-    .Call(C_mclb_graph_csr, ctx, Wt@p, Wt@j, Wt@x, lambda)
-    if (glm) .Call(C_mclb_model, ctx, data$covX, as.numeric(data$y), rep_len(as.numeric(data$n.trial), length(data$y)))
-    else .Call(C_mclb_model, ctx, model.matrix(y ~ ., data = data$data.vec), data$data.vec$y, NULL)
+    Wt <- .mclb_csr(data$W)
+    lambda <- if (is.null(data$lambda)) eigen(as.matrix(data$W), symmetric = TRUE, only.values = TRUE)$values else data$lambda
+    .Call(C_mclb_graph_csr, ctx, Wt@p, Wt@j, as.numeric(Wt@x), as.numeric(lambda))
+    nt <- if (glm && !is.null(data$n.trial)) rep_len(as.numeric(data$n.trial), length(y)) else NULL
+    .Call(C_mclb_model, ctx, X, as.numeric(y), nt)
+    .mclb$cache[[key]] <- ctx
     ctx
 }
 
+## ---------------------------------------------------------------- direct CAR (R/mcl.dCAR.R)
 mcl.prep.dCAR <- function(psi, n.samples, data) {                       # R/mcl.dCAR.R:2-8
     ctx <- .mclb_ctx(data)
     h <- .Call(C_mclb_prep_dcar, ctx, as.numeric(psi), n.samples, .mclb$control)
-    structure(list(simY = h, t10 = NA_real_, t20 = NULL), class = "mclb_simdata", ctx = ctx, n = length(data$data.vec$y))
+    structure(list(simY = h, t10 = NA_real_, t20 = NULL), class = "mclb_simdata", ctx = ctx, psi = psi,
+              n.samples = n.samples, n = length(data$data.vec$y))
+}
+## the reference's own list(simY, t10, t20) (e.g. produced on the CPU): upload once; psi0 must be known
+.mclb_simdata <- function(data, simdata) {
+    if (inherits(simdata, "mclb_simdata")) return(simdata)
+    psi <- attr(simdata, "psi")
+    if (is.null(psi)) stop("attach the importance point to a CPU-made simdata first: attr(simdata, 'psi') <- psi")
+    ctx <- .mclb_ctx(data)
+    structure(list(simY = .Call(C_mclb_samples_dcar, ctx, simdata$simY, as.numeric(psi), simdata$t20)),
+              class = "mclb_simdata", ctx = ctx, psi = psi, n.samples = ncol(simdata$simY), n = nrow(simdata$simY))
 }
 mcl.dCAR <- function(pars, data, simdata, rho.cons = c(-0.249, 0.249), Evar = FALSE) {   # R/mcl.dCAR.R:11-50
-    if (!inherits(simdata, "mclb_simdata")) {   # the reference's own list(simY, t10, t20): upload once
-        ctx <- .mclb_ctx(data)
-        simdata <- structure(list(simY = .Call(C_mclb_samples_dcar, ctx, simdata$simY, attr(simdata, "psi"), simdata$t20)),
-                             class = "mclb_simdata", ctx = ctx)
-    }
+    simdata <- .mclb_simdata(data, simdata)
     r <- .Call(C_mclb_mcl_dcar, attr(simdata, "ctx"), simdata$simY, matrix(as.numeric(pars), nrow = 1), rho.cons, NULL, NULL)
     if (Evar) as.numeric(r) else r[1, 1]
 }
 mcl.profile.dCAR <- function(rho, data, simdata, rho.cons = c(-0.249, 0.249), Evar = FALSE)   # R/mcl.dCAR.R:53-96
     mcl.dCAR(c(rho, sigmabeta(rho, data)), data, simdata, rho.cons, Evar)
 mc.gradlik.dCAR <- function(pars, data, simdata, Evar = 0) {            # R/mcl.dCAR.R:213-283
+    simdata <- .mclb_simdata(data, simdata)
     r <- .Call(C_mclb_grad_dcar, attr(simdata, "ctx"), simdata$simY, as.numeric(pars), as.integer(Evar))
     if (Evar == 0) r[[1]] else list(grad = r[[1]], grad.var = r[[2]])
 }
-mc.Hesslik.dCAR <- function(pars, data, simdata)                        # R/mcl.dCAR.R:287-394
+mc.Hesslik.dCAR <- function(pars, data, simdata) {                      # R/mcl.dCAR.R:287-394
+    simdata <- .mclb_simdata(data, simdata)
     .Call(C_mclb_hess_dcar, attr(simdata, "ctx"), simdata$simY, as.numeric(pars), 0L)
-MCMLE.var <- function(pars, data, simdata)                              # R/mcl.dCAR.R:156-165
+}
+MCMLE.var <- function(pars, data, simdata) {                            # R/mcl.dCAR.R:156-165
+    simdata <- .mclb_simdata(data, simdata)
     .Call(C_mclb_hess_dcar, attr(simdata, "ctx"), simdata$simY, as.numeric(pars), 1L)
+}
 
-## batched design-point evaluation replacing the loops of Exp.dCAR / ExpPath.dCAR (R/rsmSub.R:78-95,110)
-Exp.dCAR <- function(exp.design, data, psi, n0, mc.data) {
+## design points and path points in ONE device call each instead of a loop of mcl.dCAR calls
+Exp.dCAR <- function(exp.design, data, psi, n0, mc.data) {              # R/rsmSub.R:65-97
     if (is.null(mc.data)) stop("Please provide the Monte Carlo samples by specifying mc.data!")
+    mc.data <- .mclb_simdata(data, mc.data)
     n.samples <- attr(mc.data, "n.samples"); nb.sim <- floor(n.samples / n0)
     dd <- rsm::decode.data(exp.design); K <- nrow(exp.design)
     pars <- cbind(dd$rho, dd$sigma, matrix(as.numeric(psi[-c(1, 2)]), K, length(psi) - 2, byrow = TRUE))
@@ -61,9 +87,9 @@ Exp.dCAR <- function(exp.design, data, psi, n0, mc.data) {
     exp.design$mc.lr <- r[, 1]; exp.design$mc.var <- r[, 2]
     exp.design
 }
-
 ExpPath.dCAR <- function(exp.design, data, psi, mc.data) {              # R/rsmSub.R:102-115
     if (is.null(mc.data)) stop("Please provide the Monte Carlo samples by specifying mc.data!")
+    mc.data <- .mclb_simdata(data, mc.data)
     K <- nrow(exp.design)
     pars <- cbind(exp.design$rho, exp.design$sigma, matrix(as.numeric(psi[-c(1, 2)]), K, length(psi) - 2, byrow = TRUE))
     ## the reference's `rho.cons = NULL` sits inside c(...) (:110) and is lost: the default guard applies
@@ -72,25 +98,34 @@ ExpPath.dCAR <- function(exp.design, data, psi, mc.data) {              # R/rsmS
     exp.design
 }
 
+## ---------------------------------------------------------------- GLM with latent CAR (R/mcl.glm.R, R/postZ.R)
 mcl.prep.glm <- function(data, family, psi, Z.start = NULL, mcmc.control = list(), pilot.run = TRUE,
                          pilot.plot = FALSE, plot.diag = FALSE) {       # R/mcl.glm.R:5-40
-    con <- list(N.Zy = 1e4, thin = 5, burns = 5e3); con[names(mcmc.control)] <- mcmc.control
+    ## Z.start, pilot.run and the MALA scale have no role: parallel Metropolis-within-Gibbs chains, no scale to tune
+    con <- list(method = "mala", N.Zy = 1e4, thin = 5, burns = 5e3); con[names(mcmc.control)] <- mcmc.control
     ctx <- .mclb_ctx(data, glm = TRUE)
     fam <- c(binom = 1L, poisson = 2L)[[family]]
-    data$Zy <- .Call(C_mclb_prep_glm, ctx, fam, as.numeric(psi), (con$N.Zy - con$burns) %/% con$thin, .mclb$control)
+    n.samples <- (con$N.Zy - con$burns) %/% con$thin                    # rows of Z, R/postZsub.R:427
+    data$Zy <- .Call(C_mclb_prep_glm, ctx, fam, as.numeric(psi), n.samples, .mclb$control)
     data$lHZy.psi <- NULL; data$mcmc.pars <- con
-    structure(data, class = "mclb_mcdata", ctx = ctx)
+    structure(data, class = "mclb_mcdata", ctx = ctx, n.samples = n.samples)
+}
+postZ <- function(data, family, psi, Z.start, mcmc.control = list(), plots = FALSE) {    # R/postZ.R:2-14
+    md <- mcl.prep.glm(data, family, psi, Z.start, mcmc.control, pilot.run = FALSE)
+    ## Z: N x n, row = sample (R/postZsub.R:427); AC.r: mean acceptance rate of the chains
+    list(Z = .Call(C_mclb_fetch, attr(md, "ctx"), md$Zy, length(data$y), .mclb$ROW_IS_SAMPLE),
+         AC.r = .Call(C_mclb_samples_diag, attr(md, "ctx"), md$Zy)[1])
 }
 mcl.glm <- function(pars, mcdata, family, Evar = FALSE) {               # R/mcl.glm.R:43-47
     r <- .Call(C_mclb_mcl_glm, attr(mcdata, "ctx"), mcdata$Zy, matrix(as.numeric(pars), nrow = 1), NULL, NULL)
     if (Evar) as.numeric(r) else r[1, 1]
 }
-postZ <- function(data, family, psi, Z.start, mcmc.control = list(), plots = FALSE) {    # R/postZ.R:2-14
-    md <- mcl.prep.glm(data, family, psi, Z.start, mcmc.control, pilot.run = FALSE)
-    ## Z: N x n, row = sample (R/postZsub.R:427); AC.r: mean acceptance rate of the Metropolis-within-Gibbs chains
-    list(Z = .Call(C_mclb_fetch, attr(md, "ctx"), md$Zy, length(data$y), .mclb$ROW_IS_SAMPLE),
-         AC.r = .Call(C_mclb_samples_diag, attr(md, "ctx"), md$Zy)[1])
+mcl.grad.glm <- function(pars, mcdata, family, Evar = FALSE) {          # R/mcl.glm.R:78-82
+    r <- .Call(C_mclb_grad_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(pars), Evar)
+    if (Evar) list(grad.lr = r[[1]], grad.var = r[[2]]) else r[[1]]
 }
+mcl.Hessian.glm <- function(pars, mcdata, family)                       # R/mcl.glm.R:85-89
+    .Call(C_mclb_hess_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(pars))
 get.beta.glm <- function(beta0, rho.sig, mcdata, family) {              # R/mcl.glm.R:50-54, R/mcl.bin.R:83-95
     r <- .Call(C_mclb_get_beta_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(rho.sig), as.numeric(beta0), 2L, 1)
     list(x = r[[1]], fvec = r[[2]], termcd = r[[3]], iter = r[[4]])
@@ -100,11 +135,9 @@ mcl.profile.glm <- function(pars, beta0, mcdata, family, Evar = FALSE) {   # R/m
     lr <- mcl.glm(c(pars[1:2], r[[1]]), mcdata, family, Evar = TRUE)
     c(if (Evar) lr else lr[1], r[[1]], r[[2]])
 }
-## batched design-point evaluation replacing the loops of Exp.CAR.glm / ExpPath.CAR.glm (R/rsmSub.R:159-212)
-Exp.CAR.glm <- function(exp.design, data, family, psi, n0, mc.data) {
+Exp.CAR.glm <- function(exp.design, data, family, psi, n0, mc.data) {   # R/rsmSub.R:159-192
     if (is.null(mc.data)) stop("Please provide the Monte Carlo samples by specifying mc.data!")
-    n.samples <- (mc.data$mcmc.pars$N.Zy - mc.data$mcmc.pars$burns) %/% mc.data$mcmc.pars$thin
-    nb.sim <- floor(n.samples / n0)
+    n.samples <- attr(mc.data, "n.samples"); nb.sim <- floor(n.samples / n0)
     dd <- rsm::decode.data(exp.design); K <- nrow(exp.design)
     pars <- cbind(dd$rho, dd$sigma, matrix(as.numeric(psi[-c(1, 2)]), K, length(psi) - 2, byrow = TRUE))
     subs <- lapply(seq_len(K), function(k) if (exp.design$std.order[k] > 4) sample(n.samples, nb.sim) - 1 else numeric(0))
@@ -113,7 +146,7 @@ Exp.CAR.glm <- function(exp.design, data, family, psi, n0, mc.data) {
     exp.design$mc.var <- ifelse(r[, 2] == 0, 1e-8, pmin(1e8, r[, 2]))    # per row, as R/rsmSub.R:183,188
     exp.design
 }
-ExpPath.CAR.glm <- function(exp.design, data, family, psi, mc.data) {
+ExpPath.CAR.glm <- function(exp.design, data, family, psi, mc.data) {   # R/rsmSub.R:197-212
     if (is.null(mc.data)) stop("Please provide the Monte Carlo samples by specifying mc.data!")
     K <- nrow(exp.design)
     pars <- cbind(exp.design$rho, exp.design$sigma, matrix(as.numeric(psi[-c(1, 2)]), K, length(psi) - 2, byrow = TRUE))
@@ -122,15 +155,32 @@ ExpPath.CAR.glm <- function(exp.design, data, family, psi, mc.data) {
     exp.design$mc.var <- ifelse(r[1, 2] == 0, 1e-8, min(1e8, r[1, 2]))   # single element, as coded at R/rsmSub.R:210
     exp.design
 }
-mcl.grad.glm <- function(pars, mcdata, family, Evar = FALSE) {          # R/mcl.glm.R:78-82
-    r <- .Call(C_mclb_grad_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(pars), Evar)
-    if (Evar) list(grad.lr = r[[1]], grad.var = r[[2]]) else r[[1]]
-}
-mcl.Hessian.glm <- function(pars, mcdata, family)                       # R/mcl.glm.R:85-89
-    .Call(C_mclb_hess_glm, attr(mcdata, "ctx"), mcdata$Zy, as.numeric(pars))
 
+## ---------------------------------------------------------------- hierarchical CAR (R/HCAR.sim.R, R/mcl.HCAR.R)
+## data: list or environment with y, X, W (or NULL), M, Z (and optionally aa = eigen(W), bb = eigen(M), R/mcl.HCAR.R:166-173)
+.mclb_hcar_ctx <- function(data) {
+    g <- function(nm) if (is.environment(data)) get0(nm, envir = data) else data[[nm]]
+    y <- g("y"); X <- g("X"); W <- g("W"); M <- g("M"); Z <- g("Z")
+    key <- paste("hcar", .mclb_key(y, X, M, Z, if (is.null(W)) 0 else W))
+    if (!is.null(.mclb$cache[[key]])) return(.mclb$cache[[key]])
+    ctx <- .Call(C_mclb_ctx, 0L)
+    n <- length(y)
+    if (is.null(W)) {
+        .Call(C_mclb_graph_csr, ctx, integer(n + 1), integer(0), numeric(0), NULL)    # empty graph: the W = NULL variant
+    } else {
+        Wt <- .mclb_csr(W)
+        aa <- if (is.null(g("aa"))) eigen(as.matrix(W), symmetric = TRUE, only.values = TRUE)$values else g("aa")
+        .Call(C_mclb_graph_csr, ctx, Wt@p, Wt@j, as.numeric(Wt@x), as.numeric(aa))
+    }
+    .Call(C_mclb_model, ctx, as.matrix(X), as.numeric(y), NULL)
+    Mt <- .mclb_csr(M); Zt <- .mclb_csr(Z)
+    bb <- if (is.null(g("bb"))) eigen(as.matrix(M), symmetric = TRUE, only.values = TRUE)$values else g("bb")
+    .Call(C_mclb_hcar_model, ctx, Mt@p, Mt@j, as.numeric(Mt@x), Zt@p, Zt@j, as.numeric(Zt@x), as.numeric(bb), !is.null(W))
+    .mclb$cache[[key]] <- ctx
+    ctx
+}
 sim.HCAR <- function(psi, data, n.samples) {                            # R/HCAR.sim.R:3-87
-    ctx <- attr(data, "mclb"); stopifnot(!is.null(ctx))                 # built once by mclb.hcar.data(data)
+    ctx <- .mclb_hcar_ctx(data)
     h <- .Call(C_mclb_sim_hcar, ctx, as.numeric(psi), n.samples, .mclb$control)
     structure(list(psi = psi, n.samples = n.samples, u.y = h), class = "mclb_hcar", ctx = ctx)
 }
@@ -138,3 +188,9 @@ mcl.HCAR <- function(pars, mcdata, data, Evar = FALSE) {                # R/mcl.
     r <- .Call(C_mclb_mcl_hcar, attr(mcdata, "ctx"), mcdata$u.y, matrix(as.numeric(pars), nrow = 1))
     if (Evar) as.numeric(r) else r[1, 1]
 }
+mcl.grad.HCAR <- function(pars, mcdata, data, Evar = FALSE) {           # R/mcl.HCAR.R:101-213
+    r <- .Call(C_mclb_grad_hcar, attr(mcdata, "ctx"), mcdata$u.y, as.numeric(pars), Evar)
+    if (Evar) list(grad.lr = r[[1]], grad.var = r[[2]]) else r[[1]]
+}
+mcl.Hessian.HCAR <- function(pars, mcdata, data)                        # R/mcl.HCAR.R:216-391
+    .Call(C_mclb_hess_hcar, attr(mcdata, "ctx"), mcdata$u.y, as.numeric(pars))
