@@ -1,8 +1,9 @@
 #!/bin/bash
-# sweep-kernel experiments: each line of CONFIGS is a set of env assignments; prints the sweep time per launch
+# sweep-kernel experiments: CONFIGS is a ;-separated list of env assignments (MCLCAR_SWEEP_FUSED=0|1, MCLCAR_SWEEP_TR=<rows>);
+# prints the sweep time per launch.  EXTRA passes bench flags (e.g. "--chains 148"), NS the samples per GPU.
 out=gpurun_out/sweep_exp.log
 : > $out
-IFS=';' read -ra CFG <<< "${CONFIGS:-MCLCAR_SWEEP_FUSED=2;MCLCAR_SWEEP_FUSED=2 MCLCAR_SWEEP_NT=512;MCLCAR_SWEEP_FUSED=1}"
+IFS=';' read -ra CFG <<< "${CONFIGS:-MCLCAR_SWEEP_FUSED=1;MCLCAR_SWEEP_FUSED=1 MCLCAR_SWEEP_TR=15;MCLCAR_SWEEP_FUSED=0}"
 for cfg in "${CFG[@]}"; do
   env $cfg python bench.py --steps 2 --warmup 1 --samples-per-gpu ${NS:-1320} ${EXTRA} --no-cpu-baseline --no-fp64 2>>gpurun_out/sweep_exp.err | python -c "
 import sys, json
