@@ -61,6 +61,126 @@ __global__ void __launch_bounds__(256, 3) k(PhiloxKeys keys, int iters, float ke
     if (acc.x + acc.y + acc.z + acc.w == 123.456f || xacc == 0x12345u) out[0] = acc.x + (float)xacc;
 }
 
+// ---- candidates for the next round (same launch geometry and shared-memory traffic pattern as D) ----
+__device__ __forceinline__ Philox4 philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K, int rounds) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r)
+        if (r < rounds) philox_round(c0, c1, c2, c3, K.k[2 * r], K.k[2 * r + 1]);
+    return Philox4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ unsigned long long pk(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// VARIANT 0: E two vertically adjacent rows per iteration (4 neighbour-row loads for 2 vectors instead of 6);
+//         1: F packed f32x2 arithmetic for the vertical sums, keep*x and the final FMAs;  2: G Philox4x32-7
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 3) kV(PhiloxKeys keys, int iters, float keep, float gain, float rad2, float* out, int h) {
+    extern __shared__ __align__(128) float sm[];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int rows = 34;
+    for (int i = threadIdx.x; i < rows * h; i += blockDim.x) sm[i] = 0.001f * (float)(i & 1023);
+    __syncthreads();
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t c2 = blockIdx.x, c3 = 0x70520000u;
+    auto normals = [&](const Philox4& r, float& ra, float& sa, float& ca, float& rb, float& sb, float& cb) {
+        ra = sqrt_approx(rad2 * lg2_approx(u01(r.x)));
+        rb = sqrt_approx(rad2 * lg2_approx(u01(r.z)));
+        sincos_approx(6.2831853071795865f * u01(r.y), sa, ca);
+        sincos_approx(6.2831853071795865f * u01(r.w), sb, cb);
+    };
+    auto update = [&](const float4 o, const float4 up, const float4 d, const float e, const float4 cur, const Philox4& r) {
+        float ra, sa, ca, rb, sb, cb;
+        normals(r, ra, sa, ca, rb, sb, cb);
+        float4 v;
+        if (VARIANT == 1) {
+            const unsigned long long v01 = add2(pk(up.x, up.y), pk(d.x, d.y)), v23 = add2(pk(up.z, up.w), pk(d.z, d.w));
+            const unsigned long long s01 = add2(pk(o.x + o.y, o.y + o.z), v01), s23 = add2(pk(o.z + o.w, o.w + e), v23);
+            const unsigned long long k2 = pk(keep, keep), g2 = pk(gain, gain);
+            const unsigned long long t01 = fma2(pk(ra, ra), pk(ca, sa), mul2(k2, pk(cur.x, cur.y)));
+            const unsigned long long t23 = fma2(pk(rb, rb), pk(cb, sb), mul2(k2, pk(cur.z, cur.w)));
+            upk(fma2(g2, s01, t01), v.x, v.y);
+            upk(fma2(g2, s23, t23), v.z, v.w);
+        } else {
+            float4 s;
+            s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e;
+            s.x += up.x + d.x; s.y += up.y + d.y; s.z += up.z + d.z; s.w += up.w + d.w;
+            v.x = fmaf(gain, s.x, fmaf(ra, ca, keep * cur.x));
+            v.y = fmaf(gain, s.y, fmaf(ra, sa, keep * cur.y));
+            v.z = fmaf(gain, s.z, fmaf(rb, cb, keep * cur.z));
+            v.w = fmaf(gain, s.w, fmaf(rb, sb, keep * cur.w));
+        }
+        return v;
+    };
+    const int step = VARIANT == 0 ? 2 : 1;
+    for (int it = 0; it < iters; it += step) {
+        const int row = 1 + (ty + it) % (rows - 3);
+        const float* nm = sm + row * h;
+        float* own = sm + ((row + 5) % (rows - 1)) * h;
+        for (int cv = tx; cv < (h >> 2); cv += 32) {
+            const int c0 = cv << 2;
+            const int ce = c0 + 4 == h ? 0 : c0 + 4;
+            const Philox4 r = philox4x32_r((uint32_t)(it * 4096 + cv), 7u, c2, c3, keys, VARIANT == 2 ? 7 : 10);
+            const float4 up = *reinterpret_cast<const float4*>(nm - h + c0), o = *reinterpret_cast<const float4*>(nm + c0);
+            const float4 d = *reinterpret_cast<const float4*>(nm + h + c0);
+            const float4 cur = *reinterpret_cast<const float4*>(own + c0);
+            const float4 v = update(o, up, d, nm[ce], cur, r);
+            *reinterpret_cast<float4*>(own + c0) = v;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            if (VARIANT == 0) {   // the row below: its `up` and `o` are already in registers
+                const Philox4 r2 = philox4x32_r((uint32_t)((it + 1) * 4096 + cv), 7u, c2, c3, keys, 10);
+                const float4 d2 = *reinterpret_cast<const float4*>(nm + 2 * h + c0);
+                const float4 cur2 = *reinterpret_cast<const float4*>(own + h + c0);
+                const float4 w = update(d, o, d2, nm[h + ce], cur2, r2);
+                *reinterpret_cast<float4*>(own + h + c0) = w;
+                acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+            }
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) out[0] = acc.x;
+}
+template <int VARIANT>
+void runV(const char* name, int iters, int sms) {
+    PhiloxKeys keys = philox_keys(42);
+    float* out; cudaMalloc(&out, 4);
+    const int h = 500;
+    const size_t smem = 72 * 1024;
+    cudaFuncSetAttribute(kV<VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = sms * 3;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    kV<VARIANT><<<grid, 256, smem>>>(keys, 4, 0.25f, 0.25f, -1.2f, out, h);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        kV<VARIANT><<<grid, 256, smem>>>(keys, iters, 0.25f, 0.25f, -1.2f, out, h);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
+    }
+    const double items_per_smsp = 3.0 * 8 * iters * 4 / 4.0;
+    const double updates = (double)grid * 8 * iters * 125 * 4;
+    printf("%-28s %8.3f ms  %.1f ns per warp-item per SMSP (= %.0f cycles at 1.9 GHz)  %.3e site-updates/s  err=%s\n", name, best,
+           best * 1e6 / items_per_smsp, best * 1e6 / items_per_smsp * 1.9, updates / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
+}
+
 // T: the "triple" scheme -- 12 sites (three float4 vectors) from TWO Philox blocks: 24-bit radius + 16-bit angle
 // per Box-Muller pair (6 pairs from 256 bits... 240 used), shared-memory loads/stores as in D
 __device__ __forceinline__ void pair24_16(uint32_t wr, uint32_t ang16, float rad2, float& r, float& s, float& c) {
@@ -175,5 +295,8 @@ int main() {
     run<2>("C + sums/fma (registers)", iters, sms);
     run<3>("D + shared memory ld/st", iters, sms);
     runT(iters, sms);
+    runV<0>("E two rows per iteration", iters, sms);
+    runV<1>("F packed f32x2 arithmetic", iters, sms);
+    runV<2>("G Philox4x32-7", iters, sms);
     return 0;
 }
