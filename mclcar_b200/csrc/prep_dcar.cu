@@ -96,6 +96,12 @@ int64_t default_torus_chains(int n, int64_t N, int burn, int thin) {
     return best;
 }
 
+// the tiled red-black kernels need an even x even torus; lattices whose chains (8 at a time) fit in
+// shared memory go to the general chromatic kernel instead, which keeps them on chip for the whole run
+bool use_torus_sampler(const mclcar_ctx* ctx) {
+    return ctx->kind == GRAPH_TORUS && ctx->n1 % 2 == 0 && ctx->n2 % 2 == 0 && (size_t)ctx->n * 8 * sizeof(float) > 200 * 1024;
+}
+
 int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N) {
     const size_t cap = 200 * 1024;
     int cbmax = 0;
@@ -144,8 +150,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
     if (!s) return fail(ctx, MCLCAR_ENOMEM, "out of host memory");
     s->ctx = ctx; s->dtype = o.dtype; s->sites = n; s->N = N; s->owned = true;
     int st = MCLCAR_OK;
-    const bool use_torus = ctx->kind == GRAPH_TORUS && ctx->n1 % 2 == 0 && ctx->n2 % 2 == 0 &&
-                           (size_t)n * 8 * sizeof(float) > 200 * 1024;
+    const bool use_torus = use_torus_sampler(ctx);
     double* d_mu = nullptr;
     if (use_torus) {
         // ---- spatially tiled red-black sampler, sample-major output
@@ -251,8 +256,7 @@ extern "C" int mclcar_dcar_plan(mclcar_ctx* ctx, double rho, int64_t N, const mc
     double omega = o.omega;
     default_schedule(ctx, rho, &omega, &burn, &thin);
     const int n = ctx->n;
-    const bool use_torus = ctx->kind == GRAPH_TORUS && ctx->n1 % 2 == 0 && ctx->n2 % 2 == 0 &&
-                           (size_t)n * 8 * sizeof(float) > 200 * 1024;
+    const bool use_torus = use_torus_sampler(ctx);
     int64_t C;
     int k;
     if (use_torus) {
