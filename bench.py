@@ -118,9 +118,9 @@ def cpu_hot_path(n_samples: int, y, psis):
 
 
 def cpu_sample_size(cores: int) -> int:
-    """Bounded sample of the 12,500-sample shard for the CPU legs: about 32 samples per host thread, at
-    most 1024 (8 GB of fp64 fields), so the leg takes seconds to tens of seconds on any box."""
-    return int(min(32 * cores, 1024))
+    """Bounded sample of the 12,500-sample shard for the CPU legs: 128 samples per host thread, at most
+    4096 -- about 10 s of host work (the fields are drawn and reduced in blocks of 256, 2 GB at a time)."""
+    return int(min(128 * cores, 4096))
 
 
 def run_reference(args):

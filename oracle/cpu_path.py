@@ -104,10 +104,16 @@ def hot_path_torus(n1, n2, X, y, psi0, psis, N, seed=0, threads=None, batch=8):
         x = np.fft.irfft2(np.fft.rfft2(z, axes=(1, 2)) / d[None, :, : n2 // 2 + 1], s=(n1, n2), axes=(1, 2))
         return x.reshape(nb, n) + mu
 
-    chunks = [(k, min(batch, N - s)) for k, s in enumerate(range(0, N, batch))]
+    # draw and reduce in blocks of <= `block` samples: the host never holds more than block x n doubles
+    block = max(batch, 256)
+    qs = []
     with ThreadPoolExecutor(max_workers=threads) as ex:
-        Y = np.concatenate(list(ex.map(draw, chunks)), axis=0)
-    q = stats_torus(Y, n1, n2, X)
+        for b0 in range(0, N, block):
+            nb_tot = min(block, N - b0)
+            chunks = [(b0 // batch + k, min(batch, nb_tot - s)) for k, s in enumerate(range(0, nb_tot, batch))]
+            Y = np.concatenate(list(ex.map(draw, chunks)), axis=0)
+            qs.append(stats_torus(Y, n1, n2, X))
+    q = np.concatenate(qs, axis=0)
     c0 = affine_coef(psi0, p, G0, G1)
     t20 = c0[0] + q @ c0[1:]
     qobs = dcar.suffstats(W, X, np.asarray(y)[:, None])[0]
