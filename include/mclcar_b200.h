@@ -156,6 +156,13 @@ MCLCAR_API int mclcar_dcar_stats(mclcar_ctx* ctx, mclcar_samples* s, double* q_o
  * chromatic Gibbs sampler and attaches t10 = h(y; psi0), t20_i = h(Y_i; psi0). */
 MCLCAR_API int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
                      mclcar_samples** out);
+/* Effective sample size of each of the d rows of a statistics matrix q ([d][ldq], sample index =
+ * e * chains + chain, the order both samplers write): pooled autocovariances along the chains, Geyer's
+ * initial positive sequence, ESS = N / tau.  Pure host code (no context, no GPU).  The reference's
+ * samples are independent draws (ESS = N); this is the check that the Gibbs thinning gives the same. */
+MCLCAR_API int mclcar_ess_from_stats(const double* q, int64_t N, int d, int64_t ldq, int64_t chains, double* ess_out);
+/* the same for the sufficient statistics of a sample set drawn by mclcar_*_prep (d doubles out) */
+MCLCAR_API int mclcar_samples_ess(mclcar_ctx* ctx, mclcar_samples* s, double* ess_out);
 /* what mclcar_dcar_prep would run for (rho, N, opts) on this context's graph, without running it:
  * kind 1 = tiled red-black torus kernels, 2 = general chromatic kernel with the chains in shared
  * memory, 3 = same with the chains in global memory; chains, burn-in sweeps, sweeps per kept state,

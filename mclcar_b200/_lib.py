@@ -80,6 +80,8 @@ SIGNATURES = {
     "mclcar_samples_fetch": (_i, [_vp, _vp, _i, _pd, _i64]),
     "mclcar_samples_diag": (_i, [_vp, _vp, _pd, _pi64]),
     "mclcar_samples_schedule": (_i, [_vp, _vp, _pi64, _pi, _pi, _pd]),
+    "mclcar_ess_from_stats": (_i, [_pd, _i64, _i, _i64, _i64, _pd]),
+    "mclcar_samples_ess": (_i, [_vp, _vp, _pd]),
     "mclcar_dcar_stats": (_i, [_vp, _vp, _pd]),
     "mclcar_dcar_prep": (_i, [_vp, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
     "mclcar_dcar_plan": (_i, [_vp, _d, _i64, C.POINTER(SamplerOpts), _pi, _pi64, _pi, _pi, _pd]),

@@ -399,6 +399,26 @@ def mcl_prep_dCAR(psi, n_samples: int, data: CarData, control: Optional[dict] = 
     return SimData(data, h, psi)
 
 
+def ess_from_stats(q, chains: int) -> np.ndarray:
+    """Effective sample size of every column of q (N x d, sample index = e * chains + chain): Geyer's
+    initial positive sequence on the autocovariances pooled over the chains.  Host code."""
+    q = np.ascontiguousarray(np.atleast_2d(np.asarray(q, dtype=np.float64).T))      # [d][N]
+    d, N = q.shape
+    out = np.empty(d)
+    st = lib.mclcar_ess_from_stats(dptr(q), N, d, N, int(chains), dptr(out))
+    if st != 0:
+        raise ValueError("ess_from_stats: bad arguments")
+    return out
+
+
+def sampler_ess(data: CarData, simdata) -> np.ndarray:
+    """ESS of the sufficient statistics (x'x, x'Wx, X'x, X'Wx) of a sample set the sampler drew."""
+    n_stats = simdata.stats().shape[1]          # also makes sure the statistics exist on the device
+    out = np.empty(n_stats)
+    check(lib.mclcar_samples_ess(data.ctx.h, simdata.h, dptr(out)), data.ctx.h)
+    return out
+
+
 def plan_dCAR(psi, n_samples: int, data: CarData, control: Optional[dict] = None) -> dict:
     """What mcl_prep_dCAR(psi, n_samples, data, control) would run, without running it (host logic,
     works on a host-only context): sampler kind, chains, burn-in, thinning, over-relaxation factor."""

@@ -198,6 +198,57 @@ int mclcar_samples_diag(mclcar_ctx* ctx, mclcar_samples* s, double* accept_rate,
     return MCLCAR_OK;
 }
 
+/* Effective sample size of each row of q ([d][ldq], sample index = e * chains + chain as both samplers
+ * write them): pooled autocovariances along the chains, Geyer's initial positive sequence
+ * (rho_0 + rho_1) + (rho_2 + rho_3) + ... summed while the pairs stay positive, ESS = N / tau with
+ * tau = -1 + 2 * sum.  Pure host code: the reference draws independent samples (ESS = N), so this is
+ * the number to look at before trusting `v.lr` from a Gibbs run. */
+int mclcar_ess_from_stats(const double* q, int64_t N, int d, int64_t ldq, int64_t chains, double* ess_out) {
+    if (!q || !ess_out || N < 1 || d < 1 || ldq < N || chains < 1) return MCLCAR_EINVAL;
+    const int64_t C = chains < N ? chains : N;
+    const int64_t E = (N + C - 1) / C;                      // states per chain (the last row of states may be partial)
+    const int64_t maxlag = E - 1 < 200 ? E - 1 : 200;
+    for (int j = 0; j < d; ++j) {
+        const double* x = q + (size_t)j * ldq;
+        long double m = 0;
+        for (int64_t i = 0; i < N; ++i) m += x[i];
+        m /= N;
+        auto gamma = [&](int64_t k) {
+            long double a = 0;
+            int64_t cnt = 0;
+            for (int64_t i = 0; i + k * C < N; ++i) {       // same chain, k states later: index + k * C
+                a += ((long double)x[i] - m) * ((long double)x[i + k * C] - m);
+                ++cnt;
+            }
+            return cnt ? (double)(a / cnt) : 0.0;
+        };
+        const double g0 = gamma(0);
+        if (!(g0 > 0)) { ess_out[j] = (double)N; continue; }
+        double sum = 0.0;
+        for (int64_t k = 0; k <= maxlag; k += 2) {
+            const double pair = gamma(k) / g0 + (k + 1 <= maxlag ? gamma(k + 1) / g0 : 0.0);
+            if (pair <= 0) break;
+            sum += pair;
+        }
+        double tau = -1.0 + 2.0 * sum;
+        if (tau < 1e-3) tau = 1e-3;
+        ess_out[j] = (double)N / tau;
+    }
+    return MCLCAR_OK;
+}
+
+/* the same for the statistics of a sample set drawn by one of the samplers (x'x, x'Wx, ... rows of q) */
+int mclcar_samples_ess(mclcar_ctx* ctx, mclcar_samples* s, double* ess_out) {
+    if (!ctx || !s || !ess_out) return MCLCAR_EINVAL;
+    MCL_TRY(require_device(ctx));
+    if (!s->stats_ready || !s->d_q || s->d < 1) return fail(ctx, MCLCAR_ESTATE, "statistics not computed yet: evaluate once (or call mclcar_dcar_stats) first");
+    if (s->chains < 1) return fail(ctx, MCLCAR_ESTATE, "the sample matrix came from the caller: no chain structure");
+    std::vector<double> q((size_t)s->d * s->N);
+    MCL_CUDA(ctx, cudaMemcpyAsync(q.data(), s->d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return mclcar_ess_from_stats(q.data(), s->N, s->d, s->N, s->chains, ess_out);
+}
+
 int mclcar_samples_schedule(mclcar_ctx* ctx, mclcar_samples* s, int64_t* chains, int* burn, int* thin, double* omega) {
     if (!ctx || !s) return MCLCAR_EINVAL;
     if (chains) *chains = s->chains;

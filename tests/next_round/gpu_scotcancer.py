@@ -54,3 +54,16 @@ def test_latent_posterior_matches_the_mala_chain():
     se = np.sqrt(ref.var(axis=0) / 400 + Zg.var(axis=0) / 1000)        # generous effective sample sizes
     assert np.abs(Zg.mean(axis=0) - ref.mean(axis=0)).max() < 5 * se.max()
     assert np.allclose(Zg.std(axis=0), ref.std(axis=0), rtol=0.25)
+
+
+def test_sampler_ess_with_the_default_schedule():
+    """mclcar_samples_ess on a torus run: with the default thinning the statistics are close to
+    independent (ESS within 15 % of N); with thin = 1 the slow constant mode (X'x) is visibly not."""
+    n1 = n2 = 96
+    data = api.make_data(np.zeros(n1 * n2), X=np.ones((n1 * n2, 1)), torus=(n1, n2), seed=4)
+    N, C_ = 256 * 100, 256
+    sd = api.mcl_prep_dCAR([0.2, 1.0, 0.0], N, data, {"n.chains": C_, "keep": False})
+    ess = api.sampler_ess(data, sd)
+    assert ess.shape == (4,) and np.all(ess > 0.85 * N) and np.all(ess < 1.25 * N)
+    sd1 = api.mcl_prep_dCAR([0.2, 1.0, 0.0], N, data, {"n.chains": C_, "keep": False, "thin": 1})
+    assert api.sampler_ess(data, sd1)[2] < 0.5 * N

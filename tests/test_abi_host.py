@@ -96,6 +96,30 @@ def test_sampler_plan_rules_on_a_host_only_context():
     assert p2["sampler"] == "chromatic, chains in shared memory" and p2["chains"] % 2 == 0 and p2["thin"] == 5
 
 
+def test_effective_sample_size_of_chain_statistics():
+    """mclcar_ess_from_stats on series with known integrated autocorrelation time: AR(1) chains with
+    phi have tau = (1 + phi) / (1 - phi); independent draws have ESS = N; the sample order is the
+    samplers' (index = state * chains + chain), with a partial last row of states."""
+    rng = np.random.default_rng(0)
+    C_, E = 64, 400
+    N = C_ * E - 17                                   # the last row of states is partial
+    def ar1(phi):
+        x = np.empty((E, C_))
+        x[0] = rng.standard_normal(C_)
+        for e in range(1, E):
+            x[e] = phi * x[e - 1] + np.sqrt(1 - phi * phi) * rng.standard_normal(C_)
+        return x.reshape(-1)[:N]                      # index = e * C + chain
+    q = np.column_stack([ar1(0.0), ar1(0.5), ar1(0.8), ar1(-0.3)])
+    ess = api.ess_from_stats(q, C_)
+    tau = np.array([1.0, 3.0, 9.0, 0.7 / 1.3])
+    np.testing.assert_allclose(ess, N / tau, rtol=0.12)
+    # read with the wrong chain count the dependence is missed or misplaced: the layout matters
+    assert api.ess_from_stats(q[:, 2:3], 1)[0] > 2 * ess[2]
+    # a constant statistic (e.g. X'x of a degenerate design) does not divide by zero
+    assert api.ess_from_stats(np.ones((100, 1)), 10)[0] == 100.0
+    assert L.lib.mclcar_ess_from_stats(None, 10, 1, 10, 2, None) == L.EINVAL
+
+
 def test_colouring():
     ctx = api.Context(device=-1)
     assert L.lib.mclcar_graph_torus(ctx.h, 6, 8) == 0
