@@ -87,6 +87,13 @@ MCLCAR_API int mclcar_ctx_trim(mclcar_ctx* ctx);
 /* this context is shard `rank` of `world`: samplers draw global chains rank, rank+world,
  * ... so that the union over ranks does not depend on `world`. */
 MCLCAR_API int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world);
+/* Every sampler run (mclcar_dcar_prep, mclcar_glm_prep, mclcar_hcar_prep) uses its own Philox stream: key =
+ * seed + draw * 0x9E3779B97F4A7C15 with `draw` the number of sampler runs this context has made so far --
+ * as the reference draws fresh rnorm() in every mcl.prep.dCAR / postZ / sim.HCAR call (R/mcl.dCAR.R:3,
+ * R/HCAR.sim.R:67).  (seed, draw) reproduces a sample set; the ranks of a sharded run must make the same
+ * calls so that their counters agree.  set_draw rewinds / forwards the counter. */
+MCLCAR_API int mclcar_ctx_set_draw(mclcar_ctx* ctx, uint64_t draw);
+MCLCAR_API int mclcar_ctx_get_draw(const mclcar_ctx* ctx, uint64_t* draw);
 /* instrumentation: kernel-launch counters per category and, while enabled, CUDA-event time
  * spans recorded on the context's stream around each group of launches.  Categories:
  * 0 torus half sweeps, 1 sample emission, 2 statistics (K2), 3 reduction (K3),
@@ -107,6 +114,15 @@ MCLCAR_API int mclcar_graph_torus(mclcar_ctx* ctx, int n1, int n2);
 /* general neighbourhood matrix W in CSR (0-based, symmetric, zero diagonal; val NULL =
  * binary).  Replaces `data$W` (dense n x n in the reference).  Validated on upload. */
 MCLCAR_API int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val);
+/* The reference hands every model its W as a matrix -- CAR.simTorus returns as.matrix(W) (R/CAR.simLM.R:19) -- so
+ * the lattices of BASELINE configs 1, 2 and 5 reach this library as CSR.  mclcar_graph_csr recognises an exact
+ * rook torus (binary, every row of degree 4 with neighbours (i +- 1, j), (i, j +- 1) cyclic for some n1 * n2 = n,
+ * n1, n2 >= 3, site (i, j) at index i*n2 + j) and switches to the torus form: tiled red-black sampler, bulk-staged
+ * statistics kernel, analytic eigenvalues (no eigen(W)).  _opts with detect_torus = 0 keeps the generic kernels. */
+MCLCAR_API int mclcar_graph_csr_opts(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val,
+                                     int detect_torus);
+/* 0 = no graph, 1 = torus (n1, n2 returned), 2 = general CSR; n1 / n2 may be NULL */
+MCLCAR_API int mclcar_graph_kind(const mclcar_ctx* ctx, int* n1, int* n2);
 /* eigenvalues of W (`data$lambda`, eigen(W) at R/mcl.bin.R:176): needed by the GLM
  * gradient / Hessian and for the rho range check on CSR graphs.  Optional. */
 MCLCAR_API int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, int n);

@@ -62,12 +62,16 @@ SIGNATURES = {
     "mclcar_ctx_sync": (_i, [_vp]),
     "mclcar_ctx_trim": (_i, [_vp]),
     "mclcar_ctx_set_shard": (_i, [_vp, _i, _i]),
+    "mclcar_ctx_set_draw": (_i, [_vp, C.c_uint64]),
+    "mclcar_ctx_get_draw": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "mclcar_ctx_profile": (_i, [_vp, _i]),
     "mclcar_ctx_profile_read": (_i, [_vp, _pd, _pi64]),
     "mclcar_nccl_unique_id": (_i, [_vp, C.c_char_p]),
     "mclcar_nccl_comm_init": (_i, [_vp, C.c_char_p]),
     "mclcar_graph_torus": (_i, [_vp, _i, _i]),
     "mclcar_graph_csr": (_i, [_vp, _i, _pi, _pi, _pd]),
+    "mclcar_graph_csr_opts": (_i, [_vp, _i, _pi, _pi, _pd, _i]),
+    "mclcar_graph_kind": (_i, [_vp, _pi, _pi]),
     "mclcar_graph_set_eigenvalues": (_i, [_vp, _pd, _i]),
     "mclcar_set_design": (_i, [_vp, _pd, _i]),
     "mclcar_set_obs": (_i, [_vp, _pd, _pd]),

@@ -56,6 +56,18 @@ class Context:
     def set_shard(self, rank: int, world: int):
         check(lib.mclcar_ctx_set_shard(self.h, rank, world), self.h)
 
+    @property
+    def draw(self) -> int:
+        """Index of the next sampler run on this context: every mcl.prep.* call owns the Philox stream
+        (seed, draw), as the reference draws fresh random numbers per call."""
+        v = C.c_uint64()
+        check(lib.mclcar_ctx_get_draw(self.h, C.byref(v)), self.h)
+        return int(v.value)
+
+    @draw.setter
+    def draw(self, value: int):
+        check(lib.mclcar_ctx_set_draw(self.h, int(value)), self.h)
+
 
 @dataclass
 class CarData:
@@ -75,7 +87,7 @@ class CarData:
 
 
 def make_data(y, X=None, W=None, torus=None, n_trial=None, eigenvalues=None, device: int = 0, seed: int = 0,
-              ctx: Optional[Context] = None) -> CarData:
+              ctx: Optional[Context] = None, detect_torus: bool = True) -> CarData:
     """Upload graph, design and observations.  Exactly one of `W` (symmetric scipy sparse /
     dense, zero diagonal -- `data$W`) or `torus=(n1, n2)` (the W of CAR.simTorus,
     R/CAR.simLM.R:4-7) must be given."""
@@ -88,11 +100,14 @@ def make_data(y, X=None, W=None, torus=None, n_trial=None, eigenvalues=None, dev
         Wc = None
     else:
         Wc = sp.csr_matrix(W, dtype=np.float64)
+        Wc.eliminate_zeros()      # explicitly stored zeros are not neighbours
         Wc.sort_indices()
         rp = np.ascontiguousarray(Wc.indptr, dtype=np.int32)
         ci = np.ascontiguousarray(Wc.indices, dtype=np.int32)
         vals = np.ascontiguousarray(Wc.data, dtype=np.float64)
-        check(lib.mclcar_graph_csr(ctx.h, Wc.shape[0], iptr(rp), iptr(ci), dptr(vals)), ctx.h)
+        # a W that is exactly the rook torus of CAR.simTorus (R/CAR.simLM.R:4-7) is recognised by the library
+        # and served by the tiled red-black kernels with the analytic spectrum (detect_torus=False: generic kernels)
+        check(lib.mclcar_graph_csr_opts(ctx.h, Wc.shape[0], iptr(rp), iptr(ci), dptr(vals), int(bool(detect_torus))), ctx.h)
     n = lib.mclcar_graph_n(ctx.h)
     if y.shape[0] != n:
         raise ValueError(f"y has {y.shape[0]} entries, graph has {n} sites")
@@ -427,7 +442,7 @@ def plan_dCAR(psi, n_samples: int, data: CarData, control: Optional[dict] = None
     check(lib.mclcar_dcar_plan(data.ctx.h, float(np.asarray(psi, dtype=np.float64)[0]), int(n_samples), C.byref(o), C.byref(kind),
                                C.byref(ch), C.byref(bu), C.byref(th), C.byref(om)), data.ctx.h)
     names = {1: "torus tiles", 2: "chromatic, chains in shared memory", 3: "chromatic, chains in global memory"}
-    return {"sampler": names[kind.value], "chains": ch.value, "burn": bu.value, "thin": th.value, "omega": om.value}
+    return {"kind": kind.value, "sampler": names[kind.value], "chains": ch.value, "burn": bu.value, "thin": th.value, "omega": om.value}
 
 
 def sampler_diag(data: CarData, simdata) -> dict:

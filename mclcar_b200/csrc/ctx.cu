@@ -343,6 +343,18 @@ int mclcar_ctx_set_shard(mclcar_ctx* ctx, int rank, int world) {
     return MCLCAR_OK;
 }
 
+int mclcar_ctx_set_draw(mclcar_ctx* ctx, uint64_t draw) {
+    if (!ctx) return MCLCAR_EINVAL;
+    ctx->draw = draw;
+    return MCLCAR_OK;
+}
+
+int mclcar_ctx_get_draw(const mclcar_ctx* ctx, uint64_t* draw) {
+    if (!ctx || !draw) return MCLCAR_EINVAL;
+    *draw = ctx->draw;
+    return MCLCAR_OK;
+}
+
 int mclcar_ctx_profile(mclcar_ctx* ctx, int enable) {
     if (!ctx) return MCLCAR_EINVAL;
     MCL_TRY(require_device(ctx));
@@ -375,11 +387,7 @@ int mclcar_ctx_profile_read(mclcar_ctx* ctx, double ms_out[8], int64_t launches_
 int mclcar_graph_n(const mclcar_ctx* ctx) { return ctx ? ctx->n : 0; }
 int mclcar_graph_ncolors(const mclcar_ctx* ctx) { return ctx ? ctx->ncolors : 0; }
 
-int mclcar_graph_torus(mclcar_ctx* ctx, int n1, int n2) {
-    if (!ctx) return MCLCAR_EINVAL;
-    if (n1 < 3 || n2 < 3 || (int64_t)n1 * n2 > (int64_t)1 << 30)
-        return fail(ctx, MCLCAR_EINVAL, "torus sides must be >= 3 and n1*n2 <= 2^30 (got %d x %d)", n1, n2);
-    if (!ctx->host_only) MCL_TRY(require_device(ctx));
+static int set_torus(mclcar_ctx* ctx, int n1, int n2) {
     invalidate_model(ctx);
     ctx->kind = GRAPH_TORUS;
     ctx->n1 = n1; ctx->n2 = n2; ctx->n = n1 * n2;
@@ -410,7 +418,49 @@ int mclcar_graph_torus(mclcar_ctx* ctx, int n1, int n2) {
     return finish_graph(ctx);
 }
 
-int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val) {
+int mclcar_graph_torus(mclcar_ctx* ctx, int n1, int n2) {
+    if (!ctx) return MCLCAR_EINVAL;
+    if (n1 < 3 || n2 < 3 || (int64_t)n1 * n2 > (int64_t)1 << 30)
+        return fail(ctx, MCLCAR_EINVAL, "torus sides must be >= 3 and n1*n2 <= 2^30 (got %d x %d)", n1, n2);
+    if (!ctx->host_only) MCL_TRY(require_device(ctx));
+    return set_torus(ctx, n1, n2);
+}
+
+// Is this binary CSR matrix exactly the rook torus with site (i, j) at index i*n2 + j?  Every row has four
+// distinct neighbours; site 0's are {1, n2-1, n2, n-n2}, so n2 is its third smallest neighbour (n1, n2 >= 3;
+// sides of length 4 or less give coinciding candidates that the full comparison below sorts out).
+static bool detect_rook_torus(int n, const int* rowptr, const int* colidx, const double* val, int* n1_out, int* n2_out) {
+    if (n < 9 || rowptr[n] != (int64_t)4 * n) return false;
+    for (int i = 0; i < n; ++i)
+        if (rowptr[i + 1] - rowptr[i] != 4) return false;
+    if (val)
+        for (int64_t e = 0; e < (int64_t)4 * n; ++e)
+            if (val[e] != 1.0) return false;
+    int nb0[4] = {colidx[0], colidx[1], colidx[2], colidx[3]};
+    std::sort(nb0, nb0 + 4);
+    // candidates for n2: any neighbour index of site 0 (+1) that divides n -- at most a handful
+    for (int cand : {nb0[2], nb0[1] + 1, nb0[1], nb0[0] + 1, nb0[3]}) {
+        const int n2 = cand;
+        if (n2 < 3 || n % n2 != 0 || n / n2 < 3) continue;
+        const int n1 = n / n2;
+        bool ok = true;
+        for (int i = 0; i < n1 && ok; ++i)
+            for (int j = 0; j < n2 && ok; ++j) {
+                const int s = i * n2 + j;
+                int want[4] = {((i + n1 - 1) % n1) * n2 + j, i * n2 + (j + n2 - 1) % n2, i * n2 + (j + 1) % n2,
+                               ((i + 1) % n1) * n2 + j};
+                int got[4] = {colidx[4 * (size_t)s], colidx[4 * (size_t)s + 1], colidx[4 * (size_t)s + 2], colidx[4 * (size_t)s + 3]};
+                std::sort(want, want + 4);
+                std::sort(got, got + 4);
+                ok = want[0] == got[0] && want[1] == got[1] && want[2] == got[2] && want[3] == got[3] &&
+                     want[0] != want[1] && want[1] != want[2] && want[2] != want[3];
+            }
+        if (ok) { *n1_out = n1; *n2_out = n2; return true; }
+    }
+    return false;
+}
+
+int mclcar_graph_csr_opts(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val, int detect_torus) {
     if (!ctx || !rowptr || !colidx) return MCLCAR_EINVAL;
     if (n < 1) return fail(ctx, MCLCAR_EINVAL, "n must be positive");
     if (!ctx->host_only) MCL_TRY(require_device(ctx));
@@ -436,6 +486,8 @@ int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colid
                 found = colidx[e2] == i && (val ? val[e2] == val[e] : true);
             if (!found) return fail(ctx, MCLCAR_EINVAL, "W is not symmetric at (%d, %d)", i, j);
         }
+    int t1 = 0, t2 = 0;
+    if (detect_torus && detect_rook_torus(n, rowptr, colidx, val, &t1, &t2)) return set_torus(ctx, t1, t2);
     invalidate_model(ctx);
     ctx->kind = GRAPH_CSR;
     ctx->n = n; ctx->n1 = ctx->n2 = 0;
@@ -450,6 +502,17 @@ int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colid
     ctx->eigs.clear();
     ctx->ew_min = ctx->ew_max = 0.0;
     return finish_graph(ctx);
+}
+
+int mclcar_graph_csr(mclcar_ctx* ctx, int n, const int* rowptr, const int* colidx, const double* val) {
+    return mclcar_graph_csr_opts(ctx, n, rowptr, colidx, val, 1);
+}
+
+int mclcar_graph_kind(const mclcar_ctx* ctx, int* n1, int* n2) {
+    if (!ctx) return 0;
+    if (n1) *n1 = ctx->n1;
+    if (n2) *n2 = ctx->n2;
+    return ctx->kind;
 }
 
 int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, int n) {

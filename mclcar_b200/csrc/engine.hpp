@@ -42,6 +42,11 @@ struct mclcar_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     uint64_t seed = 0;
+    // every *_prep call owns a fresh Philox stream: key = seed + draw * golden ratio (begin_draw); the
+    // counter is part of the reproducible state (same seed + same call index => same samples) and is
+    // the same on every rank of a sharded run
+    uint64_t draw = 0;       // index of the next prep call
+    uint64_t draw_key = 0;   // Philox key of the prep call in progress
     int rank = 0, world = 1;
     int n_sm = 148;
     std::string err;
@@ -258,6 +263,12 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
                     const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
                     void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out);
 int check_rho(mclcar_ctx* ctx, double rho);
+// start of a sampler run: derive this call's Philox key and advance the context's draw counter
+inline uint64_t begin_draw(mclcar_ctx* ctx) {
+    ctx->draw_key = ctx->seed + ctx->draw * 0x9E3779B97F4A7C15ull;
+    ++ctx->draw;
+    return ctx->draw_key;
+}
 void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* burn, int* thin);
 int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N);
 int64_t default_torus_chains(int n, int64_t N, int burn, int thin);

@@ -36,6 +36,7 @@ int mclcar_multi_dcar_prep(mclcar_ctx** ctxs, int G, const double* psi0, int P, 
     MCL_TRY(check_multi(ctxs, G));
     std::vector<int> st(G, MCLCAR_OK);
     std::vector<std::thread> th;
+    for (int g = 1; g < G; ++g) ctxs[g]->draw = ctxs[0]->draw;   // the shards of one draw share its Philox key
     for (int g = 0; g < G; ++g) {
         out[g] = nullptr;
         th.emplace_back([&, g] {

@@ -163,6 +163,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         s->ld = ld;
         TorusChains tc;
         void* staging = nullptr;
+        begin_draw(ctx);   // a fresh Philox stream for every mcl.prep.dCAR call (R draws fresh rnorm() each time)
         do {
             if (!mu.empty()) {
                 if ((st = pool_alloc(ctx, (void**)&d_mu, (size_t)n * sizeof(double)))) break;

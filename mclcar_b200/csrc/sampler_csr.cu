@@ -181,6 +181,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
                     const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
                     void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out) {
     MCL_TRY(require_device(ctx));
+    begin_draw(ctx);   // a fresh Philox stream for every sampler run (the reference draws fresh rnorm() per call)
     const int n = g.n;
     const int ncol = (int)g.color_ptr->size() - 1;
     // ---- permute the CSR into colour-major position order, convert to the conditional form
@@ -272,7 +273,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
         p.mu = (const double*)d_mu; p.yv = (const float*)d_y; p.nt = (const float*)d_nt; p.xb = (const float*)d_xb;
         p.CB = CB; p.C = C; p.burn = burn; p.thin = thin; p.E = E; p.N = N;
         p.out = d_out; p.ld = ld; p.out_f64 = out_f64; p.state_g = (float*)d_state;
-        p.keys = philox_keys(ctx->seed);
+        p.keys = philox_keys(ctx->draw_key);
         p.keep = (float)(1.0 - omega); p.gain = (float)omega; p.noise = (float)std::sqrt(omega * (2.0 - omega));
         p.pair0 = ctx->rank; p.pair_stride = ctx->world;
         p.counters = (unsigned long long*)d_cnt;

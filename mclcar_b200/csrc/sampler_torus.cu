@@ -404,7 +404,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
     p.gain = (float)(omega * rho);
     p.noise = (float)std::sqrt(omega * (2.0 - omega) * sigma);
     p.rad2 = (float)(-2.0 * std::log(2.0) * omega * (2.0 - omega) * sigma);
-    p.keys = philox_keys(ctx->seed);
+    p.keys = philox_keys(ctx->draw_key);
     p.sweep = sweep;
     p.chain0 = ctx->rank; p.chain_stride = ctx->world;
     const bool vec4 = (p.h % 4) == 0;

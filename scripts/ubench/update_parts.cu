@@ -90,6 +90,21 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
     return r;
 }
 
+// Philox round with separate mul.lo / mul.hi (IMAD + IMAD.HI) instead of one 64-bit product (IMAD.WIDE)
+__device__ __forceinline__ Philox4 philox4x32_hilo(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi0) : "r"(c0), "r"(0xD2511F53u));
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo0) : "r"(c0), "r"(0xD2511F53u));
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi1) : "r"(c2), "r"(0xCD9E8D57u));
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo1) : "r"(c2), "r"(0xCD9E8D57u));
+        const uint32_t n0 = hi1 ^ c1 ^ K.k[2 * r], n2 = hi0 ^ c3 ^ K.k[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
 // VARIANT 0: E two vertically adjacent rows per iteration (4 neighbour-row loads for 2 vectors instead of 6);
 //         1: F packed f32x2 arithmetic for the vertical sums, keep*x and the final FMAs;  2: G Philox4x32-7
 template <int VARIANT>
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(256, 3) kV(PhiloxKeys keys, int iters, float k
         float ra, sa, ca, rb, sb, cb;
         normals(r, ra, sa, ca, rb, sb, cb);
         float4 v;
-        if (VARIANT == 1) {
+        if (VARIANT == 1 || VARIANT == 4) {
             const unsigned long long v01 = add2(pk(up.x, up.y), pk(d.x, d.y)), v23 = add2(pk(up.z, up.w), pk(d.z, d.w));
             const unsigned long long s01 = add2(pk(o.x + o.y, o.y + o.z), v01), s23 = add2(pk(o.z + o.w, o.w + e), v23);
             const unsigned long long k2 = pk(keep, keep), g2 = pk(gain, gain);
@@ -130,7 +145,7 @@ __global__ void __launch_bounds__(256, 3) kV(PhiloxKeys keys, int iters, float k
         }
         return v;
     };
-    const int step = VARIANT == 0 ? 2 : 1;
+    const int step = (VARIANT == 0 || VARIANT == 4) ? 2 : 1;
     for (int it = 0; it < iters; it += step) {
         const int row = 1 + (ty + it) % (rows - 3);
         const float* nm = sm + row * h;
@@ -138,14 +153,15 @@ __global__ void __launch_bounds__(256, 3) kV(PhiloxKeys keys, int iters, float k
         for (int cv = tx; cv < (h >> 2); cv += 32) {
             const int c0 = cv << 2;
             const int ce = c0 + 4 == h ? 0 : c0 + 4;
-            const Philox4 r = philox4x32_r((uint32_t)(it * 4096 + cv), 7u, c2, c3, keys, VARIANT == 2 ? 7 : 10);
+            const Philox4 r = VARIANT == 3 ? philox4x32_hilo((uint32_t)(it * 4096 + cv), 7u, c2, c3, keys)
+                                           : philox4x32_r((uint32_t)(it * 4096 + cv), 7u, c2, c3, keys, VARIANT == 2 ? 7 : 10);
             const float4 up = *reinterpret_cast<const float4*>(nm - h + c0), o = *reinterpret_cast<const float4*>(nm + c0);
             const float4 d = *reinterpret_cast<const float4*>(nm + h + c0);
             const float4 cur = *reinterpret_cast<const float4*>(own + c0);
             const float4 v = update(o, up, d, nm[ce], cur, r);
             *reinterpret_cast<float4*>(own + c0) = v;
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            if (VARIANT == 0) {   // the row below: its `up` and `o` are already in registers
+            if (VARIANT == 0 || VARIANT == 4) {   // the row below: its `up` and `o` are already in registers
                 const Philox4 r2 = philox4x32_r((uint32_t)((it + 1) * 4096 + cv), 7u, c2, c3, keys, 10);
                 const float4 d2 = *reinterpret_cast<const float4*>(nm + 2 * h + c0);
                 const float4 cur2 = *reinterpret_cast<const float4*>(own + h + c0);
@@ -262,6 +278,131 @@ void runT(int iters, int sms) {
     printf("%-28s %8.3f ms  %.3e site-updates/s  err=%s\n", "T triples (24+16 bit pairs)", best, updates / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
 }
 
+
+// T2: 12 sites (three float4 vectors) from TWO Philox blocks.  Per block three Box-Muller pairs: radius from the top 23 bits
+// of word j, angle from its low 9 bits + 10 bits of word 3 (19 bits, built in the mantissa: no int->float conversion).
+// A uniform angle on a 2^19-point grid reproduces every trigonometric moment below order 2^19 exactly.
+__device__ __forceinline__ void pair23_19(uint32_t wj, uint32_t w3, int j, float rad2, float& r, float& s, float& c) {
+    r = sqrt_approx(rad2 * lg2_approx(u01(wj)));
+    const uint32_t m = ((wj & 0x1ffu) << 14) | (((w3 >> (10 * j)) & 0x3ffu) << 4) | 0x3f800008u;
+    const float u = __uint_as_float(m) - 1.0f;
+    sincos_approx(6.2831853071795865f * u, s, c);
+}
+template <int H>
+__global__ void __launch_bounds__(256, 3) kT2(PhiloxKeys keys, int iters, float keep, float gain, float rad2, float* out) {
+    extern __shared__ __align__(128) float sm[];
+    constexpr int h = H;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int rows = 72 * 1024 / (4 * h) - 2;
+    for (int i = threadIdx.x; i < rows * h; i += blockDim.x) sm[i] = 0.001f * (float)(i & 1023);
+    __syncthreads();
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t c2 = blockIdx.x, c3 = 0x70520000u;
+    constexpr int hv = h >> 2, nt = (hv + 2) / 3;
+    for (int it = 0; it < iters; ++it) {
+        const int row = 1 + (ty + it) % (rows - 2);
+        const float* nm = sm + row * h;
+        float* own = sm + ((row + 5) % rows) * h;
+        for (int t = tx; t < nt; t += 32) {
+            const Philox4 r1 = philox4x32_10((uint32_t)(it * 4096 + 2 * t), 7u, c2, c3, keys);
+            const Philox4 r2 = philox4x32_10((uint32_t)(it * 4096 + 2 * t + 1), 7u, c2, c3, keys);
+            float rr[6], ss[6], cc[6];
+            pair23_19(r1.x, r1.w, 0, rad2, rr[0], ss[0], cc[0]);
+            pair23_19(r1.y, r1.w, 1, rad2, rr[1], ss[1], cc[1]);
+            pair23_19(r1.z, r1.w, 2, rad2, rr[2], ss[2], cc[2]);
+            pair23_19(r2.x, r2.w, 0, rad2, rr[3], ss[3], cc[3]);
+            pair23_19(r2.y, r2.w, 1, rad2, rr[4], ss[4], cc[4]);
+            pair23_19(r2.z, r2.w, 2, rad2, rr[5], ss[5], cc[5]);
+            const int cb = 12 * t;
+            const int last = min(3, hv - 3 * t);
+            float4 o[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) o[j] = *reinterpret_cast<const float4*>(nm + min(cb + 4 * j, h - 4));
+            const int ce = cb + 4 * last;
+            const float e = nm[ce == h ? 0 : ce];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (j >= last) break;
+                const int c0 = cb + 4 * j;
+                const float4 up = *reinterpret_cast<const float4*>(nm - h + c0), d = *reinterpret_cast<const float4*>(nm + h + c0);
+                const float4 cur = *reinterpret_cast<const float4*>(own + c0);
+                const float nx = (j + 1 < last) ? o[j + 1 < 3 ? j + 1 : 2].x : e;
+                float4 s;
+                s.x = o[j].x + o[j].y; s.y = o[j].y + o[j].z; s.z = o[j].z + o[j].w; s.w = o[j].w + nx;
+                s.x += up.x + d.x; s.y += up.y + d.y; s.z += up.z + d.z; s.w += up.w + d.w;
+                float4 v;
+                v.x = fmaf(gain, s.x, fmaf(rr[2 * j], cc[2 * j], keep * cur.x));
+                v.y = fmaf(gain, s.y, fmaf(rr[2 * j], ss[2 * j], keep * cur.y));
+                v.z = fmaf(gain, s.z, fmaf(rr[2 * j + 1], cc[2 * j + 1], keep * cur.z));
+                v.w = fmaf(gain, s.w, fmaf(rr[2 * j + 1], ss[2 * j + 1], keep * cur.w));
+                *reinterpret_cast<float4*>(own + c0) = v;
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) out[0] = acc.x;
+}
+// D at a compile-time half-row length (reference for kT2<H>)
+template <int H>
+__global__ void __launch_bounds__(256, 3) kD(PhiloxKeys keys, int iters, float keep, float gain, float rad2, float* out) {
+    extern __shared__ __align__(128) float sm[];
+    constexpr int h = H;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int rows = 72 * 1024 / (4 * h) - 2;
+    for (int i = threadIdx.x; i < rows * h; i += blockDim.x) sm[i] = 0.001f * (float)(i & 1023);
+    __syncthreads();
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t c2 = blockIdx.x, c3 = 0x70520000u;
+    for (int it = 0; it < iters; ++it) {
+        const int row = 1 + (ty + it) % (rows - 2);
+        const float* nm = sm + row * h;
+        float* own = sm + ((row + 5) % rows) * h;
+        for (int cv = tx; cv < (h >> 2); cv += 32) {
+            const int c0 = cv << 2;
+            const Philox4 r = philox4x32_10((uint32_t)(it * 4096 + cv), 7u, c2, c3, keys);
+            const float ra = sqrt_approx(rad2 * lg2_approx(u01(r.x)));
+            const float rb = sqrt_approx(rad2 * lg2_approx(u01(r.z)));
+            float sa, ca, sb, cb;
+            sincos_approx(6.2831853071795865f * u01(r.y), sa, ca);
+            sincos_approx(6.2831853071795865f * u01(r.w), sb, cb);
+            const float4 o = *reinterpret_cast<const float4*>(nm + c0), up = *reinterpret_cast<const float4*>(nm - h + c0);
+            const float4 d = *reinterpret_cast<const float4*>(nm + h + c0), cur = *reinterpret_cast<const float4*>(own + c0);
+            const float e = nm[c0 + 4 == h ? 0 : c0 + 4];
+            float4 s;
+            s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e;
+            s.x += up.x + d.x; s.y += up.y + d.y; s.z += up.z + d.z; s.w += up.w + d.w;
+            float4 v;
+            v.x = fmaf(gain, s.x, fmaf(ra, ca, keep * cur.x));
+            v.y = fmaf(gain, s.y, fmaf(ra, sa, keep * cur.y));
+            v.z = fmaf(gain, s.z, fmaf(rb, cb, keep * cur.z));
+            v.w = fmaf(gain, s.w, fmaf(rb, sb, keep * cur.w));
+            *reinterpret_cast<float4*>(own + c0) = v;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) out[0] = acc.x;
+}
+template <class KF>
+void runH(const char* name, KF kern, int h, int iters, int sms) {
+    PhiloxKeys keys = philox_keys(42);
+    float* out; cudaMalloc(&out, 4);
+    const size_t smem = 72 * 1024;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = sms * 3;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    kern<<<grid, 256, smem>>>(keys, 4, 0.25f, 0.25f, -1.2f, out);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        kern<<<grid, 256, smem>>>(keys, iters, 0.25f, 0.25f, -1.2f, out);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
+    }
+    const double updates = (double)grid * 8 * iters * h;
+    printf("%-44s %8.3f ms  %.3e site-updates/s  err=%s\n", name, best, updates / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int STAGE>
 void run(const char* name, int iters, int sms) {
     PhiloxKeys keys = philox_keys(42);
@@ -298,5 +439,11 @@ int main() {
     runV<0>("E two rows per iteration", iters, sms);
     runV<1>("F packed f32x2 arithmetic", iters, sms);
     runV<2>("G Philox4x32-7", iters, sms);
+    runV<3>("H Philox mul.hi/mul.lo split", iters, sms);
+    runV<4>("E+F two rows + packed f32x2", iters, sms);
+    runH("D  h=384 (4 sites per Philox)", kD<384>, 384, iters, sms);
+    runH("T2 h=384 (6 sites per Philox, 19-bit angle)", kT2<384>, 384, iters, sms);
+    runH("D  h=500", kD<500>, 500, iters, sms);
+    runH("T2 h=500", kT2<500>, 500, iters, sms);
     return 0;
 }

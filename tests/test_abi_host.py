@@ -270,3 +270,67 @@ def test_r_overrides_call_existing_glue_entries_with_matching_arity():
     for sym, nargs in sites:
         assert sym in entries, f".Call({sym}, ...) has no glue entry"
         assert entries[sym] == nargs, f".Call({sym}) passes {nargs} arguments, the glue takes {entries[sym]}"
+
+
+def _kind(data):
+    n1, n2 = C.c_int(), C.c_int()
+    k = L.lib.mclcar_graph_kind(data.ctx.h, C.byref(n1), C.byref(n2))
+    return k, n1.value, n2.value
+
+
+@pytest.mark.parametrize("n1,n2", [(3, 3), (4, 4), (3, 5), (5, 3), (4, 6), (20, 20), (16, 24), (9, 15), (256, 64)])
+def test_csr_upload_of_a_rook_torus_is_recognised(n1, n2):
+    """The reference's lattices arrive as matrices (CAR.simTorus returns as.matrix(W), R/CAR.simLM.R:19): the CSR
+    upload must switch to the torus form (analytic spectrum, tiled kernels) by itself."""
+    from oracle import graphs
+    W = graphs.torus_W(n1, n2)
+    n = n1 * n2
+    y = np.arange(n, dtype=float)
+    d = api.make_data(y, X=np.ones((n, 1)), W=W, ctx=api.Context(device=-1))
+    k, a, b = _kind(d)
+    assert k == 1 and a * b == n
+    if n1 != n2 and min(n1, n2) > 4:
+        assert (a, b) == (n1, n2)
+    # same host-side model as the explicit torus upload: spectrum-dependent answers agree
+    d2 = api.make_data(y, X=np.ones((n, 1)), torus=(a, b), ctx=api.Context(device=-1))
+    rho = np.array([0.05, 0.2, -0.1])
+    np.testing.assert_allclose(api.ploglik_dCAR(rho, d), api.ploglik_dCAR(rho, d2), rtol=1e-14)
+    # the generic kernels stay reachable
+    d3 = api.make_data(y, X=np.ones((n, 1)), W=W, ctx=api.Context(device=-1), detect_torus=False)
+    assert _kind(d3)[0] == 2
+
+
+def test_near_torus_graphs_are_not_mistaken_for_a_torus():
+    from oracle import graphs
+    import scipy.sparse as sp
+    n1, n2 = 8, 10
+    n = n1 * n2
+    y = np.zeros(n)
+    # open lattice, a torus with one rewired edge pair, a relabelled torus, a weighted torus
+    Wl = graphs.lattice_W(n1, n2)
+    assert _kind(api.make_data(y, W=Wl, ctx=api.Context(device=-1)))[0] == 2
+    W = graphs.torus_W(n1, n2).tolil()
+    W[0, 1] = W[1, 0] = 0; W[0, 2] = W[2, 0] = 1; W[1, 3] = W[3, 1] = 0   # still degree 4 at site 0 only by accident
+    assert _kind(api.make_data(y, W=W.tocsr(), ctx=api.Context(device=-1)))[0] == 2
+    perm = np.random.default_rng(0).permutation(n)
+    Wp = graphs.torus_W(n1, n2)[perm][:, perm]
+    assert _kind(api.make_data(y, W=Wp, ctx=api.Context(device=-1)))[0] == 2
+    Ww = graphs.torus_W(n1, n2) * 0.5
+    assert _kind(api.make_data(y, W=Ww, ctx=api.Context(device=-1)))[0] == 2
+
+
+def test_csr_torus_gets_the_tiled_sampler_plan():
+    from oracle import graphs
+    n1 = n2 = 256
+    d = api.make_data(np.zeros(n1 * n2), W=graphs.torus_W(n1, n2), ctx=api.Context(device=-1))
+    plan = api.plan_dCAR([0.2, 1.0], 10_000, d)
+    assert plan["kind"] == 1          # BASELINE config 2 reaches the red-black torus kernels from a CSR W
+    d2 = api.make_data(np.zeros(n1 * n2), W=graphs.torus_W(n1, n2), ctx=api.Context(device=-1), detect_torus=False)
+    assert api.plan_dCAR([0.2, 1.0], 10_000, d2)["kind"] in (2, 3)
+
+
+def test_draw_counter_bookkeeping():
+    ctx = api.Context(device=-1, seed=9)
+    assert ctx.draw == 0
+    ctx.draw = 5
+    assert ctx.draw == 5
