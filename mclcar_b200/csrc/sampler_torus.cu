@@ -29,6 +29,7 @@ namespace mclcar {
 namespace {
 
 constexpr uint32_t kTagTorus = 0x7052u;
+constexpr int kFusedMaxThreads = 256;   // launch bound of the fused sweep (three CTAs per SM)
 
 struct TorusSweepParams {
     float* red;    // [C][n1][h]
@@ -36,6 +37,7 @@ struct TorusSweepParams {
     float* red_out;    // fused sweep only: the other buffer of the ping-pong pair
     float* black_out;
     int n1, h;     // h = n2 / 2
+    int G;         // groups of 8 half-columns per row = ceil(h / 8): the unit of the random-number mapping
     int64_t C;
     // over-relaxed Gibbs update  x' = keep*x + gain*(sum of neighbours) + noise*z  with
     // keep = 1 - omega, gain = omega*rho, noise = sqrt(omega (2 - omega) sigma); omega = 1 is plain Gibbs
@@ -50,26 +52,70 @@ struct TorusSweepParams {
     int64_t ld, slot0, nch;
     const double* mu;   // [n] or null
     double mu_const;    // used when mu is null
+    // statistics-only emission (EMIT == 2): per (chain, tile) partial sums (x'x, x'Wx / 2, sum x) of the sample
+    // fl32(state + mu_const), [C][tiles][3]
+    double* stat_partial;
+    int dry;              // experiment switch: skip the random numbers (structure / memory ceiling of the sweep)
+    int prefetch_ahead;   // > 0: every CTA prefetches into L2 the tile of the CTA this many places behind it in launch order
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-// The update of four consecutive half-columns of one row (ONE Philox4x32-10 block), shared by the
-// two-launch and the fused kernels so that both produce the same bits:
-//     x' = keep * x + gain * (sum of the four neighbours) + noise * z,   z ~ N(0, 1).
+// ---------------------------------------------------------------------------------------------
+// Random numbers.  The normals of one lattice row of one colour come in GROUPS of 8 consecutive
+// half-columns (two 16-byte vectors) from ONE Philox4x32-10 block, counter row * G + group: every
+// 32-bit word of the block is one Box-Muller pair (cos, sin -> even, odd column) -- radius from its top
+// 23 bits (as in round 1), angle from its low 9 bits placed in the mantissa (no int -> float
+// conversion) and centred in their cell.  A uniform angle on an N-point grid integrates every
+// trigonometric polynomial of degree < N exactly, so all joint moments of (r cos, r sin) of total order
+// < 512 are those of two independent normals, and the characteristic function of any projection
+// a z0 + b z1 differs from the Gaussian one by Bessel terms J_512(|t| r) -- below 1e-30 for
+// |t| r < 400: far beyond anything a fp32 state or the quadratic-form statistics of this path resolve
+// (tests/test_gpu_sampler_dcar.py checks marginal and cross moments up to order 8 of the generator itself).
+// Eight normals per block instead of four: Philox4x32-10 (20 IMAD.WIDE at quarter rate) was half of the
+// cycles of the update (profiles/r01_sweep_experiments.md).  The mapping depends on (seed, draw, chain,
+// sweep, colour, row, column) only: not on the launch geometry, the kernel form or the number of GPUs.
+// ---------------------------------------------------------------------------------------------
+struct Pair {
+    float r, s, c;   // radius with the noise scale folded in (sqrt(rad2 * lg2 u), rad2 = -2 ln2 noise^2), sin, cos
+};
+
+__device__ __forceinline__ Pair bm_pair(const uint32_t w, const float rad2) {
+    Pair p;
+    if (rad2 > 0.f) {   // experiment switch (MCLCAR_SWEEP_DRY=2): no transcendental work (rad2 is negative in real runs)
+        p.r = rad2; p.s = __uint_as_float(w); p.c = 0.5f;
+        return p;
+    }
+    p.r = sqrt_approx(rad2 * lg2_approx(u01(w)));
+    // (k + 1/2) / 512, k = low 9 bits: mantissa bits 22..14 and the half-step bit 13, exponent of 1.0
+    const float u = __uint_as_float(((w << 14) & 0x007fc000u) | 0x3f802000u) - 1.0f;
+    sincos_approx(6.2831853071795865f * u, p.s, p.c);
+    return p;
+}
+__device__ __forceinline__ Pair block_pair(const Philox4& b, const int t, const float rad2) {
+    return bm_pair(t == 0 ? b.x : (t == 1 ? b.y : (t == 2 ? b.z : b.w)), rad2);
+}
+
+// the two pairs of ONE column vector (half-columns 4 cv .. 4 cv + 3) of a row, for the kernels that walk the
+// lattice vector by vector (two-launch form): same numbers, one Philox block per vector
+__device__ __forceinline__ void vector_pairs(const uint32_t row, const int cv, const int G, const uint32_t c1, const uint32_t c2,
+                                             const uint32_t c3, const PhiloxKeys& keys, const float rad2, Pair& PA, Pair& PB) {
+    const Philox4 b = philox4x32_10(row * (uint32_t)G + (uint32_t)(cv >> 1), c1, c2, c3, keys);
+    if (cv & 1) { PA = bm_pair(b.z, rad2); PB = bm_pair(b.w, rad2); }
+    else { PA = bm_pair(b.x, rad2); PB = bm_pair(b.y, rad2); }
+}
+
+// The update of four consecutive half-columns of one row, shared by all kernel forms so that they produce the
+// same bits:   x' = keep * x + gain * (sum of the four neighbours) + noise * z,   z ~ N(0, 1).
 // o/up/d: the other colour at the same half-columns in this row / the row above / below; e: the
 // same-row neighbour beyond the vector (c + 4 when FWD, c - 1 otherwise).  The noise scale is folded
-// into the Box-Muller radius (sqrt(rad2 * lg2 u), rad2 = -2 ln2 noise^2) and the product
-// radius * cos/sin into the final FMA: 6 FP32 instructions per site besides the RNG.
+// into the Box-Muller radius and the product radius * cos/sin into the final FMA: 6 FP32 instructions per
+// site besides the RNG.
 template <bool SOR, bool FWD>
 __device__ __forceinline__ float4 gibbs_update4(const float4 o, const float4 up, const float4 d, const float e,
-                                                const float4 cur, const Philox4 r, const float keep, const float gain,
-                                                const float rad2) {
-    const float ra = sqrt_approx(rad2 * lg2_approx(u01(r.x)));
-    const float rb = sqrt_approx(rad2 * lg2_approx(u01(r.z)));
-    float sa, ca, sb, cb;
-    sincos_approx(6.2831853071795865f * u01(r.y), sa, ca);
-    sincos_approx(6.2831853071795865f * u01(r.w), sb, cb);
+                                                const float4 cur, const Pair PA, const Pair PB, const float keep,
+                                                const float gain) {
     float4 s;
     if (FWD) { s.x = o.x + o.y; s.y = o.y + o.z; s.z = o.z + o.w; s.w = o.w + e; }
     else { s.x = e + o.x; s.y = o.x + o.y; s.z = o.y + o.z; s.w = o.z + o.w; }
@@ -79,12 +125,12 @@ __device__ __forceinline__ float4 gibbs_update4(const float4 o, const float4 up,
     s.w = __fadd_rn(s.w, __fadd_rn(up.w, d.w));
     float4 v;
     if (SOR) {
-        v.x = __fmaf_rn(ra, ca, __fmul_rn(keep, cur.x));
-        v.y = __fmaf_rn(ra, sa, __fmul_rn(keep, cur.y));
-        v.z = __fmaf_rn(rb, cb, __fmul_rn(keep, cur.z));
-        v.w = __fmaf_rn(rb, sb, __fmul_rn(keep, cur.w));
+        v.x = __fmaf_rn(PA.r, PA.c, __fmul_rn(keep, cur.x));
+        v.y = __fmaf_rn(PA.r, PA.s, __fmul_rn(keep, cur.y));
+        v.z = __fmaf_rn(PB.r, PB.c, __fmul_rn(keep, cur.z));
+        v.w = __fmaf_rn(PB.r, PB.s, __fmul_rn(keep, cur.w));
     } else {
-        v.x = __fmul_rn(ra, ca); v.y = __fmul_rn(ra, sa); v.z = __fmul_rn(rb, cb); v.w = __fmul_rn(rb, sb);
+        v.x = __fmul_rn(PA.r, PA.c); v.y = __fmul_rn(PA.r, PA.s); v.z = __fmul_rn(PB.r, PB.c); v.w = __fmul_rn(PB.r, PB.s);
     }
     v.x = __fmaf_rn(gain, s.x, v.x);
     v.y = __fmaf_rn(gain, s.y, v.y);
@@ -93,8 +139,54 @@ __device__ __forceinline__ float4 gibbs_update4(const float4 o, const float4 up,
     return v;
 }
 
-// 16-byte path (h % 4 == 0).  SOR: the update reads the current value too.  EMIT: the black
-// half sweep also stores the finished sample row segment (both colours are in registers).
+// finished sample values of 8 consecutive sites (4 half-columns of both colours) -> the sample matrix.
+// v: the emitting (black) colour, o: the other colour at the same half-columns; the emitting colour sits at column
+// 2c + 1 - par, the other at 2c + par (par = row & 1).
+template <typename TO>
+__device__ __forceinline__ void emit8(const TorusSweepParams& p, TO* __restrict__ dst, const double* __restrict__ mu8,
+                                      const float4 v, const float4 o, const bool par) {
+    float a[8];
+    a[0] = par ? v.x : o.x; a[1] = par ? o.x : v.x; a[2] = par ? v.y : o.y; a[3] = par ? o.y : v.y;
+    a[4] = par ? v.z : o.z; a[5] = par ? o.z : v.z; a[6] = par ? v.w : o.w; a[7] = par ? o.w : v.w;
+    if (mu8 != nullptr) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + __ldg(mu8 + t));
+    } else if (sizeof(TO) == 4) {
+        const float m = (float)p.mu_const;
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        d4[0] = make_float4(a[0] + m, a[1] + m, a[2] + m, a[3] + m);
+        d4[1] = make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + p.mu_const);
+    }
+}
+
+// Statistics-only emission: the contribution of one black vector v (new values) to (x'x, x'Wx / 2, sum x) of the
+// fp32 sample y = fl32(state + m) -- exactly what the statistics kernel would compute from the stored matrix.
+// Every edge of the even torus joins a black and a red site, so x'Wx = 2 sum_black y_b * (sum of its four red
+// neighbours); o/up/dn/e are those neighbours (the finished red values), o also contributes its own squares.
+template <bool FWD>
+__device__ __forceinline__ void stats8(const float4 v, const float4 o, const float4 up, const float4 dn, const float e,
+                                       const float m, double (&acc)[3]) {
+    const double dv[4] = {(double)(v.x + m), (double)(v.y + m), (double)(v.z + m), (double)(v.w + m)};
+    const double dO[4] = {(double)(o.x + m), (double)(o.y + m), (double)(o.z + m), (double)(o.w + m)};
+    const double du[4] = {(double)(up.x + m), (double)(up.y + m), (double)(up.z + m), (double)(up.w + m)};
+    const double dd[4] = {(double)(dn.x + m), (double)(dn.y + m), (double)(dn.z + m), (double)(dn.w + m)};
+    const double de = (double)(e + m);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double side = FWD ? (k < 3 ? dO[(k + 1) & 3] : de) : (k > 0 ? dO[(k + 3) & 3] : de);
+        const double S = (dO[k] + side) + (du[k] + dd[k]);
+        acc[1] = fma(dv[k], S, acc[1]);
+        acc[0] = fma(dv[k], dv[k], acc[0]);
+        acc[0] = fma(dO[k], dO[k], acc[0]);
+        acc[2] += dv[k] + dO[k];
+    }
+}
+
+// 16-byte path (h % 4 == 0), two launches per sweep.  SOR: the update reads the current value too.  EMIT: the
+// black half sweep also stores the finished sample row segment (both colours are in registers).
 template <bool SOR, bool EMIT, typename TO, int kRows>
 __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSweepParams p, const int col) {
     const int h = p.h, n1 = p.n1;
@@ -115,7 +207,6 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
     int row = i0 * h;                                  // offset of row i (floats)
     float4 up = ld4(oth + (i0 == 0 ? (n1 - 1) * h : row - h) + c0);
     float4 o = ld4(oth + row + c0);
-    uint32_t ctr = (uint32_t)(i0 * hv + cv);
     // loads of row i are issued one iteration ahead (software prefetch in registers)
     int rown = i0 + 1 == n1 ? 0 : row + h;
     float4 d = ld4(oth + rown + c0);
@@ -136,32 +227,17 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
             en = oth[rown + (fwd ? cl : cr)];           // row i + 1 has the opposite parity
             if (SOR) curn = ld4(own + rown + c0);
         }
-        const Philox4 r = philox4x32_10(ctr, c1, c2, c3, p.keys);
-        const float4 v = fwd ? gibbs_update4<SOR, true>(o, up, d, e, cur, r, p.keep, p.gain, p.rad2)
-                             : gibbs_update4<SOR, false>(o, up, d, e, cur, r, p.keep, p.gain, p.rad2);
-        *reinterpret_cast<float4*>(own + row + c0) = v;
+        Pair PA, PB;
+        vector_pairs((uint32_t)i, cv, p.G, c1, c2, c3, p.keys, p.rad2, PA, PB);
+        const float4 v = fwd ? gibbs_update4<SOR, true>(o, up, d, e, cur, PA, PB, p.keep, p.gain)
+                             : gibbs_update4<SOR, false>(o, up, d, e, cur, PA, PB, p.keep, p.gain);
+        st4(own + row + c0, v);
         if (EMIT) {
             if (ch < p.nch) {
-                // black half sweep (col == 1): o = finished red values, v = new black values of the same
-                // half-columns; red sits at column 2c + par, black at 2c + 1 - par (par = i & 1)
-                const bool par = (i & 1) != 0;
+                // black half sweep (col == 1): o = finished red values, v = new black values of the same half-columns
                 const size_t site = (size_t)i * 2 * h + 2 * c0;
-                float a[8];
-                a[0] = par ? v.x : o.x; a[1] = par ? o.x : v.x; a[2] = par ? v.y : o.y; a[3] = par ? o.y : v.y;
-                a[4] = par ? v.z : o.z; a[5] = par ? o.z : v.z; a[6] = par ? v.w : o.w; a[7] = par ? o.w : v.w;
                 TO* dst = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld + site;
-                if (p.mu != nullptr) {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + __ldg(p.mu + site + t));
-                } else if (sizeof(TO) == 4) {
-                    const float m = (float)p.mu_const;
-                    float4* d4 = reinterpret_cast<float4*>(dst);
-                    d4[0] = make_float4(a[0] + m, a[1] + m, a[2] + m, a[3] + m);
-                    d4[1] = make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + p.mu_const);
-                }
+                emit8<TO>(p, dst, p.mu ? p.mu + site : nullptr, v, o, (i & 1) != 0);
             }
         }
         up = o;
@@ -171,12 +247,11 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
         cur = curn;
         row = rown;
         rown = row2;
-        ctr += (uint32_t)hv;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused full sweep: ONE pass over HBM per sweep instead of two.  A CTA owns TR lattice rows of
+// Fused full sweep: ONE pass over HBM per sweep instead of two.  A CTA owns TR (even) lattice rows of
 // one chain at full width.  Black rows r0-2 .. r0+TR+1 and red rows r0-1 .. r0+TR are staged into
 // shared memory by the bulk-async copy engine (cp.async.bulk, one mbarrier); phase 1 updates red
 // for the TR rows AND the two halo rows (recomputing what the neighbouring tiles compute -- same
@@ -184,59 +259,95 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
 // red values in shared memory.  Traffic: (2TR+6)/(2TR) reads + 1 write of the state per sweep,
 // about 9 B per site update instead of 12 (over-relaxed) for the two-launch form; results are
 // bit-identical to it.
+//
+// Work item = (pair of vertically adjacent rows A, B = A + 1; group of 8 half-columns): 16 site updates
+// from TWO Philox blocks.  The pair shares its neighbour-row loads (rows A-1, A, B, B+1 of the other
+// colour: 8 vector loads for 4 vector updates instead of 12) and takes the same-row neighbours from the
+// adjacent vector it already holds (2 scalar loads instead of 4).  The items of a phase are dealt to the
+// threads of the CTA round-robin, so only the last round of a phase has idle lanes.  Tiles start at even
+// rows, hence row A is always the row whose same-row neighbour sits at c + 1 (FWD) and row B the one with
+// c - 1, in both phases: no divergent code paths.
 // ---------------------------------------------------------------------------------------------
-// One lattice row of one colour inside the fused sweep: lanes stride the column vectors.  FWD (the
-// same-row neighbour sits at c + 1, else c - 1) is uniform over the row, so it is a template
-// argument.  PH2 = black phase: the own colour is only read (current value), the new row goes to
-// global memory (and to the sample matrix when EMIT).  The loop body is kept small on purpose: a
-// four-way unrolled straight-line variant (more instruction-level parallelism, 4x the code) measured
-// 5 % slower -- the 24 resident warps already cover the latencies, instruction fetch does not.
-template <bool SOR, bool FWD, bool PH2, bool EMIT, typename TO>
-__device__ __forceinline__ void fused_row(const TorusSweepParams& p, const float* __restrict__ nm, float* __restrict__ own,
-                                          float* __restrict__ gout, TO* __restrict__ emit_row, const double* __restrict__ mu_row,
-                                          const bool par, const int tx, const int hv, const int h, const uint32_t ctr0,
-                                          const uint32_t c1, const uint32_t c2, const uint32_t c3) {
-    for (int cv = tx; cv < hv; cv += 32) {
-        const int c0 = cv << 2;
-        const float4 o = ld4(nm + c0), up = ld4(nm - h + c0), d = ld4(nm + h + c0);
-        const float e = FWD ? nm[c0 + 4 == h ? 0 : c0 + 4] : nm[c0 == 0 ? h - 1 : c0 - 1];
-        float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (SOR) cur = ld4(own + c0);
-        const Philox4 r = philox4x32_10(ctr0 + (uint32_t)cv, c1, c2, c3, p.keys);
-        const float4 v = gibbs_update4<SOR, FWD>(o, up, d, e, cur, r, p.keep, p.gain, p.rad2);
-        if (!PH2) *reinterpret_cast<float4*>(own + c0) = v;
-        if (gout) *reinterpret_cast<float4*>(gout + c0) = v;
-        if (EMIT && PH2) {
-            if (emit_row) {
-                // o = finished values of the other colour at the same half-columns; the emitting (black) colour sits at
-                // column 2c + 1 - par, the other at 2c + par
-                float a[8];
-                a[0] = par ? v.x : o.x; a[1] = par ? o.x : v.x; a[2] = par ? v.y : o.y; a[3] = par ? o.y : v.y;
-                a[4] = par ? v.z : o.z; a[5] = par ? o.z : v.z; a[6] = par ? v.w : o.w; a[7] = par ? o.w : v.w;
-                TO* dst = emit_row + 2 * c0;
-                if (mu_row != nullptr) {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + __ldg(mu_row + 2 * c0 + t));
-                } else if (sizeof(TO) == 4) {
-                    const float m = (float)p.mu_const;
-                    float4* d4 = reinterpret_cast<float4*>(dst);
-                    d4[0] = make_float4(a[0] + m, a[1] + m, a[2] + m, a[3] + m);
-                    d4[1] = make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + p.mu_const);
-                }
+// EMIT: 0 none, 1 the black phase also writes the finished samples, 2 it accumulates their statistics instead
+template <bool SOR, bool PH2, int EMIT, typename TO>
+__device__ __forceinline__ void fused_item(const TorusSweepParams& p, const float* __restrict__ nm, float* __restrict__ ownA,
+                                           float* __restrict__ goutA, float* __restrict__ goutB, TO* __restrict__ emitA,
+                                           const double* __restrict__ muA, const uint32_t iA, const uint32_t iB, const int g,
+                                           const int hv, const int h, const uint32_t c1, const uint32_t c2, const uint32_t c3,
+                                           double (&acc)[3]) {
+    const int cb = 8 * g;
+    const bool two = 2 * g + 1 < hv;                          // the last group of a row may hold one vector only
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a0 = ld4(nm + cb), b0 = ld4(nm + h + cb);    // rows A and B of the other colour
+    const float4 a1 = two ? ld4(nm + cb + 4) : z4, b1 = two ? ld4(nm + h + cb + 4) : z4;
+    const int ce = cb + (two ? 8 : 4);
+    const float eA = nm[ce == h ? 0 : ce];                    // row A: forward neighbour beyond the group
+    const float eB = nm[h + (cb == 0 ? h - 1 : cb - 1)];      // row B: backward neighbour before the group
+    float* __restrict__ ownB = ownA + h;
+    const float m = (float)p.mu_const;
+    // ---- row A
+    {
+        const Philox4 blk = p.dry ? Philox4{0x80000000u + iA, 0xa0000000u + c1, 0x90000000u + (uint32_t)g, 0xc0000000u + c2} : philox4x32_10(iA * (uint32_t)p.G + (uint32_t)g, c1, c2, c3, p.keys);
+        {
+            const float4 up = ld4(nm - h + cb);
+            const float4 cur = SOR ? ld4(ownA + cb) : z4;
+            const float e = two ? a1.x : eA;
+            const float4 v = gibbs_update4<SOR, true>(a0, up, b0, e, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
+            if (!PH2) st4(ownA + cb, v);
+            if (goutA) st4(goutA + cb, v);
+            if (PH2 && EMIT == 1) {
+                if (emitA) emit8<TO>(p, emitA + 2 * cb, muA ? muA + 2 * cb : nullptr, v, a0, (iA & 1u) != 0);
             }
+            if (PH2 && EMIT == 2) stats8<true>(v, a0, up, b0, e, m, acc);
+        }
+        if (two) {
+            const int c0 = cb + 4;
+            const float4 up = ld4(nm - h + c0);
+            const float4 cur = SOR ? ld4(ownA + c0) : z4;
+            const float4 v = gibbs_update4<SOR, true>(a1, up, b1, eA, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
+            if (!PH2) st4(ownA + c0, v);
+            if (goutA) st4(goutA + c0, v);
+            if (PH2 && EMIT == 1) {
+                if (emitA) emit8<TO>(p, emitA + 2 * c0, muA ? muA + 2 * c0 : nullptr, v, a1, (iA & 1u) != 0);
+            }
+            if (PH2 && EMIT == 2) stats8<true>(v, a1, up, b1, eA, m, acc);
+        }
+    }
+    // ---- row B
+    {
+        const Philox4 blk = p.dry ? Philox4{0x80000000u + iB, 0xa0000000u + c1, 0x90000000u + (uint32_t)g, 0xc0000000u + c2} : philox4x32_10(iB * (uint32_t)p.G + (uint32_t)g, c1, c2, c3, p.keys);
+        {
+            const float4 dn = ld4(nm + 2 * h + cb);
+            const float4 cur = SOR ? ld4(ownB + cb) : z4;
+            const float4 v = gibbs_update4<SOR, false>(b0, a0, dn, eB, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
+            if (!PH2) st4(ownB + cb, v);
+            if (goutB) st4(goutB + cb, v);
+            if (PH2 && EMIT == 1) {
+                if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * cb, muA ? muA + 2 * h + 2 * cb : nullptr, v, b0, (iB & 1u) != 0);
+            }
+            if (PH2 && EMIT == 2) stats8<false>(v, b0, a0, dn, eB, m, acc);
+        }
+        if (two) {
+            const int c0 = cb + 4;
+            const float4 dn = ld4(nm + 2 * h + c0);
+            const float4 cur = SOR ? ld4(ownB + c0) : z4;
+            const float4 v = gibbs_update4<SOR, false>(b1, a1, dn, b0.w, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
+            if (!PH2) st4(ownB + c0, v);
+            if (goutB) st4(goutB + c0, v);
+            if (PH2 && EMIT == 1) {
+                if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c0, muA ? muA + 2 * h + 2 * c0 : nullptr, v, b1, (iB & 1u) != 0);
+            }
+            if (PH2 && EMIT == 2) stats8<false>(v, b1, a1, dn, b0.w, m, acc);
         }
     }
 }
 
-template <bool SOR, bool EMIT, typename TO>
-__global__ void __launch_bounds__(256, 3) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
+template <bool SOR, int EMIT, typename TO>
+__global__ void __launch_bounds__(kFusedMaxThreads, EMIT == 2 ? 2 : 3) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
     extern __shared__ __align__(128) float fsm[];
-    const int h = p.h, n1 = p.n1, hv = h >> 2;
+    const int h = p.h, n1 = p.n1, hv = h >> 2, G = p.G;
     const int r0 = blockIdx.x * TR;
-    const int rows = min(TR, n1 - r0);
+    const int rows = min(TR, n1 - r0);                        // even: TR and n1 are
     const int64_t ch = blockIdx.y;
     const size_t plane = (size_t)n1 * h;
     const float* __restrict__ gred = p.red + ch * plane;      // read from the current buffers,
@@ -264,45 +375,97 @@ __global__ void __launch_bounds__(256, 3) gibbs_torus_sweep_fused(const TorusSwe
         };
         copy_rows(sB, gblk, r0 - 2, rows + 4);
         copy_rows(sR, gred, r0 - 1, rows + 2);
+        if (p.prefetch_ahead > 0) {
+            // warm L2 with the tile of the CTA that will follow this one onto the SM: CTAs are dispatched in linear
+            // order, about (resident CTAs of the device) behind the running front
+            const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + p.prefetch_ahead;
+            const long long pch = lin / gridDim.x;
+            if (pch < (long long)gridDim.y) {
+                const int pr0 = (int)(lin - pch * gridDim.x) * TR;
+                const int prow = min(TR, n1 - pr0);
+                const float* pb = p.black + pch * plane + (size_t)pr0 * h;
+                const float* pr = p.red + pch * plane + (size_t)pr0 * h;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pb), "r"(row_bytes * (uint32_t)prow) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pr), "r"(row_bytes * (uint32_t)prow) : "memory");
+            }
+        }
     }
     __syncthreads();
     mbar_wait(bar, 0);
 
     const uint64_t gch = (uint64_t)(p.chain0 + ch * p.chain_stride);
     const uint32_t c2 = (uint32_t)gch, c3 = (uint32_t)(gch >> 32) ^ (kTagTorus << 16);
-    // warp ty owns rows ty, ty + nw, ...; its lanes stride the column vectors of the row
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double acc[3] = {0.0, 0.0, 0.0};
 
-    // ---- phase 1: red rows r0-1 .. r0+rows (local 0 .. rows+1), black neighbours from sB
-    for (int lr = ty; lr < rows + 2; lr += nw) {
-        int i = r0 - 1 + lr;
-        i = i < 0 ? i + n1 : (i >= n1 ? i - n1 : i);
-        const float* bo = sB + (size_t)(lr + 1) * h;
-        float* rr = sR + (size_t)lr * h;
-        float* gout = (lr >= 1 && lr <= rows) ? ored + (size_t)i * h : nullptr;
-        const uint32_t ctr0 = (uint32_t)(i * hv);
-        if (i & 1) fused_row<SOR, true, false, false, TO>(p, bo, rr, gout, nullptr, nullptr, false, tx, hv, h, ctr0, p.sweep * 2u, c2, c3);
-        else fused_row<SOR, false, false, false, TO>(p, bo, rr, gout, nullptr, nullptr, false, tx, hv, h, ctr0, p.sweep * 2u, c2, c3);
+    // ---- phase 1: red rows r0-1 .. r0+rows (local 0 .. rows+1) in (rows + 2) / 2 pairs, black neighbours from sB
+    {
+        const int items = ((rows + 2) >> 1) * G;
+        for (int t = threadIdx.x; t < items; t += blockDim.x) {
+            const int q = t / G, g = t - q * G;
+            const int lA = 2 * q;                              // local red row of A; its black row in sB is lA + 1
+            int iA = r0 - 1 + lA;
+            iA = iA < 0 ? iA + n1 : iA;                        // only the first tile wraps at the top,
+            int iB = r0 + lA;
+            iB = iB >= n1 ? iB - n1 : iB;                      // only the last tile at the bottom
+            float* goutA = lA >= 1 ? ored + (size_t)iA * h : nullptr;          // halo rows are recomputed, not stored
+            float* goutB = lA + 1 <= rows ? ored + (size_t)iB * h : nullptr;
+            fused_item<SOR, false, 0, TO>(p, sB + (size_t)(lA + 1) * h, sR + (size_t)lA * h, goutA, goutB, nullptr, nullptr,
+                                          (uint32_t)iA, (uint32_t)iB, g, hv, h, p.sweep * 2u, c2, c3, acc);
+        }
     }
     __syncthreads();
-    // ---- phase 2: black rows r0 .. r0+rows-1 from the new red rows in sR
-    for (int t = ty; t < rows; t += nw) {
-        const int i = r0 + t;
-        const float* ro = sR + (size_t)(t + 1) * h;
-        float* bc = sB + (size_t)(t + 2) * h;
-        float* gout = oblk + (size_t)i * h;
-        TO* erow = nullptr;
-        const double* mrow = nullptr;
-        if (EMIT) {
-            if (ch < p.nch) {
-                erow = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld + (size_t)i * 2 * h;
-                if (p.mu != nullptr) mrow = p.mu + (size_t)i * 2 * h;
+    // ---- phase 2: black rows r0 .. r0+rows-1 in rows / 2 pairs from the new red rows in sR
+    {
+        const int items = (rows >> 1) * G;
+        for (int t = threadIdx.x; t < items; t += blockDim.x) {
+            const int q = t / G, g = t - q * G;
+            const int tA = 2 * q;
+            const int iA = r0 + tA, iB = iA + 1;
+            TO* erow = nullptr;
+            const double* mrow = nullptr;
+            if (EMIT == 1) {
+                if (ch < p.nch) {
+                    erow = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld + (size_t)iA * 2 * h;
+                    if (p.mu != nullptr) mrow = p.mu + (size_t)iA * 2 * h;
+                }
             }
+            fused_item<SOR, true, EMIT, TO>(p, sR + (size_t)(tA + 1) * h, sB + (size_t)(tA + 2) * h, oblk + (size_t)iA * h,
+                                            oblk + (size_t)iB * h, erow, mrow, (uint32_t)iA, (uint32_t)iB, g, hv, h,
+                                            p.sweep * 2u + 1u, c2, c3, acc);
         }
-        const uint32_t ctr0 = (uint32_t)(i * hv);
-        const bool par = (i & 1) != 0;
-        if (!par) fused_row<SOR, true, true, EMIT, TO>(p, ro, bc, gout, erow, mrow, par, tx, hv, h, ctr0, p.sweep * 2u + 1u, c2, c3);
-        else fused_row<SOR, false, true, EMIT, TO>(p, ro, bc, gout, erow, mrow, par, tx, hv, h, ctr0, p.sweep * 2u + 1u, c2, c3);
+    }
+    if (EMIT == 2) {
+        double* scratch = reinterpret_cast<double*>(bar + 2);
+        block_sum<3>(acc, scratch);
+        if (threadIdx.x == 0) {
+            double* o = p.stat_partial + ((size_t)ch * gridDim.x + blockIdx.x) * 3;
+            o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+        }
+    }
+}
+
+// statistics-only emission, second step: add the tile partials of every chain in tile order and expand them to
+// the d statistic rows: x'x, x'Wx, and for the (constant) design columns X'x = c sum x, (WX)'x = 4 c sum x
+struct StatFinishParams {
+    const double* partial;   // [C][tiles][3]
+    int tiles, d, nconst;
+    int dst_a[MCLCAR_MAX_COV], dst_b[MCLCAR_MAX_COV];
+    double cval[MCLCAR_MAX_COV];
+    double* q;               // [d][ldq], first sample of this emission at q[slot0]
+    int64_t ldq, slot0, nch;
+};
+__global__ void torus_stats_finish_kernel(const StatFinishParams f) {
+    const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= f.nch) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const double* pp = f.partial + (size_t)ch * f.tiles * 3;
+    for (int t = 0; t < f.tiles; ++t) { a0 += pp[3 * t]; a1 += pp[3 * t + 1]; a2 += pp[3 * t + 2]; }
+    double* o = f.q + f.slot0 + ch;
+    o[0] = a0;
+    o[f.ldq] = 2.0 * a1;
+    for (int l = 0; l < f.nconst; ++l) {
+        o[(size_t)f.dst_a[l] * f.ldq] = f.cval[l] * a2;
+        o[(size_t)f.dst_b[l] * f.ldq] = 4.0 * f.cval[l] * a2;
     }
 }
 
@@ -394,12 +557,32 @@ void torus_chains_free(mclcar_ctx* ctx, TorusChains& t) {
     t.red = t.black = t.red2 = t.black2 = nullptr;
 }
 
+// tile height of the fused sweep for this context's lattice (0: the fused sweep does not apply).  Three CTAs
+// of <= 72 KB per SM; even, so that every tile starts at an even row (row-pair work items)
+int torus_fused_tile_rows(const mclcar_ctx* ctx) {
+    const int h = ctx->n2 / 2;
+    if (ctx->n1 % 2 != 0 || ctx->n2 % 2 != 0 || h % 4 != 0) return 0;
+    const char* fe = getenv("MCLCAR_SWEEP_FUSED");  // read per call: tests toggle it (0 = two half-sweep launches)
+    if (fe && atoi(fe) == 0) return 0;
+    const size_t row_b = (size_t)h * 4;
+    int TR = (int)((72 * 1024 / row_b - 6) / 2);
+    TR = std::min(TR, 64) & ~1;
+    if (const char* e = getenv("MCLCAR_SWEEP_TR")) {
+        const int v = atoi(e);
+        if (v > 0) TR = v & ~1;
+    }
+    if (TR < 4 || ctx->n1 < TR + 4) return 0;
+    return TR;
+}
+
 // one full sweep (both colours) of all chains; omega in [1, 2): over-relaxation factor.  When
-// `emit` is given (16-byte path only) the black half sweep also writes the samples.
+// `emit` is given (16-byte path only) the black half sweep also writes the samples -- or, with
+// emit->stats_q set (fused sweep, constant mean, fp32 samples), their sufficient statistics instead.
 int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep,
                 const TorusEmit* emit) {
     TorusSweepParams p{};
     p.red = t.red; p.black = t.black; p.n1 = ctx->n1; p.h = ctx->n2 / 2; p.C = t.C;
+    p.G = (p.h + 7) / 8;
     p.keep = (float)(1.0 - omega);
     p.gain = (float)(omega * rho);
     p.noise = (float)std::sqrt(omega * (2.0 - omega) * sigma);
@@ -418,40 +601,56 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
             p.mu = emit->d_mu; p.mu_const = emit->mu_const;
         }
         const bool f32 = !emit || emit->dtype == MCLCAR_F32;
-        const char* fe = getenv("MCLCAR_SWEEP_FUSED");  // read per call: tests toggle it (0 = two half-sweep launches)
-        const int fused_cfg = fe ? atoi(fe) : 1;
-        static int tr_cfg = [] { const char* e = getenv("MCLCAR_SWEEP_TR"); return e ? atoi(e) : 0; }();
-        const size_t row_b = (size_t)p.h * 4;
-        const int fthreads = 256, nw = fthreads / 32;
-        // tile height: three CTAs of <= 72 KB per SM; the red phase covers TR + 2 rows, so TR + 2 a multiple
-        // of the warp count keeps the warps of a CTA level at the phase barrier (14 rows for 1000 x 1000)
-        int TR = (int)((72 * 1024 / row_b - 6) / 2);
-        TR = std::min(TR, 64);
-        if (TR + 2 > nw && (TR + 2) % nw != 0) TR -= (TR + 2) % nw;
-        if (tr_cfg > 0) TR = tr_cfg;
-        if (fused_cfg && TR >= 4 && p.n1 >= TR + 4) {
+        const bool want_stats = emit && emit->stats_q != nullptr;
+        const int TR = torus_fused_tile_rows(ctx);
+        if (want_stats && (!TR || emit->d_mu || !f32))
+            return fail(ctx, MCLCAR_ESTATE, "statistics-only emission needs the fused sweep, a constant mean and fp32 samples");
+        if (TR) {
+            const size_t row_b = (size_t)p.h * 4;
+            const int tiles = (p.n1 + TR - 1) / TR;
+            if (want_stats) {
+                MCL_TRY(ensure(ctx, ctx->d_partial, (size_t)t.C * tiles * 3 * sizeof(double)));
+                p.stat_partial = (double*)ctx->d_partial.p;
+            }
             ProfScope prof(ctx, PROF_SWEEP, 1);
+            if (const char* e = getenv("MCLCAR_SWEEP_PREFETCH")) p.prefetch_ahead = atoi(e);
+            if (const char* e = getenv("MCLCAR_SWEEP_DRY")) { p.dry = atoi(e); if (p.dry >= 2) p.rad2 = 1e-30f; }
             p.red_out = t.red2; p.black_out = t.black2;
             std::swap(t.red, t.red2);        // the output pair is the current state from now on
             std::swap(t.black, t.black2);
-            const size_t smem = (size_t)(2 * TR + 6) * row_b + 64;
-            dim3 grid((p.n1 + TR - 1) / TR, (unsigned)t.C);
+            int fthreads = 256;
+            if (const char* e = getenv("MCLCAR_SWEEP_THREADS")) fthreads = std::min(std::max(atoi(e), 64), kFusedMaxThreads) & ~31;
+            const size_t smem = (size_t)(2 * TR + 6) * row_b + 64 + (kFusedMaxThreads / 32) * 3 * sizeof(double);
+            dim3 grid(tiles, (unsigned)t.C);
 #define LAUNCH_FUSED(S, E, TO_)                                                                                  \
     do {                                                                                                         \
         MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gibbs_torus_sweep_fused<S, E, TO_><<<grid, fthreads, smem, ctx->stream>>>(p, TR);                            \
+        gibbs_torus_sweep_fused<S, E, TO_><<<grid, fthreads, smem, ctx->stream>>>(p, TR);                       \
     } while (0)
-            if (emit) {
-                if (sor && f32) LAUNCH_FUSED(true, true, float);
-                else if (sor) LAUNCH_FUSED(true, true, double);
-                else if (f32) LAUNCH_FUSED(false, true, float);
-                else LAUNCH_FUSED(false, true, double);
+            if (want_stats) {
+                if (sor) LAUNCH_FUSED(true, 2, float);
+                else LAUNCH_FUSED(false, 2, float);
+            } else if (emit) {
+                if (sor && f32) LAUNCH_FUSED(true, 1, float);
+                else if (sor) LAUNCH_FUSED(true, 1, double);
+                else if (f32) LAUNCH_FUSED(false, 1, float);
+                else LAUNCH_FUSED(false, 1, double);
             } else {
-                if (sor) LAUNCH_FUSED(true, false, float);
-                else LAUNCH_FUSED(false, false, float);
+                if (sor) LAUNCH_FUSED(true, 0, float);
+                else LAUNCH_FUSED(false, 0, float);
             }
 #undef LAUNCH_FUSED
             MCL_CUDA(ctx, cudaGetLastError());
+            if (want_stats) {
+                StatFinishParams f{};
+                f.partial = p.stat_partial; f.tiles = tiles; f.d = 2 + 2 * ctx->p; f.nconst = ctx->p;
+                for (int l = 0; l < ctx->p; ++l) {
+                    f.dst_a[l] = 2 + l; f.dst_b[l] = 2 + ctx->p + l; f.cval[l] = ctx->X[(size_t)l * ctx->n];
+                }
+                f.q = emit->stats_q; f.ldq = emit->stats_ldq; f.slot0 = emit->slot0; f.nch = emit->nch;
+                torus_stats_finish_kernel<<<(unsigned)((emit->nch + 127) / 128), 128, 0, ctx->stream>>>(f);
+                MCL_CUDA(ctx, cudaGetLastError());
+            }
             return MCLCAR_OK;
         }
         ProfScope prof(ctx, PROF_SWEEP, 2);

@@ -1,7 +1,7 @@
 #!/bin/bash
-# sweep-kernel experiments: CONFIGS is a ;-separated list of env assignments (MCLCAR_SWEEP_FUSED=0|1, MCLCAR_SWEEP_TR=<rows>);
-# prints the sweep time per launch.  EXTRA passes bench flags (e.g. "--chains 148"), NS the samples per GPU.
-out=gpurun_out/sweep_exp.log
+# sweep-kernel experiments: CONFIGS is a ;-separated list of env assignments (MCLCAR_SWEEP_FUSED=0|1, MCLCAR_SWEEP_TR=<rows>,
+# MCLCAR_SWEEP_THREADS=<threads>); prints the sweep time per launch.  EXTRA passes bench flags (e.g. "--chains 148"), NS the samples per GPU.
+out=${OUT:-gpurun_out/sweep_exp.log}
 : > $out
 IFS=';' read -ra CFG <<< "${CONFIGS:-MCLCAR_SWEEP_FUSED=1;MCLCAR_SWEEP_FUSED=1 MCLCAR_SWEEP_TR=15;MCLCAR_SWEEP_FUSED=0}"
 for cfg in "${CFG[@]}"; do

@@ -264,3 +264,26 @@ def test_large_general_graph_uses_global_state_fallback():
     assert np.var(q[:, 0]) == pytest.approx(mom["V_xx"], rel=0.3)
     Y = sd.simY
     np.testing.assert_allclose(q, dcar.suffstats(W, None, Y), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n1,n2,p,omega", [(128, 96, 1, 0.0), (128, 96, 0, 1.0), (200, 104, 1, 0.0), (1000, 1000, 1, 0.0)])
+def test_statistics_folded_into_the_emitting_sweep(n1, n2, p, omega, monkeypatch):
+    """keep = 0 with a constant mean: the emitting sweep accumulates x'x, x'Wx and sum x of the fp32 samples it
+    would have written (no staging buffer, no statistics pass).  Same numbers as the statistics kernel on the kept
+    matrix (different summation order: 1e-13), and as the staging path of round 1."""
+    n = n1 * n2
+    X = np.full((n, 1), 1.5) if p else None
+    psi = [0.2, 1.1, 0.7] if p else [0.2, 1.1]
+    N, C = (24, 8) if n < 500_000 else (12, 6)
+    ctl = {"n.chains": C, "burn": 4, "thin": 2, "omega": omega}
+    y = np.zeros(n)
+    kept = api.mcl_prep_dCAR(psi, N, api.make_data(y, X=X, torus=(n1, n2), seed=21), dict(ctl, keep=True))
+    fused = api.mcl_prep_dCAR(psi, N, api.make_data(y, X=X, torus=(n1, n2), seed=21), dict(ctl, keep=False))
+    np.testing.assert_allclose(fused.stats(), kept.stats(), rtol=1e-13)
+    monkeypatch.setenv("MCLCAR_NO_FUSED_STATS", "1")
+    staged = api.mcl_prep_dCAR(psi, N, api.make_data(y, X=X, torus=(n1, n2), seed=21), dict(ctl, keep=False))
+    np.testing.assert_allclose(staged.stats(), kept.stats(), rtol=1e-13)
+    # and against the oracle on the kept samples (small cases)
+    if n < 50_000:
+        qref = dcar.suffstats(graphs.torus_W(n1, n2), X, kept.simY)
+        np.testing.assert_allclose(fused.stats(), qref, rtol=1e-12)
