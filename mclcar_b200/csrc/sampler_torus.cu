@@ -37,7 +37,7 @@ struct TorusSweepParams {
     float* red_out;    // fused sweep only: the other buffer of the ping-pong pair
     float* black_out;
     int n1, h;     // h = n2 / 2
-    int G;         // groups of 8 half-columns per row = ceil(h / 8): the unit of the random-number mapping
+    int G;         // Philox blocks per row = ceil(hv / 2), hv = h / 4 column vectors: block g serves vectors g and g + G
     int64_t C;
     // over-relaxed Gibbs update  x' = keep*x + gain*(sum of neighbours) + noise*z  with
     // keep = 1 - omega, gain = omega*rho, noise = sqrt(omega (2 - omega) sigma); omega = 1 is plain Gibbs
@@ -63,10 +63,11 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ---------------------------------------------------------------------------------------------
-// Random numbers.  The normals of one lattice row of one colour come in GROUPS of 8 consecutive
-// half-columns (two 16-byte vectors) from ONE Philox4x32-10 block, counter row * G + group: every
-// 32-bit word of the block is one Box-Muller pair (cos, sin -> even, odd column) -- radius from its top
-// 23 bits (as in round 1), angle from its low 9 bits placed in the mantissa (no int -> float
+// Random numbers.  One Philox4x32-10 block, counter row * G + g, serves the two 16-byte column vectors g and
+// g + G of a row of one colour (G = ceil(vectors per row / 2)): consecutive lanes then work on consecutive
+// vectors (coalesced stores, conflict-free shared-memory loads) and still share a block between their two
+// vectors.  Every 32-bit word of the block is one Box-Muller pair (cos, sin -> even, odd column) -- radius
+// from its top 23 bits (as in round 1), angle from its low 9 bits placed in the mantissa (no int -> float
 // conversion) and centred in their cell.  A uniform angle on an N-point grid integrates every
 // trigonometric polynomial of degree < N exactly, so all joint moments of (r cos, r sin) of total order
 // < 512 are those of two independent normals, and the characteristic function of any projection
@@ -101,8 +102,9 @@ __device__ __forceinline__ Pair block_pair(const Philox4& b, const int t, const 
 // lattice vector by vector (two-launch form): same numbers, one Philox block per vector
 __device__ __forceinline__ void vector_pairs(const uint32_t row, const int cv, const int G, const uint32_t c1, const uint32_t c2,
                                              const uint32_t c3, const PhiloxKeys& keys, const float rad2, Pair& PA, Pair& PB) {
-    const Philox4 b = philox4x32_10(row * (uint32_t)G + (uint32_t)(cv >> 1), c1, c2, c3, keys);
-    if (cv & 1) { PA = bm_pair(b.z, rad2); PB = bm_pair(b.w, rad2); }
+    const bool second = cv >= G;
+    const Philox4 b = philox4x32_10(row * (uint32_t)G + (uint32_t)(second ? cv - G : cv), c1, c2, c3, keys);
+    if (second) { PA = bm_pair(b.z, rad2); PB = bm_pair(b.w, rad2); }
     else { PA = bm_pair(b.x, rad2); PB = bm_pair(b.y, rad2); }
 }
 
@@ -260,84 +262,92 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
 // about 9 B per site update instead of 12 (over-relaxed) for the two-launch form; results are
 // bit-identical to it.
 //
-// Work item = (pair of vertically adjacent rows A, B = A + 1; group of 8 half-columns): 16 site updates
-// from TWO Philox blocks.  The pair shares its neighbour-row loads (rows A-1, A, B, B+1 of the other
-// colour: 8 vector loads for 4 vector updates instead of 12) and takes the same-row neighbours from the
-// adjacent vector it already holds (2 scalar loads instead of 4).  The items of a phase are dealt to the
+// Work item = (pair of vertically adjacent rows A, B = A + 1; Philox block g = column vectors g and g + G): 16 site
+// updates from TWO Philox blocks.  The pair shares its neighbour-row loads (rows A-1, A, B, B+1 of the other
+// colour: 8 vector loads for 4 vector updates instead of 12); consecutive lanes hold consecutive vectors, so
+// the same-row neighbours come from the next / previous lane by warp shuffle.  The items of a phase are dealt to the
 // threads of the CTA round-robin, so only the last round of a phase has idle lanes.  Tiles start at even
 // rows, hence row A is always the row whose same-row neighbour sits at c + 1 (FWD) and row B the one with
 // c - 1, in both phases: no divergent code paths.
 // ---------------------------------------------------------------------------------------------
 // EMIT: 0 none, 1 the black phase also writes the finished samples, 2 it accumulates their statistics instead
 template <bool SOR, bool PH2, int EMIT, typename TO>
-__device__ __forceinline__ void fused_item(const TorusSweepParams& p, const float* __restrict__ nm, float* __restrict__ ownA,
-                                           float* __restrict__ goutA, float* __restrict__ goutB, TO* __restrict__ emitA,
-                                           const double* __restrict__ muA, const uint32_t iA, const uint32_t iB, const int g,
-                                           const int hv, const int h, const uint32_t c1, const uint32_t c2, const uint32_t c3,
-                                           double (&acc)[3]) {
-    const int cb = 8 * g;
-    const bool two = 2 * g + 1 < hv;                          // the last group of a row may hold one vector only
+__device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool valid, const float* __restrict__ nm,
+                                           float* __restrict__ ownA, float* __restrict__ goutA, float* __restrict__ goutB,
+                                           TO* __restrict__ emitA, const double* __restrict__ muA, const uint32_t iA,
+                                           const uint32_t iB, const int g, const int hv, const int h, const uint32_t c1,
+                                           const uint32_t c2, const uint32_t c3, double (&acc)[3]) {
+    const int G = p.G, lane = threadIdx.x & 31;
+    const int gb = g + G;
+    const bool two = valid && gb < hv;                        // the last block of a row may hold one vector only
+    const int c0 = 4 * g, c1v = 4 * gb;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 a0 = ld4(nm + cb), b0 = ld4(nm + h + cb);    // rows A and B of the other colour
-    const float4 a1 = two ? ld4(nm + cb + 4) : z4, b1 = two ? ld4(nm + h + cb + 4) : z4;
-    const int ce = cb + (two ? 8 : 4);
-    const float eA = nm[ce == h ? 0 : ce];                    // row A: forward neighbour beyond the group
-    const float eB = nm[h + (cb == 0 ? h - 1 : cb - 1)];      // row B: backward neighbour before the group
+    const float4 a0 = valid ? ld4(nm + c0) : z4, b0 = valid ? ld4(nm + h + c0) : z4;   // rows A and B of the other colour
+    const float4 a1 = two ? ld4(nm + c1v) : z4, b1 = two ? ld4(nm + h + c1v) : z4;
+    // same-row neighbours: the next lane holds the next vector of the row (row A looks forward), the previous lane
+    // the previous one (row B looks backward) -- except at warp ends and where the lane's neighbour belongs to
+    // another row pair
+    float eA0 = __shfl_down_sync(0xffffffffu, a0.x, 1), eA1 = __shfl_down_sync(0xffffffffu, a1.x, 1);
+    float eB0 = __shfl_up_sync(0xffffffffu, b0.w, 1), eB1 = __shfl_up_sync(0xffffffffu, b1.w, 1);
+    if (!valid) return;
+    if (lane == 31 || g + 1 >= G) eA0 = nm[g + 1 == hv ? 0 : c0 + 4];
+    if (two && (lane == 31 || g + 1 >= G || gb + 1 >= hv)) eA1 = nm[gb + 1 == hv ? 0 : c1v + 4];
+    if (lane == 0 || g == 0) eB0 = nm[h + (g == 0 ? h - 1 : c0 - 1)];
+    if (two && (lane == 0 || g == 0)) eB1 = nm[h + c1v - 1];
     float* __restrict__ ownB = ownA + h;
     const float m = (float)p.mu_const;
     // ---- row A
     {
-        const Philox4 blk = p.dry ? Philox4{0x80000000u + iA, 0xa0000000u + c1, 0x90000000u + (uint32_t)g, 0xc0000000u + c2} : philox4x32_10(iA * (uint32_t)p.G + (uint32_t)g, c1, c2, c3, p.keys);
+        const Philox4 blk = p.dry ? Philox4{0x80000000u + iA, 0xa0000000u + c1, 0x90000000u + (uint32_t)g, 0xc0000000u + c2}
+                                  : philox4x32_10(iA * (uint32_t)G + (uint32_t)g, c1, c2, c3, p.keys);
         {
-            const float4 up = ld4(nm - h + cb);
-            const float4 cur = SOR ? ld4(ownA + cb) : z4;
-            const float e = two ? a1.x : eA;
-            const float4 v = gibbs_update4<SOR, true>(a0, up, b0, e, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
-            if (!PH2) st4(ownA + cb, v);
-            if (goutA) st4(goutA + cb, v);
-            if (PH2 && EMIT == 1) {
-                if (emitA) emit8<TO>(p, emitA + 2 * cb, muA ? muA + 2 * cb : nullptr, v, a0, (iA & 1u) != 0);
-            }
-            if (PH2 && EMIT == 2) stats8<true>(v, a0, up, b0, e, m, acc);
-        }
-        if (two) {
-            const int c0 = cb + 4;
             const float4 up = ld4(nm - h + c0);
             const float4 cur = SOR ? ld4(ownA + c0) : z4;
-            const float4 v = gibbs_update4<SOR, true>(a1, up, b1, eA, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
+            const float4 v = gibbs_update4<SOR, true>(a0, up, b0, eA0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
             if (!PH2) st4(ownA + c0, v);
             if (goutA) st4(goutA + c0, v);
             if (PH2 && EMIT == 1) {
-                if (emitA) emit8<TO>(p, emitA + 2 * c0, muA ? muA + 2 * c0 : nullptr, v, a1, (iA & 1u) != 0);
+                if (emitA) emit8<TO>(p, emitA + 2 * c0, muA ? muA + 2 * c0 : nullptr, v, a0, (iA & 1u) != 0);
             }
-            if (PH2 && EMIT == 2) stats8<true>(v, a1, up, b1, eA, m, acc);
+            if (PH2 && EMIT == 2) stats8<true>(v, a0, up, b0, eA0, m, acc);
+        }
+        if (two) {
+            const float4 up = ld4(nm - h + c1v);
+            const float4 cur = SOR ? ld4(ownA + c1v) : z4;
+            const float4 v = gibbs_update4<SOR, true>(a1, up, b1, eA1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
+            if (!PH2) st4(ownA + c1v, v);
+            if (goutA) st4(goutA + c1v, v);
+            if (PH2 && EMIT == 1) {
+                if (emitA) emit8<TO>(p, emitA + 2 * c1v, muA ? muA + 2 * c1v : nullptr, v, a1, (iA & 1u) != 0);
+            }
+            if (PH2 && EMIT == 2) stats8<true>(v, a1, up, b1, eA1, m, acc);
         }
     }
     // ---- row B
     {
-        const Philox4 blk = p.dry ? Philox4{0x80000000u + iB, 0xa0000000u + c1, 0x90000000u + (uint32_t)g, 0xc0000000u + c2} : philox4x32_10(iB * (uint32_t)p.G + (uint32_t)g, c1, c2, c3, p.keys);
+        const Philox4 blk = p.dry ? Philox4{0x80000000u + iB, 0xa0000000u + c1, 0x90000000u + (uint32_t)g, 0xc0000000u + c2}
+                                  : philox4x32_10(iB * (uint32_t)G + (uint32_t)g, c1, c2, c3, p.keys);
         {
-            const float4 dn = ld4(nm + 2 * h + cb);
-            const float4 cur = SOR ? ld4(ownB + cb) : z4;
-            const float4 v = gibbs_update4<SOR, false>(b0, a0, dn, eB, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
-            if (!PH2) st4(ownB + cb, v);
-            if (goutB) st4(goutB + cb, v);
-            if (PH2 && EMIT == 1) {
-                if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * cb, muA ? muA + 2 * h + 2 * cb : nullptr, v, b0, (iB & 1u) != 0);
-            }
-            if (PH2 && EMIT == 2) stats8<false>(v, b0, a0, dn, eB, m, acc);
-        }
-        if (two) {
-            const int c0 = cb + 4;
             const float4 dn = ld4(nm + 2 * h + c0);
             const float4 cur = SOR ? ld4(ownB + c0) : z4;
-            const float4 v = gibbs_update4<SOR, false>(b1, a1, dn, b0.w, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
+            const float4 v = gibbs_update4<SOR, false>(b0, a0, dn, eB0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
             if (!PH2) st4(ownB + c0, v);
             if (goutB) st4(goutB + c0, v);
             if (PH2 && EMIT == 1) {
-                if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c0, muA ? muA + 2 * h + 2 * c0 : nullptr, v, b1, (iB & 1u) != 0);
+                if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c0, muA ? muA + 2 * h + 2 * c0 : nullptr, v, b0, (iB & 1u) != 0);
             }
-            if (PH2 && EMIT == 2) stats8<false>(v, b1, a1, dn, b0.w, m, acc);
+            if (PH2 && EMIT == 2) stats8<false>(v, b0, a0, dn, eB0, m, acc);
+        }
+        if (two) {
+            const float4 dn = ld4(nm + 2 * h + c1v);
+            const float4 cur = SOR ? ld4(ownB + c1v) : z4;
+            const float4 v = gibbs_update4<SOR, false>(b1, a1, dn, eB1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
+            if (!PH2) st4(ownB + c1v, v);
+            if (goutB) st4(goutB + c1v, v);
+            if (PH2 && EMIT == 1) {
+                if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c1v, muA ? muA + 2 * h + 2 * c1v : nullptr, v, b1, (iB & 1u) != 0);
+            }
+            if (PH2 && EMIT == 2) stats8<false>(v, b1, a1, dn, eB1, m, acc);
         }
     }
 }
@@ -400,8 +410,10 @@ __global__ void __launch_bounds__(kFusedMaxThreads, EMIT == 2 ? 2 : 3) gibbs_tor
     // ---- phase 1: red rows r0-1 .. r0+rows (local 0 .. rows+1) in (rows + 2) / 2 pairs, black neighbours from sB
     {
         const int items = ((rows + 2) >> 1) * G;
-        for (int t = threadIdx.x; t < items; t += blockDim.x) {
-            const int q = t / G, g = t - q * G;
+        for (int t0 = 0; t0 < items; t0 += blockDim.x) {         // uniform trip count: the items shuffle within their warp
+            const int t = t0 + threadIdx.x;
+            const bool valid = t < items;
+            const int q = valid ? t / G : 0, g = valid ? t - q * G : 0;
             const int lA = 2 * q;                              // local red row of A; its black row in sB is lA + 1
             int iA = r0 - 1 + lA;
             iA = iA < 0 ? iA + n1 : iA;                        // only the first tile wraps at the top,
@@ -409,7 +421,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, EMIT == 2 ? 2 : 3) gibbs_tor
             iB = iB >= n1 ? iB - n1 : iB;                      // only the last tile at the bottom
             float* goutA = lA >= 1 ? ored + (size_t)iA * h : nullptr;          // halo rows are recomputed, not stored
             float* goutB = lA + 1 <= rows ? ored + (size_t)iB * h : nullptr;
-            fused_item<SOR, false, 0, TO>(p, sB + (size_t)(lA + 1) * h, sR + (size_t)lA * h, goutA, goutB, nullptr, nullptr,
+            fused_item<SOR, false, 0, TO>(p, valid, sB + (size_t)(lA + 1) * h, sR + (size_t)lA * h, goutA, goutB, nullptr, nullptr,
                                           (uint32_t)iA, (uint32_t)iB, g, hv, h, p.sweep * 2u, c2, c3, acc);
         }
     }
@@ -417,8 +429,10 @@ __global__ void __launch_bounds__(kFusedMaxThreads, EMIT == 2 ? 2 : 3) gibbs_tor
     // ---- phase 2: black rows r0 .. r0+rows-1 in rows / 2 pairs from the new red rows in sR
     {
         const int items = (rows >> 1) * G;
-        for (int t = threadIdx.x; t < items; t += blockDim.x) {
-            const int q = t / G, g = t - q * G;
+        for (int t0 = 0; t0 < items; t0 += blockDim.x) {
+            const int t = t0 + threadIdx.x;
+            const bool valid = t < items;
+            const int q = valid ? t / G : 0, g = valid ? t - q * G : 0;
             const int tA = 2 * q;
             const int iA = r0 + tA, iB = iA + 1;
             TO* erow = nullptr;
@@ -429,7 +443,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, EMIT == 2 ? 2 : 3) gibbs_tor
                     if (p.mu != nullptr) mrow = p.mu + (size_t)iA * 2 * h;
                 }
             }
-            fused_item<SOR, true, EMIT, TO>(p, sR + (size_t)(tA + 1) * h, sB + (size_t)(tA + 2) * h, oblk + (size_t)iA * h,
+            fused_item<SOR, true, EMIT, TO>(p, valid, sR + (size_t)(tA + 1) * h, sB + (size_t)(tA + 2) * h, oblk + (size_t)iA * h,
                                             oblk + (size_t)iB * h, erow, mrow, (uint32_t)iA, (uint32_t)iB, g, hv, h,
                                             p.sweep * 2u + 1u, c2, c3, acc);
         }
@@ -582,7 +596,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
                 const TorusEmit* emit) {
     TorusSweepParams p{};
     p.red = t.red; p.black = t.black; p.n1 = ctx->n1; p.h = ctx->n2 / 2; p.C = t.C;
-    p.G = (p.h + 7) / 8;
+    p.G = (p.h / 4 + 1) / 2;
     p.keep = (float)(1.0 - omega);
     p.gain = (float)(omega * rho);
     p.noise = (float)std::sqrt(omega * (2.0 - omega) * sigma);
