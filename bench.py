@@ -34,6 +34,7 @@ N1 = N2 = 1000
 K_PSI = 200
 PSI0 = np.array([0.2, 1.0, 1.0])
 SEED = 20260101
+DTYPE = "f32 sampler state / f64 statistics+reduction"   # the arithmetic the path computes in, not a precision claim
 
 
 def psi_grid():
@@ -181,6 +182,9 @@ def run_ours(args):
 
     n = N1 * N2
     N_gpu = args.samples_per_gpu
+    if args.scaling == "strong":      # N_total = 10^5 fixed (BASELINE config 5 as worded), statistics only: 400 GB of samples never exist
+        N_gpu = args.total_samples // world + (1 if rank < args.total_samples % world else 0)
+        args.stats_only = True
     psis = psi_grid()
     y = synthetic_obs()
     X = np.ones((n, 1))
@@ -276,6 +280,61 @@ def run_ours(args):
         step_e2e()
     t_e2e, res2 = timed(step_e2e, args.steps)
 
+    # ---- result checks, outside the timed regions -------------------------------------------------------------
+    checks = {}
+    # (1) resident leg == host-buffer leg on the same (seed, draw): each sampler run owns its own Philox stream
+    d0 = ctx.draw
+    r_a = step_resident()
+    ctx.draw = d0
+    r_b = step_e2e()
+    checks["e2e_equal"] = bool(np.allclose(r_a, r_b, rtol=1e-9, atol=1e-12))
+    if world > 1:
+        # (2) the library's NCCL all-gather + merge against a host merge of the per-rank partial tuples gathered with
+        # torch.distributed (mclcar_dcar_partial -> all_gather -> mclcar_tuples_merge -> mclcar_dcar_finish)
+        sdc = api.mcl_prep_dCAR(PSI0, min(N_gpu, 2 * 149), data, dict(control, keep=False))
+        lib_res = api.mcl_dCAR_batch(psis, data, sdc, rho_cons=None)               # collective inside
+        T = int(L.lib.mclcar_tuple_len(L.WHAT_LR, 0, 2 + 2))
+        tup = np.zeros((K_PSI, T))
+        pc = np.ascontiguousarray(psis)
+        L.check(L.lib.mclcar_dcar_partial(ctx.h, sdc.h, L.dptr(pc), K_PSI, 3, L.WHAT_LR, None, None, L.SHIFT_MEAN, L.dptr(tup)), ctx.h)
+        mine = torch.from_numpy(tup).cuda()
+        allt = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine)
+        tin = np.ascontiguousarray(np.stack([t.cpu().numpy() for t in allt]))
+        merged = np.zeros((K_PSI, T))
+        assert L.lib.mclcar_tuples_merge(L.WHAT_LR, 0, 4, world, K_PSI, L.dptr(tin), L.dptr(merged)) == 0
+        lr_h, var_h = np.zeros(K_PSI), np.zeros(K_PSI)
+        p0 = np.ascontiguousarray(PSI0)
+        L.check(L.lib.mclcar_dcar_finish(ctx.h, L.dptr(p0), 3, L.dptr(pc), K_PSI, 3, L.WHAT_LR, 0, None, L.dptr(merged), L.dptr(lr_h), L.dptr(var_h)), ctx.h)
+        host = np.stack([lr_h, var_h], axis=1)
+        rel = np.abs(lib_res - host) / np.maximum(np.abs(host), 1e-300)
+        checks["nccl_merge_max_rel"] = float(rel.max())
+        checks["nccl_merge_ranks"] = world
+        sdc.close()
+    else:
+        # (2') the CUDA path against the oracle's C twin on a 64-sample subset of the same workload (kept samples)
+        from oracle import cpu_path
+        sdc = api.mcl_prep_dCAR(PSI0, 64, data, {"n.chains": 64, "keep": True})
+        got = api.mcl_dCAR_batch(psis, data, sdc, rho_cons=None)
+        Y = np.ascontiguousarray(sdc.simY.T)                                       # (64, n) sample-major fp64 copy
+        q = cpu_path.stats_torus(Y, N1, N2, X)
+        G0 = np.array([[float(n)]]); G1 = np.array([[4.0 * n]])
+        c0 = cpu_path.affine_coef(PSI0, 1, G0, G1)
+        t20 = c0[0] + q @ c0[1:]
+        qobs = np.array([y @ y, 0.0, y.sum(), 4.0 * y.sum()])
+        y2 = y.reshape(N1, N2)
+        qobs[1] = 2.0 * float((y2 * (np.roll(y2, -1, 1) + np.roll(y2, 1, 0))).sum())
+        coef = np.stack([cpu_path.affine_coef(ps, 1, G0, G1) for ps in psis])
+        s1 = coef[:, 0] + coef[:, 1:] @ qobs - (c0[0] + c0[1:] @ qobs)
+        lr_o, var_o = cpu_path.reduce_lr(q, t20, coef, s1)
+        ref = np.stack([lr_o, var_o], axis=1)
+        checks["oracle_subset_samples"] = 64
+        checks["oracle_stats_max_rel"] = float(np.abs(sdc.stats() - q).max() / np.abs(q).max())
+        checks["oracle_lr_max_abs"] = float(np.abs(got[:, 0] - ref[:, 0]).max())
+        checks["oracle_var_max_rel"] = float((np.abs(got[:, 1] - ref[:, 1]) / np.maximum(ref[:, 1], 1e-300)).max())
+        sdc.close()
+        del Y
+
     # the fp64 likelihood pass over a resident sample matrix (the shape the reference's own simY
     # has): K2<double> + K3 for all candidates, timed with the library's CUDA-event spans
     fp64 = None
@@ -310,7 +369,7 @@ def run_ours(args):
         return
 
     peak, peak_src = read_peaks()
-    N_tot = N_gpu * world
+    N_tot = args.total_samples if args.scaling == "strong" else N_gpu * world
     evals = N_tot * K_PSI * args.steps
     value = evals / t_res
     # per-kernel numbers from the CUDA-event spans recorded inside the library (this rank)
@@ -345,8 +404,8 @@ def run_ours(args):
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": workload_name(), "samples_per_gpu": N_gpu, "psi_points": K_PSI, "chains_per_gpu": chains,
                    "sweeps_per_step": sweeps_step, "omega": omega, "thin": int(diag["thin"]), "burn": int(diag["burn"]), "sample_storage": "fp32 in HBM" if not args.stats_only else "statistics only",
                    "arithmetic": "fp32 chain state and normals; fp64 statistics, weights and reductions",
@@ -381,8 +440,8 @@ def run_ours(args):
         "likelihood_fp64_resident": None if fp64 is None else dict(fp64, frac_of_hbm_peak=fp64["pass_GBps"] / peak,
                                                                     stats_kernel_frac=fp64["stats_kernel_GBps"] / peak),
         "clocks": clk,
-        "result_check": {"lr_min": float(res[:, 0].min()), "lr_max": float(res[:, 0].max()),
-                         "var_max": float(res[:, 1].max()), "e2e_equal": bool(np.allclose(res, res2, rtol=1e-9, atol=1e-12))},
+        "result_check": dict({"lr_min": float(res[:, 0].min()), "lr_max": float(res[:, 0].max()),
+                              "var_max": float(res[:, 1].max())}, **checks),
     }
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (the reference arm times it at every N)
         from oracle import cpu_path
@@ -396,6 +455,11 @@ def run_ours(args):
     _print_json(line)
     if world > 1:
         dist.destroy_process_group()
+    bad = (not checks.get("e2e_equal", True)) or checks.get("nccl_merge_max_rel", 0.0) > 1e-12 or \
+        checks.get("oracle_stats_max_rel", 0.0) > 1e-12 or checks.get("oracle_lr_max_abs", 0.0) > 1e-8
+    if bad and not os.environ.get("MCLCAR_SWEEP_DRY"):
+        sys.stderr.write(f"bench.py: result check failed: {checks}\n")
+        os._exit(4)
 
 
 class _CleanStdout:
@@ -461,6 +525,11 @@ def main():
     ap.add_argument("--no-fp64", action="store_true")
     ap.add_argument("--fp64-samples", type=int, default=1500)
     ap.add_argument("--watchdog", type=float, default=1500.0, help="abort after this many seconds (0 = never)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --samples-per-gpu per rank (headline); strong: --total-samples split over the ranks, statistics only")
+    ap.add_argument("--total-samples", type=int, default=100_000)
+    ap.add_argument("--config", default="c5", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configuration; c5 is the headline (the others: bench_configs.py)")
     args = ap.parse_args()
     if args.watchdog > 0:
         _watchdog(args.watchdog)
@@ -469,6 +538,9 @@ def main():
         _OUT = out
         if args.impl == "reference":
             run_reference(args)
+        elif args.config != "c5":
+            import bench_configs
+            bench_configs.run(args, _print_json)
         else:
             run_ours(args)
     _OUT = None

@@ -46,6 +46,7 @@ struct mclcar_ctx {
     // counter is part of the reproducible state (same seed + same call index => same samples) and is
     // the same on every rank of a sharded run
     uint64_t draw = 0;       // index of the next prep call
+    uint64_t draw_salt = 0;  // > 0: a repeated run inside one prep call (pilot-checked GLM thinning)
     uint64_t draw_key = 0;   // Philox key of the prep call in progress
     int rank = 0, world = 1;
     int n_sm = 148;
@@ -187,6 +188,8 @@ int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64
                                 const std::vector<int>& rowptr, const std::vector<int>& colidx,
                                 const std::vector<double>& val, int L, const double* const* d_vecs, double* d_out,
                                 int64_t ldq);
+int edge_cache_get(mclcar_ctx* ctx, int n, const std::vector<int>& rowptr, const std::vector<int>& colidx,
+                   const std::vector<double>& val, const mclcar::EdgeCache** out);
 int samples_alloc_stats(mclcar_ctx* ctx, mclcar_samples* s, int d);
 int samples_update_qbar(mclcar_ctx* ctx, mclcar_samples* s);
 int merge_tuples(int what, int F, int d, int G, int K, const double* in, double* out);
@@ -270,7 +273,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
 int check_rho(mclcar_ctx* ctx, double rho);
 // start of a sampler run: derive this call's Philox key and advance the context's draw counter
 inline uint64_t begin_draw(mclcar_ctx* ctx) {
-    ctx->draw_key = ctx->seed + ctx->draw * 0x9E3779B97F4A7C15ull;
+    ctx->draw_key = ctx->seed + ctx->draw * 0x9E3779B97F4A7C15ull + ctx->draw_salt * 0xD1B54A32D192ED03ull;
     ++ctx->draw;
     return ctx->draw_key;
 }

@@ -24,7 +24,10 @@ namespace mclcar {
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kBT = 2;  // candidate betas per pass
+// candidate betas per pass over the sample matrix: all betas of a tile share the load / conversion of z and of the
+// site's y, n, X row.  The tile is as wide as the accumulators allow: 8 for log-ratio batches (one accumulator per
+// beta), 4 with gradients, 2 with Hessian blocks
+constexpr int tile_of(int mode) { return mode == 0 ? 8 : (mode == 1 ? 4 : 2); }
 
 struct GlmTermsParams {
     const void* M;  // [n][ld] site-major
@@ -34,20 +37,28 @@ struct GlmTermsParams {
     const double* y;   // [n]
     const double* nt;  // [n] or null (== 1)
     const double* beta;  // [nb][p] this tile's betas
-    int nb;              // betas in this tile (<= kBT)
+    int nb;              // betas in this tile (<= tile_of(mode))
     int chunk;           // sites per chunk
     double* out;         // [chunks][nb * ns][ldq]
     int64_t ldq;
     int ns;              // statistics per beta: 1 (+ p (+ p(p+1)/2))
+    // STATS: the same pass also forms z'z and z'Wz (rows of `sout`, [chunks][2][ldq]) -- the whole GLM likelihood
+    // pass reads the sample matrix once (upper-triangle edge list of W as in stats_csr.cu)
+    const int* eptr;
+    const int* ei;
+    const int* ej;
+    const double* ew;
+    double* sout;
 };
 
 // MODE 0: D only; 1: D + gradient; 2: D + gradient + Hessian block
-template <typename T, int FAM, int PT, int MODE>
+template <typename T, int FAM, int PT, int MODE, bool STATS>
 __global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParams prm) {
+    constexpr int BT = tile_of(MODE);
     constexpr int NH = PT * (PT + 1) / 2;
     constexpr int NS = 1 + (MODE >= 1 ? PT : 0) + (MODE >= 2 ? NH : 0);
-    __shared__ double sbeta[kBT * PT];
-    if (threadIdx.x < kBT * PT) {
+    __shared__ double sbeta[BT * PT];
+    if (threadIdx.x < BT * PT) {
         const int b = threadIdx.x / PT, a = threadIdx.x % PT;
         sbeta[threadIdx.x] = (b < prm.nb && a < prm.p) ? prm.beta[b * prm.p + a] : 0.0;
     }
@@ -56,81 +67,101 @@ __global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParam
     if (i >= prm.N) return;
     const T* M = reinterpret_cast<const T*>(prm.M);
     const int s0 = blockIdx.y * prm.chunk, s1 = min(prm.n, s0 + prm.chunk);
-    double acc[kBT][NS];
+    double acc[BT][NS];
 #pragma unroll
-    for (int b = 0; b < kBT; ++b)
+    for (int b = 0; b < BT; ++b)
 #pragma unroll
         for (int t = 0; t < NS; ++t) acc[b][t] = 0.0;
+    double zz = 0.0;
     for (int s = s0; s < s1; ++s) {
         const double z = (double)ld_stream(M + (size_t)s * prm.ld + i);
         const double ys = __ldg(prm.y + s);
         const double ns = prm.nt ? __ldg(prm.nt + s) : 1.0;
+        if (STATS) zz = fma(z, z, zz);
         double xr[PT];
 #pragma unroll
         for (int a = 0; a < PT; ++a) xr[a] = a < prm.p ? __ldg(prm.X + (size_t)a * prm.n + s) : 0.0;
 #pragma unroll
-        for (int b = 0; b < kBT; ++b) {
-            if (b >= prm.nb) break;
-            double eta = z;
+        for (int b = 0; b < BT; ++b) {
+            if (b < prm.nb) {
+                double eta = z;
 #pragma unroll
-            for (int a = 0; a < PT; ++a) eta = fma(xr[a], sbeta[b * PT + a], eta);
-            double mu, v;
-            if (FAM == FAM_BINOM) {
-                // log(1 + e^eta) without overflow; p = e^eta / (1 + e^eta)
-                const double t = exp(-fabs(eta));
-                const double l1p = log1p(t);
-                const double inv = 1.0 / (1.0 + t);
-                const double pz = eta >= 0.0 ? inv : t * inv;
-                acc[b][0] += ys * eta - ns * (fmax(eta, 0.0) + l1p);
-                mu = ns * pz;
-                v = -ns * pz * (1.0 - pz);   // -n p (1 - p): R/mcl.bin.R:262,268
-            } else {
-                const double ex = exp(eta);
-                acc[b][0] += ys * eta - ex;
-                mu = ex;
-                v = ex * ex;                 // +exp(eta)^2, as coded at R/mcl.pois.R:268
-            }
-            if (MODE >= 1) {
-                const double r = ys - mu;
+                for (int a = 0; a < PT; ++a) eta = fma(xr[a], sbeta[b * PT + a], eta);
+                double mu, v;
+                if (FAM == FAM_BINOM) {
+                    // log(1 + e^eta) without overflow; p = e^eta / (1 + e^eta); t = e^-|eta| serves both
+                    const double t = exp(-fabs(eta));
+                    acc[b][0] += ys * eta - ns * (fmax(eta, 0.0) + log1p(t));
+                    if (MODE >= 1) {
+                        const double inv = 1.0 / (1.0 + t);
+                        const double pz = eta >= 0.0 ? inv : t * inv;
+                        mu = ns * pz;
+                        v = -ns * pz * (1.0 - pz);   // -n p (1 - p): R/mcl.bin.R:262,268
+                    }
+                } else {
+                    const double ex = exp(eta);
+                    acc[b][0] += ys * eta - ex;
+                    mu = ex;
+                    v = ex * ex;                 // +exp(eta)^2, as coded at R/mcl.pois.R:268
+                }
+                if (MODE >= 1) {
+                    const double r = ys - mu;
 #pragma unroll
-                for (int a = 0; a < PT; ++a) acc[b][1 + a] = fma(xr[a], r, acc[b][1 + a]);
-            }
-            if (MODE >= 2) {
-                int t = 1 + PT;
+                    for (int a = 0; a < PT; ++a) acc[b][1 + a] = fma(xr[a], r, acc[b][1 + a]);
+                }
+                if (MODE >= 2) {
+                    int t = 1 + PT;
 #pragma unroll
-                for (int a = 0; a < PT; ++a) {
-                    const double va = v * xr[a];
+                    for (int a = 0; a < PT; ++a) {
+                        const double va = v * xr[a];
 #pragma unroll
-                    for (int c = a; c < PT; ++c) {
-                        acc[b][t] = fma(va, xr[c], acc[b][t]);
-                        ++t;
+                        for (int c = a; c < PT; ++c) {
+                            acc[b][t] = fma(va, xr[c], acc[b][t]);
+                            ++t;
+                        }
                     }
                 }
             }
         }
     }
+    if (STATS) {
+        // z'Wz / 2 over the chunk's edges: independent iterations, many gathers in flight (the rows were just streamed:
+        // they come from L2)
+        double zwz = 0.0;
+        const int e0 = prm.eptr[s0], e1 = prm.eptr[s1];
+#pragma unroll 4
+        for (int e = e0; e < e1; ++e) {
+            const double a = (double)__ldg(M + (size_t)__ldg(prm.ei + e) * prm.ld + i);
+            const double b = (double)__ldg(M + (size_t)__ldg(prm.ej + e) * prm.ld + i);
+            zwz = fma(prm.ew ? __ldg(prm.ew + e) * a : a, b, zwz);
+        }
+        double* so = prm.sout + (size_t)blockIdx.y * 2 * prm.ldq + i;
+        so[0] = zz;
+        so[prm.ldq] = 2.0 * zwz;
+    }
     // compact (exact p) output order: D, g[0..p), H packed upper over p
     const int p = prm.p;
     double* o = prm.out + (size_t)blockIdx.y * prm.nb * prm.ns * prm.ldq + i;
 #pragma unroll
-    for (int b = 0; b < kBT; ++b) {
-        if (b >= prm.nb) break;
-        double* ob = o + (size_t)b * prm.ns * prm.ldq;
-        ob[0] = acc[b][0];
-        if (MODE >= 1) {
+    for (int b = 0; b < BT; ++b) {
+        if (b < prm.nb) {
+            double* ob = o + (size_t)b * prm.ns * prm.ldq;
+            ob[0] = acc[b][0];
+            if (MODE >= 1) {
 #pragma unroll
-            for (int a = 0; a < PT; ++a)
-                if (a < p) ob[(size_t)(1 + a) * prm.ldq] = acc[b][1 + a];
-        }
-        if (MODE >= 2) {
-            int t = 1 + PT, tc = 1 + p;
+                for (int a = 0; a < PT; ++a)
+                    if (a < p) ob[(size_t)(1 + a) * prm.ldq] = acc[b][1 + a];
+            }
+            if (MODE >= 2) {
+                int t = 1 + PT, tc = 1 + p;
 #pragma unroll
-            for (int a = 0; a < PT; ++a)
+                for (int a = 0; a < PT; ++a)
 #pragma unroll
-                for (int c = a; c < PT; ++c) {
-                    if (a < p && c < p) ob[(size_t)(tc++) * prm.ldq] = acc[b][t];
-                    ++t;
-                }
+                    for (int c = a; c < PT; ++c) {
+                        if (a < p && c < p) ob[(size_t)(tc++) * prm.ldq] = acc[b][t];
+                        ++t;
+                    }
+            }
         }
     }
 }
@@ -145,61 +176,81 @@ __global__ void glm_chunk_sum_kernel(const double* partial, double* q, int S, in
     }
 }
 
-template <typename T, int FAM, int PT>
+template <typename T, int FAM, int PT, bool STATS>
 void launch_mode(const GlmTermsParams& p, int mode, dim3 grid, cudaStream_t st) {
-    if (mode == 0) glm_terms_kernel<T, FAM, PT, 0><<<grid, kThreads, 0, st>>>(p);
-    else if (mode == 1) glm_terms_kernel<T, FAM, PT, 1><<<grid, kThreads, 0, st>>>(p);
-    else glm_terms_kernel<T, FAM, PT, 2><<<grid, kThreads, 0, st>>>(p);
+    if (mode == 0) glm_terms_kernel<T, FAM, PT, 0, STATS><<<grid, kThreads, 0, st>>>(p);
+    else if (mode == 1) glm_terms_kernel<T, FAM, PT, 1, STATS><<<grid, kThreads, 0, st>>>(p);
+    else glm_terms_kernel<T, FAM, PT, 2, STATS><<<grid, kThreads, 0, st>>>(p);
+}
+template <typename T, int FAM, bool STATS>
+void launch_p(const GlmTermsParams& p, int mode, dim3 grid, cudaStream_t st) {
+    if (p.p <= 1) launch_mode<T, FAM, 1, STATS>(p, mode, grid, st);
+    else if (p.p <= 2) launch_mode<T, FAM, 2, STATS>(p, mode, grid, st);
+    else if (p.p <= 4) launch_mode<T, FAM, 4, STATS>(p, mode, grid, st);
+    else launch_mode<T, FAM, 8, STATS>(p, mode, grid, st);
 }
 template <typename T, int FAM>
-void launch_p(const GlmTermsParams& p, int mode, dim3 grid, cudaStream_t st) {
-    if (p.p <= 1) launch_mode<T, FAM, 1>(p, mode, grid, st);
-    else if (p.p <= 2) launch_mode<T, FAM, 2>(p, mode, grid, st);
-    else if (p.p <= 4) launch_mode<T, FAM, 4>(p, mode, grid, st);
-    else launch_mode<T, FAM, 8>(p, mode, grid, st);
+void launch_s(const GlmTermsParams& p, int mode, dim3 grid, cudaStream_t st) {
+    if (p.sout) launch_p<T, FAM, true>(p, mode, grid, st);
+    else launch_p<T, FAM, false>(p, mode, grid, st);
 }
 
-// data terms of `nb_total` distinct betas -> rows [row0 + b*ns, ...) of q [.][ldq]
+// data terms of `nb_total` distinct betas -> rows [row0 + b*ns, ...) of q [.][ldq]; with d_static != null the first
+// pass also writes z'z, z'Wz there ([2][ldq]): ONE read of the sample matrix for the whole likelihood pass when the
+// batch fits one beta tile
 int glm_data_terms(mclcar_ctx* ctx, const mclcar_samples* s, int fam, const std::vector<double>& betas, int nb_total,
-                   int mode, double* d_q, int64_t ldq, int row0) {
+                   int mode, double* d_q, int64_t ldq, int row0, double* d_static) {
     const int p = ctx->p, n = ctx->n;
     const int ns = 1 + (mode >= 1 ? p : 0) + (mode >= 2 ? p * (p + 1) / 2 : 0);
+    const int BT = tile_of(mode);
     const int64_t N = s->N;
     const int64_t xblocks = (N + kThreads - 1) / kThreads;
     int chunks = (int)std::max<int64_t>(1, ((int64_t)4 * ctx->n_sm + xblocks - 1) / xblocks);
     chunks = std::min(chunks, std::max(1, n / 32));
     const int chunk = (n + chunks - 1) / chunks;
     chunks = (n + chunk - 1) / chunk;
+    const EdgeCache* ec = nullptr;
+    if (d_static) MCL_TRY(edge_cache_get(ctx, n, ctx->rowptr, ctx->colidx, ctx->val, &ec));
     double* d_beta = nullptr;
     MCL_TRY(pool_alloc(ctx, (void**)&d_beta, betas.size() * sizeof(double)));
     MCL_CUDA(ctx, cudaMemcpyAsync(d_beta, betas.data(), betas.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    double* partial = nullptr;
-    if (chunks > 1) MCL_TRY(pool_alloc(ctx, (void**)&partial, (size_t)chunks * kBT * ns * ldq * sizeof(double)));
+    double *partial = nullptr, *spartial = nullptr;
+    if (chunks > 1) MCL_TRY(pool_alloc(ctx, (void**)&partial, (size_t)chunks * BT * ns * ldq * sizeof(double)));
+    if (chunks > 1 && d_static) MCL_TRY(pool_alloc(ctx, (void**)&spartial, (size_t)chunks * 2 * ldq * sizeof(double)));
     int st = MCLCAR_OK;
-    for (int b0 = 0; b0 < nb_total && st == MCLCAR_OK; b0 += kBT) {
+    for (int b0 = 0; b0 < nb_total && st == MCLCAR_OK; b0 += BT) {
         GlmTermsParams prm{};
         prm.M = s->d_M; prm.ld = s->ld; prm.N = N; prm.n = n; prm.p = p;
         prm.X = ctx->d_X; prm.y = ctx->d_y; prm.nt = ctx->d_ntrial;
-        prm.beta = d_beta + (size_t)b0 * p; prm.nb = std::min(kBT, nb_total - b0);
+        prm.beta = d_beta + (size_t)b0 * p; prm.nb = std::min(BT, nb_total - b0);
         prm.chunk = chunk; prm.ldq = ldq; prm.ns = ns;
         double* dst = d_q + (size_t)(row0 + b0 * ns) * ldq;
         prm.out = chunks > 1 ? partial : dst;
+        const bool with_stats = d_static && b0 == 0;
+        if (with_stats) {
+            prm.eptr = ec->d_eptr; prm.ei = ec->d_ei; prm.ej = ec->d_ej; prm.ew = ec->d_ew;
+            prm.sout = chunks > 1 ? spartial : d_static;
+        }
         dim3 grid((unsigned)xblocks, (unsigned)chunks);
-        ProfScope prof(ctx, PROF_GLM, chunks > 1 ? 2 : 1);
+        ProfScope prof(ctx, PROF_GLM, (chunks > 1 ? 2 : 1) + (with_stats && chunks > 1 ? 1 : 0));
         const bool f32 = s->dtype == MCLCAR_F32;
         if (fam == FAM_BINOM) {
-            if (f32) launch_p<float, FAM_BINOM>(prm, mode, grid, ctx->stream);
-            else launch_p<double, FAM_BINOM>(prm, mode, grid, ctx->stream);
+            if (f32) launch_s<float, FAM_BINOM>(prm, mode, grid, ctx->stream);
+            else launch_s<double, FAM_BINOM>(prm, mode, grid, ctx->stream);
         } else {
-            if (f32) launch_p<float, FAM_POIS>(prm, mode, grid, ctx->stream);
-            else launch_p<double, FAM_POIS>(prm, mode, grid, ctx->stream);
+            if (f32) launch_s<float, FAM_POIS>(prm, mode, grid, ctx->stream);
+            else launch_s<double, FAM_POIS>(prm, mode, grid, ctx->stream);
         }
-        if (chunks > 1)
+        if (chunks > 1) {
             glm_chunk_sum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(partial, dst, chunks, prm.nb * ns, ldq, N);
+            if (with_stats)
+                glm_chunk_sum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(spartial, d_static, chunks, 2, ldq, N);
+        }
         if (cudaGetLastError() != cudaSuccess) st = fail(ctx, MCLCAR_ECUDA, "GLM data-term kernel launch failed");
     }
     pool_free(ctx, partial);
+    pool_free(ctx, spartial);
     pool_free(ctx, d_beta);
     return st;
 }
@@ -267,16 +318,6 @@ int glm_check(mclcar_ctx* ctx, mclcar_samples* s, int P) {
     return need_eigs(ctx);
 }
 
-// z'z and z'Wz of every sample -> rows 0, 1 of s->d_q (kept with the sample set)
-int glm_static_stats(mclcar_ctx* ctx, mclcar_samples* s) {
-    if (s->stats_ready && s->d == 2) return MCLCAR_OK;
-    MCL_TRY(samples_alloc_stats(ctx, s, 2));
-    MCL_TRY(launch_quadforms_site_major(ctx, s->d_M, s->dtype, s->N, s->ld, ctx->n, ctx->rowptr, ctx->colidx, ctx->val, 0, nullptr,
-                                        s->d_q, s->N));
-    s->stats_ready = true;
-    return MCLCAR_OK;
-}
-
 int glm_build_batch(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int mode, GlmBatch& gb) {
     const int p = ctx->p;
     gb.fam = s->family; gb.p = p; gb.P = P; gb.K = K; gb.mode = mode;
@@ -291,10 +332,13 @@ int glm_build_batch(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
     if (!s->d_base) find_or_add(s->psi0.data() + 2);  // index 0: importance beta
     for (int k = 0; k < K; ++k) gb.bidx[k] = find_or_add(psi + (size_t)k * P + 2);
     gb.d = 2 + gb.nb * gb.ns;
-    MCL_TRY(glm_static_stats(ctx, s));
+    // z'z and z'Wz stay with the sample set; the first evaluation forms them in the same pass as the data terms
+    const bool have_static = s->stats_ready && s->d == 2;
+    if (!have_static) MCL_TRY(samples_alloc_stats(ctx, s, 2));
     MCL_TRY(pool_alloc(ctx, (void**)&gb.d_q, (size_t)gb.d * s->N * sizeof(double)));
+    MCL_TRY(glm_data_terms(ctx, s, gb.fam, gb.betas, gb.nb, mode, gb.d_q, s->N, 2, have_static ? nullptr : s->d_q));
+    s->stats_ready = true;
     MCL_CUDA(ctx, cudaMemcpyAsync(gb.d_q, s->d_q, (size_t)2 * s->N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    MCL_TRY(glm_data_terms(ctx, s, gb.fam, gb.betas, gb.nb, mode, gb.d_q, s->N, 2));
     // column means (shift and centres)
     mclcar_samples tmp;
     tmp.N = s->N; tmp.d = gb.d; tmp.d_q = gb.d_q;
@@ -628,9 +672,16 @@ int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int6
     int burn = o.burn, thin = o.thin;
     double omega = 1.0;  // Metropolis-within-Gibbs: no over-relaxation
     default_schedule(ctx, rho, &omega, &burn, &thin);
-    // the likelihood sharpens the conditionals and the accept step slows the chain: be generous
+    // The accept step slows the chain below the Gibbs rate the schedule is made for, the more so the sharper the
+    // likelihood (sites with large n p (1 - p) rarely accept a draw from their prior conditional).  Start from 4x the
+    // Gibbs burn-in and 3x its thinning, then CHECK: the reference's v.lr and step rule take the draws as
+    // independent (R/mcl.bin.R:70-72), so the kept states must have an effective sample size >= 0.85 N in both
+    // z'z and z'Wz; otherwise the run was a pilot (the reference's mcl.prep.glm has one too, R/mcl.glm.R:17-26):
+    // its autocorrelation time gives the thinning that brings the lag-one autocorrelation of kept states to 5 %,
+    // and the chains are run again.  A thinning given by the caller is taken as is.
+    const bool tune = o.thin <= 0;
     if (o.burn <= 0) burn = std::max(4 * burn, 200);
-    if (o.thin <= 0) thin = std::max(2 * thin, 10);
+    if (tune) thin = std::max(3 * thin, 10);
     const int n = ctx->n;
     const size_t es = o.dtype == MCLCAR_F32 ? 4 : 8;
     std::vector<double> xb(n, 0.0);
@@ -648,10 +699,37 @@ int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int6
     for (size_t e = 0; e < g.qoff.size(); ++e) g.qoff[e] = -rho * (ctx->binary ? 1.0 : ctx->val[e]) / sigma;
     int st = pool_alloc(ctx, &s->d_M, (size_t)n * s->ld * es);
     const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
-    if (st == MCLCAR_OK)
+    const uint64_t draw0 = ctx->draw;
+    int64_t sweeps_total = 0;
+    for (int attempt = 0; attempt < 3 && st == MCLCAR_OK; ++attempt) {
+        ctx->draw = draw0;               // one prep call = one draw index, whatever the number of pilot runs
+        ctx->draw_salt = (uint64_t)attempt;
         st = run_csr_sampler(ctx, g, family == MCLCAR_FAMILY_BINOM ? FAM_BINOM : FAM_POIS, 1.0, nullptr, ctx->y.data(),
                              ctx->ntrial.empty() ? nullptr : ctx->ntrial.data(), xb.data(), N, C, burn, thin, s->d_M,
                              o.dtype == MCLCAR_F64, s->ld, &s->accept, &s->sweeps);
+        sweeps_total += s->sweeps;
+        if (st != MCLCAR_OK || !tune || attempt == 2 || N < 4 * C) break;   // fewer than 4 states per chain: no autocorrelation to estimate
+        // z'z, z'Wz of the kept states (they stay with the sample set) and their effective sample size
+        if ((st = samples_alloc_stats(ctx, s, 2))) break;
+        if ((st = launch_quadforms_site_major(ctx, s->d_M, s->dtype, N, s->ld, n, ctx->rowptr, ctx->colidx, ctx->val, 0, nullptr, s->d_q, N))) break;
+        std::vector<double> q((size_t)2 * N);
+        cudaError_t e = cudaMemcpyAsync(q.data(), s->d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ECUDA, "copy of the statistics failed: %s", cudaGetErrorString(e)); break; }
+        double ess[2];
+        mclcar_ess_from_stats(q.data(), N, 2, N, C, ess);
+        const double worst = std::min(ess[0], ess[1]);
+        if (worst >= 0.85 * (double)N) { s->stats_ready = true; break; }
+        const double tau = (double)N / std::max(worst, 1.0);
+        const double rho1 = std::min((tau - 1.0) / (tau + 1.0), 0.98);       // lag-one autocorrelation of the kept states
+        const double per_sweep = std::pow(rho1, 1.0 / thin);
+        int want = (int)std::ceil(std::log(0.05) / std::log(per_sweep));
+        want = std::min(std::max(want, thin + thin / 4 + 1), 8 * thin);
+        thin = want;
+    }
+    ctx->draw = draw0 + 1;
+    ctx->draw_salt = 0;
+    s->sweeps = sweeps_total;
     s->chains = C; s->burn = burn; s->thin = thin; s->omega = 1.0;
     if (st == MCLCAR_OK) st = mclcar_glm_attach(ctx, s, family, psi0, P, nullptr);
     if (st != MCLCAR_OK) {

@@ -114,12 +114,10 @@ int launch_typed(mclcar_ctx* ctx, const SiteMajorParams& p, dim3 grid) {
 
 // generic form: any symmetric CSR matrix (host copy given), any list of dense device vectors.  The
 // upper-triangle edge list is built on the host and cached on the context keyed by the CSR arrays.
-int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, int n,
-                                const std::vector<int>& rowptr, const std::vector<int>& colidx,
-                                const std::vector<double>& val, int L, const double* const* d_vecs, double* d_out,
-                                int64_t ldq) {
-    if (L > 2 * MCLCAR_MAX_COV) return fail(ctx, MCLCAR_ELIMIT, "too many linear forms (%d)", L);
-    // ---- edge list (cached)
+// upper-triangle edge list of a symmetric CSR matrix on the device, built once per matrix and cached on the context
+// keyed by the host CSR arrays
+int edge_cache_get(mclcar_ctx* ctx, int n, const std::vector<int>& rowptr, const std::vector<int>& colidx,
+                   const std::vector<double>& val, const EdgeCache** out) {
     EdgeCache* ec = nullptr;
     for (auto& c : ctx->edge_cache)
         if (c.key_rowptr == rowptr.data() && c.key_colidx == colidx.data() && c.n == n && c.nnz == (int)colidx.size()) ec = &c;
@@ -154,6 +152,17 @@ int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64
         if (any_diag) MCL_TRY(up(diag.data(), diag.size() * sizeof(double), (void**)&ec->d_diag));
         MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors are locals
     }
+    *out = ec;
+    return MCLCAR_OK;
+}
+
+int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, int n,
+                                const std::vector<int>& rowptr, const std::vector<int>& colidx,
+                                const std::vector<double>& val, int L, const double* const* d_vecs, double* d_out,
+                                int64_t ldq) {
+    if (L > 2 * MCLCAR_MAX_COV) return fail(ctx, MCLCAR_ELIMIT, "too many linear forms (%d)", L);
+    const EdgeCache* ec = nullptr;
+    MCL_TRY(edge_cache_get(ctx, n, rowptr, colidx, val, &ec));
     SiteMajorParams p{};
     p.M = M; p.ld = ld; p.N = N; p.n = n;
     p.eptr = ec->d_eptr; p.ei = ec->d_ei; p.ej = ec->d_ej; p.ew = ec->d_ew; p.diag = ec->d_diag;

@@ -81,9 +81,16 @@ __global__ void __launch_bounds__(kThreads, 2) stats_torus_kernel(const StatsTor
     uint32_t phase = 0;  // bit b = parity to wait for on barrier b (uniform over the CTA)
 
     const int nvr = n2 / VEC;  // vectors per row
-    // first vector of this thread in a stage and its step, tracked without divisions
-    const int row_t = threadIdx.x / nvr, cv_t = threadIdx.x - row_t * nvr;
-    const int drow = kThreads / nvr, dcv = kThreads - drow * nvr;
+    // A thread walks DOWN a column vector through a block of consecutive rows of the stage and keeps the row
+    // above in registers: every element is loaded from shared memory and converted to fp64 once (plus the
+    // first element of the next vector, and the row above its block: ~1.4 conversions per fp32 element
+    // instead of 2.25 when every vector re-read its upper neighbour -- the conversion unit, not HBM, was
+    // the limit of the fp32 path).  Rows narrower than the CTA are shared by `groups` row blocks.
+    const bool wide = nvr > kThreads;
+    const int groups = wide ? 1 : min(kThreads / nvr, p.RB);
+    const int cv_t = wide ? (int)threadIdx.x : (int)threadIdx.x % nvr;
+    const int rg = wide ? 0 : (int)threadIdx.x / nvr;
+    const int cstride = wide ? kThreads : nvr;
 
     for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int64_t i = item / p.S;
@@ -122,42 +129,42 @@ __global__ void __launch_bounds__(kThreads, 2) stats_torus_kernel(const StatsTor
                                           (size_t)(p.RB - 1) * n2;
             const int rs = r0 + it * p.RB;
             const int rows_here = min(p.RB, r1 - rs);
-            int row = row_t, cv = cv_t;
-            while (row < rows_here) {
-                const int c = cv * VEC;
-                const T* rowp = buf + (size_t)row * n2;
-                const VT v = *reinterpret_cast<const VT*>(rowp + c);
-                const VT u = *reinterpret_cast<const VT*>((row > 0 ? rowp - n2 : prev) + c);
-                const int cn = (cv + 1 == nvr) ? 0 : c + VEC;
-                double x[VEC], up[VEC];
-                unpack<T>(v, x);
-                unpack<T>(u, up);
-                const double xr = (double)rowp[cn];
+            const int rpg = (rows_here + groups - 1) / groups;
+            const int rb0 = rg * rpg, rb1 = min(rows_here, rb0 + rpg);
+            if (rg < groups && rb0 < rb1) {
+                for (int cv = cv_t; cv < nvr; cv += cstride) {
+                    const int c = cv * VEC;
+                    const int cn = (cv + 1 == nvr) ? 0 : c + VEC;
+                    double up[VEC];
+                    unpack<T>(*reinterpret_cast<const VT*>((rb0 > 0 ? buf + (size_t)(rb0 - 1) * n2 : prev) + c), up);
+                    for (int row = rb0; row < rb1; ++row) {
+                        const T* rowp = buf + (size_t)row * n2;
+                        double x[VEC];
+                        unpack<T>(*reinterpret_cast<const VT*>(rowp + c), x);
+                        const double xr = (double)rowp[cn];
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const double right = (e + 1 < VEC) ? x[(e + 1) % VEC] : xr;
-                    acc[0] = fma(x[e], x[e], acc[0]);
-                    acc[1] = fma(x[e], right + up[e], acc[1]);
-                    acc[2] += x[e];
-                }
-                if constexpr (NC > 0) {
-                    const size_t site = (size_t)(rs + row) * n2 + c;
+                        for (int e = 0; e < VEC; ++e) {
+                            const double right = (e + 1 < VEC) ? x[(e + 1) % VEC] : xr;
+                            acc[0] = fma(x[e], x[e], acc[0]);
+                            acc[1] = fma(x[e], right + up[e], acc[1]);
+                            acc[2] += x[e];
+                        }
+                        if constexpr (NC > 0) {
+                            const size_t site = (size_t)(rs + row) * n2 + c;
 #pragma unroll
-                    for (int l = 0; l < NC; ++l) {
-                        if (l < p.nc) {
+                            for (int l = 0; l < NC; ++l) {
+                                if (l < p.nc) {
 #pragma unroll
-                            for (int e = 0; e < VEC; ++e) {
-                                acc[3 + l] = fma(__ldg(p.Xc[l] + site + e), x[e], acc[3 + l]);
-                                acc[3 + NC + l] = fma(__ldg(p.WXc[l] + site + e), x[e], acc[3 + NC + l]);
+                                    for (int e = 0; e < VEC; ++e) {
+                                        acc[3 + l] = fma(__ldg(p.Xc[l] + site + e), x[e], acc[3 + l]);
+                                        acc[3 + NC + l] = fma(__ldg(p.WXc[l] + site + e), x[e], acc[3 + NC + l]);
+                                    }
+                                }
                             }
                         }
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) up[e] = x[e];
                     }
-                }
-                row += drow;
-                cv += dcv;
-                if (cv >= nvr) {
-                    cv -= nvr;
-                    ++row;
                 }
             }
             __syncthreads();  // stage it consumed; stage it-1 (the carry) is no longer needed

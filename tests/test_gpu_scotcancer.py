@@ -1,7 +1,4 @@
-"""NOT COLLECTED (no test_ prefix): written after the round's GPU budget was spent, to be renamed to
-tests/test_gpu_scotcancer.py and run on a B200 next round.
-
-GPU parity on the reference's real-data fixture (data/ScotCancer.rda -> tests/golden/scotcancer.npz):
+"""GPU parity on the reference's real-data fixture (data/ScotCancer.rda -> tests/golden/scotcancer.npz):
 Poisson GLM with latent CAR effects on the 56-district map, through the C ABI against the oracle on
 the oracle's own latent samples; and the Metropolis-within-Gibbs posterior mean against the
 oracle's MALA chain (R/postZsub.R:939-1072)."""
@@ -14,7 +11,7 @@ from mclcar_b200 import api
 from oracle import glm
 
 pytestmark = pytest.mark.gpu
-GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _scot():
