@@ -97,7 +97,7 @@ MCLCAR_API int mclcar_ctx_get_draw(const mclcar_ctx* ctx, uint64_t* draw);
 /* instrumentation: kernel-launch counters per category and, while enabled, CUDA-event time
  * spans recorded on the context's stream around each group of launches.  Categories:
  * 0 torus half sweeps, 1 sample emission, 2 statistics (K2), 3 reduction (K3),
- * 4 shared-memory chain sampler, 5 GLM data terms.  profile(enable) resets both. */
+ * 4 shared-memory chain sampler, 5 GLM data terms, 6 spectrum estimate.  profile(enable) resets both. */
 MCLCAR_API int mclcar_ctx_profile(mclcar_ctx* ctx, int enable);
 MCLCAR_API int mclcar_ctx_profile_read(mclcar_ctx* ctx, double ms_out[8], int64_t launches_out[8]);
 /* NCCL (dlopen'ed on first use, libnccl.so.2): rank 0 obtains a 128-byte unique id,
@@ -126,6 +126,16 @@ MCLCAR_API int mclcar_graph_kind(const mclcar_ctx* ctx, int* n1, int* n2);
 /* eigenvalues of W (`data$lambda`, eigen(W) at R/mcl.bin.R:176): needed by the GLM
  * gradient / Hessian and for the rho range check on CSR graphs.  Optional. */
 MCLCAR_API int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, int n);
+/* Without eigenvalues the library estimates the spectral measure of W itself, once per graph and on the device, the
+ * first time a log-determinant, a gradient / Hessian sum or the rho range needs it: stochastic Lanczos quadrature
+ * (64 Rademacher probes, `steps` Lanczos steps, 0 = 80; mclcar_b200/csrc/spectrum.cu) calibrated to the exact
+ * tr I, tr W, tr W^2.  It replaces the per-call eigen(W) / chol.spam of R/mcl.bin.R:22-24,50-52,176 and
+ * R/mcl.HCAR.R:71-75,166-173, which cannot be formed beyond a few thousand regions.  Tolerance: 2e-3 relative on
+ * log det(I - rho W), 1 % of its change between two candidates, 2e-2 on the gradient / Hessian sums; exact
+ * eigenvalues (set_eigenvalues, or the analytic torus spectrum) take precedence and make every sum exact. */
+MCLCAR_API int mclcar_graph_estimate_spectrum(mclcar_ctx* ctx, int steps, uint64_t seed);
+/* 0 = no spectrum yet, 1 = exact eigenvalues, 2 = Lanczos quadrature; *nodes (may be NULL) = number of nodes */
+MCLCAR_API int mclcar_graph_spectrum_kind(const mclcar_ctx* ctx, int* nodes);
 /* design matrix X = model.matrix(y ~ ., data.vec) / covX, n x p column-major; p may be 0 */
 MCLCAR_API int mclcar_set_design(mclcar_ctx* ctx, const double* X, int p);
 /* observed response y (n) and, for the binomial family, n.trial (n, or NULL) */
@@ -289,6 +299,19 @@ MCLCAR_API int mclcar_multi_dcar_prep(mclcar_ctx** ctxs, int G, const double* ps
  * mclcar_dcar_finish */
 MCLCAR_API int mclcar_multi_dcar_run(mclcar_ctx** ctxs, mclcar_samples** samples, int G, const double* psi, int K, int P, int what,
                           int evar, const double* rho_cons, int shift_mode, double* out0, double* out1);
+
+/* the same for the GLM and the hierarchical model: mcl.prep.glm / sim.HCAR with N_total samples split over the G
+ * contexts, and mcl.glm / mcl.grad.glm / mcl.Hessian.glm (mcl.HCAR / ...) over all shards -- what: 0 = log-ratio
+ * (out0 = lr[K], out1 = var[K] or NULL), 1 = gradient (out0 = grad[K*P], out1 = gradvar[K*P*P] or NULL), 2 = Hessian
+ * (out0 = hess[K*P*P]).  Every context must hold the same model (graph, design, observations; hcar_set_model). */
+MCLCAR_API int mclcar_multi_glm_prep(mclcar_ctx** ctxs, int G, int family, const double* psi0, int P, int64_t N_total,
+                          const mclcar_sampler_opts* opts, mclcar_samples** out /* G handles */);
+MCLCAR_API int mclcar_multi_glm_run(mclcar_ctx** ctxs, mclcar_samples** samples, int G, const double* psi, int K, int P, int what,
+                         int evar, int shift_mode, double* out0, double* out1);
+MCLCAR_API int mclcar_multi_hcar_prep(mclcar_ctx** ctxs, int G, const double* psi0, int P, int64_t N_total,
+                           const mclcar_sampler_opts* opts, mclcar_samples** out /* G handles */);
+MCLCAR_API int mclcar_multi_hcar_run(mclcar_ctx** ctxs, mclcar_samples** samples, int G, const double* psi, int K, int P, int what,
+                          int evar, int shift_mode, double* out0, double* out1, int* n_clamped);
 
 /* ---- staged evaluation (what the one-shot calls above are made of) ------------------------
  * stage 1, device: per-candidate partial tuples of this context's samples, to host memory;

@@ -73,6 +73,8 @@ SIGNATURES = {
     "mclcar_graph_csr_opts": (_i, [_vp, _i, _pi, _pi, _pd, _i]),
     "mclcar_graph_kind": (_i, [_vp, _pi, _pi]),
     "mclcar_graph_set_eigenvalues": (_i, [_vp, _pd, _i]),
+    "mclcar_graph_estimate_spectrum": (_i, [_vp, _i, C.c_uint64]),
+    "mclcar_graph_spectrum_kind": (_i, [_vp, _pi]),
     "mclcar_set_design": (_i, [_vp, _pd, _i]),
     "mclcar_set_obs": (_i, [_vp, _pd, _pd]),
     "mclcar_graph_n": (_i, [_vp]),
@@ -115,6 +117,10 @@ SIGNATURES = {
     "mclcar_hcar_hess": (_i, [_vp, _vp, _pd, _i, _i, _i, _pd]),
     "mclcar_multi_dcar_prep": (_i, [C.POINTER(_vp), _i, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
     "mclcar_multi_dcar_run": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _pd, _i, _i, _i, _i, _pd, _i, _pd, _pd]),
+    "mclcar_multi_glm_prep": (_i, [C.POINTER(_vp), _i, _i, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
+    "mclcar_multi_glm_run": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _pd, _i, _i, _i, _i, _i, _pd, _pd]),
+    "mclcar_multi_hcar_prep": (_i, [C.POINTER(_vp), _i, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
+    "mclcar_multi_hcar_run": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _pd, _i, _i, _i, _i, _i, _pd, _pd, _pi]),
     "mclcar_tuple_len": (_i64, [_i, _i, _i]),
     "mclcar_dcar_partial": (_i, [_vp, _vp, _pd, _i, _i, _i, _pi64, _pi64, _i, _pd]),
     "mclcar_tuples_merge": (_i, [_i, _i, _i, _i, _i, _pd, _pd]),

@@ -130,6 +130,19 @@ def make_data(y, X=None, W=None, torus=None, n_trial=None, eigenvalues=None, dev
     return CarData(ctx=ctx, n=n, X=X, y=y, W=Wc, torus=tuple(torus) if torus is not None else None, n_trial=nt)
 
 
+def estimate_spectrum(data: CarData, steps: int = 0, seed: int = 0) -> dict:
+    """Spectral measure of W by stochastic Lanczos quadrature on the device, in place of eigen(W) (R/mcl.bin.R:176):
+    done by itself the first time a log-determinant is needed and no eigenvalues were given; explicit here."""
+    check(lib.mclcar_graph_estimate_spectrum(data.ctx.h, int(steps), int(seed) & (2**64 - 1)), data.ctx.h)
+    return spectrum_kind(data)
+
+
+def spectrum_kind(data: CarData) -> dict:
+    nn = C.c_int()
+    k = lib.mclcar_graph_spectrum_kind(data.ctx.h, C.byref(nn))
+    return {"kind": {0: "none", 1: "exact", 2: "lanczos quadrature"}[k], "nodes": nn.value}
+
+
 def set_design_obs(data: CarData, X, y, n_trial=None) -> CarData:
     """Replace design and observations on an existing context (the graph stays uploaded)."""
     ctx = data.ctx
@@ -879,3 +892,74 @@ def mc_Hesslik_dCAR_multi(pars, md: MultiData, sd: MultiSimData, shift=L.SHIFT_M
     P = len(pars)
     H, _ = _multi_run(md, sd, np.asarray(pars)[None, :], L.WHAT_HESS, 0, None, shift, lambda K, P: K * P * P, lambda K, P: K * P * P)
     return H.reshape(P, P)
+
+
+# --- GLM and hierarchical model over several GPUs of one process (in-process group: tuples meet in host memory) ---
+class MultiMcData:
+    def __init__(self, datas, handles, psi, family, cls):
+        self.datas, self.psi, self.family = list(datas), np.asarray(psi, dtype=np.float64), family
+        self.parts = [cls(d, C.c_void_p(h), psi, family) if family else cls(d, C.c_void_p(h), psi) for d, h in zip(datas, handles)]
+        self.G = len(self.parts)
+        self._ctx_arr = (C.c_void_p * self.G)(*[d.ctx.h for d in datas])
+        self._arr = (C.c_void_p * self.G)(*[p.h for p in self.parts])
+
+    @property
+    def n_samples(self):
+        return sum(p.n_samples for p in self.parts)
+
+
+def mcl_prep_glm_multi(datas: Sequence[CarData], family: str, psi, n_samples: int, control: Optional[dict] = None) -> MultiMcData:
+    """mcl.prep.glm with the samples split over one context per device (every context holds the same model)."""
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    o = _sampler_opts(control)
+    G = len(datas)
+    ctxs = (C.c_void_p * G)(*[d.ctx.h for d in datas])
+    out = (C.c_void_p * G)()
+    check(lib.mclcar_multi_glm_prep(ctxs, G, _FAMILY[family], dptr(psi), psi.size, int(n_samples), C.byref(o), out), datas[0].ctx.h)
+    return MultiMcData(datas, list(out), psi, family, McData)
+
+
+def _multi_family_run(fn, mm: MultiMcData, psis, what, evar, shift, extra=()):
+    psis = np.ascontiguousarray(np.atleast_2d(psis), dtype=np.float64)
+    K, P = psis.shape
+    n0 = K if what == 0 else (K * P if what == 1 else K * P * P)
+    n1 = K if what == 0 else K * P * P
+    out0, out1 = np.empty(n0), np.zeros(n1)
+    check(fn(mm._ctx_arr, mm._arr, mm.G, dptr(psis), K, P, what, int(evar), shift, dptr(out0), dptr(out1), *extra), mm.datas[0].ctx.h)
+    return out0, out1, K, P
+
+
+def mcl_glm_batch_multi(psis, mm: MultiMcData, shift=L.SHIFT_MEAN) -> np.ndarray:
+    lr, var, _, _ = _multi_family_run(lib.mclcar_multi_glm_run, mm, psis, 0, 0, shift)
+    return np.stack([lr, var], axis=1)
+
+
+def mcl_grad_glm_multi(pars, mm: MultiMcData, Evar=False, shift=L.SHIFT_MEAN):
+    g, v, _, P = _multi_family_run(lib.mclcar_multi_glm_run, mm, np.asarray(pars)[None, :], 1, 1 if Evar else 0, shift)
+    return {"grad.lr": g, "grad.var": v.reshape(P, P)} if Evar else g
+
+
+def mcl_Hessian_glm_multi(pars, mm: MultiMcData, shift=L.SHIFT_MEAN) -> np.ndarray:
+    H, _, _, P = _multi_family_run(lib.mclcar_multi_glm_run, mm, np.asarray(pars)[None, :], 2, 0, shift)
+    return H.reshape(P, P)
+
+
+def sim_HCAR_multi(datas: Sequence[CarData], psi, n_samples: int, control: Optional[dict] = None) -> MultiMcData:
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    o = _sampler_opts(control)
+    G = len(datas)
+    ctxs = (C.c_void_p * G)(*[d.ctx.h for d in datas])
+    out = (C.c_void_p * G)()
+    check(lib.mclcar_multi_hcar_prep(ctxs, G, dptr(psi), psi.size, int(n_samples), C.byref(o), out), datas[0].ctx.h)
+    return MultiMcData(datas, list(out), psi, None, HcarMc)
+
+
+def mcl_HCAR_batch_multi(psis, mm: MultiMcData) -> np.ndarray:
+    ncl = C.c_int(0)
+    lr, var, _, _ = _multi_family_run(lib.mclcar_multi_hcar_run, mm, psis, 0, 0, L.SHIFT_MAX, extra=(C.byref(ncl),))
+    return np.stack([lr, var], axis=1)
+
+
+def mcl_grad_HCAR_multi(pars, mm: MultiMcData, Evar=False, shift=L.SHIFT_MEAN):
+    g, v, _, P = _multi_family_run(lib.mclcar_multi_hcar_run, mm, np.asarray(pars)[None, :], 1, 1 if Evar else 0, shift, extra=(None,))
+    return {"grad.lr": g, "grad.var": v.reshape(P, P)} if Evar else g

@@ -4,7 +4,9 @@
 // never touches it.
 #include <dlfcn.h>
 
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 
 #include "engine.hpp"
 
@@ -60,23 +62,70 @@ void comm_destroy(mclcar_ctx* ctx) {
     ctx->nccl_comm = nullptr;
 }
 
-// all-gather the K tuples of every rank and merge them in rank order; in place on `tuples`
-int gather_and_merge(mclcar_ctx* ctx, int what, int F, int d, int K, double* tuples) {
-    if (!ctx->nccl_comm || ctx->world <= 1) return MCLCAR_OK;
-    const int G = ctx->world;
+int nccl_all_gather_dev(mclcar_ctx* ctx, const double* d_send, double* d_recv, size_t cnt) {
+    ncclResult_t r = g_nccl.AllGather(d_send, d_recv, cnt, kNcclFloat64, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != 0) return fail(ctx, MCLCAR_ENCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+    return MCLCAR_OK;
+}
+
+// ---- in-process group: G contexts driven by G host threads of one process meet here instead of in NCCL ----
+struct HostGroup {
+    int G = 0, refs = 0;
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0;
+    uint64_t generation = 0;
+    std::vector<double> buf[2];   // alternate buffers: a slow member may still merge round r while round r + 1 fills
+    int failed = 0;
+};
+
+static int host_group_exchange(mclcar_ctx* ctx, int what, int F, int d, int K, double* tuples) {
+    HostGroup* hg = (HostGroup*)ctx->host_group;
+    const int G = hg->G;
     const int64_t T = tuple_len(what, F, d);
     const size_t cnt = (size_t)K * T;
-    MCL_TRY(ensure(ctx, ctx->d_gather, (size_t)(G + 1) * cnt * sizeof(double)));
-    double* send = (double*)ctx->d_gather.p;
-    double* recv = send + cnt;
-    cudaStream_t st = ctx->stream;
-    MCL_CUDA(ctx, cudaMemcpyAsync(send, tuples, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
-    ncclResult_t r = g_nccl.AllGather(send, recv, cnt, kNcclFloat64, (ncclComm_t)ctx->nccl_comm, st);
-    if (r != 0) return fail(ctx, MCLCAR_ENCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
-    std::vector<double> all((size_t)G * cnt);
-    MCL_CUDA(ctx, cudaMemcpyAsync(all.data(), recv, all.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    MCL_CUDA(ctx, cudaStreamSynchronize(st));
-    return merge_tuples(what, F, d, G, K, all.data(), tuples);
+    std::unique_lock<std::mutex> lk(hg->m);
+    const uint64_t gen = hg->generation;
+    std::vector<double>& b = hg->buf[gen & 1];
+    if (hg->arrived == 0) b.assign((size_t)G * cnt, 0.0);
+    if (b.size() != (size_t)G * cnt) hg->failed = 1;        // members disagree on the batch
+    else std::memcpy(b.data() + (size_t)ctx->rank * cnt, tuples, cnt * sizeof(double));
+    if (++hg->arrived == G) {
+        hg->arrived = 0;
+        ++hg->generation;
+        hg->cv.notify_all();
+    } else {
+        hg->cv.wait(lk, [&] { return hg->generation != gen; });
+    }
+    const int failed = hg->failed;
+    lk.unlock();
+    if (failed) return fail(ctx, MCLCAR_ESTATE, "the contexts of the group were called with different candidate batches");
+    return merge_tuples(what, F, d, G, K, b.data(), tuples);
+}
+
+void host_group_leave(mclcar_ctx* ctx) {
+    HostGroup* hg = (HostGroup*)ctx->host_group;
+    if (!hg) return;
+    ctx->host_group = nullptr;
+    bool last;
+    {
+        std::lock_guard<std::mutex> lk(hg->m);
+        last = --hg->refs <= 0;
+    }
+    if (last) delete hg;
+}
+
+void* host_group_new(int G) {
+    HostGroup* hg = new (std::nothrow) HostGroup();
+    if (hg) hg->G = hg->refs = G;
+    return hg;
+}
+
+// exchange of the K tuples with the other members of an in-process group, merged in rank order in place
+int gather_and_merge(mclcar_ctx* ctx, int what, int F, int d, int K, double* tuples) {
+    if (ctx->host_group) return host_group_exchange(ctx, what, F, d, K, tuples);
+    // ranks of an NCCL job: run_reduce(merge_ranks = true) has gathered on the device and merged already
+    return MCLCAR_OK;
 }
 
 }  // namespace mclcar

@@ -384,6 +384,23 @@ int mclcar_ctx_profile_read(mclcar_ctx* ctx, double ms_out[8], int64_t launches_
     return MCLCAR_OK;
 }
 
+}  // extern "C"
+
+namespace mclcar {
+// The reference recomputes eigen(W) / chol.spam inside every call when the caller gave no spectrum (R/mcl.bin.R:176,
+// R/mcl.HCAR.R:166-173).  Here: estimate the spectral measure once per graph on the device (spectrum.cu).
+int ensure_spectrum(mclcar_ctx* ctx) {
+    if (!ctx->eigs.empty()) return MCLCAR_OK;
+    if (ctx->kind == GRAPH_NONE) return fail(ctx, MCLCAR_ESTATE, "set the graph first");
+    if (ctx->host_only)
+        return fail(ctx, MCLCAR_ESTATE, "the eigenvalues of W are needed (mclcar_graph_set_eigenvalues): a host-only context cannot estimate them");
+    if (ctx->rowptr[ctx->n] == 0) return MCLCAR_OK;    // empty graph (hierarchical model without W): nothing to sum
+    return mclcar_graph_estimate_spectrum(ctx, 0, ctx->seed);
+}
+}  // namespace mclcar
+
+extern "C" {
+
 int mclcar_graph_n(const mclcar_ctx* ctx) { return ctx ? ctx->n : 0; }
 int mclcar_graph_ncolors(const mclcar_ctx* ctx) { return ctx ? ctx->ncolors : 0; }
 
@@ -407,6 +424,7 @@ static int set_torus(mclcar_ctx* ctx, int n1, int n2) {
         }
     ctx->rowptr[n] = 4 * n;
     // analytic spectrum: 2cos(2 pi j/n1) + 2cos(2 pi k/n2) (replaces eigen(W), R/CAR.simLM.R:8)
+    ctx->eig_w.clear();
     ctx->eigs.resize(n);
     std::vector<double> a(n1), b(n2);
     for (int j = 0; j < n1; ++j) a[j] = 2.0 * std::cos(2.0 * M_PI * j / n1);
@@ -500,6 +518,7 @@ int mclcar_graph_csr_opts(mclcar_ctx* ctx, int n, const int* rowptr, const int* 
     if (ctx->binary) ctx->val.clear();
     else ctx->val.assign(val, val + nnz);
     ctx->eigs.clear();
+    ctx->eig_w.clear();
     ctx->ew_min = ctx->ew_max = 0.0;
     return finish_graph(ctx);
 }
@@ -520,6 +539,7 @@ int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, int n) {
     if (ctx->kind == GRAPH_NONE) return fail(ctx, MCLCAR_ESTATE, "set the graph first");
     if (n != ctx->n) return fail(ctx, MCLCAR_EINVAL, "expected %d eigenvalues, got %d", ctx->n, n);
     ctx->eigs.assign(ew, ew + n);
+    ctx->eig_w.clear();
     ctx->ew_min = *std::min_element(ctx->eigs.begin(), ctx->eigs.end());
     ctx->ew_max = *std::max_element(ctx->eigs.begin(), ctx->eigs.end());
     return MCLCAR_OK;

@@ -185,7 +185,7 @@ static int build_plan(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int
 }
 
 int dcar_partial(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int what,
-                 const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* tuples) {
+                 const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* tuples, bool merge_ranks) {
     MCL_TRY(check_ready(ctx, s, true));
     MCL_TRY(require_device(ctx));   // binds this host thread to the context's device
     if (K < 1 || !psi || !tuples) return fail(ctx, MCLCAR_EINVAL, "empty candidate batch");
@@ -194,7 +194,7 @@ int dcar_partial(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, i
     MCL_TRY(dcar_ensure_stats(ctx, s));
     ReducePlan plan;
     MCL_TRY(build_plan(ctx, s, psi, K, P, what, shift_mode, subset_idx, subset_ptr, plan));
-    return run_reduce(ctx, plan, tuples);
+    return run_reduce(ctx, plan, tuples, merge_ranks);
 }
 
 // tuples -> reference outputs (host only)
@@ -276,7 +276,7 @@ static int dcar_run(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
     const int64_t T = tuple_len(what, F, d);
     if (T < 0) return fail(ctx, MCLCAR_EINVAL, "bad 'what'");
     std::vector<double> tuples((size_t)K * T);
-    MCL_TRY(dcar_partial(ctx, s, psi, K, P, what, subset_idx, subset_ptr, shift_mode, tuples.data()));
+    MCL_TRY(dcar_partial(ctx, s, psi, K, P, what, subset_idx, subset_ptr, shift_mode, tuples.data(), true));
     MCL_TRY(gather_and_merge(ctx, what, F, d, K, tuples.data()));
     return dcar_finish(ctx, s->psi0.data(), (int)s->psi0.size(), psi, K, P, what, evar, rho_cons, tuples.data(), out0, out1);
 }
@@ -371,7 +371,7 @@ int mclcar_dcar_mcmle_var(mclcar_ctx* ctx, mclcar_samples* s, const double* psi,
 
 int mclcar_dcar_partial(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int what,
                         const int64_t* subset_idx, const int64_t* subset_ptr, int shift_mode, double* tuples) {
-    return dcar_partial(ctx, s, psi, K, P, what, subset_idx, subset_ptr, shift_mode, tuples);
+    return dcar_partial(ctx, s, psi, K, P, what, subset_idx, subset_ptr, shift_mode, tuples, false);
 }
 
 int mclcar_dcar_finish(mclcar_ctx* ctx, const double* psi0, int P0, const double* psi, int K, int P, int what, int evar,

@@ -18,7 +18,7 @@ enum GraphKind { GRAPH_NONE = 0, GRAPH_TORUS = 1, GRAPH_CSR = 2 };
 enum { WHAT_LR = 0, WHAT_GRAD = 1, WHAT_HESS = 2 };
 
 // instrumentation categories (mclcar_ctx_profile_read)
-enum { PROF_SWEEP = 0, PROF_EMIT = 1, PROF_STATS = 2, PROF_REDUCE = 3, PROF_CSR_SAMPLER = 4, PROF_GLM = 5, PROF_NCAT = 8 };
+enum { PROF_SWEEP = 0, PROF_EMIT = 1, PROF_STATS = 2, PROF_REDUCE = 3, PROF_CSR_SAMPLER = 4, PROF_GLM = 5, PROF_SPECTRUM = 6, PROF_NCAT = 8 };
 
 // upper-triangle edge list of a symmetric CSR matrix, on the device (stats_csr.cu), cached per matrix
 struct EdgeCache {
@@ -58,7 +58,9 @@ struct mclcar_ctx {
     bool binary = true;
     std::vector<int> rowptr, colidx;
     std::vector<double> val;   // empty when binary
-    std::vector<double> eigs;  // eigenvalues of W (analytic on the torus, else user-supplied)
+    std::vector<double> eigs;  // eigenvalues of W (analytic on the torus, else user-supplied) -- or the nodes of a Lanczos
+                               // quadrature of its spectral measure (spectrum.cu), then with weights:
+    std::vector<double> eig_w; // empty = every node counts once (exact spectrum)
     double ew_min = 0, ew_max = 0;
     int max_deg = 0;
     // greedy colouring: sites of colour c are order[color_ptr[c] .. color_ptr[c+1])
@@ -103,6 +105,9 @@ struct mclcar_ctx {
     // ---- NCCL (dlopen'ed)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
+    // ---- in-process group (one R session driving several GPUs from host threads): the contexts of a group
+    // exchange their partial tuples through host memory at the point where ranks of a job use NCCL
+    void* host_group = nullptr;
 
     // ---- instrumentation: kernel launches per category and (when enabled) CUDA-event spans
     bool profiling = false;
@@ -195,6 +200,10 @@ int samples_update_qbar(mclcar_ctx* ctx, mclcar_samples* s);
 int merge_tuples(int what, int F, int d, int G, int K, const double* in, double* out);
 void centred_moments(const double* tup, int V, double* vbar, double* C);
 int gather_and_merge(mclcar_ctx* ctx, int what, int F, int d, int K, double* tuples);
+// NCCL all-gather of `cnt` doubles per rank, device to device, on the context's stream (no host round trip)
+int nccl_all_gather_dev(mclcar_ctx* ctx, const double* d_send, double* d_recv, size_t cnt);
+inline bool nccl_active(const mclcar_ctx* ctx) { return ctx->nccl_comm != nullptr && ctx->world > 1; }
+void host_group_leave(mclcar_ctx* ctx);
 void comm_destroy(mclcar_ctx* ctx);
 void hcar_forget(mclcar_ctx* ctx);
 void edge_cache_clear(mclcar_ctx* ctx);
@@ -224,8 +233,11 @@ inline int coef_off_n(int d) { return 2 + d; }
 inline int coef_off_centre(int d) { return 3 + d; }
 inline int coef_off_feat(int d, int F) { return 3 + d + (1 + F); }
 int64_t tuple_len(int what, int F, int d);
-// runs the reduction; leaves K tuples in ctx->d_tuples (device) and copies them to `tuples` (host)
-int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples);
+// runs the reduction; leaves K tuples in ctx->d_tuples (device) and copies them to `tuples` (host).  With
+// merge_ranks and an NCCL communicator the device tuples of all ranks are all-gathered on the stream first and ONE
+// device-to-host copy brings everything back: one synchronisation per candidate batch; `tuples` then holds the
+// rank-ordered merge (the same on every rank).
+int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples, bool merge_ranks = false);
 
 
 // ---- samplers (sampler_torus.cu / sampler_csr.cu) ---------------------------------------------
@@ -271,6 +283,16 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
                     const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
                     void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out);
 int check_rho(mclcar_ctx* ctx, double rho);
+// sum_i w_i f(lambda_i) over the context's spectral nodes: tr f(W), exactly (eigenvalues) or by quadrature
+template <class Fn>
+inline long double spectral_sum(const mclcar_ctx* ctx, Fn f) {
+    long double a = 0;
+    if (ctx->eig_w.empty()) for (double l : ctx->eigs) a += f(l);
+    else for (size_t i = 0; i < ctx->eigs.size(); ++i) a += (long double)ctx->eig_w[i] * f(ctx->eigs[i]);
+    return a;
+}
+// make sure the context has a spectrum: estimates one on the device when the caller supplied none
+int ensure_spectrum(mclcar_ctx* ctx);
 // start of a sampler run: derive this call's Philox key and advance the context's draw counter
 inline uint64_t begin_draw(mclcar_ctx* ctx) {
     ctx->draw_key = ctx->seed + ctx->draw * 0x9E3779B97F4A7C15ull + ctx->draw_salt * 0xD1B54A32D192ED03ull;

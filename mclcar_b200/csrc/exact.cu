@@ -15,11 +15,12 @@
 namespace mclcar {
 namespace {
 
-__global__ void __launch_bounds__(256) logdet_kernel(const double* eig, int n, const double* rho, double* out) {
+// sum_i w_i log(1 - rho lam_i) over the spectral nodes (w null: every node counts once)
+__global__ void __launch_bounds__(256) logdet_kernel(const double* eig, const double* w, int n, const double* rho, double* out) {
     __shared__ double scratch[8];
     const double r = rho[blockIdx.x];
     double a[1] = {0.0};
-    for (int i = threadIdx.x; i < n; i += blockDim.x) a[0] += log1p(-r * eig[i]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a[0] += (w ? w[i] : 1.0) * log1p(-r * eig[i]);
     block_sum<1>(a, scratch);
     if (threadIdx.x == 0) out[blockIdx.x] = a[0];
 }
@@ -72,33 +73,33 @@ int sigmabeta_one(mclcar_ctx* ctx, double rho, double* out) {
 
 // sum_i log(1 - rho_k lam_i) for K values of rho: device when available, host otherwise
 int logdet_sums(mclcar_ctx* ctx, const double* rho, int K, double* out) {
-    if (ctx->eigs.empty()) return fail(ctx, MCLCAR_ESTATE, "the eigenvalues of W are needed (data$lambda): mclcar_graph_set_eigenvalues");
-    if (ctx->host_only || (int64_t)K * ctx->n < 200000) {
-        for (int k = 0; k < K; ++k) {
-            long double a = 0;
-            for (double l : ctx->eigs) a += std::log1p(-rho[k] * l);
-            out[k] = (double)a;
-        }
+    MCL_TRY(ensure_spectrum(ctx));
+    const int nn = (int)ctx->eigs.size();
+    if (ctx->host_only || (int64_t)K * nn < 200000) {
+        for (int k = 0; k < K; ++k)
+            out[k] = (double)spectral_sum(ctx, [&](double l) { return (long double)std::log1p(-rho[k] * l); });
         return MCLCAR_OK;
     }
     MCL_TRY(require_device(ctx));
-    double *d_e = nullptr, *d_r = nullptr, *d_o = nullptr;
+    double *d_e = nullptr, *d_r = nullptr, *d_o = nullptr, *d_w = nullptr;
     int st = pool_alloc(ctx, (void**)&d_e, ctx->eigs.size() * sizeof(double));
+    if (!st && !ctx->eig_w.empty()) st = pool_alloc(ctx, (void**)&d_w, ctx->eig_w.size() * sizeof(double));
     if (!st) st = pool_alloc(ctx, (void**)&d_r, (size_t)K * sizeof(double));
     if (!st) st = pool_alloc(ctx, (void**)&d_o, (size_t)K * sizeof(double));
     if (!st) {
         cudaError_t e = cudaMemcpyAsync(d_e, ctx->eigs.data(), ctx->eigs.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_r, rho, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && d_w) e = cudaMemcpyAsync(d_w, ctx->eig_w.data(), ctx->eig_w.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) {
             ProfScope prof(ctx, PROF_REDUCE, 1);
-            logdet_kernel<<<K, 256, 0, ctx->stream>>>(d_e, ctx->n, d_r, d_o);
+            logdet_kernel<<<K, 256, 0, ctx->stream>>>(d_e, d_w, nn, d_r, d_o);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) st = fail(ctx, MCLCAR_ECUDA, "logdet kernel: %s", cudaGetErrorString(e));
     }
-    pool_free(ctx, d_e); pool_free(ctx, d_r); pool_free(ctx, d_o);
+    pool_free(ctx, d_e); pool_free(ctx, d_r); pool_free(ctx, d_o); pool_free(ctx, d_w);
     return st;
 }
 

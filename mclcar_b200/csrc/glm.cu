@@ -256,24 +256,16 @@ int glm_data_terms(mclcar_ctx* ctx, const mclcar_samples* s, int fam, const std:
 }
 
 // ---- host-side scalars -----------------------------------------------------------------
-int need_eigs(mclcar_ctx* ctx) {
-    if (ctx->eigs.empty())
-        return fail(ctx, MCLCAR_ESTATE, "the GLM functions need the eigenvalues of W (mclcar_graph_set_eigenvalues): "
-                                       "log-determinant and the gradient / Hessian terms of R/mcl.bin.R:176-177,192,265");
-    return MCLCAR_OK;
-}
+int need_eigs(mclcar_ctx* ctx) { return ensure_spectrum(ctx); }
 double half_logdet_Q(const mclcar_ctx* ctx, double rho, double sigma) {
-    long double a = 0;
-    for (double l : ctx->eigs) a += std::log1p(-rho * l);
+    const long double a = spectral_sum(ctx, [&](double l) { return (long double)std::log1p(-rho * l); });
     return (double)(0.5L * (a - (long double)ctx->n * std::log(sigma)));
 }
 double sum_lam_ratio(const mclcar_ctx* ctx, double rho, int power) {
-    long double a = 0;
-    for (double l : ctx->eigs) {
+    return (double)spectral_sum(ctx, [&](double l) {
         const double r = l / (1.0 - rho * l);
-        a += power == 1 ? r : r * r;
-    }
-    return (double)a;
+        return (long double)(power == 1 ? r : r * r);
+    });
 }
 // psi-independent data constant: sum(sapply(y, lchoose, n = n.trial)) | -sum(lfactorial(y))
 double glm_cterm(const mclcar_ctx* ctx, int fam) {
@@ -420,7 +412,7 @@ int glm_partial(mclcar_ctx* ctx, mclcar_samples* s, GlmBatch& gb, const double* 
             cf[coef_off_centre(d) + 1 + a] = fbar;
         }
     }
-    MCL_TRY(run_reduce(ctx, plan, tuples));
+    MCL_TRY(run_reduce(ctx, plan, tuples, true));
     return gather_and_merge(ctx, what, F, d, K, tuples);
 }
 

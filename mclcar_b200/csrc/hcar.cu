@@ -172,7 +172,7 @@ void hcar_affine(const mclcar_ctx* ctx, const HcarModel& hm, const HcarPars& t, 
     // const.pars = 1/2 logdet Qe + 1/2 logdet Qu from the spectra (chol logdets at R/mcl.HCAR.R:71-75)
     long double ld = -(long double)n * std::log(t.se) - (long double)K * std::log(t.su);
     if (hm.has_W)
-        for (double a : ctx->eigs) ld += std::log1p(-t.rho * a);
+        ld += spectral_sum(ctx, [&](double a) { return (long double)std::log1p(-t.rho * a); });
     for (double b : hm.bb) ld += std::log1p(-t.lam * b);
     m.cst = (double)(0.5L * ld);
     if (!want_grad) return;
@@ -182,7 +182,7 @@ void hcar_affine(const mclcar_ctx* ctx, const HcarModel& hm, const HcarPars& t, 
     int a = 0;
     long double sa = 0, sb = 0;
     if (hm.has_W) {
-        for (double x : ctx->eigs) sa += x / (1.0 - t.rho * x);
+        sa += spectral_sum(ctx, [&](double x) { return (long double)(x / (1.0 - t.rho * x)); });
         // g.rho = e'We/(2 se) - sum(aa/(1 - rho aa))/2
         m.a0[a] = bG1b / (2 * t.se) - (double)sa / 2;
         row(a)[1] = 1.0 / (2 * t.se);
@@ -224,7 +224,7 @@ int hcar_check(mclcar_ctx* ctx, mclcar_samples* s, HcarModel** hm) {
     if (!*hm) return fail(ctx, MCLCAR_ESTATE, "call mclcar_hcar_set_model first");
     if (s->ctx != ctx) return fail(ctx, MCLCAR_EINVAL, "sample set belongs to another context");
     if (s->sites != (*hm)->K) return fail(ctx, MCLCAR_EINVAL, "sample matrix has %lld rows, the model has %d districts", (long long)s->sites, (*hm)->K);
-    if ((*hm)->has_W && ctx->eigs.empty()) return fail(ctx, MCLCAR_ESTATE, "the eigenvalues of W are needed (data$aa): mclcar_graph_set_eigenvalues");
+    if ((*hm)->has_W) MCL_TRY(ensure_spectrum(ctx));
     return MCLCAR_OK;
 }
 
@@ -465,7 +465,7 @@ static int hcar_run(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
     }
     const int64_t T = tuple_len(what, F, d);
     std::vector<double> tuples((size_t)Kc * T);
-    MCL_TRY(run_reduce(ctx, plan, tuples.data()));
+    MCL_TRY(run_reduce(ctx, plan, tuples.data(), true));
     MCL_TRY(gather_and_merge(ctx, what, F, d, Kc, tuples.data()));
     if (n_clamped) *n_clamped = 0;
     std::vector<double> vbar(1 + F), C((size_t)(1 + F) * (1 + F));
@@ -502,7 +502,10 @@ static int hcar_run(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
             for (int x = 0; x < P * P; ++x) o[x] = 0.0;
             long double sa2 = 0, sb2 = 0, sa1 = 0, sb1 = 0;
             for (double x : hm.bb) { const double r = x / (1.0 - t.lam * x); sb1 += r; sb2 += r * r; }
-            if (hm.has_W) for (double x : ctx->eigs) { const double r = x / (1.0 - t.rho * x); sa1 += r; sa2 += r * r; }
+            if (hm.has_W) {
+                sa1 = spectral_sum(ctx, [&](double x) { return (long double)(x / (1.0 - t.rho * x)); });
+                sa2 = spectral_sum(ctx, [&](double x) { const double r = x / (1.0 - t.rho * x); return (long double)(r * r); });
+            }
             const int head = hm.has_W ? 4 : 3;
             const int il = hm.has_W ? 1 : 0, ie = il + 1, iuu = il + 2;
             // weighted means of the raw forms recovered from the gradient features
@@ -561,7 +564,7 @@ int mclcar_hcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, cons
     HcarModel* hmp = model_of(ctx);
     if (!hmp) return fail(ctx, MCLCAR_ESTATE, "call mclcar_hcar_set_model first");
     HcarModel& hm = *hmp;
-    if (hm.has_W && ctx->eigs.empty()) return fail(ctx, MCLCAR_ESTATE, "the eigenvalues of W are needed: mclcar_graph_set_eigenvalues");
+    if (hm.has_W) MCL_TRY(ensure_spectrum(ctx));
     HcarPars t;
     MCL_TRY(split_pars(ctx, hm, psi0, P, t));
     if (N < 1 || N >= ((int64_t)1 << 31)) return fail(ctx, MCLCAR_EINVAL, "bad sample count");

@@ -12,7 +12,7 @@ namespace mclcar {
 
 // rho must keep I - rho W positive definite: (1/min(ew), 1/max(ew)), R/CAR.simLM.R:9-11
 int check_rho(mclcar_ctx* ctx, double rho) {
-    if (!ctx->eigs.empty()) {
+    if (!ctx->eigs.empty() && ctx->ew_min < 0 && ctx->ew_max > 0) {
         const double lo = 1.0 / ctx->ew_min, hi = 1.0 / ctx->ew_max;
         if (rho < lo || rho > hi) return fail(ctx, MCLCAR_ERHO, "rho should be within %.10g %.10g", lo, hi);
         return MCLCAR_OK;

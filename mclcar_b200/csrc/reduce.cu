@@ -321,6 +321,22 @@ void launch_moments(const K3Params& p, dim3 grid_kt1, dim3 grid_kt4, bool tile4,
 
 }  // namespace
 
+// every K3 instantiation may use up to 200 KB of dynamic shared memory (set once per process)
+static int k3_allow_large_smem(mclcar_ctx* ctx) {
+    static bool done = false;
+    if (done) return MCLCAR_OK;
+    const int big = 200 * 1024;
+#define ALLOW(fn) MCL_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
+    ALLOW((k3_prepare_max<MCLCAR_MAX_P>));
+    ALLOW((k3_moments<0, 4>)); ALLOW((k3_moments<0, 1>)); ALLOW((k3_moments<2, 1>)); ALLOW((k3_moments<4, 1>));
+    ALLOW((k3_moments<6, 1>)); ALLOW((k3_moments<8, 1>)); ALLOW((k3_moments<10, 1>)); ALLOW((k3_moments<12, 1>));
+    ALLOW(k3_hess<2>); ALLOW(k3_hess<4>); ALLOW(k3_hess<6>); ALLOW(k3_hess<8>); ALLOW(k3_hess<10>); ALLOW(k3_hess<12>);
+    ALLOW(k3_first);
+#undef ALLOW
+    done = true;
+    return MCLCAR_OK;
+}
+
 int64_t tuple_len(int what, int F, int d) {
     const int V = 1 + F;
     switch (what) {
@@ -331,7 +347,7 @@ int64_t tuple_len(int what, int F, int d) {
     }
 }
 
-int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host) {
+int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host, bool merge_ranks) {
     MCL_TRY(require_device(ctx));
     const int K = plan.K, d = plan.d;
     const int F = plan.what == WHAT_LR ? 0 : plan.F;
@@ -398,6 +414,15 @@ int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host) {
     p.sub_idx = d_idx; p.sub_ptr = d_ptr;
     p.partial = (double*)ctx->d_partial.p; p.S = S; p.T = (int)Tr;
 
+    // the kernels keep a candidate's coefficient block (x 4 for the lr tile) in dynamic shared memory: d grows with
+    // the number of distinct betas of a GLM batch -- opt in beyond 48 KB, refuse beyond what the SM has
+    {
+        const size_t need = ((size_t)(tile4 ? 4 : 1) * csr + (kThreads / 32) * (size_t)(1 + Fr + (1 + Fr) * (2 + Fr) / 2 + 16)) * sizeof(double);
+        if (need > (size_t)200 * 1024)
+            return fail(ctx, MCLCAR_ELIMIT, "candidate batch too wide for the reduction kernels: %zu bytes of coefficients per candidate "
+                                           "(split the batch: fewer distinct betas per call)", (size_t)csr * sizeof(double));
+        if (need > (size_t)40 * 1024) MCL_TRY(k3_allow_large_smem(ctx));
+    }
     ProfScope prof(ctx, PROF_REDUCE, 2 + (plan.shift_mode == MCLCAR_SHIFT_MAX ? 1 : 0) +
                                          (plan.what == WHAT_HESS ? (d + 15) / 16 : 0));
     if (plan.shift_mode == MCLCAR_SHIFT_MAX) {
@@ -443,34 +468,53 @@ int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host) {
     MCL_CUDA(ctx, cudaGetLastError());
     prof.close();
 
-    // device tuples (padded F) -> host tuples (exact F)
-    MCL_TRY(ensure_pinned(ctx, (size_t)K * Tr * sizeof(double)));
+    // device tuples (padded F) -> host tuples (exact F); with several ranks: all-gather on the device first, then
+    // ONE copy and ONE synchronisation for the whole candidate batch, and the rank-ordered merge on the host
+    const bool merge = merge_ranks && nccl_active(ctx);
+    const int G = merge ? ctx->world : 1;
+    const size_t cnt = (size_t)K * Tr;
+    const double* d_src = (const double*)ctx->d_tuples.p;
+    if (merge) {
+        MCL_TRY(ensure(ctx, ctx->d_gather, (size_t)G * cnt * sizeof(double)));
+        MCL_TRY(nccl_all_gather_dev(ctx, (const double*)ctx->d_tuples.p, (double*)ctx->d_gather.p, cnt));
+        d_src = (const double*)ctx->d_gather.p;
+    }
+    MCL_TRY(ensure_pinned(ctx, (size_t)G * cnt * sizeof(double)));
     double* hp = (double*)ctx->h_pinned;
-    MCL_CUDA(ctx, cudaMemcpyAsync(hp, ctx->d_tuples.p, (size_t)K * Tr * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCL_CUDA(ctx, cudaMemcpyAsync(hp, d_src, (size_t)G * cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
     MCL_CUDA(ctx, cudaStreamSynchronize(st));
     const int V = 1 + F, Vr = 1 + Fr;
-    for (int k = 0; k < K; ++k) {
-        const double* src = hp + (size_t)k * Tr;
-        double* dst = tuples_host + (size_t)k * T;
-        dst[0] = src[0];
-        dst[1] = src[1];
-        if (plan.what == WHAT_HESS) {
-            for (int a = 0; a <= F; ++a) dst[2 + a] = src[2 + a];
-            int s = 0, sr = 0;
-            for (int a = 0; a < Fr; ++a)
-                for (int b = a; b < Fr; ++b, ++sr)
-                    if (a < F && b < F) dst[3 + F + s++] = src[3 + Fr + sr];
-            for (int j = 0; j < d; ++j) dst[3 + F + F * (F + 1) / 2 + j] = src[3 + Fr + Fr * (Fr + 1) / 2 + j];
-        } else {
-            for (int a = 0; a < V; ++a) {
-                dst[2 + a] = src[2 + a];               // centre
-                dst[2 + V + a] = src[2 + Vr + a];      // S1
+    std::vector<double> all;
+    if (merge) all.resize((size_t)G * K * T);
+    for (int g = 0; g < G; ++g)
+        for (int k = 0; k < K; ++k) {
+            const double* src = hp + (size_t)g * cnt + (size_t)k * Tr;
+            double* dst = (merge ? all.data() + (size_t)g * K * T : tuples_host) + (size_t)k * T;
+            dst[0] = src[0];
+            dst[1] = src[1];
+            if (plan.what == WHAT_HESS) {
+                for (int a = 0; a <= F; ++a) dst[2 + a] = src[2 + a];
+                int s = 0, sr = 0;
+                for (int a = 0; a < Fr; ++a)
+                    for (int b = a; b < Fr; ++b, ++sr)
+                        if (a < F && b < F) dst[3 + F + s++] = src[3 + Fr + sr];
+                for (int j = 0; j < d; ++j) dst[3 + F + F * (F + 1) / 2 + j] = src[3 + Fr + Fr * (Fr + 1) / 2 + j];
+            } else {
+                for (int a = 0; a < V; ++a) {
+                    dst[2 + a] = src[2 + a];               // centre
+                    dst[2 + V + a] = src[2 + Vr + a];      // S1
+                }
+                int s = 0, sr = 0;
+                for (int a = 0; a < Vr; ++a)
+                    for (int b = a; b < Vr; ++b, ++sr)
+                        if (a < V && b < V) dst[2 + 2 * V + s++] = src[2 + 2 * Vr + sr];
             }
-            int s = 0, sr = 0;
-            for (int a = 0; a < Vr; ++a)
-                for (int b = a; b < Vr; ++b, ++sr)
-                    if (a < V && b < V) dst[2 + 2 * V + s++] = src[2 + 2 * Vr + sr];
         }
+    if (merge) {
+        for (int g = 0; g < G; ++g)
+            if (!(all[(size_t)g * K * T] >= 0.0))   // a rank that failed before the collective sends NaN tuples
+                return fail(ctx, MCLCAR_ENCCL, "rank %d failed before the tuple exchange", g);
+        MCL_TRY(merge_tuples(plan.what, F, d, G, K, all.data(), tuples_host));
     }
     return MCLCAR_OK;
 }

@@ -125,10 +125,23 @@ def test_sampler_matches_long_mala_run(family):
     assert np.isfinite(r).all() and r[1] < 0.05
 
 
-def test_glm_needs_eigenvalues():
+def test_glm_without_eigenvalues_estimates_the_spectrum_itself():
+    """No data$lambda from the caller: the library estimates the spectral measure of W on the device the first time
+    it is needed (the reference recomputes eigen(W) / chol.spam inside every call, R/mcl.bin.R:22-24,176)."""
     W = graphs.random_planar_map(40, seed=1)
     rng = np.random.default_rng(0)
     gd = api.make_data(rng.integers(0, 5, 40).astype(float), X=np.ones((40, 1)), W=W)
+    assert api.spectrum_kind(gd)["kind"] == "none"
+    md = api.mcl_prep_glm(gd, "poisson", [0.05, 1.0, 0.1], {"n.samples": 10})
+    assert api.spectrum_kind(gd)["kind"] == "lanczos quadrature"
+    assert np.isfinite(api.mcl_glm([0.051, 1.01, 0.1], md, Evar=True)).all()
+    # n = 40 <= 64 probes: the probes are the canonical basis and every Lanczos quadrature is exact
+    ew = np.linalg.eigvalsh(W.toarray())
+    ex = api.make_data(gd.y, X=np.ones((40, 1)), W=W, eigenvalues=ew)
+    r = np.array([0.03, 0.06]) / 1.0
+    np.testing.assert_allclose(api.ploglik_dCAR(r, gd), api.ploglik_dCAR(r, ex), rtol=1e-8)
+    # a host-only context cannot estimate: the old error stays
+    hd = api.make_data(gd.y, X=np.ones((40, 1)), W=W, ctx=api.Context(device=-1))
     with pytest.raises(api.MclcarError) as ei:
-        api.mcl_prep_glm(gd, "poisson", [0.05, 1.0, 0.1], {"n.samples": 10})
+        api.ploglik_dCAR(r, hd)
     assert ei.value.code == L.ESTATE and "eigenvalues" in str(ei.value)

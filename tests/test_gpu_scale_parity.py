@@ -47,10 +47,11 @@ def test_statistics_and_reduction_at_full_lattice_size(n1, n2, p, dtype, K):
     t20 = c0[0] + q_ref @ c0[1:]
     qobs = _qobs_torus(y, X, n1, n2)
     coef = np.stack([cpu_path.affine_coef(ps, p, G0, G1) for ps in psis])
-    s1 = coef[:, 0] + coef[:, 1:] @ qobs - (c0[0] + c0[1:] @ qobs)
+    dcoef = coef - c0[None, :]
+    s1 = dcoef[:, 0] + dcoef[:, 1:] @ qobs
     # s2_i = h(Y_i; theta) - t20_i with |h| ~ n/2: difference the affine coefficients first (as the library does) so that
     # the C twin's own cancellation error (1e-16 n) stays below the tolerance asked of the GPU
-    lr_ref, var_ref = cpu_path.reduce_lr(q_ref, np.zeros(Ns), coef - c0[None, :], s1)
+    lr_ref, var_ref = cpu_path.reduce_lr(q_ref, np.zeros(Ns), dcoef, s1)
     got = api.mcl_dCAR_batch(psis, data, sd, rho_cons=None)
     np.testing.assert_allclose(got[:, 0], lr_ref, rtol=1e-10, atol=1e-9)
     np.testing.assert_allclose(got[:, 1], var_ref, rtol=1e-9, atol=1e-300)
