@@ -132,7 +132,8 @@ MCLCAR_API int mclcar_graph_set_eigenvalues(mclcar_ctx* ctx, const double* ew, i
  * tr I, tr W, tr W^2.  It replaces the per-call eigen(W) / chol.spam of R/mcl.bin.R:22-24,50-52,176 and
  * R/mcl.HCAR.R:71-75,166-173, which cannot be formed beyond a few thousand regions.  Tolerance: 2e-3 relative on
  * log det(I - rho W), 1 % of its change between two candidates, 2e-2 on the gradient / Hessian sums; exact
- * eigenvalues (set_eigenvalues, or the analytic torus spectrum) take precedence and make every sum exact. */
+ * eigenvalues (set_eigenvalues, or the analytic torus spectrum) take precedence and make every sum exact.  A graph of
+ * at most 64 sites (the probe block) gets its exact eigenvalues instead (Jacobi rotations on the host). */
 MCLCAR_API int mclcar_graph_estimate_spectrum(mclcar_ctx* ctx, int steps, uint64_t seed);
 /* 0 = no spectrum yet, 1 = exact eigenvalues, 2 = Lanczos quadrature; *nodes (may be NULL) = number of nodes */
 MCLCAR_API int mclcar_graph_spectrum_kind(const mclcar_ctx* ctx, int* nodes);
@@ -230,6 +231,35 @@ MCLCAR_API int mclcar_dcar_loglik(mclcar_ctx* ctx, const double* psi, int K, int
 /* ploglik.dCAR(rho, data), R/loglik.dCAR.R:45-69, K values of rho */
 MCLCAR_API int mclcar_dcar_ploglik(mclcar_ctx* ctx, const double* rho, int K, double* out);
 
+/* Hessian.dCAR(pars, data), R/loglik.dCAR.R:171-219: exact Hessian of the log-likelihood at `pars` (P = 2 or 2 + p) from the
+ * p x p design constants, the statistics of y and the spectrum, with the reference's rho-beta block -X'r/sigma as coded
+ * (:198) -- the `hessian` that summary.OptimMCL / summary.rsmMCL pass to vmle.dCAR (R/summary.OptimMCL.R:24-26).
+ * out: P x P.  Host arithmetic; works on a host-only context when the eigenvalues are known. */
+MCLCAR_API int mclcar_dcar_hessian_exact(mclcar_ctx* ctx, const double* pars, int P, double* out);
+
+/* ---- Monte Carlo likelihood SURFACES and retained statistics ------------------------------
+ * mcl.dCAR(c(rho_i, sigma_j, beta), data, simdata, rho.cons, Evar = TRUE) on the whole grid expand.grid(r.vec, s.vec)
+ * that rsmMCL evaluates loglik.dCAR on for plot.rsmMCL (R/rsmMCL.R:26-28,95-102; drawn by plot.RSM,
+ * R/rsmSub.R:315-327): rho varies fastest, lr[i + nr * j] / var[i + nr * j], i.e. the nr x ns column-major matrix of
+ * `Exacts[[i]]$lrs`.  beta: pb = 0 or p regression coefficients shared by the grid.  var may be NULL. */
+MCLCAR_API int mclcar_dcar_surface(mclcar_ctx* ctx, mclcar_samples* s, const double* rho, int nr, const double* sigma, int ns,
+                        const double* beta, int pb, const double* rho_cons, int shift_mode, double* lr, double* var);
+/* the same for mcl.glm: the only likelihood backdrop there is for a non-Gaussian family (rsmMCL stops with "No exact
+ * value for non-Guassin data", R/rsmMCL.R:106); beta: the p coefficients shared by the grid */
+MCLCAR_API int mclcar_glm_surface(mclcar_ctx* ctx, mclcar_samples* s, const double* rho, int nr, const double* sigma, int ns,
+                       const double* beta, int shift_mode, double* lr, double* var);
+/* Retained statistics.  The reference's result objects keep every iteration's sample matrix (`MC.datas`, `Sim.data`:
+ * R/OptimMCL.R:80-93, R/rsmMCL.R:252-270) only so that summary() can evaluate vmle.dCAR / mc.gradlik.dCAR on it again
+ * (R/summary.OptimMCL.R:24-26, R/summary.rsmMCL.R:20-22).  Every estimator of the path is a function of the N x d
+ * sufficient statistics, so a result object keeps those and re-creates a sample set from them later.
+ * stats_export: q_out N x d column-major, *d_out = d (q_out NULL: just ask for d); the statistics must have been
+ * formed (any evaluation, mclcar_dcar_stats or mclcar_hcar_stats).  from_stats: a statistics-only sample set
+ * (sites = n for the direct CAR model, K for the hierarchical one; chains = the sampler's parallel chains or 0);
+ * attach the importance point afterwards with mclcar_dcar_attach / mclcar_hcar_attach. */
+MCLCAR_API int mclcar_samples_stats_export(mclcar_ctx* ctx, mclcar_samples* s, int* d_out, double* q_out);
+MCLCAR_API int mclcar_samples_from_stats(mclcar_ctx* ctx, const double* q, int64_t N, int d, int64_t sites, int64_t chains,
+                              mclcar_samples** out);
+
 /* ---- Binomial / Poisson GLM with latent CAR effects (R/mcl.glm.R, R/mcl.bin.R, R/mcl.pois.R) ----
  * Sample sets are the N x n matrix Zy, ROW = sample (MCLCAR_ROW_IS_SAMPLE).  The eigenvalues of
  * W must be known (torus: analytic; CSR: mclcar_graph_set_eigenvalues) -- they replace the
@@ -277,6 +307,9 @@ MCLCAR_API int mclcar_hcar_set_model(mclcar_ctx* ctx, int K, const int* M_rowptr
 MCLCAR_API int mclcar_hcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, const mclcar_sampler_opts* opts,
                      mclcar_samples** out);
 MCLCAR_API int mclcar_hcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, int P, const double* lpsi);
+/* the 4 + 2p statistics (r0'r0, r0'W r0, X'r0[p], X'W r0[p], u'u, u'Mu), r0 = y - Zu, of every sample: q_out N x (4 + 2p)
+ * column-major, may be NULL (just form them) */
+MCLCAR_API int mclcar_hcar_stats(mclcar_ctx* ctx, mclcar_samples* s, double* q_out);
 MCLCAR_API int mclcar_hcar_lpsi(mclcar_ctx* ctx, mclcar_samples* s, double* lpsi /* N or NULL */, double* const_psi);
 /* mcl.HCAR(pars, mcdata, data, Evar), R/mcl.HCAR.R:4-97, for K candidates.  The reference takes
  * exp() unshifted and clamps +-Inf to +-1e5 with a warning (:81-84): candidates where that would

@@ -101,6 +101,12 @@ SIGNATURES = {
     "mclcar_dcar_profile_eval": (_i, [_vp, _vp, _pd, _i, _pd, _i, _pd, _pd]),
     "mclcar_dcar_loglik": (_i, [_vp, _pd, _i, _i, _pd, _pd]),
     "mclcar_dcar_ploglik": (_i, [_vp, _pd, _i, _pd]),
+    "mclcar_dcar_hessian_exact": (_i, [_vp, _pd, _i, _pd]),
+    "mclcar_dcar_surface": (_i, [_vp, _vp, _pd, _i, _pd, _i, _pd, _i, _pd, _i, _pd, _pd]),
+    "mclcar_glm_surface": (_i, [_vp, _vp, _pd, _i, _pd, _i, _pd, _i, _pd, _pd]),
+    "mclcar_samples_stats_export": (_i, [_vp, _vp, _pi, _pd]),
+    "mclcar_samples_from_stats": (_i, [_vp, _pd, _i64, _i, _i64, _i64, C.POINTER(_vp)]),
+    "mclcar_hcar_stats": (_i, [_vp, _vp, _pd]),
     "mclcar_glm_prep": (_i, [_vp, _i, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),
     "mclcar_glm_attach": (_i, [_vp, _vp, _i, _pd, _i, _pd]),
     "mclcar_glm_lhzy": (_i, [_vp, _vp, _pd]),

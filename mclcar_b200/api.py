@@ -244,6 +244,45 @@ def simdata_from_device(psi, data: CarData, dev_ptr: int, n_samples: int, ld: in
     return sd
 
 
+def retained_stats(simdata) -> dict:
+    """What a result object needs to keep of a sample set instead of its matrix (`MC.datas`, `Sim.data`:
+    R/OptimMCL.R:80-93, R/rsmMCL.R:252-270): the N x d sufficient statistics, the importance point and the
+    sampler's chain count -- a plain dict of arrays (what saveRDS would store on the R side)."""
+    ctx = simdata.data.ctx
+    dd = C.c_int()
+    if isinstance(simdata, HcarMc):
+        check(lib.mclcar_hcar_stats(ctx.h, simdata.h, None), ctx.h)
+    else:
+        check(lib.mclcar_dcar_stats(ctx.h, simdata.h, None), ctx.h)
+    check(lib.mclcar_samples_stats_export(ctx.h, simdata.h, C.byref(dd), None), ctx.h)
+    q = np.empty((dd.value, simdata.n_samples), dtype=np.float64)
+    check(lib.mclcar_samples_stats_export(ctx.h, simdata.h, C.byref(dd), dptr(q)), ctx.h)
+    ch = C.c_int64()
+    check(lib.mclcar_samples_schedule(ctx.h, simdata.h, C.byref(ch), None, None, None), ctx.h)
+    return {"q": q.T.copy(), "psi": np.array(simdata.psi), "chains": int(ch.value),
+            "model": "hcar" if isinstance(simdata, HcarMc) else "dcar"}
+
+
+def simdata_from_stats(retained: dict, data: CarData):
+    """Re-create a (statistics-only) sample set from `retained_stats` output: every likelihood function works on it,
+    `simY` / `u_y` do not exist any more."""
+    ctx = data.ctx
+    q = np.ascontiguousarray(np.asarray(retained["q"], dtype=np.float64).T)   # [d][N]
+    d, N = q.shape
+    h = C.c_void_p()
+    hcar_model = retained.get("model") == "hcar"
+    sites = data.extra["K"] if hcar_model else data.n
+    check(lib.mclcar_samples_from_stats(ctx.h, dptr(q), N, d, int(sites), int(retained.get("chains", 0)), C.byref(h)), ctx.h)
+    psi = np.ascontiguousarray(retained["psi"], dtype=np.float64)
+    if hcar_model:
+        mc = HcarMc(data, h, psi)
+        check(lib.mclcar_hcar_attach(ctx.h, h, dptr(psi), psi.size, None), ctx.h)
+        return mc
+    sd = SimData(data, h, psi)
+    check(lib.mclcar_dcar_attach(ctx.h, h, dptr(psi), psi.size, None), ctx.h)
+    return sd
+
+
 def _subsets(subsets, K):
     if subsets is None:
         return None, None, None
@@ -347,6 +386,28 @@ def ploglik_dCAR(rho, data: CarData):
     out = np.empty(r.size)
     check(lib.mclcar_dcar_ploglik(data.ctx.h, dptr(r), r.size, dptr(out)), data.ctx.h)
     return float(out[0]) if np.ndim(rho) == 0 else out
+
+
+def Hessian_dCAR(pars, data: CarData) -> np.ndarray:
+    """Hessian.dCAR(pars, data), R/loglik.dCAR.R:171-219 (exact Hessian handed to vmle.dCAR by the summaries)."""
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    out = np.empty((pars.size, pars.size), dtype=np.float64)
+    check(lib.mclcar_dcar_hessian_exact(data.ctx.h, dptr(pars), pars.size, dptr(out)), data.ctx.h)
+    return out
+
+
+def mcl_surface_dCAR(r_vec, s_vec, beta, data: CarData, simdata: "SimData", rho_cons=None, shift=L.SHIFT_MEAN) -> dict:
+    """Monte Carlo likelihood surface on expand.grid(r.vec, s.vec) in the shape of rsmMCL's `Exacts[[i]]`
+    (R/rsmMCL.R:26-28,95-102): list(r.vec, s.vec, lrs [nr x ns], vars [nr x ns])."""
+    r_vec = np.ascontiguousarray(r_vec, dtype=np.float64)
+    s_vec = np.ascontiguousarray(s_vec, dtype=np.float64)
+    beta = np.ascontiguousarray(np.atleast_1d(beta) if beta is not None else np.empty(0), dtype=np.float64)
+    lr = np.empty((s_vec.size, r_vec.size), dtype=np.float64)       # C order [j][i] == column-major nr x ns
+    var = np.empty_like(lr)
+    rc = None if rho_cons is None else np.ascontiguousarray(rho_cons, dtype=np.float64)
+    check(lib.mclcar_dcar_surface(data.ctx.h, simdata.h, dptr(r_vec), r_vec.size, dptr(s_vec), s_vec.size,
+                                  dptr(beta) if beta.size else None, beta.size, dptr(rc), shift, dptr(lr), dptr(var)), data.ctx.h)
+    return {"r.vec": r_vec, "s.vec": s_vec, "lrs": lr.T, "vars": var.T}
 
 
 def mcl_profile_dCAR_batch(rhos, data: CarData, simdata: "SimData", rho_cons=(-0.249, 0.249), shift=L.SHIFT_MEAN) -> np.ndarray:
@@ -594,6 +655,19 @@ def mcl_Hessian_glm(pars, mcdata: McData, family: Optional[str] = None, shift=L.
     ctx = mcdata.data.ctx
     check(lib.mclcar_glm_hess(ctx.h, mcdata.h, dptr(pars), 1, P, shift, dptr(H)), ctx.h)
     return H
+
+
+def mcl_surface_glm(r_vec, s_vec, beta, mcdata: "McData", shift=L.SHIFT_MEAN) -> dict:
+    """Monte Carlo likelihood surface of the GLM on expand.grid(r.vec, s.vec): list(r.vec, s.vec, lrs, vars)."""
+    r_vec = np.ascontiguousarray(r_vec, dtype=np.float64)
+    s_vec = np.ascontiguousarray(s_vec, dtype=np.float64)
+    beta = np.ascontiguousarray(np.atleast_1d(beta), dtype=np.float64)
+    lr = np.empty((s_vec.size, r_vec.size), dtype=np.float64)
+    var = np.empty_like(lr)
+    ctx = mcdata.data.ctx
+    check(lib.mclcar_glm_surface(ctx.h, mcdata.h, dptr(r_vec), r_vec.size, dptr(s_vec), s_vec.size, dptr(beta), shift,
+                                 dptr(lr), dptr(var)), ctx.h)
+    return {"r.vec": r_vec, "s.vec": s_vec, "lrs": lr.T, "vars": var.T}
 
 
 def Exp_CAR_glm(exp_design, mcdata: McData, family: Optional[str], psi, n0: int, rng=None, subsets=None) -> np.ndarray:

@@ -329,11 +329,13 @@ int mclcar_dcar_t10_t20(mclcar_ctx* ctx, mclcar_samples* s, double* t10, double*
     if (t10) *t10 = s->t10;
     if (t20) {
         if (s->d_base) {
-            MCL_CUDA(ctx, cudaMemcpy(t20, s->d_base, (size_t)s->N * sizeof(double), cudaMemcpyDeviceToHost));
+            MCL_CUDA(ctx, cudaMemcpyAsync(t20, s->d_base, (size_t)s->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         } else {
             MCL_TRY(dcar_ensure_stats(ctx, s));
             std::vector<double> q((size_t)s->d * s->N);
-            MCL_CUDA(ctx, cudaMemcpy(q.data(), s->d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            MCL_CUDA(ctx, cudaMemcpyAsync(q.data(), s->d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             DcarAffine m0;
             MCL_TRY(build_affine(ctx, s->psi0.data(), (int)s->psi0.size(), m0));
             std::vector<double> qi(s->d);

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mclcar_b200.h"
@@ -62,6 +63,9 @@ struct mclcar_ctx {
                                // quadrature of its spectral measure (spectrum.cu), then with weights:
     std::vector<double> eig_w; // empty = every node counts once (exact spectrum)
     double ew_min = 0, ew_max = 0;
+    // transient, sorted by rho: sum log(1 - rho lam) for the distinct rho values of a surface call in progress
+    // (mclcar_glm_surface) -- a grid of nr x ns candidates needs nr spectral sums, not nr * ns
+    std::vector<std::pair<double, long double>> logdet_tab;
     int max_deg = 0;
     // greedy colouring: sites of colour c are order[color_ptr[c] .. color_ptr[c+1])
     int ncolors = 0;

@@ -168,4 +168,72 @@ int mclcar_dcar_ploglik(mclcar_ctx* ctx, const double* rho, int K, double* out) 
     return MCLCAR_OK;
 }
 
+/* Hessian.dCAR(pars, data), R/loglik.dCAR.R:171-219: the exact Hessian at a parameter value, from the p x p design
+ * constants, the observation's statistics and the spectrum -- what summary.OptimMCL / summary.rsmMCL hand to vmle.dCAR
+ * (R/summary.OptimMCL.R:24-26).  As coded in the reference: the rho-beta block is -X'r/sigma (:198), the rho-rho entry
+ * -1/2 sum (lam/(1 - rho lam))^2 with no data term.  out: P x P, P = 2 or 2 + p.  Works on a host-only context when
+ * the eigenvalues are known. */
+int mclcar_dcar_hessian_exact(mclcar_ctx* ctx, const double* pars, int P, double* out) {
+    if (!ctx || !pars || !out) return MCLCAR_EINVAL;
+    if (!ctx->has_obs) return fail(ctx, MCLCAR_ESTATE, "set graph, design and observations first");
+    const int p = ctx->p, n = ctx->n;
+    if (P != 2 && P != 2 + p) return fail(ctx, MCLCAR_EINVAL, "parameter vector of length %d; expected 2 or %d", P, 2 + p);
+    MCL_TRY(ensure_spectrum(ctx));
+    const int pb = P - 2;
+    const double rho = pars[0], sg = pars[1];
+    const double* beta = pars + 2;
+    const double* q = ctx->qobs.data();
+    // residual forms from the statistics of y: r'r, r'Wr, X'r, X'Wr
+    double rr = q[0], rwr = q[1];
+    std::vector<double> xr(pb), xwr(pb);
+    for (int a = 0; a < pb; ++a) {
+        xr[a] = q[2 + a];
+        xwr[a] = q[2 + p + a];
+        rr -= 2.0 * beta[a] * q[2 + a];
+        rwr -= 2.0 * beta[a] * q[2 + p + a];
+        for (int c = 0; c < pb; ++c) {
+            const double g0 = ctx->G0[(size_t)a * p + c], g1 = ctx->G1[(size_t)a * p + c];
+            xr[a] -= g0 * beta[c];
+            xwr[a] -= g1 * beta[c];
+            rr += beta[a] * g0 * beta[c];
+            rwr += beta[a] * g1 * beta[c];
+        }
+    }
+    for (int t = 0; t < P * P; ++t) out[t] = 0.0;
+    out[0] = -0.5 * (double)spectral_sum(ctx, [&](double l) { const long double u = l / (1.0L - rho * l); return u * u; });
+    out[1] = out[P] = -rwr / (2.0 * sg * sg);
+    out[P + 1] = n / (2.0 * sg * sg) - (rr - rho * rwr) / (sg * sg * sg);
+    for (int a = 0; a < pb; ++a) {
+        out[2 + a] = out[(size_t)(2 + a) * P] = -xr[a] / sg;                                   // as coded at :198
+        out[P + 2 + a] = out[(size_t)(2 + a) * P + 1] = -(xr[a] - rho * xwr[a]) / (sg * sg);
+        for (int c = a; c < pb; ++c)
+            out[(size_t)(2 + a) * P + 2 + c] = out[(size_t)(2 + c) * P + 2 + a] =
+                -(ctx->G0[(size_t)a * p + c] - rho * ctx->G1[(size_t)a * p + c]) / sg;
+    }
+    return MCLCAR_OK;
+}
+
+/* The Monte Carlo likelihood surface: mcl.dCAR(c(rho_i, sigma_j, beta), ..., Evar = TRUE) on the whole nr x ns grid
+ * expand.grid(r.vec, s.vec) that rsmMCL evaluates loglik.dCAR on for its plots (R/rsmMCL.R:26-28,95-102) -- rho varies
+ * fastest, lr[i + nr * j], the layout of `Exacts[[i]]$lrs` that plot.RSM draws (R/rsmSub.R:315-327).  One statistics
+ * pass (already done for the sample set) and one reduction launch per 16384 grid points. */
+int mclcar_dcar_surface(mclcar_ctx* ctx, mclcar_samples* s, const double* rho, int nr, const double* sigma, int ns,
+                        const double* beta, int pb, const double* rho_cons, int shift_mode, double* lr, double* var) {
+    if (!ctx || !s || !rho || !sigma || !lr || nr < 1 || ns < 1 || pb < 0 || (pb > 0 && !beta)) return MCLCAR_EINVAL;
+    const int P = 2 + pb;
+    const int64_t K = (int64_t)nr * ns, chunk = 16384;
+    std::vector<double> psi((size_t)std::min(K, chunk) * P);
+    for (int64_t k0 = 0; k0 < K; k0 += chunk) {
+        const int kc = (int)std::min(chunk, K - k0);
+        for (int k = 0; k < kc; ++k) {
+            double* t = psi.data() + (size_t)k * P;
+            t[0] = rho[(k0 + k) % nr];
+            t[1] = sigma[(k0 + k) / nr];
+            for (int a = 0; a < pb; ++a) t[2 + a] = beta[a];
+        }
+        MCL_TRY(mclcar_dcar_eval(ctx, s, psi.data(), kc, P, rho_cons, nullptr, nullptr, shift_mode, lr + k0, var ? var + k0 : nullptr));
+    }
+    return MCLCAR_OK;
+}
+
 }  // extern "C"

@@ -258,7 +258,10 @@ int glm_data_terms(mclcar_ctx* ctx, const mclcar_samples* s, int fam, const std:
 // ---- host-side scalars -----------------------------------------------------------------
 int need_eigs(mclcar_ctx* ctx) { return ensure_spectrum(ctx); }
 double half_logdet_Q(const mclcar_ctx* ctx, double rho, double sigma) {
-    const long double a = spectral_sum(ctx, [&](double l) { return (long double)std::log1p(-rho * l); });
+    long double a = 0;
+    auto it = std::lower_bound(ctx->logdet_tab.begin(), ctx->logdet_tab.end(), std::make_pair(rho, (long double)-INFINITY));
+    if (it != ctx->logdet_tab.end() && it->first == rho) a = it->second;
+    else a = spectral_sum(ctx, [&](double l) { return (long double)std::log1p(-rho * l); });
     return (double)(0.5L * (a - (long double)ctx->n * std::log(sigma)));
 }
 double sum_lam_ratio(const mclcar_ctx* ctx, double rho, int power) {
@@ -451,7 +454,8 @@ int mclcar_glm_lhzy(mclcar_ctx* ctx, mclcar_samples* s, double* out) {
     MCL_TRY(glm_check(ctx, s, (int)s->psi0.size()));
     MCL_TRY(require_device(ctx));
     if (s->d_base) {
-        MCL_CUDA(ctx, cudaMemcpy(out, s->d_base, (size_t)s->N * sizeof(double), cudaMemcpyDeviceToHost));
+        MCL_CUDA(ctx, cudaMemcpyAsync(out, s->d_base, (size_t)s->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return MCLCAR_OK;
     }
     // the batch holds one "candidate" = psi0 itself: its beta is the importance beta (index 0)
@@ -551,6 +555,40 @@ int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
 }
 int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode, double* hess) {
     return glm_run(ctx, s, psi, K, P, WHAT_HESS, 0, nullptr, nullptr, shift_mode, hess, nullptr);
+}
+
+/* Monte Carlo likelihood surface of the GLM: mcl.glm(c(rho_i, sigma_j, beta), mcdata, family, Evar = TRUE) on the grid
+ * expand.grid(r.vec, s.vec), rho fastest (lr[i + nr * j]) -- the backdrop plot.rsmMCL has no exact values for when the
+ * family is not Gaussian (R/rsmMCL.R:95-108 stops with "No exact value"; R/plot.rsmMCL.R:3).  At beta = the importance
+ * beta (every rsm design point, R/rsmSub.R:169-174) the data terms cancel and the whole grid is ONE reduction over
+ * (z'z, z'Wz); the log-determinants are formed once per distinct rho. */
+int mclcar_glm_surface(mclcar_ctx* ctx, mclcar_samples* s, const double* rho, int nr, const double* sigma, int ns,
+                       const double* beta, int shift_mode, double* lr, double* var) {
+    if (!ctx || !s || !rho || !sigma || !beta || !lr || nr < 1 || ns < 1) return MCLCAR_EINVAL;
+    const int p = ctx->p, P = 2 + p;
+    MCL_TRY(glm_check(ctx, s, P));
+    MCL_TRY(need_eigs(ctx));
+    struct TabGuard {
+        mclcar_ctx* c;
+        ~TabGuard() { c->logdet_tab.clear(); }
+    } guard{ctx};
+    ctx->logdet_tab.clear();
+    for (int i = 0; i < nr; ++i)
+        ctx->logdet_tab.emplace_back(rho[i], spectral_sum(ctx, [&](double l) { return (long double)std::log1p(-rho[i] * l); }));
+    std::sort(ctx->logdet_tab.begin(), ctx->logdet_tab.end());
+    const int64_t K = (int64_t)nr * ns, chunk = 16384;
+    std::vector<double> psi((size_t)std::min(K, chunk) * P);
+    for (int64_t k0 = 0; k0 < K; k0 += chunk) {
+        const int kc = (int)std::min(chunk, K - k0);
+        for (int k = 0; k < kc; ++k) {
+            double* t = psi.data() + (size_t)k * P;
+            t[0] = rho[(k0 + k) % nr];
+            t[1] = sigma[(k0 + k) / nr];
+            for (int a = 0; a < p; ++a) t[2 + a] = beta[a];
+        }
+        MCL_TRY(glm_run(ctx, s, psi.data(), kc, P, WHAT_LR, 0, nullptr, nullptr, shift_mode, lr + k0, var ? var + k0 : nullptr));
+    }
+    return MCLCAR_OK;
 }
 
 /* get.beta.glm (R/mcl.bin.R:83-95, R/mcl.glm.R:50-54) and the beta solve inside mcl.*.profile

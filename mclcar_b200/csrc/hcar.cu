@@ -138,6 +138,26 @@ int split_pars(mclcar_ctx* ctx, const HcarModel& hm, const double* pars, int P, 
     return MCLCAR_OK;
 }
 
+// lambda inside (1/min(bb), 1/max(bb)) -- the eigenvalues of M (data$bb) -- or, without them, inside the Gershgorin bound
+int check_lambda(mclcar_ctx* ctx, const HcarModel& hm, double lam) {
+    if (!hm.bb.empty()) {
+        const double mn = *std::min_element(hm.bb.begin(), hm.bb.end()), mx = *std::max_element(hm.bb.begin(), hm.bb.end());
+        if (mn < 0 && mx > 0) {
+            if (lam < 1.0 / mn || lam > 1.0 / mx) return fail(ctx, MCLCAR_ERHO, "lambda should be within %.10g %.10g", 1.0 / mn, 1.0 / mx);
+            return MCLCAR_OK;
+        }
+    }
+    double rs = 0;
+    for (int k = 0; k < hm.K; ++k) {
+        double a = 0;
+        for (int e = hm.M.rowptr[k]; e < hm.M.rowptr[k + 1]; ++e) a += std::fabs(hm.M.val[e]);
+        rs = std::max(rs, a);
+    }
+    if (std::fabs(lam) * rs >= 1.0)
+        return fail(ctx, MCLCAR_ERHO, "lambda should be within %.10g %.10g (Gershgorin bound; supply the eigenvalues of M for the exact range)", -1.0 / rs, 1.0 / rs);
+    return MCLCAR_OK;
+}
+
 // lpars = c0 + c.q ; gradient features (order of the reference's grad.uy) ; const.pars
 struct HcarAffine {
     double c0 = 0, cst = 0;
@@ -380,6 +400,20 @@ int mclcar_hcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, i
     return MCLCAR_OK;
 }
 
+/* the 4 + 2p sufficient statistics of every sample, q_out N x (4 + 2p) column-major (may be NULL: just form them):
+ * (r0'r0, r0'W r0, X'r0[p], X'W r0[p], u'u, u'Mu) with r0 = y - Zu */
+int mclcar_hcar_stats(mclcar_ctx* ctx, mclcar_samples* s, double* q_out) {
+    HcarModel* hm = nullptr;
+    MCL_TRY(hcar_check(ctx, s, &hm));
+    MCL_TRY(require_device(ctx));
+    MCL_TRY(hcar_stats(ctx, *hm, s));
+    if (q_out) {
+        MCL_CUDA(ctx, cudaMemcpyAsync(q_out, s->d_q, (size_t)s->d * s->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MCLCAR_OK;
+}
+
 /* lpsi_i and const.psi of sim.HCAR's return list (R/HCAR.sim.R:71-85) */
 int mclcar_hcar_lpsi(mclcar_ctx* ctx, mclcar_samples* s, double* lpsi, double* const_psi) {
     HcarModel* hm = nullptr;
@@ -394,11 +428,13 @@ int mclcar_hcar_lpsi(mclcar_ctx* ctx, mclcar_samples* s, double* lpsi, double* c
     if (const_psi) *const_psi = m.cst;
     if (lpsi) {
         if (s->d_base) {
-            MCL_CUDA(ctx, cudaMemcpy(lpsi, s->d_base, (size_t)s->N * sizeof(double), cudaMemcpyDeviceToHost));
+            MCL_CUDA(ctx, cudaMemcpyAsync(lpsi, s->d_base, (size_t)s->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         } else {
             MCL_TRY(hcar_stats(ctx, *hm, s));
             std::vector<double> q((size_t)s->d * s->N);
-            MCL_CUDA(ctx, cudaMemcpy(q.data(), s->d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            MCL_CUDA(ctx, cudaMemcpyAsync(q.data(), s->d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             for (int64_t i = 0; i < s->N; ++i) {
                 double h = m.c0;
                 for (int j = 0; j < s->d; ++j) h += m.c[j] * q[(size_t)j * s->N + i];
@@ -568,6 +604,10 @@ int mclcar_hcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, cons
     HcarPars t;
     MCL_TRY(split_pars(ctx, hm, psi0, P, t));
     if (N < 1 || N >= ((int64_t)1 << 31)) return fail(ctx, MCLCAR_EINVAL, "bad sample count");
+    // Q* = Z'Qe Z + Qu is positive definite when Qe and Qu are: the reference's chol() of either stops otherwise
+    // (R/HCAR.sim.R:37-40,66) -- a positive diagonal of Q* alone would let an indefinite Q* through and the chain diverge
+    if (hm.has_W) MCL_TRY(check_rho(ctx, t.rho));
+    MCL_TRY(check_lambda(ctx, hm, t.lam));
     const int K = hm.K, p = ctx->p;
     // Q* = (Z'Z - rho Z'WZ)/se + (I - lam M)/su ;  b = ((Z'y - rho Z'Wy) - (Z'X - rho Z'WX) beta)/se
     std::vector<std::map<int, double>> rows(K);

@@ -1,6 +1,8 @@
 // Sample-set handles: the reference's simY / Zy / u.y matrices on the device.
 #include <cstring>
 
+#include <cmath>
+
 #include "common.cuh"
 #include "engine.hpp"
 
@@ -247,6 +249,57 @@ int mclcar_samples_ess(mclcar_ctx* ctx, mclcar_samples* s, double* ess_out) {
     MCL_CUDA(ctx, cudaMemcpyAsync(q.data(), s->d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return mclcar_ess_from_stats(q.data(), s->N, s->d, s->N, s->chains, ess_out);
+}
+
+/* Retained sufficient statistics.  The reference keeps every iteration's sample matrix in its
+ * result object (`MC.datas`, `Sim.data`: R/OptimMCL.R:80-93, R/rsmMCL.R:252-270) only so that summary() can call
+ * vmle.dCAR / mc.gradlik.dCAR on it again (R/summary.OptimMCL.R:24-26, R/summary.rsmMCL.R:20-22).  Every estimator of
+ * the path is a function of the N x d statistics alone, so a result object keeps those (N * d doubles instead of
+ * N * n) and re-creates a sample set from them -- in a later R session, or on another GPU.
+ * stats_export: q_out N x d column-major (as mclcar_dcar_stats); *d_out = d; q_out NULL just asks for d.  The
+ * statistics must have been formed (any evaluation, mclcar_dcar_stats or mclcar_hcar_stats does it). */
+int mclcar_samples_stats_export(mclcar_ctx* ctx, mclcar_samples* s, int* d_out, double* q_out) {
+    if (!ctx || !s) return MCLCAR_EINVAL;
+    if (s->ctx != ctx) return fail(ctx, MCLCAR_EINVAL, "sample set belongs to another context");
+    MCL_TRY(require_device(ctx));
+    if (!s->stats_ready || !s->d_q || s->d < 1)
+        return fail(ctx, MCLCAR_ESTATE, "statistics not computed yet: evaluate once (or call mclcar_dcar_stats / mclcar_hcar_stats) first");
+    if (d_out) *d_out = s->d;
+    if (q_out) {
+        MCL_CUDA(ctx, cudaMemcpyAsync(q_out, s->d_q, (size_t)s->d * s->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MCLCAR_OK;
+}
+
+/* a statistics-only sample set (no matrix: fetch fails, every likelihood entry works) from exported statistics;
+ * `sites` = n (direct CAR) or K (hierarchical model), d = 2 + 2p or 4 + 2p; `chains` = the sampler's parallel chains
+ * (mclcar_samples_schedule) or 0 for independent draws.  Attach the importance point afterwards as usual. */
+int mclcar_samples_from_stats(mclcar_ctx* ctx, const double* q, int64_t N, int d, int64_t sites, int64_t chains,
+                              mclcar_samples** out) {
+    if (!ctx || !q || !out) return MCLCAR_EINVAL;
+    *out = nullptr;
+    MCL_TRY(require_device(ctx));
+    if (d < 2 || d > 4 + 2 * MCLCAR_MAX_COV) return fail(ctx, MCLCAR_EINVAL, "bad number of statistics %d", d);
+    for (int64_t i = 0; i < (int64_t)d * N; ++i)
+        if (!std::isfinite(q[i])) return fail(ctx, MCLCAR_EINVAL, "non-finite statistic at position %lld", (long long)i);
+    mclcar_samples* s = nullptr;
+    MCL_TRY(make_samples(ctx, MCLCAR_F64, MCLCAR_COL_IS_SAMPLE, sites, N, sites, &s));
+    int st = samples_alloc_stats(ctx, s, d);
+    if (st == MCLCAR_OK) {
+        cudaError_t e = cudaMemcpyAsync(s->d_q, q, (size_t)d * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, MCLCAR_ECUDA, "upload of the statistics failed: %s", cudaGetErrorString(e));
+    }
+    if (st == MCLCAR_OK) st = samples_update_qbar(ctx, s);
+    if (st != MCLCAR_OK) {
+        mclcar_samples_free(s);
+        return st;
+    }
+    s->stats_ready = true;
+    s->chains = chains > 0 ? chains : 0;
+    *out = s;
+    return MCLCAR_OK;
 }
 
 int mclcar_samples_schedule(mclcar_ctx* ctx, mclcar_samples* s, int64_t* chains, int* burn, int* thin, double* omega) {

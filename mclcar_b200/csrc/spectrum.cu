@@ -122,6 +122,36 @@ void tridiag_quadrature(std::vector<double>& d, std::vector<double>& e, std::vec
     }
 }
 
+// all eigenvalues of a small dense symmetric matrix (cyclic Jacobi rotations, a: n x n row-major, destroyed)
+void jacobi_eigenvalues(std::vector<double>& a, int n, std::vector<double>& ev) {
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) (i == j ? diag : off) += a[(size_t)i * n + j] * a[(size_t)i * n + j];
+        if (off <= 1e-32 * (diag + off)) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = a[(size_t)p * n + q];
+                if (apq == 0.0) continue;
+                const double th = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (2.0 * apq);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::hypot(th, 1.0));
+                const double c = 1.0 / std::hypot(t, 1.0), s = t * c;
+                for (int r = 0; r < n; ++r) {      // columns p, q
+                    const double arp = a[(size_t)r * n + p], arq = a[(size_t)r * n + q];
+                    a[(size_t)r * n + p] = c * arp - s * arq;
+                    a[(size_t)r * n + q] = s * arp + c * arq;
+                }
+                for (int r = 0; r < n; ++r) {      // rows p, q
+                    const double apr = a[(size_t)p * n + r], aqr = a[(size_t)q * n + r];
+                    a[(size_t)p * n + r] = c * apr - s * aqr;
+                    a[(size_t)q * n + r] = s * apr + c * aqr;
+                }
+            }
+    }
+    ev.resize(n);
+    for (int i = 0; i < n; ++i) ev[i] = a[(size_t)i * n + i];
+}
+
 }  // namespace
 }  // namespace mclcar
 
@@ -136,12 +166,25 @@ extern "C" int mclcar_graph_estimate_spectrum(mclcar_ctx* ctx, int steps, uint64
     MCL_TRY(require_device(ctx));
     if (ctx->kind == GRAPH_NONE) return fail(ctx, MCLCAR_ESTATE, "set the graph first");
     const int n = ctx->n;
+    if (n <= kM) {
+        // a graph no larger than the probe block: a quadrature has nothing to gain over the spectrum itself (and Lanczos
+        // without re-orthogonalisation loses its exactness to ghost eigenvalues here) -- Jacobi rotations on the host
+        std::vector<double> a((size_t)n * n, 0.0), ev;
+        for (int i = 0; i < n; ++i)
+            for (int e2 = ctx->rowptr[i]; e2 < ctx->rowptr[i + 1]; ++e2)
+                a[(size_t)i * n + ctx->colidx[e2]] = ctx->binary ? 1.0 : ctx->val[e2];
+        jacobi_eigenvalues(a, n, ev);
+        std::sort(ev.begin(), ev.end());
+        ctx->eigs = ev;
+        ctx->eig_w.clear();
+        ctx->ew_min = ev.front();
+        ctx->ew_max = ev.back();
+        return MCLCAR_OK;
+    }
     int k = steps > 0 ? steps : 80;
     k = std::min(k, n);
     const size_t nm = (size_t)n * kM;
-    // Rademacher probes from a splitmix64 stream -- or, for a graph of at most 64 sites, the canonical basis: then
-    // the sum over probes IS the trace and (with k = n steps) every quadrature is exact
-    const bool basis = n <= kM;
+    // Rademacher probes from a splitmix64 stream
     std::vector<double> v0(nm);
     uint64_t x = seed ^ 0x9E3779B97F4A7C15ull;
     auto next = [&] { x += 0x9E3779B97F4A7C15ull; uint64_t z = x; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
@@ -151,10 +194,6 @@ extern "C" int mclcar_graph_estimate_spectrum(mclcar_ctx* ctx, int steps, uint64
     }
     const double inv = 1.0 / std::sqrt((double)n);
     for (double& t : v0) t *= inv;
-    if (basis) {
-        std::fill(v0.begin(), v0.end(), 0.0);
-        for (int j = 0; j < n; ++j) v0[(size_t)j * kM + j] = 1.0;
-    }
     double *d_v = nullptr, *d_vp = nullptr, *d_w = nullptr, *d_part = nullptr, *d_sc = nullptr;
     const int rows_per_block = 256;
     const int blocks = (n + rows_per_block - 1) / rows_per_block;
@@ -199,7 +238,7 @@ extern "C" int mclcar_graph_estimate_spectrum(mclcar_ctx* ctx, int steps, uint64
     nodes.reserve((size_t)k * kM);
     weights.reserve((size_t)k * kM);
     std::vector<double> d(k), e, z0;
-    for (int j = 0; j < (basis ? n : kM); ++j) {
+    for (int j = 0; j < kM; ++j) {
         int kk = k;
         for (int i = 0; i < k - 1; ++i)
             if (beta[(size_t)i * kM + j] == 0.0) { kk = i + 1; break; }     // Krylov space exhausted
@@ -210,7 +249,7 @@ extern "C" int mclcar_graph_estimate_spectrum(mclcar_ctx* ctx, int steps, uint64
         tridiag_quadrature(d, e, z0);
         for (int i = 0; i < kk; ++i) {
             nodes.push_back(d[i]);
-            weights.push_back((basis ? 1.0 : (double)n / kM) * z0[i] * z0[i]);
+            weights.push_back((double)n / kM * z0[i] * z0[i]);
         }
     }
     // calibrate: tr I, tr W and tr W^2 are known exactly -> quadratic reweighting w (a + b theta + c theta^2)

@@ -290,6 +290,39 @@ def ploglik_dCAR(rho, data, eigs) -> float:
     return float(-n / 2.0 * np.log(sigma) + 0.5 * np.sum(np.log(1.0 - rho * lam)) - n / 2.0)
 
 
+def Hessian_dCAR(pars, data, eigs) -> np.ndarray:
+    """Hessian.dCAR, R/loglik.dCAR.R:171-219, literally (dense I - rho W): the exact Hessian the summaries hand to
+    vmle.dCAR (R/summary.OptimMCL.R:24-26).  Kept as coded: drho.beta = -X'res/sigma (:198)."""
+    y = np.asarray(data["y"], dtype=np.float64)
+    n = y.shape[0]
+    W = _dense(data["W"])
+    lam = np.asarray(eigs, dtype=np.float64).ravel()
+    I = np.eye(n)
+    rho, sigma = float(pars[0]), float(pars[1])
+    drho2 = -0.5 * np.sum((lam / (1.0 - rho * lam)) ** 2)
+    if len(pars) > 2:
+        P = len(pars)
+        H = np.zeros((P, P))
+        X = data["X"]
+        res = y - X @ np.asarray(pars[2:], dtype=np.float64)
+        Q1 = I - rho * W
+        dsigma2 = n / (2.0 * sigma**2) - res @ (Q1 @ res) / sigma**3
+        dbeta2 = -X.T @ Q1 @ X / sigma
+        drho_sig = -res @ W @ res / (2.0 * sigma**2)
+        drho_beta = -X.T @ res / sigma
+        dsig_beta = -X.T @ Q1 @ res / sigma**2
+        H[0, 0] = drho2
+        H[0, 1] = H[1, 0] = drho_sig
+        H[0, 2:] = H[2:, 0] = drho_beta
+        H[1, 1] = dsigma2
+        H[1, 2:] = H[2:, 1] = dsig_beta
+        H[2:, 2:] = dbeta2
+        return H
+    dsigma2 = n / (2.0 * sigma**2) - y @ ((I - rho * W) @ y) / sigma**3
+    drhosig = -y @ W @ y / (2.0 * sigma**2)
+    return np.array([[drho2, drhosig], [drhosig, dsigma2]])
+
+
 def mple_dCAR(data, tol=1e-6, rho0=0.0) -> np.ndarray:
     """Maximum pseudo-likelihood start value, R/loglik.dCAR.R:104-136."""
     W, X, y = data["W"], data["X"], np.asarray(data["y"], dtype=np.float64)

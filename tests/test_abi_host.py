@@ -211,6 +211,22 @@ def test_profile_and_exact_likelihood_on_host_context():
     assert api.loglik_dCAR(psis[0][:2], data) == pytest.approx(dcar.loglik_dCAR(psis[0][:2], odata, eig), rel=1e-12)
 
 
+def test_exact_hessian_on_host_context():
+    """Hessian.dCAR (R/loglik.dCAR.R:171-219) from the design constants, the statistics of y and the analytic torus
+    spectrum against the oracle's literal dense restatement (with the rho-beta block as coded, :198); P = 2 + p and P = 2."""
+    from oracle import graphs
+    odata, psi0, simdata, rng = helpers.torus_case(8, 7, 10, seed=21)
+    data = api.make_data(odata["y"], X=odata["X"], torus=(8, 7), ctx=api.Context(device=-1))
+    eig = graphs.torus_eigenvalues(8, 7)
+    for pars in (psi0, psi0 * np.array([0.5, 1.3, 0.9, 1.2]), psi0[:2]):
+        H = api.Hessian_dCAR(pars, data)
+        R = dcar.Hessian_dCAR(pars, odata, eig)
+        np.testing.assert_allclose(H, R, rtol=1e-11, atol=1e-11 * np.abs(R).max())
+        np.testing.assert_array_equal(H, H.T)
+    with pytest.raises(api.MclcarError):
+        api.Hessian_dCAR(psi0[:3], data)
+
+
 # ---------------------------------------------------------------------------------------------
 # R side of the boundary (R is not installed): the .Call glue must at least type-check against the
 # C-ABI header, and every .Call in r/overrides.R must name a glue entry with the right arity.

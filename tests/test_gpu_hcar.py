@@ -3,6 +3,7 @@ R/mcl.HCAR.R), both the W-given (4+p parameters) and the W = NULL (3+p) variants
 import numpy as np
 import pytest
 
+from mclcar_b200 import _lib as L
 from mclcar_b200 import api
 from oracle import hcar
 
@@ -75,3 +76,24 @@ def test_sampler_posterior_moments(with_W):
     np.testing.assert_allclose(gmc.lpsi, ref["lpsi"], rtol=1e-10)
     th = psi * (1.0 + 0.02 * rng.standard_normal(len(psi)))
     np.testing.assert_allclose(api.mcl_HCAR(th, gmc, Evar=True), hcar.mcl_HCAR(th, ref, data, Evar=True), rtol=1e-9)
+
+
+@pytest.mark.parametrize("with_W", [True, False])
+def test_sampling_point_outside_the_positive_definite_range_is_refused(with_W):
+    """sim.HCAR's chol() of Qu / Qe stops for lambda or rho outside the eigenvalue range (R/HCAR.sim.R:37-40): the Gibbs
+    chain on an indefinite Q* would diverge silently, so the library refuses the point with the admissible range."""
+    data, mc, psi, gd, rng = _case(with_W, seed=11, N=10)
+    il = 1 if with_W else 0
+    bad = psi.copy()
+    bad[il] = 1.05 / data["bb"].max()
+    with pytest.raises(api.MclcarError, match="lambda should be within") as ei:
+        api.sim_HCAR(bad, gd, 16)
+    assert ei.value.code == L.ERHO
+    if with_W:
+        bad = psi.copy()
+        bad[0] = 1.05 / data["aa"].max()
+        with pytest.raises(api.MclcarError, match="rho should be within"):
+            api.sim_HCAR(bad, gd, 16)
+    ok = psi.copy()
+    ok[il] = 0.9 / data["bb"].max()
+    assert np.isfinite(api.sim_HCAR(ok, gd, 16).lpsi).all()
