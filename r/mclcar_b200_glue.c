@@ -17,6 +17,7 @@
 #include <Rinternals.h>
 #include <R_ext/Random.h>
 #include <stdint.h>
+#include <string.h>
 #include "mclcar_b200.h"
 
 static void ctx_finalizer(SEXP p) {
@@ -314,3 +315,136 @@ SEXP C_mclb_hess_hcar(SEXP ctx, SEXP samples, SEXP pars) { /* P x P  [R/mcl.HCAR
     return H;
 }
 
+
+/* ---- graph bookkeeping: what the library made of an uploaded W ------------------------------------------------- */
+/* c(kind, n1, n2): kind 1 = rook torus recognised in the CSR upload (tiled sampler, analytic spectrum), 2 = general */
+SEXP C_mclb_graph_kind(SEXP ctx) {
+    mclcar_ctx* c = ctx_of(ctx);
+    int n1 = 0, n2 = 0;
+    int kind = mclcar_graph_kind(c, &n1, &n2);
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, 3));
+    INTEGER(out)[0] = kind; INTEGER(out)[1] = n1; INTEGER(out)[2] = n2;
+    UNPROTECT(1);
+    return out;
+}
+SEXP C_mclb_set_eigenvalues(SEXP ctx, SEXP eig) {
+    mclcar_ctx* c = ctx_of(ctx);
+    CHECK(c, mclcar_graph_set_eigenvalues(c, REAL(eig), LENGTH(eig)));
+    return R_NilValue;
+}
+/* CAR.simTorus(n1, n2, rho, prec)$X (R/CAR.simLM.R:2-22): one draw of N(0, (prec (I - rho W))^-1) on the n1 x n2 torus by
+ * the tiled red-black sampler instead of a sparse Cholesky of the n x n precision */
+SEXP C_mclb_sim_torus(SEXP n1, SEXP n2, SEXP rho, SEXP prec) {
+    const int a = Rf_asInteger(n1), b = Rf_asInteger(n2);
+    GetRNGstate();
+    uint64_t seed = ((uint64_t)(unif_rand() * 4294967296.0) << 32) | (uint64_t)(unif_rand() * 4294967296.0);
+    PutRNGstate();
+    mclcar_ctx* c = NULL;
+    if (mclcar_ctx_create(0, seed, &c) != MCLCAR_OK) Rf_error("%s", mclcar_last_error(NULL));
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)a * b));
+    double* zero = (double*)R_alloc((size_t)a * b, sizeof(double));
+    for (R_xlen_t i = 0; i < (R_xlen_t)a * b; ++i) zero[i] = 0.0;
+    double psi[2] = {Rf_asReal(rho), 1.0 / Rf_asReal(prec)};
+    mclcar_sampler_opts o = {0};
+    o.keep = 1; o.dtype = MCLCAR_F64;
+    mclcar_samples* s = NULL;
+    int st = mclcar_graph_torus(c, a, b);
+    if (st == MCLCAR_OK) st = mclcar_set_design(c, NULL, 0);
+    if (st == MCLCAR_OK) st = mclcar_set_obs(c, zero, NULL);
+    if (st == MCLCAR_OK) st = mclcar_dcar_prep(c, psi, 2, 1, &o, &s);
+    if (st == MCLCAR_OK) st = mclcar_samples_fetch(c, s, MCLCAR_COL_IS_SAMPLE, REAL(out), (int64_t)a * b);
+    char msg[512];
+    if (st != MCLCAR_OK) { strncpy(msg, mclcar_last_error(c), sizeof msg - 1); msg[sizeof msg - 1] = 0; }
+    mclcar_samples_free(s);
+    mclcar_ctx_destroy(c);
+    UNPROTECT(1);
+    if (st != MCLCAR_OK) Rf_error("%s", msg);     /* "rho should be within ..." as R/CAR.simLM.R:11 */
+    return out;
+}
+
+/* ---- profile / exact pieces the summaries and plots use ----------------------------------------- */
+/* sigmabeta(rho, data) for a vector of rho: K x (1 + p)  [R/loglik.dCAR.R:72-86] */
+SEXP C_mclb_sigmabeta(SEXP ctx, SEXP rho, SEXP p) {
+    mclcar_ctx* c = ctx_of(ctx);
+    int K = LENGTH(rho), w = 1 + Rf_asInteger(p);
+    double* tmp = (double*)R_alloc((size_t)K * w, sizeof(double));
+    int st = mclcar_dcar_sigmabeta(c, REAL(rho), K, tmp);
+    if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, K, w));
+    for (int k = 0; k < K; ++k) for (int j = 0; j < w; ++j) REAL(out)[k + (size_t)j * K] = tmp[(size_t)k * w + j];
+    UNPROTECT(1);
+    return out;
+}
+/* loglik.dCAR over the rows of pars (K x P)  [R/loglik.dCAR.R:7-42]: the exact backdrop of plot.rsmMCL in one call */
+SEXP C_mclb_loglik_dcar(SEXP ctx, SEXP pars, SEXP rho_cons) {
+    mclcar_ctx* c = ctx_of(ctx);
+    int K = Rf_nrows(pars), P = Rf_ncols(pars);
+    double* psi = (double*)R_alloc((size_t)K * P, sizeof(double));
+    for (int k = 0; k < K; ++k) for (int j = 0; j < P; ++j) psi[(size_t)k * P + j] = REAL(pars)[k + (size_t)j * K];
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, K));
+    int st = mclcar_dcar_loglik(c, psi, K, P, Rf_isNull(rho_cons) ? NULL : REAL(rho_cons), REAL(out));
+    UNPROTECT(1);
+    if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
+    return out;
+}
+/* Hessian.dCAR(pars, data): P x P  [R/loglik.dCAR.R:171-219] */
+SEXP C_mclb_hessian_dcar(SEXP ctx, SEXP pars) {
+    mclcar_ctx* c = ctx_of(ctx);
+    int P = LENGTH(pars);
+    SEXP H = PROTECT(Rf_allocMatrix(REALSXP, P, P));
+    int st = mclcar_dcar_hessian_exact(c, REAL(pars), P, REAL(H));
+    UNPROTECT(1);
+    if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
+    return H;
+}
+/* Monte Carlo likelihood surface on expand.grid(r.vec, s.vec): list(lrs, vars), each length(r.vec) x length(s.vec)
+ * -- the shape of Exacts[[i]]$lrs (R/rsmMCL.R:95-102); family 0 = direct CAR (rho_cons may be NULL), 1/2 = GLM */
+SEXP C_mclb_surface(SEXP ctx, SEXP samples, SEXP family, SEXP rvec, SEXP svec, SEXP beta, SEXP rho_cons) {
+    mclcar_ctx* c = ctx_of(ctx);
+    int nr = LENGTH(rvec), ns = LENGTH(svec), pb = Rf_isNull(beta) ? 0 : LENGTH(beta);
+    SEXP lr = PROTECT(Rf_allocMatrix(REALSXP, nr, ns));
+    SEXP vr = PROTECT(Rf_allocMatrix(REALSXP, nr, ns));
+    int st;
+    if (Rf_asInteger(family) == MCLCAR_FAMILY_DCAR)
+        st = mclcar_dcar_surface(c, samples_of(samples), REAL(rvec), nr, REAL(svec), ns, pb ? REAL(beta) : NULL, pb,
+                                 Rf_isNull(rho_cons) ? NULL : REAL(rho_cons), MCLCAR_SHIFT_MEAN, REAL(lr), REAL(vr));
+    else
+        st = mclcar_glm_surface(c, samples_of(samples), REAL(rvec), nr, REAL(svec), ns, REAL(beta), MCLCAR_SHIFT_MEAN,
+                                REAL(lr), REAL(vr));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, lr);
+    SET_VECTOR_ELT(out, 1, vr);
+    UNPROTECT(3);
+    if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
+    return out;
+}
+
+/* ---- retained statistics: what a result object keeps of a sample set (R/OptimMCL.R:80-93, R/rsmMCL.R:252-270) ---- */
+/* N x d matrix of sufficient statistics (hcar: 4 + 2p columns, else 2 + 2p) with attribute "chains" */
+SEXP C_mclb_stats_export(SEXP ctx, SEXP samples, SEXP hcar) {
+    mclcar_ctx* c = ctx_of(ctx);
+    mclcar_samples* s = samples_of(samples);
+    int d = 0;
+    CHECK(c, Rf_asLogical(hcar) ? mclcar_hcar_stats(c, s, NULL) : mclcar_dcar_stats(c, s, NULL));
+    CHECK(c, mclcar_samples_stats_export(c, s, &d, NULL));
+    int64_t N = mclcar_samples_count(s), chains = 0;
+    SEXP q = PROTECT(Rf_allocMatrix(REALSXP, (int)N, d));
+    int st = mclcar_samples_stats_export(c, s, &d, REAL(q));
+    if (st == MCLCAR_OK) st = mclcar_samples_schedule(c, s, &chains, NULL, NULL, NULL);
+    SEXP ch = PROTECT(Rf_ScalarReal((double)chains));
+    Rf_setAttrib(q, Rf_install("chains"), ch);
+    UNPROTECT(2);
+    if (st != MCLCAR_OK) Rf_error("%s", mclcar_last_error(c));
+    return q;
+}
+/* a statistics-only sample set from such a matrix, importance point attached */
+SEXP C_mclb_samples_from_stats(SEXP ctx, SEXP q, SEXP sites, SEXP chains, SEXP psi, SEXP hcar) {
+    mclcar_ctx* c = ctx_of(ctx);
+    mclcar_samples* s = NULL;
+    CHECK(c, mclcar_samples_from_stats(c, REAL(q), Rf_nrows(q), Rf_ncols(q), (int64_t)Rf_asReal(sites),
+                                       (int64_t)Rf_asReal(chains), &s));
+    int st = Rf_asLogical(hcar) ? mclcar_hcar_attach(c, s, REAL(psi), LENGTH(psi), NULL)
+                                : mclcar_dcar_attach(c, s, REAL(psi), LENGTH(psi), NULL);
+    if (st != MCLCAR_OK) { mclcar_samples_free(s); Rf_error("%s", mclcar_last_error(c)); }
+    return wrap_samples(s);
+}

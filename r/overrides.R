@@ -14,27 +14,68 @@
 .mclb$control <- list(n.chains = 0, burn = 0L, thin = 0L, keep = TRUE, dtype = 1L, omega = 0)  # dtype 1 = fp32 samples
 .mclb$COL_IS_SAMPLE <- 0L   # MCLCAR_COL_IS_SAMPLE: simY (n x N), u.y (K x N)
 .mclb$ROW_IS_SAMPLE <- 1L   # MCLCAR_ROW_IS_SAMPLE: Zy (N x n)
-.mclb$cache <- new.env()
+.mclb$cache <- list()       # most recently used first; at most .mclb$cache.max contexts stay alive
+.mclb$cache.max <- 8L
+.mclb$eigen.max <- 2000L    # general graphs up to this size get eigen(W) from R (exact); larger ones the device quadrature
 
-.mclb_csr <- function(A) {   # symmetric matrix -> 0-based CSR slots (p, j, x)
-    methods::as(methods::as(Matrix::Matrix(as.matrix(A), sparse = TRUE), "generalMatrix"), "RsparseMatrix")
+## W -> 0-based CSR slots (p, j, x) WITHOUT densifying: spam (1-based CSR already), Matrix, or a base matrix
+.mclb_csr <- function(A) {
+    if (inherits(A, "spam"))
+        return(list(p = as.integer(A@rowpointers - 1L), j = as.integer(A@colindices - 1L), x = as.numeric(A@entries)))
+    if (!inherits(A, "Matrix")) A <- Matrix::Matrix(A, sparse = TRUE)
+    R <- methods::as(methods::as(A, "generalMatrix"), "RsparseMatrix")
+    list(p = R@p, j = R@j, x = as.numeric(R@x))
 }
-.mclb_key <- function(...) paste(vapply(list(...), function(v) format(sum(as.numeric(v)), digits = 17), ""), collapse = "|")
+## cached context whose stored inputs are identical() to `parts` (content check, not a checksum: two data sets with
+## equal sums, a permuted y or another n.trial must never share a context); least recently used contexts are dropped
+.mclb_cached <- function(kind, parts, make) {
+    for (i in seq_along(.mclb$cache)) {
+        e <- .mclb$cache[[i]]
+        if (identical(e$kind, kind) && identical(e$parts, parts)) {
+            .mclb$cache <- c(list(e), .mclb$cache[-i])
+            return(e$ctx)
+        }
+    }
+    ctx <- make()
+    .mclb$cache <- utils::head(c(list(list(kind = kind, parts = parts, ctx = ctx)), .mclb$cache), .mclb$cache.max)
+    ctx          # dropped contexts are released by their finalizers once no sample set refers to them
+}
+## upload W; the library recognises an exact rook torus in the CSR (tiled sampler, analytic spectrum: no eigen(W)).
+## Otherwise: the caller's data$lambda, or eigen() in R up to .mclb$eigen.max sites, or nothing -- the library then
+## estimates the spectral sums on the device the first time they are needed (mclcar_graph_estimate_spectrum).
+.mclb_graph <- function(ctx, W, lambda) {
+    Wt <- .mclb_csr(W)
+    .Call(C_mclb_graph_csr, ctx, Wt$p, Wt$j, Wt$x, if (is.null(lambda)) NULL else as.numeric(lambda))
+    if (is.null(lambda) && .Call(C_mclb_graph_kind, ctx)[1] == 2L && nrow(W) <= .mclb$eigen.max)
+        .Call(C_mclb_set_eigenvalues, ctx, as.numeric(eigen(as.matrix(W), symmetric = TRUE, only.values = TRUE)$values))
+    invisible(ctx)
+}
 
 ## context for the direct CAR model (data$data.vec, data$W) or the GLM (data$y, data$covX, data$W, data$n.trial)
 .mclb_ctx <- function(data, glm = FALSE) {
     y <- if (glm) data$y else data$data.vec$y
     X <- if (glm) data$covX else stats::model.matrix(y ~ ., data = data$data.vec)
-    key <- paste(if (glm) "glm" else "lm", .mclb_key(y, X, data$W, length(y)))
-    if (!is.null(.mclb$cache[[key]])) return(.mclb$cache[[key]])
-    ctx <- .Call(C_mclb_ctx, 0L)
-    Wt <- .mclb_csr(data$W)
-    lambda <- if (is.null(data$lambda)) eigen(as.matrix(data$W), symmetric = TRUE, only.values = TRUE)$values else data$lambda
-    .Call(C_mclb_graph_csr, ctx, Wt@p, Wt@j, as.numeric(Wt@x), as.numeric(lambda))
     nt <- if (glm && !is.null(data$n.trial)) rep_len(as.numeric(data$n.trial), length(y)) else NULL
-    .Call(C_mclb_model, ctx, X, as.numeric(y), nt)
-    .mclb$cache[[key]] <- ctx
-    ctx
+    .mclb_cached(if (glm) "glm" else "lm", list(y = y, X = X, W = data$W, n.trial = nt, lambda = data$lambda), function() {
+        ctx <- .Call(C_mclb_ctx, 0L)
+        .mclb_graph(ctx, data$W, data$lambda)
+        .Call(C_mclb_model, ctx, X, as.numeric(y), nt)
+        ctx
+    })
+}
+
+## CAR.simTorus(n1, n2, rho, prec) (R/CAR.simLM.R:2-22): W stays SPARSE (the reference returns as.matrix(W), n^2 doubles
+## -- 8 TB at 1000 x 1000) and the draw comes from the tiled red-black sampler.  Everything downstream takes the sparse W:
+## the overrides upload it as CSR, where the library recognises the torus again.
+CAR.simTorus <- function(n1, n2, rho, prec) {
+    Wx <- spam::circulant.spam(list(c(2, n2), rep(1, 2)), n = n2)
+    W <- spam::kronecker.spam(spam::diag.spam(1, n1), Wx) + spam::kronecker.spam(spam::circulant.spam(list(c(2, n1), rep(1, 2)), n = n1), spam::diag.spam(1, n2))
+    list(W = W, X = .Call(C_mclb_sim_torus, as.integer(n1), as.integer(n2), as.numeric(rho), as.numeric(prec)))
+}
+## CAR.simLM(pars, data) (R/CAR.simLM.R:37-50): one draw of the linear model with CAR errors through the cached context
+CAR.simLM <- function(pars, data) {
+    sd <- mcl.prep.dCAR(pars, 1L, data)
+    as.numeric(.Call(C_mclb_fetch, attr(sd, "ctx"), sd$simY, length(data$data.vec$y), .mclb$COL_IS_SAMPLE))
 }
 
 ## ---------------------------------------------------------------- direct CAR (R/mcl.dCAR.R)
@@ -161,23 +202,16 @@ ExpPath.CAR.glm <- function(exp.design, data, family, psi, mc.data) {   # R/rsmS
 .mclb_hcar_ctx <- function(data) {
     g <- function(nm) if (is.environment(data)) get0(nm, envir = data) else data[[nm]]
     y <- g("y"); X <- g("X"); W <- g("W"); M <- g("M"); Z <- g("Z")
-    key <- paste("hcar", .mclb_key(y, X, M, Z, if (is.null(W)) 0 else W))
-    if (!is.null(.mclb$cache[[key]])) return(.mclb$cache[[key]])
-    ctx <- .Call(C_mclb_ctx, 0L)
-    n <- length(y)
-    if (is.null(W)) {
-        .Call(C_mclb_graph_csr, ctx, integer(n + 1), integer(0), numeric(0), NULL)    # empty graph: the W = NULL variant
-    } else {
-        Wt <- .mclb_csr(W)
-        aa <- if (is.null(g("aa"))) eigen(as.matrix(W), symmetric = TRUE, only.values = TRUE)$values else g("aa")
-        .Call(C_mclb_graph_csr, ctx, Wt@p, Wt@j, as.numeric(Wt@x), as.numeric(aa))
-    }
-    .Call(C_mclb_model, ctx, as.matrix(X), as.numeric(y), NULL)
-    Mt <- .mclb_csr(M); Zt <- .mclb_csr(Z)
-    bb <- if (is.null(g("bb"))) eigen(as.matrix(M), symmetric = TRUE, only.values = TRUE)$values else g("bb")
-    .Call(C_mclb_hcar_model, ctx, Mt@p, Mt@j, as.numeric(Mt@x), Zt@p, Zt@j, as.numeric(Zt@x), as.numeric(bb), !is.null(W))
-    .mclb$cache[[key]] <- ctx
-    ctx
+    .mclb_cached("hcar", list(y = y, X = X, W = W, M = M, Z = Z, aa = g("aa"), bb = g("bb")), function() {
+        ctx <- .Call(C_mclb_ctx, 0L)
+        if (is.null(W)) .Call(C_mclb_graph_csr, ctx, integer(length(y) + 1), integer(0), numeric(0), NULL)    # the W = NULL variant
+        else .mclb_graph(ctx, W, g("aa"))
+        .Call(C_mclb_model, ctx, as.matrix(X), as.numeric(y), NULL)
+        Mt <- .mclb_csr(M); Zt <- .mclb_csr(Z)
+        bb <- if (is.null(g("bb"))) eigen(as.matrix(M), symmetric = TRUE, only.values = TRUE)$values else g("bb")   # K x K: districts
+        .Call(C_mclb_hcar_model, ctx, Mt$p, Mt$j, Mt$x, Zt$p, Zt$j, Zt$x, as.numeric(bb), !is.null(W))
+        ctx
+    })
 }
 sim.HCAR <- function(psi, data, n.samples) {                            # R/HCAR.sim.R:3-87
     ctx <- .mclb_hcar_ctx(data)
@@ -194,3 +228,71 @@ mcl.grad.HCAR <- function(pars, mcdata, data, Evar = FALSE) {           # R/mcl.
 }
 mcl.Hessian.HCAR <- function(pars, mcdata, data)                        # R/mcl.HCAR.R:216-391
     .Call(C_mclb_hess_hcar, attr(mcdata, "ctx"), mcdata$u.y, as.numeric(pars))
+
+
+## ---------------------------------------------------------------- profile / exact pieces and summaries (SURVEY.md 8f)
+sigmabeta <- function(rho, data) {                                      # R/loglik.dCAR.R:72-86
+    ctx <- .mclb_ctx(data)
+    as.numeric(.Call(C_mclb_sigmabeta, ctx, as.numeric(rho), ncol(stats::model.matrix(y ~ ., data = data$data.vec)))[1, ])
+}
+loglik.dCAR <- function(pars, data, rho.cons = c(-0.249, 0.249))        # R/loglik.dCAR.R:7-42
+    .Call(C_mclb_loglik_dcar, .mclb_ctx(data), matrix(as.numeric(pars), nrow = 1), rho.cons)
+Hessian.dCAR <- function(pars, data)                                    # R/loglik.dCAR.R:171-219
+    .Call(C_mclb_hessian_dcar, .mclb_ctx(data), as.numeric(pars))
+## the exact backdrop of plot.rsmMCL -- R/rsmMCL.R:95-102 apply()s loglik.dCAR over the 100 x 100 grid -- in ONE call;
+## same list shape as Exacts[[i]]
+exact.surface.dCAR <- function(r.vec, s.vec, psi, data) {
+    g <- as.matrix(expand.grid(r.vec, s.vec))
+    pars <- cbind(g, matrix(as.numeric(psi[-c(1, 2)]), nrow(g), length(psi) - 2, byrow = TRUE))
+    ctx <- .mclb_ctx(data)
+    lrs <- .Call(C_mclb_loglik_dcar, ctx, pars, c(-0.249, 0.249)) - .Call(C_mclb_loglik_dcar, ctx, matrix(as.numeric(psi), nrow = 1), c(-0.249, 0.249))
+    list(r.vec = r.vec, s.vec = s.vec, lrs = matrix(lrs, length(r.vec), length(s.vec)))
+}
+## the MONTE CARLO likelihood surface on the same grid: what the rsm design points sample from.  Returned in the shape
+## of Exacts[[i]] (plus $vars), so plot.RSM(..., exact = mc.surface(...), exact.vals = TRUE) draws it as the image
+## behind the fitted response surface -- for the GLM families this is the only backdrop there is (R/rsmMCL.R:106).
+mc.surface <- function(r.vec, s.vec, psi, mc.data, data = NULL, family = "gauss", rho.cons = NULL) {
+    if (family == "gauss") mc.data <- .mclb_simdata(data, mc.data)
+    h <- if (family == "gauss") mc.data$simY else mc.data$Zy
+    fam <- c(gauss = 0L, binom = 1L, poisson = 2L)[[family]]
+    beta <- if (length(psi) > 2) as.numeric(psi[-c(1, 2)]) else NULL
+    r <- .Call(C_mclb_surface, attr(mc.data, "ctx"), h, fam, as.numeric(r.vec), as.numeric(s.vec), beta, rho.cons)
+    list(r.vec = r.vec, s.vec = s.vec, lrs = r[[1]], vars = r[[2]])
+}
+## plot.rsmMCL with the Monte Carlo surface of each iteration's sample set as the backdrop (mc.surface = TRUE), on the
+## grid the exact values use; everything else is the reference's plot (R/plot.rsmMCL.R:2-88)
+plot.rsmMCL <- function(x, family, trace.all = TRUE, plain = TRUE, mc.surface = FALSE, length = 100, ...) {
+    if (mc.surface) {
+        Psis <- rbind(x$psi0, do.call(rbind, x$Psi))
+        for (i in seq_len(if (trace.all) x$N.iter else 1L)) {
+            sim <- x$Sim.data[[i]]
+            if (inherits(sim, "mclb_retained")) sim <- restore.mcdata(sim, x$data)
+            r.vec <- if (is.list(x$Exacts[[i]])) x$Exacts[[i]]$r.vec else seq(-0.24, 0.24, length.out = length)
+            s.vec <- if (is.list(x$Exacts[[i]])) x$Exacts[[i]]$s.vec else seq(0.5, 2, length.out = length) * Psis[i, 2]
+            x$Exacts[[i]] <- mc.surface(r.vec, s.vec, Psis[i, ], sim, x$data, family)
+        }
+        family <- "gauss"          # plot.exact <- family == "gauss" (R/plot.rsmMCL.R:3): draw the backdrop
+    }
+    get("plot.rsmMCL", envir = asNamespace("mclcar"))(x, family, trace.all, plain, ...)
+}
+
+## ---------------------------------------------------------------- retained statistics instead of retained matrices
+## OptimMCL / rsmMCL keep every iteration's sample set in MC.datas / Sim.data (R/OptimMCL.R:80-93, R/rsmMCL.R:252-270)
+## for summary() to re-evaluate vmle.* on (R/summary.OptimMCL.R:24-26).  A device handle does not survive saveRDS();
+## retain.mcdata() turns one into a plain R object holding the N x d sufficient statistics (N * d doubles instead of
+## N * n), restore.mcdata() rebuilds a statistics-only sample set from it -- every mcl.* / vmle.* function works on it.
+retain.mcdata <- function(mc.data) {
+    hcar <- inherits(mc.data, "mclb_hcar")
+    h <- if (hcar) mc.data$u.y else mc.data$simY
+    q <- .Call(C_mclb_stats_export, attr(mc.data, "ctx"), h, hcar)
+    structure(list(q = q, psi = if (hcar) mc.data$psi else attr(mc.data, "psi"), hcar = hcar,
+                   n = attr(mc.data, "n"), n.samples = nrow(q)), class = "mclb_retained")
+}
+restore.mcdata <- function(kept, data) {
+    ctx <- if (kept$hcar) .mclb_hcar_ctx(data) else .mclb_ctx(data)
+    sites <- if (kept$hcar) { M <- if (is.environment(data)) get("M", envir = data) else data$M; nrow(M) } else kept$n
+    h <- .Call(C_mclb_samples_from_stats, ctx, kept$q, sites, attr(kept$q, "chains"), as.numeric(kept$psi), kept$hcar)
+    if (kept$hcar) structure(list(psi = kept$psi, n.samples = kept$n.samples, u.y = h), class = "mclb_hcar", ctx = ctx)
+    else structure(list(simY = h, t10 = NA_real_, t20 = NULL), class = "mclb_simdata", ctx = ctx, psi = kept$psi,
+                   n.samples = kept$n.samples, n = kept$n)
+}

@@ -31,6 +31,9 @@ SEXP Rf_allocMatrix(unsigned int type, int nrow, int ncol);
 int Rf_nrows(SEXP);
 int Rf_ncols(SEXP);
 SEXP Rf_ScalarInteger(int);
+SEXP Rf_ScalarReal(double);
+SEXP Rf_install(const char*);
+SEXP Rf_setAttrib(SEXP vec, SEXP name, SEXP val);
 SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
 SEXP VECTOR_ELT(SEXP x, R_xlen_t i);
 char* R_alloc(size_t n, int size);
