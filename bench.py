@@ -396,7 +396,7 @@ def run_ours(args):
 
     traffic = None
     try:  # measured DRAM traffic of the dominant kernel (one ncu --set full capture, profiles/)
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)["gibbs_torus_sweep_fused"]
         if launches_per_sweep < 1.5:
             traffic = tr["dram_bytes_per_launch"] * chains / tr["chains"]
