@@ -284,6 +284,11 @@ MCLCAR_API int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double*
 MCLCAR_API int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode,
                     double* hess);
 
+/* diagnostic (pure host code): the piecewise degree-8 table of L(a) = log1p(exp(-a)), a = |eta|, that the binomial data-term
+ * kernel evaluates instead of exp + log1p + divide (log(1 + e^eta) = max(eta, 0) + L(|eta|), expit(|eta|) = 1 + L'),
+ * with the kernel's own arithmetic: L_out[i], dL_out[i] (may be NULL).  Absolute error <= 2e-15 / 1e-12. */
+MCLCAR_API int mclcar_glm_softplus_table_eval(const double* eta, int64_t n, double* L_out, double* dL_out);
+
 /* get.beta.glm(beta0, rho.sig, mcdata, family) (R/mcl.glm.R:50-54 -> get.beta.bin, R/mcl.bin.R:83-95)
  * and the beta solve of mcl.profile.glm (R/mcl.bin.R:111-123): root of the beta block of
  * mcl.grad.glm at fixed (rho, sigma) by Newton steps on a batched forward-difference Jacobian

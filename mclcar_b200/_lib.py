@@ -113,6 +113,7 @@ SIGNATURES = {
     "mclcar_glm_eval": (_i, [_vp, _vp, _pd, _i, _i, _pi64, _pi64, _i, _pd, _pd]),
     "mclcar_glm_grad": (_i, [_vp, _vp, _pd, _i, _i, _i, _i, _pd, _pd]),
     "mclcar_glm_hess": (_i, [_vp, _vp, _pd, _i, _i, _i, _pd]),
+    "mclcar_glm_softplus_table_eval": (_i, [_pd, _i64, _pd, _pd]),
     "mclcar_glm_get_beta": (_i, [_vp, _vp, _pd, _pd, _i, C.c_double, _pd, _pd, _pi, _pi]),
     "mclcar_hcar_set_model": (_i, [_vp, _i, _pi, _pi, _pd, _pi, _pi, _pd, _pd, _i]),
     "mclcar_hcar_prep": (_i, [_vp, _pd, _i, _i64, C.POINTER(SamplerOpts), C.POINTER(_vp)]),

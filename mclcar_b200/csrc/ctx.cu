@@ -299,7 +299,7 @@ void mclcar_ctx_destroy(mclcar_ctx* ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         void* ptrs[] = {ctx->d_coef.p, ctx->d_partial.p, ctx->d_tuples.p, ctx->d_subidx.p,
-                        ctx->d_gather.p};
+                        ctx->d_gather.p, ctx->d_sptab.p};
         for (void* p : ptrs)
             if (p) cudaFree(p);
         pool_release_all(ctx);

@@ -92,6 +92,7 @@ struct mclcar_ctx {
 
     // ---- scratch reused across calls (grown on demand)
     mclcar::DeviceBuf d_coef, d_partial, d_tuples, d_subidx, d_gather;
+    mclcar::DeviceBuf d_sptab;   // piecewise-polynomial table of log1p(exp(-a)) for the binomial data term (glm.cu)
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
 

@@ -29,7 +29,64 @@ constexpr int kThreads = 128;
 // beta), 4 with gradients, 2 with Hessian blocks
 constexpr int tile_of(int mode) { return mode == 0 ? 8 : (mode == 1 ? 4 : 2); }
 
+// ---- binomial data term without exp / log1p / divide ---------------------------------------------------------
+// log(1 + e^eta) = max(eta, 0) + L(|eta|),  L(a) = log1p(e^-a):  L is analytic with its nearest singularities at
+// a = +- i pi, so a degree-8 polynomial per interval of width 1/4 (Chebyshev interpolation, Bernstein-ellipse
+// parameter ~50) is exact to 1.2e-15 absolute on [0, 40) (L(40) = 4e-18); its derivative gives
+// expit(a) = 1 + L'(a) to 5e-13.  One table row (9 doubles, shared memory) and 8 (16 with the derivative) DFMA
+// replace the ~65 fp64 instructions of exp + log1p + divide: the binomial likelihood pass is bound by exactly
+// that arithmetic (scripts/ubench/fp64_peaks.cu).  Rows are 9 doubles = 18 banks apart: lanes whose |eta| differ
+// by less than 4 read conflict-free, equal intervals broadcast.
+constexpr int kSpDeg = 8, kSpRow = kSpDeg + 1, kSpIntervals = 160;      // [0, 40) in steps of 1/4
+constexpr double kSpMax = 39.999999;
+
+const std::vector<double>& softplus_table() {
+    static const std::vector<double> tab = [] {
+        std::vector<double> t((size_t)kSpIntervals * kSpRow);
+        const int m = kSpRow;
+        for (int k = 0; k < kSpIntervals; ++k) {
+            const long double c = (k + 0.5L) * 0.25L;
+            long double f[kSpRow], a[kSpRow];
+            for (int j = 0; j < m; ++j) f[j] = log1pl(expl(-(c + 0.125L * cosl(M_PIl * (j + 0.5L) / m))));
+            for (int d = 0; d < m; ++d) {
+                long double acc = 0;
+                for (int j = 0; j < m; ++j) acc += f[j] * cosl(M_PIl * d * (j + 0.5L) / m);
+                a[d] = acc * (d == 0 ? 1.0L : 2.0L) / m;
+            }
+            // Chebyshev -> monomial in t in [-1, 1]: T_0 = 1, T_1 = t, T_{d+1} = 2 t T_d - T_{d-1}
+            long double mono[kSpRow] = {0}, T0[kSpRow] = {0}, T1[kSpRow] = {0}, T2[kSpRow];
+            T0[0] = 1; T1[1] = 1;
+            for (int i = 0; i < m; ++i) mono[i] += a[0] * T0[i] + (m > 1 ? a[1] * T1[i] : 0);
+            for (int d = 2; d < m; ++d) {
+                for (int i = 0; i < m; ++i) T2[i] = (i > 0 ? 2 * T1[i - 1] : 0) - T0[i];
+                for (int i = 0; i < m; ++i) { mono[i] += a[d] * T2[i]; T0[i] = T1[i]; T1[i] = T2[i]; }
+            }
+            for (int i = 0; i < m; ++i) t[(size_t)k * m + i] = (double)mono[i];
+        }
+        return t;
+    }();
+    return tab;
+}
+
+// L(|eta|) and (WANT_D) dL/da at a = |eta| from the table (host and device: the same arithmetic)
+template <bool WANT_D>
+__host__ __device__ __forceinline__ double softplus_tail(const double* __restrict__ tab, double eta, double& dL) {
+    const double a = fmin(fabs(eta), kSpMax);
+    const int k = (int)(a * 4.0);
+    const double t = fma(a, 8.0, -(double)(2 * k + 1));
+    const double* c = tab + k * kSpRow;
+    double p = c[kSpDeg], dp = 0.0;
+#pragma unroll
+    for (int j = kSpDeg - 1; j >= 0; --j) {
+        if (WANT_D) dp = fma(dp, t, p);
+        p = fma(p, t, c[j]);
+    }
+    dL = 8.0 * dp;
+    return p;
+}
+
 struct GlmTermsParams {
+    const double* sptab;  // softplus table (device), kSpIntervals x kSpRow
     const void* M;  // [n][ld] site-major
     int64_t ld, N;
     int n, p;
@@ -58,10 +115,13 @@ __global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParam
     constexpr int NH = PT * (PT + 1) / 2;
     constexpr int NS = 1 + (MODE >= 1 ? PT : 0) + (MODE >= 2 ? NH : 0);
     __shared__ double sbeta[BT * PT];
+    __shared__ double stab[FAM == FAM_BINOM ? kSpIntervals * kSpRow : 1];
     if (threadIdx.x < BT * PT) {
         const int b = threadIdx.x / PT, a = threadIdx.x % PT;
         sbeta[threadIdx.x] = (b < prm.nb && a < prm.p) ? prm.beta[b * prm.p + a] : 0.0;
     }
+    if (FAM == FAM_BINOM)
+        for (int t = threadIdx.x; t < kSpIntervals * kSpRow; t += blockDim.x) stab[t] = __ldg(prm.sptab + t);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= prm.N) return;
@@ -89,12 +149,12 @@ __global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParam
                 for (int a = 0; a < PT; ++a) eta = fma(xr[a], sbeta[b * PT + a], eta);
                 double mu, v;
                 if (FAM == FAM_BINOM) {
-                    // log(1 + e^eta) without overflow; p = e^eta / (1 + e^eta); t = e^-|eta| serves both
-                    const double t = exp(-fabs(eta));
-                    acc[b][0] += ys * eta - ns * (fmax(eta, 0.0) + log1p(t));
+                    // log(1 + e^eta) = max(eta, 0) + L(|eta|); p = expit(eta) = 1 + L'(|eta|) for eta >= 0, -L'(|eta|) below
+                    double dL;
+                    const double Lt = softplus_tail<(MODE >= 1)>(stab, eta, dL);
+                    acc[b][0] += ys * eta - ns * (fmax(eta, 0.0) + Lt);
                     if (MODE >= 1) {
-                        const double inv = 1.0 / (1.0 + t);
-                        const double pz = eta >= 0.0 ? inv : t * inv;
+                        const double pz = eta >= 0.0 ? 1.0 + dL : -dL;
                         mu = ns * pz;
                         v = -ns * pz * (1.0 - pz);   // -n p (1 - p): R/mcl.bin.R:262,268
                     }
@@ -211,6 +271,12 @@ int glm_data_terms(mclcar_ctx* ctx, const mclcar_samples* s, int fam, const std:
     chunks = (n + chunk - 1) / chunk;
     const EdgeCache* ec = nullptr;
     if (d_static) MCL_TRY(edge_cache_get(ctx, n, ctx->rowptr, ctx->colidx, ctx->val, &ec));
+    if (fam == FAM_BINOM && !ctx->d_sptab.p) {
+        const std::vector<double>& tab = softplus_table();
+        MCL_TRY(ensure(ctx, ctx->d_sptab, tab.size() * sizeof(double)));
+        MCL_CUDA(ctx, cudaMemcpyAsync(ctx->d_sptab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     double* d_beta = nullptr;
     MCL_TRY(pool_alloc(ctx, (void**)&d_beta, betas.size() * sizeof(double)));
     MCL_CUDA(ctx, cudaMemcpyAsync(d_beta, betas.data(), betas.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -222,6 +288,7 @@ int glm_data_terms(mclcar_ctx* ctx, const mclcar_samples* s, int fam, const std:
     for (int b0 = 0; b0 < nb_total && st == MCLCAR_OK; b0 += BT) {
         GlmTermsParams prm{};
         prm.M = s->d_M; prm.ld = s->ld; prm.N = N; prm.n = n; prm.p = p;
+        prm.sptab = (const double*)ctx->d_sptab.p;
         prm.X = ctx->d_X; prm.y = ctx->d_y; prm.nt = ctx->d_ntrial;
         prm.beta = d_beta + (size_t)b0 * p; prm.nb = std::min(BT, nb_total - b0);
         prm.chunk = chunk; prm.ldq = ldq; prm.ns = ns;
@@ -555,6 +622,19 @@ int mclcar_glm_grad(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K
 }
 int mclcar_glm_hess(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K, int P, int shift_mode, double* hess) {
     return glm_run(ctx, s, psi, K, P, WHAT_HESS, 0, nullptr, nullptr, shift_mode, hess, nullptr);
+}
+
+/* diagnostic: L(|eta|) = log1p(exp(-|eta|)) and its derivative from the table the binomial data-term kernel uses,
+ * evaluated on the host with the kernel's arithmetic (pure host code; tests/test_abi_host.py checks it against libm) */
+int mclcar_glm_softplus_table_eval(const double* eta, int64_t n, double* L_out, double* dL_out) {
+    if (!eta || !L_out || n < 0) return MCLCAR_EINVAL;
+    const std::vector<double>& tab = softplus_table();
+    for (int64_t i = 0; i < n; ++i) {
+        double d;
+        L_out[i] = softplus_tail<true>(tab.data(), eta[i], d);
+        if (dL_out) dL_out[i] = d;
+    }
+    return MCLCAR_OK;
 }
 
 /* Monte Carlo likelihood surface of the GLM: mcl.glm(c(rho_i, sigma_j, beta), mcdata, family, Evar = TRUE) on the grid

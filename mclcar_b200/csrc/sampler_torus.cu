@@ -38,6 +38,7 @@ struct TorusSweepParams {
     float* black_out;
     int n1, h;     // h = n2 / 2
     int G;         // Philox blocks per row = ceil(hv / 2), hv = h / 4 column vectors: block g serves vectors g and g + G
+    uint32_t Gmagic;  // floor(2^32 / G) + 1: t / G == umulhi(t, Gmagic) for every item index t of a tile (checked on the host)
     int64_t C;
     // over-relaxed Gibbs update  x' = keep*x + gain*(sum of neighbours) + noise*z  with
     // keep = 1 - omega, gain = omega*rho, noise = sqrt(omega (2 - omega) sigma); omega = 1 is plain Gibbs
@@ -89,8 +90,9 @@ __device__ __forceinline__ Pair bm_pair(const uint32_t w, const float rad2) {
         return p;
     }
     p.r = sqrt_approx(rad2 * lg2_approx(u01(w)));
-    // (k + 1/2) / 512, k = low 9 bits: mantissa bits 22..14 and the half-step bit 13, exponent of 1.0
-    const float u = __uint_as_float(((w << 14) & 0x007fc000u) | 0x3f802000u) - 1.0f;
+    // 1 + (k + 1/2) / 512, k = low 9 bits: mantissa bits 22..14 and the half-step bit 13, exponent of 1.0 -- the angle
+    // 2 pi u runs over [2 pi, 4 pi): sin and cos do not care about the whole turn, and the subtraction is saved
+    const float u = __uint_as_float(((w << 14) & 0x007fc000u) | 0x3f802000u);
     sincos_approx(6.2831853071795865f * u, p.s, p.c);
     return p;
 }
@@ -352,8 +354,8 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
     }
 }
 
-template <bool SOR, int EMIT, typename TO>
-__global__ void __launch_bounds__(kFusedMaxThreads, EMIT == 2 ? 2 : 3) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
+template <bool SOR, int EMIT, typename TO, int MINB>
+__global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
     extern __shared__ __align__(128) float fsm[];
     const int h = p.h, n1 = p.n1, hv = h >> 2, G = p.G;
     const int r0 = blockIdx.x * TR;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, EMIT == 2 ? 2 : 3) gibbs_tor
         for (int t0 = 0; t0 < items; t0 += blockDim.x) {         // uniform trip count: the items shuffle within their warp
             const int t = t0 + threadIdx.x;
             const bool valid = t < items;
-            const int q = valid ? t / G : 0, g = valid ? t - q * G : 0;
+            const int q = valid ? (int)__umulhi((uint32_t)t, p.Gmagic) : 0, g = valid ? t - q * G : 0;
             const int lA = 2 * q;                              // local red row of A; its black row in sB is lA + 1
             int iA = r0 - 1 + lA;
             iA = iA < 0 ? iA + n1 : iA;                        // only the first tile wraps at the top,
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, EMIT == 2 ? 2 : 3) gibbs_tor
         for (int t0 = 0; t0 < items; t0 += blockDim.x) {
             const int t = t0 + threadIdx.x;
             const bool valid = t < items;
-            const int q = valid ? t / G : 0, g = valid ? t - q * G : 0;
+            const int q = valid ? (int)__umulhi((uint32_t)t, p.Gmagic) : 0, g = valid ? t - q * G : 0;
             const int tA = 2 * q;
             const int iA = r0 + tA, iB = iA + 1;
             TO* erow = nullptr;
@@ -571,15 +573,25 @@ void torus_chains_free(mclcar_ctx* ctx, TorusChains& t) {
     t.red = t.black = t.red2 = t.black2 = nullptr;
 }
 
-// tile height of the fused sweep for this context's lattice (0: the fused sweep does not apply).  Three CTAs
-// of <= 72 KB per SM; even, so that every tile starts at an even row (row-pair work items)
+// resident CTAs per SM the fused sweep is built for: 3 (<= 72 KB of tile each, up to 80 registers) or 4 (<= 54 KB,
+// 64 registers: more warps to hide the latency of the dependent Philox / Box-Muller chains, shorter tiles)
+int torus_fused_ctas() {
+    if (const char* e = getenv("MCLCAR_SWEEP_CTAS")) {
+        const int v = atoi(e);
+        if (v == 3 || v == 4) return v;
+    }
+    return 3;
+}
+
+// tile height of the fused sweep for this context's lattice (0: the fused sweep does not apply); even, so that every
+// tile starts at an even row (row-pair work items)
 int torus_fused_tile_rows(const mclcar_ctx* ctx) {
     const int h = ctx->n2 / 2;
     if (ctx->n1 % 2 != 0 || ctx->n2 % 2 != 0 || h % 4 != 0) return 0;
     const char* fe = getenv("MCLCAR_SWEEP_FUSED");  // read per call: tests toggle it (0 = two half-sweep launches)
     if (fe && atoi(fe) == 0) return 0;
     const size_t row_b = (size_t)h * 4;
-    int TR = (int)((72 * 1024 / row_b - 6) / 2);
+    int TR = (int)(((torus_fused_ctas() == 4 ? 54 : 72) * 1024 / row_b - 6) / 2);
     TR = std::min(TR, 64) & ~1;
     if (const char* e = getenv("MCLCAR_SWEEP_TR")) {
         const int v = atoi(e);
@@ -632,18 +644,29 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
             p.red_out = t.red2; p.black_out = t.black2;
             std::swap(t.red, t.red2);        // the output pair is the current state from now on
             std::swap(t.black, t.black2);
+            const int nctas = torus_fused_ctas();
+            {   // item index -> (row pair, block) by a multiply: exact for every index a tile can have
+                p.Gmagic = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)p.G) + 1u;
+                const uint32_t tmax = (uint32_t)(((TR + 2) / 2) * p.G + kFusedMaxThreads);
+                if ((uint64_t)tmax * p.G >= ((uint64_t)1 << 32)) return fail(ctx, MCLCAR_ELIMIT, "lattice row too long for the fused sweep");
+            }
             int fthreads = 256;
             if (const char* e = getenv("MCLCAR_SWEEP_THREADS")) fthreads = std::min(std::max(atoi(e), 64), kFusedMaxThreads) & ~31;
             const size_t smem = (size_t)(2 * TR + 6) * row_b + 64 + (kFusedMaxThreads / 32) * 3 * sizeof(double);
             dim3 grid(tiles, (unsigned)t.C);
+#define LAUNCH_FUSED_B(S, E, TO_, B_)                                                                            \
+    do {                                                                                                         \
+        MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gibbs_torus_sweep_fused<S, E, TO_, B_><<<grid, fthreads, smem, ctx->stream>>>(p, TR);                   \
+    } while (0)
 #define LAUNCH_FUSED(S, E, TO_)                                                                                  \
     do {                                                                                                         \
-        MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gibbs_torus_sweep_fused<S, E, TO_><<<grid, fthreads, smem, ctx->stream>>>(p, TR);                       \
+        if (nctas == 4) LAUNCH_FUSED_B(S, E, TO_, 4);                                                            \
+        else LAUNCH_FUSED_B(S, E, TO_, 3);                                                                       \
     } while (0)
             if (want_stats) {
-                if (sor) LAUNCH_FUSED(true, 2, float);
-                else LAUNCH_FUSED(false, 2, float);
+                if (sor) LAUNCH_FUSED_B(true, 2, float, 2);      // fp64 accumulators: two CTAs per SM
+                else LAUNCH_FUSED_B(false, 2, float, 2);
             } else if (emit) {
                 if (sor && f32) LAUNCH_FUSED(true, 1, float);
                 else if (sor) LAUNCH_FUSED(true, 1, double);
@@ -654,6 +677,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
                 else LAUNCH_FUSED(false, 0, float);
             }
 #undef LAUNCH_FUSED
+#undef LAUNCH_FUSED_B
             MCL_CUDA(ctx, cudaGetLastError());
             if (want_stats) {
                 StatFinishParams f{};

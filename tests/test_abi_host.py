@@ -211,6 +211,28 @@ def test_profile_and_exact_likelihood_on_host_context():
     assert api.loglik_dCAR(psis[0][:2], data) == pytest.approx(dcar.loglik_dCAR(psis[0][:2], odata, eig), rel=1e-12)
 
 
+def test_softplus_table_of_the_binomial_data_term():
+    """The binomial data-term kernel evaluates log(1 + e^eta) = max(eta, 0) + L(|eta|), L(a) = log1p(e^-a), and
+    expit = 1 + L' from a piecewise degree-8 table instead of exp / log1p / divide (R/mcl.bin.R:54-59,188-196 need
+    sum n log(1 + e^eta) and n expit(eta)).  The table, evaluated on the host with the kernel's arithmetic, against
+    extended precision: 2e-15 absolute on L, 1e-12 on the derivative, everywhere including the clamped tail."""
+    rng = np.random.default_rng(1)
+    eta = np.concatenate([rng.uniform(-45, 45, 200_000), rng.normal(0, 2, 100_000), np.arange(0, 40.25, 0.25),
+                          np.nextafter(np.arange(0.25, 40.25, 0.25), 0), [0.0, -0.0, 39.999999, 40.0, 700.0, -700.0, np.inf]])
+    Lh, dL = np.empty_like(eta), np.empty_like(eta)
+    assert L.lib.mclcar_glm_softplus_table_eval(L.dptr(eta), eta.size, L.dptr(Lh), L.dptr(dL)) == L.OK
+    a = np.abs(eta).astype(np.longdouble)
+    ref = np.log1p(np.exp(-a))
+    dref = -np.exp(-a) / (1 + np.exp(-a))
+    assert np.max(np.abs(Lh - ref)) < 2e-15
+    assert np.max(np.abs(dL - dref)) < 1e-12
+    # what the kernel forms from it
+    sp = np.maximum(eta[:-1], 0) + Lh[:-1]
+    np.testing.assert_allclose(sp, np.logaddexp(0, eta[:-1].astype(np.longdouble)).astype(float), rtol=1e-15, atol=2e-15)
+    pz = np.where(eta >= 0, 1 + dL, -dL)
+    np.testing.assert_allclose(pz, (1 / (1 + np.exp(-eta.astype(np.longdouble)))).astype(float), atol=1e-12)
+
+
 def test_exact_hessian_on_host_context():
     """Hessian.dCAR (R/loglik.dCAR.R:171-219) from the design constants, the statistics of y and the analytic torus
     spectrum against the oracle's literal dense restatement (with the rho-beta block as coded, :198); P = 2 + p and P = 2."""
