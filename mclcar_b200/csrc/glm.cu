@@ -85,6 +85,34 @@ __host__ __device__ __forceinline__ double softplus_tail(const double* __restric
     return p;
 }
 
+// The candidate betas of a tile are close (line-search points, Jacobian columns): for one (sample, site) their eta
+// almost always fall into the same table interval.  The row is therefore kept in registers across the tile's betas
+// and re-read only by the lanes whose interval changed: ~1 row read per (sample, site) instead of one per beta --
+// the pass is then bound by its 8 (16 with the derivative) DFMA per evaluation, not by shared-memory reads.
+struct SoftplusRow {
+    int k = -1;
+    double c[kSpRow];
+};
+template <bool WANT_D>
+__device__ __forceinline__ double softplus_tail_cached(const double* __restrict__ tab, SoftplusRow& row, double eta, double& dL) {
+    const double a = fmin(fabs(eta), kSpMax);
+    const int k = (int)(a * 4.0);
+    if (k != row.k) {
+        row.k = k;
+#pragma unroll
+        for (int j = 0; j < kSpRow; ++j) row.c[j] = tab[k * kSpRow + j];
+    }
+    const double t = fma(a, 8.0, -(double)(2 * k + 1));
+    double p = row.c[kSpDeg], dp = 0.0;
+#pragma unroll
+    for (int j = kSpDeg - 1; j >= 0; --j) {
+        if (WANT_D) dp = fma(dp, t, p);
+        p = fma(p, t, row.c[j]);
+    }
+    dL = 8.0 * dp;
+    return p;
+}
+
 struct GlmTermsParams {
     const double* sptab;  // softplus table (device), kSpIntervals x kSpRow
     const void* M;  // [n][ld] site-major
@@ -141,6 +169,7 @@ __global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParam
         double xr[PT];
 #pragma unroll
         for (int a = 0; a < PT; ++a) xr[a] = a < prm.p ? __ldg(prm.X + (size_t)a * prm.n + s) : 0.0;
+        SoftplusRow sprow;
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
             if (b < prm.nb) {
@@ -151,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParam
                 if (FAM == FAM_BINOM) {
                     // log(1 + e^eta) = max(eta, 0) + L(|eta|); p = expit(eta) = 1 + L'(|eta|) for eta >= 0, -L'(|eta|) below
                     double dL;
-                    const double Lt = softplus_tail<(MODE >= 1)>(stab, eta, dL);
+                    const double Lt = softplus_tail_cached<(MODE >= 1)>(stab, sprow, eta, dL);
                     acc[b][0] += ys * eta - ns * (fmax(eta, 0.0) + Lt);
                     if (MODE >= 1) {
                         const double pz = eta >= 0.0 ? 1.0 + dL : -dL;

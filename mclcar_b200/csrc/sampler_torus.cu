@@ -573,25 +573,16 @@ void torus_chains_free(mclcar_ctx* ctx, TorusChains& t) {
     t.red = t.black = t.red2 = t.black2 = nullptr;
 }
 
-// resident CTAs per SM the fused sweep is built for: 3 (<= 72 KB of tile each, up to 80 registers) or 4 (<= 54 KB,
-// 64 registers: more warps to hide the latency of the dependent Philox / Box-Muller chains, shorter tiles)
-int torus_fused_ctas() {
-    if (const char* e = getenv("MCLCAR_SWEEP_CTAS")) {
-        const int v = atoi(e);
-        if (v == 3 || v == 4) return v;
-    }
-    return 3;
-}
-
-// tile height of the fused sweep for this context's lattice (0: the fused sweep does not apply); even, so that every
-// tile starts at an even row (row-pair work items)
+// tile height of the fused sweep for this context's lattice (0: the fused sweep does not apply).  Three CTAs of <= 72 KB
+// per SM (a 4-CTA build at 64 registers and 10-row tiles measured 17 % slower: profiles/r02_sweep_experiments.md); even,
+// so that every tile starts at an even row (row-pair work items)
 int torus_fused_tile_rows(const mclcar_ctx* ctx) {
     const int h = ctx->n2 / 2;
     if (ctx->n1 % 2 != 0 || ctx->n2 % 2 != 0 || h % 4 != 0) return 0;
     const char* fe = getenv("MCLCAR_SWEEP_FUSED");  // read per call: tests toggle it (0 = two half-sweep launches)
     if (fe && atoi(fe) == 0) return 0;
     const size_t row_b = (size_t)h * 4;
-    int TR = (int)(((torus_fused_ctas() == 4 ? 54 : 72) * 1024 / row_b - 6) / 2);
+    int TR = (int)((72 * 1024 / row_b - 6) / 2);
     TR = std::min(TR, 64) & ~1;
     if (const char* e = getenv("MCLCAR_SWEEP_TR")) {
         const int v = atoi(e);
@@ -644,7 +635,6 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
             p.red_out = t.red2; p.black_out = t.black2;
             std::swap(t.red, t.red2);        // the output pair is the current state from now on
             std::swap(t.black, t.black2);
-            const int nctas = torus_fused_ctas();
             {   // item index -> (row pair, block) by a multiply: exact for every index a tile can have
                 p.Gmagic = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)p.G) + 1u;
                 const uint32_t tmax = (uint32_t)(((TR + 2) / 2) * p.G + kFusedMaxThreads);
@@ -659,11 +649,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
         MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         gibbs_torus_sweep_fused<S, E, TO_, B_><<<grid, fthreads, smem, ctx->stream>>>(p, TR);                   \
     } while (0)
-#define LAUNCH_FUSED(S, E, TO_)                                                                                  \
-    do {                                                                                                         \
-        if (nctas == 4) LAUNCH_FUSED_B(S, E, TO_, 4);                                                            \
-        else LAUNCH_FUSED_B(S, E, TO_, 3);                                                                       \
-    } while (0)
+#define LAUNCH_FUSED(S, E, TO_) LAUNCH_FUSED_B(S, E, TO_, 3)
             if (want_stats) {
                 if (sor) LAUNCH_FUSED_B(true, 2, float, 2);      // fp64 accumulators: two CTAs per SM
                 else LAUNCH_FUSED_B(false, 2, float, 2);
