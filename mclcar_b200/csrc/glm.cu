@@ -15,6 +15,7 @@
 // candidate betas, lane = sample, fp64 exp / log1p.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -86,31 +87,51 @@ __host__ __device__ __forceinline__ double softplus_tail(const double* __restric
 }
 
 // The candidate betas of a tile are close (line-search points, Jacobian columns): for one (sample, site) their eta
-// almost always fall into the same table interval.  The row is therefore kept in registers across the tile's betas
-// and re-read only by the lanes whose interval changed: ~1 row read per (sample, site) instead of one per beta --
-// the pass is then bound by its 8 (16 with the derivative) DFMA per evaluation, not by shared-memory reads.
-struct SoftplusRow {
-    int k = -1;
-    double c[kSpRow];
-};
-template <bool WANT_D>
-__device__ __forceinline__ double softplus_tail_cached(const double* __restrict__ tab, SoftplusRow& row, double eta, double& dL) {
-    const double a = fmin(fabs(eta), kSpMax);
-    const int k = (int)(a * 4.0);
-    if (k != row.k) {
-        row.k = k;
+// almost always fall into the same table interval.  All betas of the tile are therefore evaluated together: one row
+// read serves them all and their Horner chains interleave (eight independent DFMA chains instead of one dependent
+// chain per beta behind a branch); only the lanes where the intervals differ read a row per beta.
+template <int BT, bool WANT_D>
+__device__ __forceinline__ void softplus_tail_tile(const double* __restrict__ tab, const double (&eta)[BT], double (&L)[BT],
+                                                   double (&dL)[BT]) {
+    double t[BT];
+    int k[BT];
+    bool same = true;
 #pragma unroll
-        for (int j = 0; j < kSpRow; ++j) row.c[j] = tab[k * kSpRow + j];
+    for (int b = 0; b < BT; ++b) {
+        double a = fabs(eta[b]);
+        if (__double2hiint(a) >= 0x40440000) a = kSpMax;        // a >= 40 (or NaN): L = 0 to 4e-18; integer compare of the high word
+        k[b] = (int)(a * 4.0);
+        t[b] = fma(a, 8.0, -(double)(2 * k[b] + 1));
+        same = same && k[b] == k[0];
     }
-    const double t = fma(a, 8.0, -(double)(2 * k + 1));
-    double p = row.c[kSpDeg], dp = 0.0;
+    double p[BT], dp[BT];
+    if (same) {
+        double c[kSpRow];
 #pragma unroll
-    for (int j = kSpDeg - 1; j >= 0; --j) {
-        if (WANT_D) dp = fma(dp, t, p);
-        p = fma(p, t, row.c[j]);
+        for (int j = 0; j < kSpRow; ++j) c[j] = tab[k[0] * kSpRow + j];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) { p[b] = c[kSpDeg]; dp[b] = 0.0; }
+#pragma unroll
+        for (int j = kSpDeg - 1; j >= 0; --j)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                if (WANT_D) dp[b] = fma(dp[b], t[b], p[b]);
+                p[b] = fma(p[b], t[b], c[j]);
+            }
+    } else {
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            const double* c = tab + k[b] * kSpRow;
+            p[b] = c[kSpDeg]; dp[b] = 0.0;
+#pragma unroll
+            for (int j = kSpDeg - 1; j >= 0; --j) {
+                if (WANT_D) dp[b] = fma(dp[b], t[b], p[b]);
+                p[b] = fma(p[b], t[b], c[j]);
+            }
+        }
     }
-    dL = 8.0 * dp;
-    return p;
+#pragma unroll
+    for (int b = 0; b < BT; ++b) { L[b] = p[b]; dL[b] = 8.0 * dp[b]; }
 }
 
 struct GlmTermsParams {
@@ -137,9 +158,8 @@ struct GlmTermsParams {
 };
 
 // MODE 0: D only; 1: D + gradient; 2: D + gradient + Hessian block
-template <typename T, int FAM, int PT, int MODE, bool STATS>
+template <typename T, int FAM, int PT, int MODE, bool STATS, int BT>
 __global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParams prm) {
-    constexpr int BT = tile_of(MODE);
     constexpr int NH = PT * (PT + 1) / 2;
     constexpr int NS = 1 + (MODE >= 1 ? PT : 0) + (MODE >= 2 ? NH : 0);
     __shared__ double sbeta[BT * PT];
@@ -169,21 +189,25 @@ __global__ void __launch_bounds__(kThreads) glm_terms_kernel(const GlmTermsParam
         double xr[PT];
 #pragma unroll
         for (int a = 0; a < PT; ++a) xr[a] = a < prm.p ? __ldg(prm.X + (size_t)a * prm.n + s) : 0.0;
-        SoftplusRow sprow;
+        double etas[BT], Lt[BT], dLt[BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {          // slots beyond nb hold beta = 0: computed, never stored
+            etas[b] = z;
+#pragma unroll
+            for (int a = 0; a < PT; ++a) etas[b] = fma(xr[a], sbeta[b * PT + a], etas[b]);
+        }
+        if (FAM == FAM_BINOM) softplus_tail_tile<BT, (MODE >= 1)>(stab, etas, Lt, dLt);
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
             if (b < prm.nb) {
-                double eta = z;
-#pragma unroll
-                for (int a = 0; a < PT; ++a) eta = fma(xr[a], sbeta[b * PT + a], eta);
+                const double eta = etas[b];
                 double mu, v;
                 if (FAM == FAM_BINOM) {
-                    // log(1 + e^eta) = max(eta, 0) + L(|eta|); p = expit(eta) = 1 + L'(|eta|) for eta >= 0, -L'(|eta|) below
-                    double dL;
-                    const double Lt = softplus_tail_cached<(MODE >= 1)>(stab, sprow, eta, dL);
-                    acc[b][0] += ys * eta - ns * (fmax(eta, 0.0) + Lt);
+                    // log(1 + e^eta) = max(eta, 0) + L(|eta|), max(eta, 0) = (eta + |eta|)/2;
+                    // p = expit(eta) = 1 + L'(|eta|) for eta >= 0, -L'(|eta|) below
+                    acc[b][0] += ys * eta - ns * (0.5 * (eta + fabs(eta)) + Lt[b]);
                     if (MODE >= 1) {
-                        const double pz = eta >= 0.0 ? 1.0 + dL : -dL;
+                        const double pz = eta >= 0.0 ? 1.0 + dLt[b] : -dLt[b];
                         mu = ns * pz;
                         v = -ns * pz * (1.0 - pz);   // -n p (1 - p): R/mcl.bin.R:262,268
                     }
@@ -267,9 +291,12 @@ __global__ void glm_chunk_sum_kernel(const double* partial, double* q, int S, in
 
 template <typename T, int FAM, int PT, bool STATS>
 void launch_mode(const GlmTermsParams& p, int mode, dim3 grid, cudaStream_t st) {
-    if (mode == 0) glm_terms_kernel<T, FAM, PT, 0, STATS><<<grid, kThreads, 0, st>>>(p);
-    else if (mode == 1) glm_terms_kernel<T, FAM, PT, 1, STATS><<<grid, kThreads, 0, st>>>(p);
-    else glm_terms_kernel<T, FAM, PT, 2, STATS><<<grid, kThreads, 0, st>>>(p);
+    // a tile's slots are all evaluated: log-ratio passes with one or two betas (lHZy.psi, the tail of a batch) take the
+    // two-slot build
+    if (mode == 0 && p.nb <= 2) glm_terms_kernel<T, FAM, PT, 0, STATS, 2><<<grid, kThreads, 0, st>>>(p);
+    else if (mode == 0) glm_terms_kernel<T, FAM, PT, 0, STATS, tile_of(0)><<<grid, kThreads, 0, st>>>(p);
+    else if (mode == 1) glm_terms_kernel<T, FAM, PT, 1, STATS, tile_of(1)><<<grid, kThreads, 0, st>>>(p);
+    else glm_terms_kernel<T, FAM, PT, 2, STATS, tile_of(2)><<<grid, kThreads, 0, st>>>(p);
 }
 template <typename T, int FAM, bool STATS>
 void launch_p(const GlmTermsParams& p, int mode, dim3 grid, cudaStream_t st) {
@@ -294,7 +321,10 @@ int glm_data_terms(mclcar_ctx* ctx, const mclcar_samples* s, int fam, const std:
     const int BT = tile_of(mode);
     const int64_t N = s->N;
     const int64_t xblocks = (N + kThreads - 1) / kThreads;
-    int chunks = (int)std::max<int64_t>(1, ((int64_t)4 * ctx->n_sm + xblocks - 1) / xblocks);
+    // site chunks: eight CTAs (32 warps) per SM in ONE balanced wave -- the Horner chains are latency-bound with fewer
+    // warps, and a grid of 4.3 CTAs per SM (chunks from 4 x SMs) left a fifth of the machine idle in its last wave
+    int chunks = (int)std::max<int64_t>(1, ((int64_t)8 * ctx->n_sm + xblocks / 2) / xblocks);
+    if (const char* e = getenv("MCLCAR_GLM_CHUNKS")) chunks = std::max(1, atoi(e));
     chunks = std::min(chunks, std::max(1, n / 32));
     const int chunk = (n + chunks - 1) / chunks;
     chunks = (n + chunk - 1) / chunk;
