@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "engine.hpp"
 
@@ -164,27 +165,83 @@ static int upload(mclcar_ctx* ctx, T*& dptr, const std::vector<T>& h) {
     return MCLCAR_OK;
 }
 
-// dot product with four independent accumulators (vectorises; error ~ sqrt(n) eps)
-static double dot4(const double* a, const double* b, int n) {
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int i = 0;
-    for (; i + 3 < n; i += 4) {
-        s0 += a[i] * b[i];
-        s1 += a[i + 1] * b[i + 1];
-        s2 += a[i + 2] * b[i + 2];
-        s3 += a[i + 3] * b[i + 3];
+template <typename T>
+static int upload_from(mclcar_ctx* ctx, T*& dptr, const T* src, size_t count) {   // straight from the caller's buffer (fast when it is pinned)
+    if (ctx->host_only) return MCLCAR_OK;
+    if (dptr) {
+        pool_free(ctx, dptr);
+        dptr = nullptr;
     }
-    for (; i < n; ++i) s0 += a[i] * b[i];
-    return (s0 + s1) + (s2 + s3);
+    if (!count) return MCLCAR_OK;
+    MCL_TRY(pool_alloc(ctx, (void**)&dptr, count * sizeof(T)));
+    MCL_CUDA(ctx, cudaMemcpyAsync(dptr, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    MCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MCLCAR_OK;
 }
 
-// y = W x on the host CSR copy
-static void spmv(const mclcar_ctx* c, const double* x, double* y) {
-    for (int i = 0; i < c->n; ++i) {
-        double a = 0.0;
-        for (int e = c->rowptr[i]; e < c->rowptr[i + 1]; ++e) a += (c->binary ? 1.0 : c->val[e]) * x[c->colidx[e]];
-        y[i] = a;
+// The host algebra of set_design / set_obs (W X, X'X, X'WX, the statistics of y) is O(n) per call and sits in every
+// end-to-end step: large lattices split it over a FIXED number of index ranges (results do not depend on the number
+// of host threads that happen to run them), each range on its own thread.
+constexpr int kHostParts = 8;
+template <class Fn>
+static void host_parts(int n, Fn fn) {   // fn(part, begin, end)
+    if (n < (1 << 17)) {
+        for (int k = 0; k < kHostParts; ++k) fn(k, (int)((int64_t)n * k / kHostParts), (int)((int64_t)n * (k + 1) / kHostParts));
+        return;
     }
+    std::vector<std::thread> th;
+    for (int k = 0; k < kHostParts; ++k)
+        th.emplace_back([=] { fn(k, (int)((int64_t)n * k / kHostParts), (int)((int64_t)n * (k + 1) / kHostParts)); });
+    for (auto& t : th) t.join();
+}
+
+// dot product: four independent accumulators per index range (vectorises; error ~ sqrt(n) eps), ranges added in order
+static double dot4(const double* a, const double* b, int n) {
+    double part[kHostParts];
+    host_parts(n, [&](int k, int i0, int i1) {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        int i = i0;
+        for (; i + 3 < i1; i += 4) {
+            s0 += a[i] * b[i];
+            s1 += a[i + 1] * b[i + 1];
+            s2 += a[i + 2] * b[i + 2];
+            s3 += a[i + 3] * b[i + 3];
+        }
+        for (; i < i1; ++i) s0 += a[i] * b[i];
+        part[k] = (s0 + s1) + (s2 + s3);
+    });
+    double s = 0;
+    for (int k = 0; k < kHostParts; ++k) s += part[k];
+    return s;
+}
+
+// y = W x on the host: the rook torus as a stencil (no index loads), anything else through the CSR copy
+static void spmv(const mclcar_ctx* c, const double* x, double* y) {
+    if (c->kind == GRAPH_TORUS) {
+        const int n1 = c->n1, n2 = c->n2;
+        host_parts(n1, [&](int, int r0, int r1) {
+            for (int i = r0; i < r1; ++i) {
+                const double* row = x + (size_t)i * n2;
+                const double* up = x + (size_t)(i == 0 ? n1 - 1 : i - 1) * n2;
+                const double* dn = x + (size_t)(i + 1 == n1 ? 0 : i + 1) * n2;
+                double* o = y + (size_t)i * n2;
+                // same association as the CSR row (columns in increasing order) is not needed: W x is exact to rounding
+                // either way, and every consumer takes it through tolerance-checked sums
+                for (int j = 0; j < n2; ++j) {
+                    const int jl = j == 0 ? n2 - 1 : j - 1, jr = j + 1 == n2 ? 0 : j + 1;
+                    o[j] = (row[jl] + row[jr]) + (up[j] + dn[j]);
+                }
+            }
+        });
+        return;
+    }
+    host_parts(c->n, [&](int, int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+            double a = 0.0;
+            for (int e = c->rowptr[i]; e < c->rowptr[i + 1]; ++e) a += (c->binary ? 1.0 : c->val[e]) * x[c->colidx[e]];
+            y[i] = a;
+        }
+    });
 }
 
 static void invalidate_model(mclcar_ctx* ctx) {
@@ -565,7 +622,7 @@ int mclcar_set_design(mclcar_ctx* ctx, const double* X, int p) {
             ctx->G0[(size_t)a * p + b] = dot4(xa, xb, n);
             ctx->G1[(size_t)a * p + b] = dot4(xa, wb, n);
         }
-    MCL_TRY(upload(ctx, ctx->d_X, ctx->X));
+    MCL_TRY(upload_from(ctx, ctx->d_X, X, (size_t)n * p));
     MCL_TRY(upload(ctx, ctx->d_WX, ctx->WX));
     ctx->has_design = true;
     ctx->has_obs = false;  // qobs depends on X
@@ -583,7 +640,8 @@ int mclcar_set_obs(mclcar_ctx* ctx, const double* y, const double* ntrial) {
     ctx->y.assign(y, y + n);
     if (ntrial) ctx->ntrial.assign(ntrial, ntrial + n);
     else ctx->ntrial.clear();
-    std::vector<double> Wy(n);
+    std::vector<double>& Wy = ctx->h_scratch;   // kept across calls: no 8 MB allocation and page faults per step
+    Wy.resize(n);
     spmv(ctx, ctx->y.data(), Wy.data());
     ctx->qobs.assign(2 + 2 * p, 0.0);
     ctx->qobs[0] = dot4(y, y, n);
@@ -593,7 +651,7 @@ int mclcar_set_obs(mclcar_ctx* ctx, const double* y, const double* ntrial) {
         ctx->qobs[2 + a] = dot4(xa, y, n);
         ctx->qobs[2 + p + a] = dot4(xa, Wy.data(), n);
     }
-    MCL_TRY(upload(ctx, ctx->d_y, ctx->y));
+    MCL_TRY(upload_from(ctx, ctx->d_y, y, (size_t)n));
     MCL_TRY(upload(ctx, ctx->d_ntrial, ctx->ntrial));
     ctx->has_obs = true;
     return MCLCAR_OK;

@@ -87,6 +87,7 @@ struct mclcar_ctx {
     bool has_obs = false;
     std::vector<double> y, ntrial;
     std::vector<double> qobs;  // (y'y, y'Wy, X'y[p], X'Wy[p])
+    std::vector<double> h_scratch;  // W y of the last set_obs (host scratch)
     double* d_y = nullptr;
     double* d_ntrial = nullptr;
 

@@ -321,9 +321,10 @@ int glm_data_terms(mclcar_ctx* ctx, const mclcar_samples* s, int fam, const std:
     const int BT = tile_of(mode);
     const int64_t N = s->N;
     const int64_t xblocks = (N + kThreads - 1) / kThreads;
-    // site chunks: eight CTAs (32 warps) per SM in ONE balanced wave -- the Horner chains are latency-bound with fewer
-    // warps, and a grid of 4.3 CTAs per SM (chunks from 4 x SMs) left a fifth of the machine idle in its last wave
-    int chunks = (int)std::max<int64_t>(1, ((int64_t)8 * ctx->n_sm + xblocks / 2) / xblocks);
+    // site chunks: ~16 CTAs per SM in the grid (six resident at 80 registers): the round-1 grid of 4.3 CTAs per SM left a
+    // fifth of the machine idle in its last wave; measured on config 3 (79 sample blocks): 8 chunks 6.4 ms per step,
+    // 15: 4.8, 30: 4.4, 45-60: 4.4
+    int chunks = (int)std::max<int64_t>(1, ((int64_t)16 * ctx->n_sm + xblocks / 2) / xblocks);
     if (const char* e = getenv("MCLCAR_GLM_CHUNKS")) chunks = std::max(1, atoi(e));
     chunks = std::min(chunks, std::max(1, n / 32));
     const int chunk = (n + chunks - 1) / chunks;
