@@ -347,7 +347,30 @@ int64_t tuple_len(int what, int F, int d) {
     }
 }
 
+static int run_reduce_body(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host, bool merge_ranks, bool* gathered);
+
+// A rank that fails on its own (a CUDA error, an allocation) before it reaches the tuple exchange must not leave the
+// other ranks waiting in ncclAllGather: it still takes part, with tuples of all-ones bytes (NaN), and every rank --
+// this one included -- returns an error for the batch.  (Argument errors are the same on every rank: the candidates
+// and the model are replicated, so those ranks all stop before the exchange.)
 int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host, bool merge_ranks) {
+    bool gathered = false;
+    const int st = run_reduce_body(ctx, plan, tuples_host, merge_ranks, &gathered);
+    if (st != MCLCAR_OK && merge_ranks && nccl_active(ctx) && !gathered) {
+        const std::string keep = ctx->err;
+        const int F = plan.what == WHAT_LR ? 0 : plan.F;
+        const size_t cnt = (size_t)plan.K * (size_t)tuple_len(plan.what, (F + 1) & ~1, plan.d);
+        if (ensure(ctx, ctx->d_tuples, cnt * sizeof(double)) == MCLCAR_OK &&
+            ensure(ctx, ctx->d_gather, (size_t)ctx->world * cnt * sizeof(double)) == MCLCAR_OK &&
+            cudaMemsetAsync(ctx->d_tuples.p, 0xFF, cnt * sizeof(double), ctx->stream) == cudaSuccess &&
+            nccl_all_gather_dev(ctx, (const double*)ctx->d_tuples.p, (double*)ctx->d_gather.p, cnt) == MCLCAR_OK)
+            cudaStreamSynchronize(ctx->stream);
+        ctx->err = keep;
+    }
+    return st;
+}
+
+static int run_reduce_body(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host, bool merge_ranks, bool* gathered) {
     MCL_TRY(require_device(ctx));
     const int K = plan.K, d = plan.d;
     const int F = plan.what == WHAT_LR ? 0 : plan.F;
@@ -476,6 +499,7 @@ int run_reduce(mclcar_ctx* ctx, ReducePlan& plan, double* tuples_host, bool merg
     const double* d_src = (const double*)ctx->d_tuples.p;
     if (merge) {
         MCL_TRY(ensure(ctx, ctx->d_gather, (size_t)G * cnt * sizeof(double)));
+        *gathered = true;
         MCL_TRY(nccl_all_gather_dev(ctx, (const double*)ctx->d_tuples.p, (double*)ctx->d_gather.p, cnt));
         d_src = (const double*)ctx->d_gather.p;
     }
