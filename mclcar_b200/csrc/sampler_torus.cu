@@ -85,10 +85,12 @@ struct Pair {
 
 __device__ __forceinline__ Pair bm_pair(const uint32_t w, const float rad2) {
     Pair p;
+#ifdef MCLCAR_SWEEP_EXPERIMENTS
     if (rad2 > 0.f) {   // experiment switch (MCLCAR_SWEEP_DRY=2): no transcendental work (rad2 is negative in real runs)
         p.r = rad2; p.s = __uint_as_float(w); p.c = 0.5f;
         return p;
     }
+#endif
     p.r = sqrt_approx(rad2 * lg2_approx(u01(w)));
     // 1 + (k + 1/2) / 512, k = low 9 bits: mantissa bits 22..14 and the half-step bit 13, exponent of 1.0 -- the angle
     // 2 pi u runs over [2 pi, 4 pi): sin and cos do not care about the whole turn, and the subtraction is saved
@@ -272,53 +274,74 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v4(const TorusSwee
 // rows, hence row A is always the row whose same-row neighbour sits at c + 1 (FWD) and row B the one with
 // c - 1, in both phases: no divergent code paths.
 // ---------------------------------------------------------------------------------------------
-// EMIT: 0 none, 1 the black phase also writes the finished samples, 2 it accumulates their statistics instead
+// Shared memory is addressed through explicit 32-bit shared-space addresses (ld.shared / st.shared): with generic
+// pointers the compiler re-derives the shared window for every access (the kernel uses the cluster-scoped bulk copy,
+// so the window depends on the CTA's place in its cluster) -- ~60 instructions per item in round 1's SASS.
+__device__ __forceinline__ float4 lds4(const uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds1(const uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts4(const uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// EMIT: 0 none, 1 the black phase also writes the finished samples, 2 it accumulates their statistics instead.
+// nm: shared address of row A of the OTHER colour (rows A-1, A, B, B+1 at nm - hb .. nm + 2 hb, hb = 4 h bytes);
+// own: shared address of row A of the colour being updated; gout: the output half-lattice of the chain, offA / offB
+// the element offsets of rows A and B in it (stA / stB: whether the row is stored -- halo rows are not).
 template <bool SOR, bool PH2, int EMIT, typename TO>
-__device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool valid, const float* __restrict__ nm,
-                                           float* __restrict__ ownA, float* __restrict__ goutA, float* __restrict__ goutB,
+__device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool valid, const uint32_t nm, const uint32_t own,
+                                           float* __restrict__ gout, const int offA, const int offB, const bool stA, const bool stB,
                                            TO* __restrict__ emitA, const double* __restrict__ muA, const uint32_t iA,
                                            const uint32_t iB, const int g, const int hv, const int h, const uint32_t c1,
                                            const uint32_t c2, const uint32_t c3, double (&acc)[3]) {
-    const int G = p.G, lane = threadIdx.x & 31;
+    const int G = p.G;
     const int gb = g + G;
     const bool two = valid && gb < hv;                        // the last block of a row may hold one vector only
     const int c0 = 4 * g, c1v = 4 * gb;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 a0 = valid ? ld4(nm + c0) : z4, b0 = valid ? ld4(nm + h + c0) : z4;   // rows A and B of the other colour
-    const float4 a1 = two ? ld4(nm + c1v) : z4, b1 = two ? ld4(nm + h + c1v) : z4;
-    // same-row neighbours: the next lane holds the next vector of the row (row A looks forward), the previous lane
-    // the previous one (row B looks backward) -- except at warp ends and where the lane's neighbour belongs to
-    // another row pair
-    float eA0 = __shfl_down_sync(0xffffffffu, a0.x, 1), eA1 = __shfl_down_sync(0xffffffffu, a1.x, 1);
-    float eB0 = __shfl_up_sync(0xffffffffu, b0.w, 1), eB1 = __shfl_up_sync(0xffffffffu, b1.w, 1);
+    const uint32_t hb = (uint32_t)h * 4u, b0a = (uint32_t)c0 * 4u, b1a = (uint32_t)c1v * 4u;   // byte offsets
     if (!valid) return;
-    if (lane == 31 || g + 1 >= G) eA0 = nm[g + 1 == hv ? 0 : c0 + 4];
-    if (two && (lane == 31 || g + 1 >= G || gb + 1 >= hv)) eA1 = nm[gb + 1 == hv ? 0 : c1v + 4];
-    if (lane == 0 || g == 0) eB0 = nm[h + (g == 0 ? h - 1 : c0 - 1)];
-    if (two && (lane == 0 || g == 0)) eB1 = nm[h + c1v - 1];
-    float* __restrict__ ownB = ownA + h;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a0 = lds4(nm + b0a), b0 = lds4(nm + hb + b0a);           // rows A and B of the other colour
+    const float4 a1 = two ? lds4(nm + b1a) : z4, b1 = two ? lds4(nm + hb + b1a) : z4;
+    // same-row neighbours beyond the vector: row A looks forward (c + 4, cyclic), row B backward (c - 1, cyclic)
+    const float eA0 = lds1(nm + (g + 1 == hv ? 0u : b0a + 16u));
+    const float eA1 = two ? lds1(nm + (gb + 1 == hv ? 0u : b1a + 16u)) : 0.f;
+    const float eB0 = lds1(nm + hb + (g == 0 ? hb - 4u : b0a - 4u));
+    const float eB1 = two ? lds1(nm + hb + b1a - 4u) : 0.f;
+    const uint32_t ownB = own + hb;
     const float m = (float)p.mu_const;
     // ---- row A
     {
+#ifdef MCLCAR_SWEEP_EXPERIMENTS
         const Philox4 blk = p.dry ? Philox4{0x80000000u + iA, 0xa0000000u + c1, 0x90000000u + (uint32_t)g, 0xc0000000u + c2}
                                   : philox4x32_10(iA * (uint32_t)G + (uint32_t)g, c1, c2, c3, p.keys);
+#else
+        const Philox4 blk = philox4x32_10(iA * (uint32_t)G + (uint32_t)g, c1, c2, c3, p.keys);
+#endif
         {
-            const float4 up = ld4(nm - h + c0);
-            const float4 cur = SOR ? ld4(ownA + c0) : z4;
+            const float4 up = lds4(nm - hb + b0a);
+            const float4 cur = SOR ? lds4(own + b0a) : z4;
             const float4 v = gibbs_update4<SOR, true>(a0, up, b0, eA0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
-            if (!PH2) st4(ownA + c0, v);
-            if (goutA) st4(goutA + c0, v);
+            if (!PH2) sts4(own + b0a, v);
+            if (stA) st4(gout + offA + c0, v);
             if (PH2 && EMIT == 1) {
                 if (emitA) emit8<TO>(p, emitA + 2 * c0, muA ? muA + 2 * c0 : nullptr, v, a0, (iA & 1u) != 0);
             }
             if (PH2 && EMIT == 2) stats8<true>(v, a0, up, b0, eA0, m, acc);
         }
         if (two) {
-            const float4 up = ld4(nm - h + c1v);
-            const float4 cur = SOR ? ld4(ownA + c1v) : z4;
+            const float4 up = lds4(nm - hb + b1a);
+            const float4 cur = SOR ? lds4(own + b1a) : z4;
             const float4 v = gibbs_update4<SOR, true>(a1, up, b1, eA1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
-            if (!PH2) st4(ownA + c1v, v);
-            if (goutA) st4(goutA + c1v, v);
+            if (!PH2) sts4(own + b1a, v);
+            if (stA) st4(gout + offA + c1v, v);
             if (PH2 && EMIT == 1) {
                 if (emitA) emit8<TO>(p, emitA + 2 * c1v, muA ? muA + 2 * c1v : nullptr, v, a1, (iA & 1u) != 0);
             }
@@ -327,25 +350,29 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
     }
     // ---- row B
     {
+#ifdef MCLCAR_SWEEP_EXPERIMENTS
         const Philox4 blk = p.dry ? Philox4{0x80000000u + iB, 0xa0000000u + c1, 0x90000000u + (uint32_t)g, 0xc0000000u + c2}
                                   : philox4x32_10(iB * (uint32_t)G + (uint32_t)g, c1, c2, c3, p.keys);
+#else
+        const Philox4 blk = philox4x32_10(iB * (uint32_t)G + (uint32_t)g, c1, c2, c3, p.keys);
+#endif
         {
-            const float4 dn = ld4(nm + 2 * h + c0);
-            const float4 cur = SOR ? ld4(ownB + c0) : z4;
+            const float4 dn = lds4(nm + 2u * hb + b0a);
+            const float4 cur = SOR ? lds4(ownB + b0a) : z4;
             const float4 v = gibbs_update4<SOR, false>(b0, a0, dn, eB0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
-            if (!PH2) st4(ownB + c0, v);
-            if (goutB) st4(goutB + c0, v);
+            if (!PH2) sts4(ownB + b0a, v);
+            if (stB) st4(gout + offB + c0, v);
             if (PH2 && EMIT == 1) {
                 if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c0, muA ? muA + 2 * h + 2 * c0 : nullptr, v, b0, (iB & 1u) != 0);
             }
             if (PH2 && EMIT == 2) stats8<false>(v, b0, a0, dn, eB0, m, acc);
         }
         if (two) {
-            const float4 dn = ld4(nm + 2 * h + c1v);
-            const float4 cur = SOR ? ld4(ownB + c1v) : z4;
+            const float4 dn = lds4(nm + 2u * hb + b1a);
+            const float4 cur = SOR ? lds4(ownB + b1a) : z4;
             const float4 v = gibbs_update4<SOR, false>(b1, a1, dn, eB1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
-            if (!PH2) st4(ownB + c1v, v);
-            if (goutB) st4(goutB + c1v, v);
+            if (!PH2) sts4(ownB + b1a, v);
+            if (stB) st4(gout + offB + c1v, v);
             if (PH2 && EMIT == 1) {
                 if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c1v, muA ? muA + 2 * h + 2 * c1v : nullptr, v, b1, (iB & 1u) != 0);
             }
@@ -370,6 +397,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
     float* sR = fsm + (size_t)(TR + 4) * h;                // [TR + 2][h]: red rows r0-1 ..
     uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + (size_t)(2 * TR + 6) * h);
     const uint32_t row_bytes = (uint32_t)h * 4u;
+    const uint32_t aB = smem_u32(sB), aR = smem_u32(sR);   // shared-space addresses
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -387,6 +415,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
         };
         copy_rows(sB, gblk, r0 - 2, rows + 4);
         copy_rows(sR, gred, r0 - 1, rows + 2);
+#ifdef MCLCAR_SWEEP_EXPERIMENTS
         if (p.prefetch_ahead > 0) {
             // warm L2 with the tile of the CTA that will follow this one onto the SM: CTAs are dispatched in linear
             // order, about (resident CTAs of the device) behind the running front
@@ -401,6 +430,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pr), "r"(row_bytes * (uint32_t)prow) : "memory");
             }
         }
+#endif
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -421,10 +451,10 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
             iA = iA < 0 ? iA + n1 : iA;                        // only the first tile wraps at the top,
             int iB = r0 + lA;
             iB = iB >= n1 ? iB - n1 : iB;                      // only the last tile at the bottom
-            float* goutA = lA >= 1 ? ored + (size_t)iA * h : nullptr;          // halo rows are recomputed, not stored
-            float* goutB = lA + 1 <= rows ? ored + (size_t)iB * h : nullptr;
-            fused_item<SOR, false, 0, TO>(p, valid, sB + (size_t)(lA + 1) * h, sR + (size_t)lA * h, goutA, goutB, nullptr, nullptr,
-                                          (uint32_t)iA, (uint32_t)iB, g, hv, h, p.sweep * 2u, c2, c3, acc);
+            // halo rows (the first A, the last B) are recomputed, not stored
+            fused_item<SOR, false, 0, TO>(p, valid, aB + (uint32_t)(lA + 1) * row_bytes, aR + (uint32_t)lA * row_bytes, ored, iA * h,
+                                          iB * h, lA >= 1, lA + 1 <= rows, nullptr, nullptr, (uint32_t)iA, (uint32_t)iB, g, hv, h,
+                                          p.sweep * 2u, c2, c3, acc);
         }
     }
     __syncthreads();
@@ -445,8 +475,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
                     if (p.mu != nullptr) mrow = p.mu + (size_t)iA * 2 * h;
                 }
             }
-            fused_item<SOR, true, EMIT, TO>(p, valid, sR + (size_t)(tA + 1) * h, sB + (size_t)(tA + 2) * h, oblk + (size_t)iA * h,
-                                            oblk + (size_t)iB * h, erow, mrow, (uint32_t)iA, (uint32_t)iB, g, hv, h,
+            fused_item<SOR, true, EMIT, TO>(p, valid, aR + (uint32_t)(tA + 1) * row_bytes, aB + (uint32_t)(tA + 2) * row_bytes, oblk,
+                                            iA * h, iB * h, true, true, erow, mrow, (uint32_t)iA, (uint32_t)iB, g, hv, h,
                                             p.sweep * 2u + 1u, c2, c3, acc);
         }
     }
@@ -630,8 +660,10 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
                 p.stat_partial = (double*)ctx->d_partial.p;
             }
             ProfScope prof(ctx, PROF_SWEEP, 1);
+#ifdef MCLCAR_SWEEP_EXPERIMENTS   // build with -DMCLCAR_SWEEP_EXPERIMENTS for the switches of profiles/r02_sweep_experiments.md
             if (const char* e = getenv("MCLCAR_SWEEP_PREFETCH")) p.prefetch_ahead = atoi(e);
             if (const char* e = getenv("MCLCAR_SWEEP_DRY")) { p.dry = atoi(e); if (p.dry >= 2) p.rad2 = 1e-30f; }
+#endif
             p.red_out = t.red2; p.black_out = t.black2;
             std::swap(t.red, t.red2);        // the output pair is the current state from now on
             std::swap(t.black, t.black2);
