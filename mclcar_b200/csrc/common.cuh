@@ -65,7 +65,8 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 // uniform in (0, 1) from the top 23 bits, built in the mantissa (no int->float conversion):
 // (k23 * 2^-23) + 2^-24, exactly representable, never 0 or 1
 __device__ __forceinline__ float u01(uint32_t k) {
-    return __uint_as_float(0x3f800000u | (k >> 9)) - 0.99999994039535522461f;  // 1 - 2^-24
+    // 0x3f800000 | (k >> 9) in ONE funnel shift: the 64-bit value (0x7f : k) shifted right by 9
+    return __uint_as_float(__funnelshift_r(k, 0x7fu, 9)) - 0.99999994039535522461f;  // 1 - 2^-24
 }
 
 __device__ __forceinline__ float sqrt_approx(float x) {

@@ -94,7 +94,7 @@ __device__ __forceinline__ Pair bm_pair(const uint32_t w, const float rad2) {
     p.r = sqrt_approx(rad2 * lg2_approx(u01(w)));
     // 1 + (k + 1/2) / 512, k = low 9 bits: mantissa bits 22..14 and the half-step bit 13, exponent of 1.0 -- the angle
     // 2 pi u runs over [2 pi, 4 pi): sin and cos do not care about the whole turn, and the subtraction is saved
-    const float u = __uint_as_float(((w << 14) & 0x007fc000u) | 0x3f802000u);
+    const float u = __uint_as_float((w & 0x1ffu) * 0x4000u + 0x3f802000u);     // and + shift-add (LEA): two instructions
     sincos_approx(6.2831853071795865f * u, p.s, p.c);
     return p;
 }
@@ -291,13 +291,21 @@ __device__ __forceinline__ void sts4(const uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// 16-byte global store at base + 4 * elem_off: one IMAD.WIDE.U32 for the address (the compiler's own pointer arithmetic
+// re-adds the chain's plane offset and the buffer base with carries for every store)
+__device__ __forceinline__ void stg4_off(const float* base, const uint32_t elem_off, const float4 v) {
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(elem_off), "l"(base));
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // EMIT: 0 none, 1 the black phase also writes the finished samples, 2 it accumulates their statistics instead.
 // nm: shared address of row A of the OTHER colour (rows A-1, A, B, B+1 at nm - hb .. nm + 2 hb, hb = 4 h bytes);
 // own: shared address of row A of the colour being updated; gout: the output half-lattice of the chain, offA / offB
 // the element offsets of rows A and B in it (stA / stB: whether the row is stored -- halo rows are not).
 template <bool SOR, bool PH2, int EMIT, typename TO>
 __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool valid, const uint32_t nm, const uint32_t own,
-                                           float* __restrict__ gout, const int offA, const int offB, const bool stA, const bool stB,
+                                           float* __restrict__ gout, const uint32_t offA, const uint32_t offB, const bool stA, const bool stB,
                                            TO* __restrict__ emitA, const double* __restrict__ muA, const uint32_t iA,
                                            const uint32_t iB, const int g, const int hv, const int h, const uint32_t c1,
                                            const uint32_t c2, const uint32_t c3, double (&acc)[3]) {
@@ -330,7 +338,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 cur = SOR ? lds4(own + b0a) : z4;
             const float4 v = gibbs_update4<SOR, true>(a0, up, b0, eA0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
             if (!PH2) sts4(own + b0a, v);
-            if (stA) st4(gout + offA + c0, v);
+            if (stA) stg4_off(gout, offA + (uint32_t)c0, v);
             if (PH2 && EMIT == 1) {
                 if (emitA) emit8<TO>(p, emitA + 2 * c0, muA ? muA + 2 * c0 : nullptr, v, a0, (iA & 1u) != 0);
             }
@@ -341,7 +349,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 cur = SOR ? lds4(own + b1a) : z4;
             const float4 v = gibbs_update4<SOR, true>(a1, up, b1, eA1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
             if (!PH2) sts4(own + b1a, v);
-            if (stA) st4(gout + offA + c1v, v);
+            if (stA) stg4_off(gout, offA + (uint32_t)c1v, v);
             if (PH2 && EMIT == 1) {
                 if (emitA) emit8<TO>(p, emitA + 2 * c1v, muA ? muA + 2 * c1v : nullptr, v, a1, (iA & 1u) != 0);
             }
@@ -361,7 +369,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 cur = SOR ? lds4(ownB + b0a) : z4;
             const float4 v = gibbs_update4<SOR, false>(b0, a0, dn, eB0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
             if (!PH2) sts4(ownB + b0a, v);
-            if (stB) st4(gout + offB + c0, v);
+            if (stB) stg4_off(gout, offB + (uint32_t)c0, v);
             if (PH2 && EMIT == 1) {
                 if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c0, muA ? muA + 2 * h + 2 * c0 : nullptr, v, b0, (iB & 1u) != 0);
             }
@@ -372,7 +380,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 cur = SOR ? lds4(ownB + b1a) : z4;
             const float4 v = gibbs_update4<SOR, false>(b1, a1, dn, eB1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
             if (!PH2) sts4(ownB + b1a, v);
-            if (stB) st4(gout + offB + c1v, v);
+            if (stB) stg4_off(gout, offB + (uint32_t)c1v, v);
             if (PH2 && EMIT == 1) {
                 if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c1v, muA ? muA + 2 * h + 2 * c1v : nullptr, v, b1, (iB & 1u) != 0);
             }
@@ -452,8 +460,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
             int iB = r0 + lA;
             iB = iB >= n1 ? iB - n1 : iB;                      // only the last tile at the bottom
             // halo rows (the first A, the last B) are recomputed, not stored
-            fused_item<SOR, false, 0, TO>(p, valid, aB + (uint32_t)(lA + 1) * row_bytes, aR + (uint32_t)lA * row_bytes, ored, iA * h,
-                                          iB * h, lA >= 1, lA + 1 <= rows, nullptr, nullptr, (uint32_t)iA, (uint32_t)iB, g, hv, h,
+            fused_item<SOR, false, 0, TO>(p, valid, aB + (uint32_t)(lA + 1) * row_bytes, aR + (uint32_t)lA * row_bytes, ored, (uint32_t)(iA * h),
+                                          (uint32_t)(iB * h), lA >= 1, lA + 1 <= rows, nullptr, nullptr, (uint32_t)iA, (uint32_t)iB, g, hv, h,
                                           p.sweep * 2u, c2, c3, acc);
         }
     }
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
                 }
             }
             fused_item<SOR, true, EMIT, TO>(p, valid, aR + (uint32_t)(tA + 1) * row_bytes, aB + (uint32_t)(tA + 2) * row_bytes, oblk,
-                                            iA * h, iB * h, true, true, erow, mrow, (uint32_t)iA, (uint32_t)iB, g, hv, h,
+                                            (uint32_t)(iA * h), (uint32_t)(iB * h), true, true, erow, mrow, (uint32_t)iA, (uint32_t)iB, g, hv, h,
                                             p.sweep * 2u + 1u, c2, c3, acc);
         }
     }
