@@ -422,10 +422,9 @@ def run_ours(args):
                      "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
                      "launches": sweep_launches, "peak_source": peak_src,
                      "share_of_step": sweep_ms / (1e3 * t_res) if t_res > 0 else None,
-                     "note": "reported against the HBM roofline as the contract asks.  ncu (profiles/r02_ncu_sweep.md): DRAM 58 %, issue slots "
-                             "67 % busy, neither pipe saturated -- bound by the load / red / barrier / black / store structure of a tile at three "
-                             "tiles per SM and, at full size, by the power cap (the launch time scales with the SM clock: 232 us at 1.9 GHz, "
-                             "~269 us capped); profiles/r02_sweep_experiments.md"},
+                     "note": "reported against the HBM roofline as the contract asks.  ncu without the power cap (profiles/r02_ncu_sweep.md): 170 us per "
+                             "launch of 130 chains = 0.93 of the HBM peak, DRAM 71 %, issue slots 65 % busy; the full-size bench runs under the 1 kW "
+                             "power cap (sw_power_cap), where the launch time follows the energy per site update (profiles/r02_sweep_experiments.md)"},
         "phases": {
             "sampler": {"metric": "gibbs_site_updates_per_s", "value": site_updates_per_s, "ms_per_step": sweep_ms / args.steps,
                         "bytes_per_site_update": bytes_per_update,

@@ -94,7 +94,9 @@ __device__ __forceinline__ Pair bm_pair(const uint32_t w, const float rad2) {
     p.r = sqrt_approx(rad2 * lg2_approx(u01(w)));
     // 1 + (k + 1/2) / 512, k = low 9 bits: mantissa bits 22..14 and the half-step bit 13, exponent of 1.0 -- the angle
     // 2 pi u runs over [2 pi, 4 pi): sin and cos do not care about the whole turn, and the subtraction is saved
-    const float u = __uint_as_float((w & 0x1ffu) * 0x4000u + 0x3f802000u);     // and + shift-add (LEA): two instructions
+    uint32_t ub;                                  // (w & 0x1ff) * 2^14 + 0x3f802000 as and + multiply-add: two instructions
+    asm("mad.lo.u32 %0, %1, 16384, 1065361408;" : "=r"(ub) : "r"(w & 0x1ffu));
+    const float u = __uint_as_float(ub);
     sincos_approx(6.2831853071795865f * u, p.s, p.c);
     return p;
 }
@@ -145,6 +147,14 @@ __device__ __forceinline__ float4 gibbs_update4(const float4 o, const float4 up,
     return v;
 }
 
+// 16-byte global store at base + 4 * elem_off: one IMAD.WIDE.U32 for the address (the compiler's own pointer arithmetic
+// re-adds the chain's plane offset and the buffer base with carries for every store)
+__device__ __forceinline__ void stg4_off(const float* base, const uint32_t elem_off, const float4 v) {
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(elem_off), "l"(base));
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // finished sample values of 8 consecutive sites (4 half-columns of both colours) -> the sample matrix.
 // v: the emitting (black) colour, o: the other colour at the same half-columns; the emitting colour sits at column
 // 2c + 1 - par, the other at 2c + par (par = row & 1).
@@ -165,6 +175,27 @@ __device__ __forceinline__ void emit8(const TorusSweepParams& p, TO* __restrict_
     } else {
 #pragma unroll
         for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + p.mu_const);
+    }
+}
+
+// the same for the fused sweep: element offset from the chain's sample (one IMAD.WIDE per store) and the row parity known
+// at compile time (tiles start at even rows: row A of a pair is even, row B odd)
+template <typename TO, bool PAR>
+__device__ __forceinline__ void emit8_off(const TorusSweepParams& p, TO* __restrict__ sample, const uint32_t off,
+                                          const double* __restrict__ mu, const float4 v, const float4 o) {
+    float a[8];
+    a[0] = PAR ? v.x : o.x; a[1] = PAR ? o.x : v.x; a[2] = PAR ? v.y : o.y; a[3] = PAR ? o.y : v.y;
+    a[4] = PAR ? v.z : o.z; a[5] = PAR ? o.z : v.z; a[6] = PAR ? v.w : o.w; a[7] = PAR ? o.w : v.w;
+    if (mu != nullptr) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sample[off + t] = (TO)((double)a[t] + __ldg(mu + off + t));
+    } else if (sizeof(TO) == 4) {
+        const float m = (float)p.mu_const;
+        stg4_off(reinterpret_cast<const float*>(sample), off, make_float4(a[0] + m, a[1] + m, a[2] + m, a[3] + m));
+        stg4_off(reinterpret_cast<const float*>(sample), off + 4u, make_float4(a[4] + m, a[5] + m, a[6] + m, a[7] + m));
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sample[off + t] = (TO)((double)a[t] + p.mu_const);
     }
 }
 
@@ -291,14 +322,6 @@ __device__ __forceinline__ void sts4(const uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// 16-byte global store at base + 4 * elem_off: one IMAD.WIDE.U32 for the address (the compiler's own pointer arithmetic
-// re-adds the chain's plane offset and the buffer base with carries for every store)
-__device__ __forceinline__ void stg4_off(const float* base, const uint32_t elem_off, const float4 v) {
-    uint64_t a;
-    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(elem_off), "l"(base));
-    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
 // EMIT: 0 none, 1 the black phase also writes the finished samples, 2 it accumulates their statistics instead.
 // nm: shared address of row A of the OTHER colour (rows A-1, A, B, B+1 at nm - hb .. nm + 2 hb, hb = 4 h bytes);
 // own: shared address of row A of the colour being updated; gout: the output half-lattice of the chain, offA / offB
@@ -306,7 +329,7 @@ __device__ __forceinline__ void stg4_off(const float* base, const uint32_t elem_
 template <bool SOR, bool PH2, int EMIT, typename TO>
 __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool valid, const uint32_t nm, const uint32_t own,
                                            float* __restrict__ gout, const uint32_t offA, const uint32_t offB, const bool stA, const bool stB,
-                                           TO* __restrict__ emitA, const double* __restrict__ muA, const uint32_t iA,
+                                           TO* __restrict__ esample, const uint32_t eoff, const double* __restrict__ mu, const uint32_t iA,
                                            const uint32_t iB, const int g, const int hv, const int h, const uint32_t c1,
                                            const uint32_t c2, const uint32_t c3, double (&acc)[3]) {
     const int G = p.G;
@@ -340,7 +363,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             if (!PH2) sts4(own + b0a, v);
             if (stA) stg4_off(gout, offA + (uint32_t)c0, v);
             if (PH2 && EMIT == 1) {
-                if (emitA) emit8<TO>(p, emitA + 2 * c0, muA ? muA + 2 * c0 : nullptr, v, a0, (iA & 1u) != 0);
+                if (esample) emit8_off<TO, false>(p, esample, eoff + 2u * (uint32_t)c0, mu, v, a0);
             }
             if (PH2 && EMIT == 2) stats8<true>(v, a0, up, b0, eA0, m, acc);
         }
@@ -351,7 +374,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             if (!PH2) sts4(own + b1a, v);
             if (stA) stg4_off(gout, offA + (uint32_t)c1v, v);
             if (PH2 && EMIT == 1) {
-                if (emitA) emit8<TO>(p, emitA + 2 * c1v, muA ? muA + 2 * c1v : nullptr, v, a1, (iA & 1u) != 0);
+                if (esample) emit8_off<TO, false>(p, esample, eoff + 2u * (uint32_t)c1v, mu, v, a1);
             }
             if (PH2 && EMIT == 2) stats8<true>(v, a1, up, b1, eA1, m, acc);
         }
@@ -371,7 +394,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             if (!PH2) sts4(ownB + b0a, v);
             if (stB) stg4_off(gout, offB + (uint32_t)c0, v);
             if (PH2 && EMIT == 1) {
-                if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c0, muA ? muA + 2 * h + 2 * c0 : nullptr, v, b0, (iB & 1u) != 0);
+                if (esample) emit8_off<TO, true>(p, esample, eoff + 2u * (uint32_t)(h + c0), mu, v, b0);
             }
             if (PH2 && EMIT == 2) stats8<false>(v, b0, a0, dn, eB0, m, acc);
         }
@@ -382,7 +405,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             if (!PH2) sts4(ownB + b1a, v);
             if (stB) stg4_off(gout, offB + (uint32_t)c1v, v);
             if (PH2 && EMIT == 1) {
-                if (emitA) emit8<TO>(p, emitA + 2 * h + 2 * c1v, muA ? muA + 2 * h + 2 * c1v : nullptr, v, b1, (iB & 1u) != 0);
+                if (esample) emit8_off<TO, true>(p, esample, eoff + 2u * (uint32_t)(h + c1v), mu, v, b1);
             }
             if (PH2 && EMIT == 2) stats8<false>(v, b1, a1, dn, eB1, m, acc);
         }
@@ -461,12 +484,16 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
             iB = iB >= n1 ? iB - n1 : iB;                      // only the last tile at the bottom
             // halo rows (the first A, the last B) are recomputed, not stored
             fused_item<SOR, false, 0, TO>(p, valid, aB + (uint32_t)(lA + 1) * row_bytes, aR + (uint32_t)lA * row_bytes, ored, (uint32_t)(iA * h),
-                                          (uint32_t)(iB * h), lA >= 1, lA + 1 <= rows, nullptr, nullptr, (uint32_t)iA, (uint32_t)iB, g, hv, h,
+                                          (uint32_t)(iB * h), lA >= 1, lA + 1 <= rows, nullptr, 0u, nullptr, (uint32_t)iA, (uint32_t)iB, g, hv, h,
                                           p.sweep * 2u, c2, c3, acc);
         }
     }
     __syncthreads();
     // ---- phase 2: black rows r0 .. r0+rows-1 in rows / 2 pairs from the new red rows in sR
+    TO* esample = nullptr;                                    // this chain's sample in the output matrix (emitting sweeps)
+    if (EMIT == 1) {
+        if (ch < p.nch) esample = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld;
+    }
     {
         const int items = (rows >> 1) * G;
         for (int t0 = 0; t0 < items; t0 += blockDim.x) {
@@ -475,16 +502,9 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
             const int q = valid ? (int)__umulhi((uint32_t)t, p.Gmagic) : 0, g = valid ? t - q * G : 0;
             const int tA = 2 * q;
             const int iA = r0 + tA, iB = iA + 1;
-            TO* erow = nullptr;
-            const double* mrow = nullptr;
-            if (EMIT == 1) {
-                if (ch < p.nch) {
-                    erow = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld + (size_t)iA * 2 * h;
-                    if (p.mu != nullptr) mrow = p.mu + (size_t)iA * 2 * h;
-                }
-            }
             fused_item<SOR, true, EMIT, TO>(p, valid, aR + (uint32_t)(tA + 1) * row_bytes, aB + (uint32_t)(tA + 2) * row_bytes, oblk,
-                                            (uint32_t)(iA * h), (uint32_t)(iB * h), true, true, erow, mrow, (uint32_t)iA, (uint32_t)iB, g, hv, h,
+                                            (uint32_t)(iA * h), (uint32_t)(iB * h), true, true, esample, (uint32_t)(iA * 2 * h), p.mu,
+                                            (uint32_t)iA, (uint32_t)iB, g, hv, h,
                                             p.sweep * 2u + 1u, c2, c3, acc);
         }
     }
