@@ -63,7 +63,32 @@ constexpr int kMaxThreads = 1024;
 
 __device__ __forceinline__ float softplusf(float t) { return t > 15.f ? t : __logf(1.f + __expf(t)); }
 
-template <int FAM>
+// The chain state of a CTA, [site][CB] floats: in shared memory (SMEM: explicit 32-bit shared-space addresses, so the
+// gathers are LDS.64 with one integer multiply-add each -- through a pointer that may be shared OR global every access
+// was a generic load behind 64-bit address arithmetic) or, for graphs too large for that, in global memory.
+template <bool SMEM>
+struct ChainState {
+    uint32_t sbase;      // shared-space byte address of the state (SMEM)
+    float* g;            // global state of this CTA (!SMEM)
+    __device__ __forceinline__ float2 ld2(const int elem) const {   // elem = site * CB + 2 * pair
+        if (SMEM) {
+            float2 v;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(sbase + 4u * (uint32_t)elem));
+            return v;
+        }
+        return *reinterpret_cast<const float2*>(g + elem);
+    }
+    __device__ __forceinline__ void st2(const int elem, const float2 v) const {
+        if (SMEM) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sbase + 4u * (uint32_t)elem), "f"(v.x), "f"(v.y) : "memory");
+        else *reinterpret_cast<float2*>(g + elem) = v;
+    }
+    __device__ __forceinline__ void zero(const int elem) const {
+        if (SMEM) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbase + 4u * (uint32_t)elem), "f"(0.f) : "memory");
+        else g[elem] = 0.f;
+    }
+};
+
+template <int FAM, bool SMEM>
 __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSamplerParams p) {
     const int kThreads = blockDim.x;
     extern __shared__ float sm_state[];
@@ -71,8 +96,10 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
     const int pr = threadIdx.x % hp;            // chain pair within the CTA
     const int slot = threadIdx.x / hp;
     const int nslots = kThreads / hp;
-    float* x = p.state_g ? p.state_g + (size_t)blockIdx.x * p.n * CB : sm_state;
-    for (int t = threadIdx.x; t < p.n * CB; t += kThreads) x[t] = 0.f;
+    ChainState<SMEM> x;
+    x.sbase = smem_u32(sm_state);
+    x.g = SMEM ? nullptr : p.state_g + (size_t)blockIdx.x * p.n * CB;
+    for (int t = threadIdx.x; t < p.n * CB; t += kThreads) x.zero(t);
     __syncthreads();
 
     const uint64_t gpair = (uint64_t)(p.pair0 + ((int64_t)blockIdx.x * hp + pr) * p.pair_stride);
@@ -100,7 +127,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float2 v = *reinterpret_cast<const float2*>(x + (size_t)j[k] * CB + 2 * pr);
+                        const float2 v = x.ld2(j[k] * CB + 2 * pr);
                         m0 = fmaf(c[k], v.x, m0);
                         m1 = fmaf(c[k], v.y, m1);
                     }
@@ -112,7 +139,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                 const float sdv = p.sd[s];
                 float2 nv;
                 if constexpr (FAM == FAM_GAUSS) {
-                    const float2 cur = *reinterpret_cast<const float2*>(x + (size_t)s * CB + 2 * pr);
+                    const float2 cur = x.ld2(s * CB + 2 * pr);
                     nv.x = fmaf(p.keep, cur.x, fmaf(p.gain, m0, p.noise * sdv * z0));
                     nv.y = fmaf(p.keep, cur.y, fmaf(p.gain, m1, p.noise * sdv * z1));
                 } else {
@@ -120,7 +147,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                     nv.y = fmaf(sdv, z1, m1);
                 }
                 if constexpr (FAM != FAM_GAUSS) {
-                    const float2 cur = *reinterpret_cast<const float2*>(x + (size_t)s * CB + 2 * pr);
+                    const float2 cur = x.ld2(s * CB + 2 * pr);
                     const float ys = p.yv[s], xbs = p.xb[s];
                     float la0, la1;
                     if constexpr (FAM == FAM_BINOM) {
@@ -137,7 +164,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                     acc_cnt += (a0 ? 1u : 0u) + (a1 ? 1u : 0u);
                     prop_cnt += 2u;
                 }
-                *reinterpret_cast<float2*>(x + (size_t)s * CB + 2 * pr) = nv;
+                x.st2(s * CB + 2 * pr, nv);
             }
             __syncthreads();
         }
@@ -145,7 +172,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
             // keep this state: sample index = e * C + chain
             const int64_t i0 = (int64_t)e_next * p.C + chain_local;
             for (int s = slot; s < p.n; s += nslots) {
-                const float2 v = *reinterpret_cast<const float2*>(x + (size_t)s * CB + 2 * pr);
+                const float2 v = x.ld2(s * CB + 2 * pr);
                 const double m = p.mu ? p.mu[s] : 0.0;
                 if (p.out_f64) {
                     double* o = reinterpret_cast<double*>(p.out) + (size_t)s * p.ld;
@@ -286,16 +313,15 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
         if (const char* te = getenv("MCLCAR_CSR_THREADS")) threads = atoi(te);
         cudaError_t e = cudaSuccess;
         ProfScope prof(ctx, PROF_CSR_SAMPLER, 1);
-        if (fam == FAM_GAUSS) {
-            e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
-            if (e == cudaSuccess) gibbs_csr_kernel<FAM_GAUSS><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
-        } else if (fam == FAM_BINOM) {
-            e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_BINOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
-            if (e == cudaSuccess) gibbs_csr_kernel<FAM_BINOM><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
-        } else {
-            e = cudaFuncSetAttribute(gibbs_csr_kernel<FAM_POIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
-            if (e == cudaSuccess) gibbs_csr_kernel<FAM_POIS><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
-        }
+#define LAUNCH_CSR(F_, S_)                                                                                              \
+    do {                                                                                                                \
+        e = cudaFuncSetAttribute(gibbs_csr_kernel<F_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);  \
+        if (e == cudaSuccess) gibbs_csr_kernel<F_, S_><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);              \
+    } while (0)
+        if (fam == FAM_GAUSS) { if (in_smem) LAUNCH_CSR(FAM_GAUSS, true); else LAUNCH_CSR(FAM_GAUSS, false); }
+        else if (fam == FAM_BINOM) { if (in_smem) LAUNCH_CSR(FAM_BINOM, true); else LAUNCH_CSR(FAM_BINOM, false); }
+        else { if (in_smem) LAUNCH_CSR(FAM_POIS, true); else LAUNCH_CSR(FAM_POIS, false); }
+#undef LAUNCH_CSR
         if (e == cudaSuccess) e = cudaGetLastError();
         unsigned long long cnt[2] = {0, 0};
         if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream);
