@@ -3,6 +3,7 @@
 // sparse Cholesky per sample); here N/C kept states of C parallel Gibbs chains.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <cstdint>
 #include <cstdlib>
 
@@ -107,7 +108,7 @@ int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N) {
     const size_t cap = 200 * 1024;
     int cbmax = 0;
     for (int cb : {32, 16, 8, 4, 2})
-        if ((size_t)n * cb * sizeof(float) <= cap) { cbmax = cb; break; }
+        if ((size_t)(n + 1) * cb * sizeof(float) <= cap) { cbmax = cb; break; }
     if (!cbmax) return std::min<int64_t>(N + (N & 1), (int64_t)ctx->n_sm * 2 * 32);
     int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, cap / ((size_t)n * cbmax * sizeof(float))));
     const int64_t c_auto = (int64_t)ctx->n_sm * per_sm * cbmax;
@@ -168,7 +169,15 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         do {
             if (!mu.empty()) {
                 if ((st = pool_alloc(ctx, (void**)&d_mu, (size_t)n * sizeof(double)))) break;
-                cudaError_t e = cudaMemcpyAsync(d_mu, mu.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+                // fp32 samples: the emitting kernels add the mean as an fp32 pair (hi, lo) stored in the 8-byte slot
+                std::vector<double> mu_dev(mu);
+                if (o.dtype == MCLCAR_F32)
+                    for (int i = 0; i < n; ++i) {
+                        const float hi = (float)mu[i], lo = (float)(mu[i] - (double)hi);
+                        float pair[2] = {hi, lo};
+                        std::memcpy(&mu_dev[i], pair, sizeof(double));
+                    }
+                cudaError_t e = cudaMemcpyAsync(d_mu, mu_dev.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
                 if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // mu is a local
                 if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ECUDA, "upload of X beta0 failed: %s", cudaGetErrorString(e)); break; }
             }
@@ -278,7 +287,7 @@ extern "C" int mclcar_dcar_plan(mclcar_ctx* ctx, double rho, int64_t N, const mc
         k = 1;
     } else {
         C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
-        k = (size_t)n * 2 * sizeof(float) <= 200 * 1024 ? 2 : 3;
+        k = (size_t)(n + 1) * 2 * sizeof(float) <= 200 * 1024 ? 2 : 3;
     }
     if (kind) *kind = k;
     if (chains) *chains = C;

@@ -26,22 +26,24 @@
 
 namespace mclcar {
 
+struct alignas(16) CsrSite {
+    int s;         // site id
+    int e0, e1;    // its (padded) neighbour entries
+    float hm;      // b_s / Q_ss
+    float sd;      // 1 / sqrt(Q_ss)
+    float y, nt, xb;   // GLM data of the site (observation, trials, X beta)
+};
+
 struct CsrSamplerParams {
     int n, ncolors;
     const int* color_ptr;  // [ncolors + 1] positions
-    const int* site_of;    // [n] position -> site
-    const int* rowptr;     // [n + 1] by position
-    const int* colidx;     // neighbour SITE ids
-    const float* coef;     // -Q_sj / Q_ss per entry
+    const struct CsrSite* meta;  // [n] by position: everything a site update reads besides its neighbours, in one 32-byte record
+    const int* colidx;     // neighbour SITE ids; every row padded to a multiple of four entries with the dummy site n,
+                           // whose state row stays zero: the gather loop runs on whole int4 / float4 groups, no predicates
+    const float* coef;     // -Q_sj / Q_ss per entry (0 for the padding)
     int coef_uniform;      // all entries equal (binary W, constant diagonal): use coef_value, skip the loads
     float coef_value;
-    const float* hm;       // b_s / Q_ss per site
-    const float* sd;       // 1/sqrt(Q_ss) per site
     const double* mu;      // added to kept states (site order) or null
-    // GLM data (site order)
-    const float* yv;
-    const float* nt;
-    const float* xb;
     int CB;            // chains per CTA (even)
     int64_t C;         // chains on this context = CB * gridDim.x
     int burn, thin, E; // E kept states per chain
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
     const int nslots = kThreads / hp;
     ChainState<SMEM> x;
     x.sbase = smem_u32(sm_state);
-    x.g = SMEM ? nullptr : p.state_g + (size_t)blockIdx.x * p.n * CB;
-    for (int t = threadIdx.x; t < p.n * CB; t += kThreads) x.zero(t);
+    x.g = SMEM ? nullptr : p.state_g + (size_t)blockIdx.x * (p.n + 1) * CB;   // row n: the dummy site of the padding, always zero
+    for (int t = threadIdx.x; t < (p.n + 1) * CB; t += kThreads) x.zero(t);
     __syncthreads();
 
     const uint64_t gpair = (uint64_t)(p.pair0 + ((int64_t)blockIdx.x * hp + pr) * p.pair_stride);
@@ -111,32 +113,29 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
         for (int col = 0; col < p.ncolors; ++col) {
             const int t1 = p.color_ptr[col + 1];
             for (int t = p.color_ptr[col] + slot; t < t1; t += nslots) {
-                const int s = p.site_of[t];
-                float m0 = p.hm[s], m1 = m0;
-                const int e1 = p.rowptr[t + 1];
-                // neighbour gathers four at a time: the index loads are independent, so the dependent
-                // index -> shared-memory chains overlap instead of serialising
-                for (int e = p.rowptr[t]; e < e1; e += 4) {
-                    int j[4];
-                    float c[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const bool ok = e + k < e1;
-                        j[k] = ok ? p.colidx[e + k] : s;
-                        c[k] = ok ? (p.coef_uniform ? p.coef_value : p.coef[e + k]) : 0.f;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float2 v = x.ld2(j[k] * CB + 2 * pr);
-                        m0 = fmaf(c[k], v.x, m0);
-                        m1 = fmaf(c[k], v.y, m1);
-                    }
+                const int4 ma = __ldg(reinterpret_cast<const int4*>(p.meta + t));          // s, e0, e1, hm
+                const float4 mb = __ldg(reinterpret_cast<const float4*>(p.meta + t) + 1);  // sd, y, nt, xb
+                const int s = ma.x;
+                float m0 = __int_as_float(ma.w), m1 = m0;
+                // neighbour gathers four at a time (rows are padded to whole groups): one 16-byte index load, four
+                // independent index -> shared-memory chains in flight
+                for (int e = ma.y; e < ma.z; e += 4) {
+                    const int4 j = __ldg(reinterpret_cast<const int4*>(p.colidx + e));
+                    float4 c;
+                    if (p.coef_uniform) c = make_float4(p.coef_value, p.coef_value, p.coef_value, p.coef_value);
+                    else c = __ldg(reinterpret_cast<const float4*>(p.coef + e));
+                    const float2 v0 = x.ld2(j.x * CB + 2 * pr), v1 = x.ld2(j.y * CB + 2 * pr);
+                    const float2 v2 = x.ld2(j.z * CB + 2 * pr), v3 = x.ld2(j.w * CB + 2 * pr);
+                    m0 = fmaf(c.x, v0.x, m0); m1 = fmaf(c.x, v0.y, m1);
+                    m0 = fmaf(c.y, v1.x, m0); m1 = fmaf(c.y, v1.y, m1);
+                    m0 = fmaf(c.z, v2.x, m0); m1 = fmaf(c.z, v2.y, m1);
+                    m0 = fmaf(c.w, v3.x, m0); m1 = fmaf(c.w, v3.y, m1);
                 }
                 const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)sweep, (uint32_t)gpair,
                                                 (uint32_t)(gpair >> 32) ^ (kTagCsr << 16), p.keys);
                 float z0, z1;
                 box_muller(r.x, r.y, z0, z1);
-                const float sdv = p.sd[s];
+                const float sdv = mb.x;
                 float2 nv;
                 if constexpr (FAM == FAM_GAUSS) {
                     const float2 cur = x.ld2(s * CB + 2 * pr);
@@ -148,10 +147,10 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                 }
                 if constexpr (FAM != FAM_GAUSS) {
                     const float2 cur = x.ld2(s * CB + 2 * pr);
-                    const float ys = p.yv[s], xbs = p.xb[s];
+                    const float ys = mb.y, xbs = mb.w;
                     float la0, la1;
                     if constexpr (FAM == FAM_BINOM) {
-                        const float ns = p.nt[s];
+                        const float ns = mb.z;
                         la0 = ys * (nv.x - cur.x) - ns * (softplusf(xbs + nv.x) - softplusf(xbs + cur.x));
                         la1 = ys * (nv.y - cur.y) - ns * (softplusf(xbs + nv.y) - softplusf(xbs + cur.y));
                     } else {
@@ -212,27 +211,43 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
     const int n = g.n;
     const int ncol = (int)g.color_ptr->size() - 1;
     // ---- permute the CSR into colour-major position order, convert to the conditional form
-    std::vector<int> rp(n + 1, 0), ci;
-    std::vector<float> coef, hm(n), sd(n);
-    ci.reserve(g.colidx->size());
-    coef.reserve(g.colidx->size());
+    // (rows padded to whole groups of four entries with the dummy site n, coefficient 0) and one 32-byte record per
+    // position with everything else a site update reads
+    std::vector<int> ci;
+    std::vector<float> coef;
+    std::vector<CsrSite> meta(n);
+    ci.reserve(g.colidx->size() + 3 * (size_t)n);
+    coef.reserve(g.colidx->size() + 3 * (size_t)n);
+    bool coef_uniform = true;
+    float coef_first = 0.f;
+    bool have_first = false;
     for (int t = 0; t < n; ++t) {
         const int s = (*g.order)[t];
         const double qss = g.qdiag[s];
         if (!(qss > 0)) return fail(ctx, MCLCAR_EINVAL, "precision matrix has a non-positive diagonal at site %d", s);
+        CsrSite& ms = meta[t];
+        ms.s = s;
+        ms.e0 = (int)ci.size();
         for (int e = (*g.rowptr)[s]; e < (*g.rowptr)[s + 1]; ++e) {
+            const float c = (float)(-g.qoff[e] / qss);
             ci.push_back((*g.colidx)[e]);
-            coef.push_back((float)(-g.qoff[e] / qss));
+            coef.push_back(c);
+            if (!have_first) { coef_first = c; have_first = true; }
+            coef_uniform = coef_uniform && c == coef_first;
         }
-        rp[t + 1] = (int)ci.size();
-        hm[s] = g.b.empty() ? 0.f : (float)(g.b[s] / qss);
-        sd[s] = (float)(1.0 / std::sqrt(qss));
+        while (ci.size() % 4) { ci.push_back(n); coef.push_back(0.f); }
+        ms.e1 = (int)ci.size();
+        ms.hm = g.b.empty() ? 0.f : (float)(g.b[s] / qss);
+        ms.sd = (float)(1.0 / std::sqrt(qss));
+        ms.y = fam != FAM_GAUSS ? (float)y[s] : 0.f;
+        ms.nt = fam != FAM_GAUSS ? (ntrial ? (float)ntrial[s] : 1.f) : 0.f;
+        ms.xb = fam != FAM_GAUSS ? (float)xb[s] : 0.f;
     }
     // ---- chains per CTA: largest CB whose state fits in shared memory and still fills the SMs
     const size_t smem_cap = 200 * 1024;
     int CB = 0;
     for (int cb : {32, 16, 8, 4, 2})
-        if ((size_t)n * cb * sizeof(float) <= smem_cap) {
+        if ((size_t)(n + 1) * cb * sizeof(float) <= smem_cap) {
             CB = cb;
             if ((C_want + cb - 1) / cb >= ctx->n_sm) break;
         }
@@ -258,53 +273,35 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
     };
     CsrSamplerParams p{};
     int st = MCLCAR_OK;
-    std::vector<float> yf, ntf, xbf;
     std::vector<double> mu;
-    void *d_cp = nullptr, *d_so = nullptr, *d_rp = nullptr, *d_ci = nullptr, *d_coef = nullptr, *d_hm = nullptr,
-         *d_sd = nullptr, *d_mu = nullptr, *d_y = nullptr, *d_nt = nullptr, *d_xb = nullptr, *d_cnt = nullptr,
-         *d_state = nullptr;
+    void *d_cp = nullptr, *d_meta = nullptr, *d_ci = nullptr, *d_coef = nullptr, *d_mu = nullptr, *d_cnt = nullptr, *d_state = nullptr;
     do {
         if ((st = upv(g.color_ptr->data(), (ncol + 1) * sizeof(int), &d_cp))) break;
-        if ((st = upv(g.order->data(), n * sizeof(int), &d_so))) break;
-        if ((st = upv(rp.data(), (n + 1) * sizeof(int), &d_rp))) break;
+        if ((st = upv(meta.data(), meta.size() * sizeof(CsrSite), &d_meta))) break;
         if ((st = upv(ci.data(), ci.size() * sizeof(int), &d_ci))) break;
         if ((st = upv(coef.data(), coef.size() * sizeof(float), &d_coef))) break;
-        if ((st = upv(hm.data(), n * sizeof(float), &d_hm))) break;
-        if ((st = upv(sd.data(), n * sizeof(float), &d_sd))) break;
         if (mu_host) {
             if ((st = upv(mu_host, n * sizeof(double), &d_mu))) break;
-        }
-        if (fam != FAM_GAUSS) {
-            yf.resize(n); ntf.resize(n); xbf.resize(n);
-            for (int s = 0; s < n; ++s) {
-                yf[s] = (float)y[s];
-                ntf[s] = ntrial ? (float)ntrial[s] : 1.f;
-                xbf[s] = (float)xb[s];
-            }
-            if ((st = upv(yf.data(), n * sizeof(float), &d_y))) break;
-            if ((st = upv(ntf.data(), n * sizeof(float), &d_nt))) break;
-            if ((st = upv(xbf.data(), n * sizeof(float), &d_xb))) break;
         }
         unsigned long long zero[2] = {0, 0};
         if ((st = upv(zero, sizeof zero, &d_cnt))) break;
         if (!in_smem) {
-            if ((st = pool_alloc(ctx, &d_state, (size_t)grid * n * CB * sizeof(float)))) break;
+            if ((st = pool_alloc(ctx, &d_state, (size_t)grid * (n + 1) * CB * sizeof(float)))) break;
             owned.push_back(d_state);
         }
         p.n = n; p.ncolors = ncol;
-        p.color_ptr = (const int*)d_cp; p.site_of = (const int*)d_so; p.rowptr = (const int*)d_rp;
+        p.color_ptr = (const int*)d_cp; p.meta = (const CsrSite*)d_meta;
         p.colidx = (const int*)d_ci; p.coef = (const float*)d_coef;
-        p.coef_uniform = 1;
-        for (size_t e = 1; e < coef.size() && p.coef_uniform; ++e) p.coef_uniform = coef[e] == coef[0];
-        p.coef_value = coef.empty() ? 0.f : coef[0]; p.hm = (const float*)d_hm; p.sd = (const float*)d_sd;
-        p.mu = (const double*)d_mu; p.yv = (const float*)d_y; p.nt = (const float*)d_nt; p.xb = (const float*)d_xb;
+        p.coef_uniform = coef_uniform ? 1 : 0;
+        p.coef_value = coef_first;
+        p.mu = (const double*)d_mu;
         p.CB = CB; p.C = C; p.burn = burn; p.thin = thin; p.E = E; p.N = N;
         p.out = d_out; p.ld = ld; p.out_f64 = out_f64; p.state_g = (float*)d_state;
         p.keys = philox_keys(ctx->draw_key);
         p.keep = (float)(1.0 - omega); p.gain = (float)omega; p.noise = (float)std::sqrt(omega * (2.0 - omega));
         p.pair0 = ctx->rank; p.pair_stride = ctx->world;
         p.counters = (unsigned long long*)d_cnt;
-        const size_t smem = in_smem ? (size_t)n * CB * sizeof(float) : 0;
+        const size_t smem = in_smem ? (size_t)(n + 1) * CB * sizeof(float) : 0;
         // all warps of the CTA share the resident state: as many as the largest colour class can feed
         int max_class = 1;
         for (int c = 0; c < ncol; ++c) max_class = std::max(max_class, (*g.color_ptr)[c + 1] - (*g.color_ptr)[c]);

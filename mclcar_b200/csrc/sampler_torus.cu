@@ -51,7 +51,7 @@ struct TorusSweepParams {
     // written in the reference's site order to out[(slot0 + chain) * ld + site]
     void* out;
     int64_t ld, slot0, nch;
-    const double* mu;   // [n] or null
+    const double* mu;   // [n] or null; for fp32 samples every 8-byte slot holds the fp32 pair (fl32(mu), fl32(mu - hi))
     double mu_const;    // used when mu is null
     // statistics-only emission (EMIT == 2): per (chain, tile) partial sums (x'x, x'Wx / 2, sum x) of the sample
     // fl32(state + mu_const), [C][tiles][3]
@@ -155,6 +155,17 @@ __device__ __forceinline__ void stg4_off(const float* base, const uint32_t elem_
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// fp32 sample = state + per-site mean, the mean given as an fp32 pair (hi, lo) = (fl32(mu), fl32(mu - hi)): TwoSum of state and
+// hi, then the low parts -- the fp64 sum rounded to fp32 to within 2^-24 relative of half an ulp, in full-rate FP32
+// instructions.  (fp64 add + two conversions per element ran on the conversion unit at 16 lanes per clock and made an
+// emitting sweep with a non-constant mean 2.5 x as long as a plain one.)
+__device__ __forceinline__ float add_mean_f32(const float a, const float2 m) {
+    const float s = a + m.x;
+    const float bb = s - a;
+    const float err = (a - (s - bb)) + (m.x - bb);
+    return s + (err + m.y);
+}
+
 // finished sample values of 8 consecutive sites (4 half-columns of both colours) -> the sample matrix.
 // v: the emitting (black) colour, o: the other colour at the same half-columns; the emitting colour sits at column
 // 2c + 1 - par, the other at 2c + par (par = row & 1).
@@ -164,7 +175,19 @@ __device__ __forceinline__ void emit8(const TorusSweepParams& p, TO* __restrict_
     float a[8];
     a[0] = par ? v.x : o.x; a[1] = par ? o.x : v.x; a[2] = par ? v.y : o.y; a[3] = par ? o.y : v.y;
     a[4] = par ? v.z : o.z; a[5] = par ? o.z : v.z; a[6] = par ? v.w : o.w; a[7] = par ? o.w : v.w;
-    if (mu8 != nullptr) {
+    if (mu8 != nullptr && sizeof(TO) == 4) {     // fp32 samples: the mean array holds (hi, lo) fp32 pairs
+        const float4* m4 = reinterpret_cast<const float4*>(mu8);
+        float r[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float4 mm = __ldg(m4 + t);
+            r[2 * t] = add_mean_f32(a[2 * t], make_float2(mm.x, mm.y));
+            r[2 * t + 1] = add_mean_f32(a[2 * t + 1], make_float2(mm.z, mm.w));
+        }
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        d4[0] = make_float4(r[0], r[1], r[2], r[3]);
+        d4[1] = make_float4(r[4], r[5], r[6], r[7]);
+    } else if (mu8 != nullptr) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) dst[t] = (TO)((double)a[t] + __ldg(mu8 + t));
     } else if (sizeof(TO) == 4) {
@@ -186,7 +209,18 @@ __device__ __forceinline__ void emit8_off(const TorusSweepParams& p, TO* __restr
     float a[8];
     a[0] = PAR ? v.x : o.x; a[1] = PAR ? o.x : v.x; a[2] = PAR ? v.y : o.y; a[3] = PAR ? o.y : v.y;
     a[4] = PAR ? v.z : o.z; a[5] = PAR ? o.z : v.z; a[6] = PAR ? v.w : o.w; a[7] = PAR ? o.w : v.w;
-    if (mu != nullptr) {
+    if (mu != nullptr && sizeof(TO) == 4) {      // fp32 samples: the mean array holds (hi, lo) fp32 pairs
+        const float4* m4 = reinterpret_cast<const float4*>(mu + off);
+        float r[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float4 mm = __ldg(m4 + t);
+            r[2 * t] = add_mean_f32(a[2 * t], make_float2(mm.x, mm.y));
+            r[2 * t + 1] = add_mean_f32(a[2 * t + 1], make_float2(mm.z, mm.w));
+        }
+        stg4_off(reinterpret_cast<const float*>(sample), off, make_float4(r[0], r[1], r[2], r[3]));
+        stg4_off(reinterpret_cast<const float*>(sample), off + 4u, make_float4(r[4], r[5], r[6], r[7]));
+    } else if (mu != nullptr) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) sample[off + t] = (TO)((double)a[t] + __ldg(mu + off + t));
     } else if (sizeof(TO) == 4) {
@@ -582,10 +616,16 @@ __global__ void __launch_bounds__(256) torus_emit_kernel(const float* red, const
     const float b = black[ch * plane + (size_t)i * h + c];
     const int par = i & 1;  // red sits at column 2c + par, black at 2c + 1 - par
     const size_t site = (size_t)i * 2 * h + 2 * c;
+    TO* o = out + (size_t)(slot0 + ch) * ld + site;
+    if (mu != nullptr && sizeof(TO) == 4) {      // (hi, lo) fp32 pairs, as in emit8
+        const float4 mm = *reinterpret_cast<const float4*>(mu + site);
+        o[0] = (TO)add_mean_f32(par ? b : r, make_float2(mm.x, mm.y));
+        o[1] = (TO)add_mean_f32(par ? r : b, make_float2(mm.z, mm.w));
+        return;
+    }
     const double m0 = mu ? mu[site] : 0.0, m1 = mu ? mu[site + 1] : 0.0;
     const double v0 = (par ? (double)b : (double)r) + m0;
     const double v1 = (par ? (double)r : (double)b) + m1;
-    TO* o = out + (size_t)(slot0 + ch) * ld + site;
     o[0] = (TO)v0;
     o[1] = (TO)v1;
 }
