@@ -191,6 +191,27 @@ def test_fused_sweep_fp64_samples_with_site_mean(monkeypatch):
     np.testing.assert_array_equal(out["1"], out["0"])
 
 
+@pytest.mark.parametrize("n1,n2", [(64, 128), (40, 36)])
+def test_fp32_samples_with_site_mean_are_the_rounded_fp64_sums(n1, n2):
+    """fp32 samples with a non-constant mean X beta0: the emitting kernels add the mean as a compensated fp32 pair
+    (hi, lo) instead of an fp64 add with two conversions per element.  Same seed, fp64 samples: state + mean exactly;
+    the fp32 sample must be that sum rounded to fp32 (half an ulp, plus the 2^-24 of the pair's low part).  The second
+    lattice (n2 / 2 not a multiple of 4) takes the separate emission kernel."""
+    n = n1 * n2
+    rng = np.random.default_rng(4)
+    X = np.column_stack([np.ones(n), 3.0 * rng.standard_normal(n)])
+    y = rng.standard_normal(n)
+    psi = [0.2, 1.1, 0.7, -1.3]
+    out = {}
+    for dt in ("f32", "f64"):
+        d = api.make_data(y, X=X, torus=(n1, n2), seed=21)
+        out[dt] = api.mcl_prep_dCAR(psi, 24, d, {"n.chains": 8, "burn": 3, "thin": 2, "dtype": dt}).simY
+    exact = out["f64"]
+    ulp = np.spacing(np.abs(exact).astype(np.float32)).astype(np.float64)
+    assert np.all(np.abs(out["f32"] - exact) <= 0.5000002 * ulp + 1e-30)
+    assert np.abs(exact - (X @ np.array(psi[2:]))[:, None]).std() > 0.5      # a field around the mean, not the mean itself
+
+
 @pytest.mark.parametrize("omega", [0.0, 1.0])
 def test_default_thinning_decorrelates_kept_states(omega):
     """The default schedule promises <= ~1 % autocorrelation between consecutive kept states
