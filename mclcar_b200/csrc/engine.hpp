@@ -287,7 +287,8 @@ struct GmrfHost {
 };
 int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, const double* mu_host, const double* y,
                     const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
-                    void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out);
+                    void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out, double* d_stat_q = nullptr,
+                    int64_t stat_ldq = 0, bool* stats_done = nullptr);
 int check_rho(mclcar_ctx* ctx, double rho);
 // sum_i w_i f(lambda_i) over the context's spectral nodes: tr f(W), exactly (eigenvalues) or by quadrature
 template <class Fn>

@@ -871,17 +871,24 @@ int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int6
     const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
     const uint64_t draw0 = ctx->draw;
     int64_t sweeps_total = 0;
+    // z'z and z'Wz of the kept states come out of the chain kernel itself (binary W, fp32 samples): at emission the state
+    // and all its neighbours are in shared memory -- no second pass over the sample matrix (whose edge gathers miss L2 on
+    // a map in arbitrary site order: 2.7 x the algorithmic traffic, profiles/r02_ncu_stats_site_major.md)
+    if (st == MCLCAR_OK) st = samples_alloc_stats(ctx, s, 2);
+    bool stats_done = false;
     for (int attempt = 0; attempt < 3 && st == MCLCAR_OK; ++attempt) {
         ctx->draw = draw0;               // one prep call = one draw index, whatever the number of pilot runs
         ctx->draw_salt = (uint64_t)attempt;
         st = run_csr_sampler(ctx, g, family == MCLCAR_FAMILY_BINOM ? FAM_BINOM : FAM_POIS, 1.0, nullptr, ctx->y.data(),
                              ctx->ntrial.empty() ? nullptr : ctx->ntrial.data(), xb.data(), N, C, burn, thin, s->d_M,
-                             o.dtype == MCLCAR_F64, s->ld, &s->accept, &s->sweeps);
+                             o.dtype == MCLCAR_F64, s->ld, &s->accept, &s->sweeps, getenv("MCLCAR_NO_CHAIN_STATS") ? nullptr : s->d_q, N,
+                             &stats_done);
         sweeps_total += s->sweeps;
+        s->stats_ready = stats_done;
         if (st != MCLCAR_OK || !tune || attempt == 2 || N < 4 * C) break;   // fewer than 4 states per chain: no autocorrelation to estimate
         // z'z, z'Wz of the kept states (they stay with the sample set) and their effective sample size
-        if ((st = samples_alloc_stats(ctx, s, 2))) break;
-        if ((st = launch_quadforms_site_major(ctx, s->d_M, s->dtype, N, s->ld, n, ctx->rowptr, ctx->colidx, ctx->val, 0, nullptr, s->d_q, N))) break;
+        if (!stats_done &&
+            (st = launch_quadforms_site_major(ctx, s->d_M, s->dtype, N, s->ld, n, ctx->rowptr, ctx->colidx, ctx->val, 0, nullptr, s->d_q, N))) break;
         std::vector<double> q((size_t)2 * N);
         cudaError_t e = cudaMemcpyAsync(q.data(), s->d_q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -56,6 +56,12 @@ struct CsrSamplerParams {
     float keep, gain, noise;   // over-relaxation: x' = keep*x + gain*m + noise*sd*z (Gaussian family)
     int64_t pair0, pair_stride;  // global pair id = pair0 + local_pair * pair_stride
     unsigned long long* counters;  // [0] accepted, [1] proposed
+    // statistics of the kept states formed at emission, where the state and all its neighbours are on chip:
+    // stat_q[i] = x_i'x_i, stat_q[stat_ldq + i] = x_i'W x_i for a BINARY neighbourhood matrix (every real neighbour entry
+    // counts once; the padding's dummy site holds zeros), in fp64 from the fp32 values that are written out -- what the
+    // site-major statistics kernel would compute from the stored matrix, without its second pass over it.  null: off
+    double* stat_q;
+    int64_t stat_ldq;
 };
 
 namespace {
@@ -183,6 +189,50 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                     if (i0 + 1 < p.N) o[i0 + 1] = (float)((double)v.y + m);
                 }
             }
+            if (p.stat_q != nullptr) {
+                // x'x and x'Wx of the state just written: every thread takes its share of the sites for its chain pair,
+                // lanes of a warp holding the same pair are added by shuffles, the warps through shared memory
+                double zz0 = 0.0, zz1 = 0.0, zw0 = 0.0, zw1 = 0.0;
+                for (int t = slot; t < p.n; t += nslots) {
+                    const int4 ma = __ldg(reinterpret_cast<const int4*>(p.meta + t));
+                    const float2 v = x.ld2(ma.x * CB + 2 * pr);
+                    double g0 = 0.0, g1 = 0.0;
+                    for (int e = ma.y; e < ma.z; e += 4) {
+                        const int4 j = __ldg(reinterpret_cast<const int4*>(p.colidx + e));
+                        const float2 v0 = x.ld2(j.x * CB + 2 * pr), v1 = x.ld2(j.y * CB + 2 * pr);
+                        const float2 v2 = x.ld2(j.z * CB + 2 * pr), v3 = x.ld2(j.w * CB + 2 * pr);
+                        g0 += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+                        g1 += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+                    }
+                    zz0 = fma((double)v.x, (double)v.x, zz0);
+                    zz1 = fma((double)v.y, (double)v.y, zz1);
+                    zw0 = fma((double)v.x, g0, zw0);
+                    zw1 = fma((double)v.y, g1, zw1);
+                }
+                for (int o = hp; o < 32; o <<= 1) {          // lanes l, l + hp, l + 2 hp, ... hold the same pair (hp <= 16)
+                    zz0 += __shfl_xor_sync(0xffffffffu, zz0, o); zz1 += __shfl_xor_sync(0xffffffffu, zz1, o);
+                    zw0 += __shfl_xor_sync(0xffffffffu, zw0, o); zw1 += __shfl_xor_sync(0xffffffffu, zw1, o);
+                }
+                double* sc = reinterpret_cast<double*>(sm_state + (SMEM ? (size_t)(p.n + 1) * CB : 0));   // [warps][hp][4]
+                const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = kThreads >> 5;
+                __syncthreads();
+                if (lane < hp) {
+                    double* d = sc + ((size_t)wid * hp + lane) * 4;
+                    d[0] = zz0; d[1] = zz1; d[2] = zw0; d[3] = zw1;
+                }
+                __syncthreads();
+                if (threadIdx.x < hp) {                       // thread = pair: add the warps in order (deterministic)
+                    double a[4] = {0.0, 0.0, 0.0, 0.0};
+                    for (int w = 0; w < nw; ++w) {
+                        const double* d = sc + ((size_t)w * hp + threadIdx.x) * 4;
+                        a[0] += d[0]; a[1] += d[1]; a[2] += d[2]; a[3] += d[3];
+                    }
+                    const int64_t i0s = (int64_t)e_next * p.C + (int64_t)blockIdx.x * CB + 2 * threadIdx.x;
+                    if (i0s < p.N) { p.stat_q[i0s] = a[0]; p.stat_q[p.stat_ldq + i0s] = a[2]; }
+                    if (i0s + 1 < p.N) { p.stat_q[i0s + 1] = a[1]; p.stat_q[p.stat_ldq + i0s + 1] = a[3]; }
+                }
+                __syncthreads();
+            }
             ++e_next;
         }
     }
@@ -205,8 +255,10 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
 
 int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, const double* mu_host, const double* y,
                     const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
-                    void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out) {
+                    void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out, double* d_stat_q, int64_t stat_ldq,
+                    bool* stats_done) {
     MCL_TRY(require_device(ctx));
+    if (stats_done) *stats_done = false;
     begin_draw(ctx);   // a fresh Philox stream for every sampler run (the reference draws fresh rnorm() per call)
     const int n = g.n;
     const int ncol = (int)g.color_ptr->size() - 1;
@@ -301,18 +353,24 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
         p.keep = (float)(1.0 - omega); p.gain = (float)omega; p.noise = (float)std::sqrt(omega * (2.0 - omega));
         p.pair0 = ctx->rank; p.pair_stride = ctx->world;
         p.counters = (unsigned long long*)d_cnt;
-        const size_t smem = in_smem ? (size_t)(n + 1) * CB * sizeof(float) : 0;
+        // statistics at emission: binary neighbourhood matrices, no mean added to the kept states, fp32 output (the
+        // statistics must be those of the values written)
+        const bool on_chip_stats = d_stat_q != nullptr && coef_uniform && have_first && !mu_host && !out_f64;
+        if (on_chip_stats) { p.stat_q = d_stat_q; p.stat_ldq = stat_ldq; }
+        if (stats_done) *stats_done = on_chip_stats;
+        size_t smem = in_smem ? (size_t)(n + 1) * CB * sizeof(float) : 0;
         // all warps of the CTA share the resident state: as many as the largest colour class can feed
         int max_class = 1;
         for (int c = 0; c < ncol; ++c) max_class = std::max(max_class, (*g.color_ptr)[c + 1] - (*g.color_ptr)[c]);
         int threads = 256;
         while (threads < kMaxThreads && (threads / (CB / 2)) < max_class) threads *= 2;
         if (const char* te = getenv("MCLCAR_CSR_THREADS")) threads = atoi(te);
+        if (on_chip_stats) smem += (size_t)(threads / 32) * (CB / 2) * 4 * sizeof(double);   // scratch of the statistics
         cudaError_t e = cudaSuccess;
         ProfScope prof(ctx, PROF_CSR_SAMPLER, 1);
 #define LAUNCH_CSR(F_, S_)                                                                                              \
     do {                                                                                                                \
-        e = cudaFuncSetAttribute(gibbs_csr_kernel<F_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);  \
+        e = cudaFuncSetAttribute(gibbs_csr_kernel<F_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap + 20 * 1024));  \
         if (e == cudaSuccess) gibbs_csr_kernel<F_, S_><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);              \
     } while (0)
         if (fam == FAM_GAUSS) { if (in_smem) LAUNCH_CSR(FAM_GAUSS, true); else LAUNCH_CSR(FAM_GAUSS, false); }

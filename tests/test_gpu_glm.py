@@ -1,5 +1,7 @@
 """GPU parity and sampler validation for the Binomial / Poisson GLM with latent CAR effects
 (R/mcl.bin.R, R/mcl.pois.R, R/mcl.glm.R, R/postZsub.R)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -145,3 +147,35 @@ def test_glm_without_eigenvalues_estimates_the_spectrum_itself():
     with pytest.raises(api.MclcarError) as ei:
         api.ploglik_dCAR(r, hd)
     assert ei.value.code == L.ESTATE and "eigenvalues" in str(ei.value)
+
+
+@pytest.mark.parametrize("n,chains", [(300, 0), (2500, 64)])
+def test_latent_statistics_formed_by_the_chain_kernel(n, chains, monkeypatch):
+    """z'z and z'Wz of the kept states come out of the chain kernel at emission (state and neighbours in shared memory)
+    instead of a second pass over Zy: they must be the statistics of the very values written -- against the oracle on
+    the fetched matrix, and equal to what the separate statistics kernel computes when the fused path is switched off."""
+    W = graphs.random_planar_map(n, seed=n)
+    ew = np.linalg.eigvalsh(W.toarray())
+    rng = np.random.default_rng(n)
+    X = np.column_stack([np.ones(n), rng.standard_normal(n) * 0.5])
+    psi = np.array([0.7 / ew.max(), 1.3, 0.4, 0.6])
+    od = glm.sim_glm_data("binom", W, psi, X, 12.0, rng)
+    ctl = {"n.samples": 333, "burn": 20, "thin": 3}
+    if chains:
+        ctl["n.chains"] = chains
+    q = {}
+    for off in ("", "1"):
+        if off:
+            monkeypatch.setenv("MCLCAR_NO_CHAIN_STATS", "1")
+        gd = api.make_data(od["y"], X=X, W=W, n_trial=12, eigenvalues=ew, seed=8)
+        md = api.mcl_prep_glm(gd, "binom", psi, ctl)
+        api.mcl_glm(psi, md)                                   # forms the statistics when the chain kernel did not
+        dd = C.c_int()
+        api.check(L.lib.mclcar_samples_stats_export(gd.ctx.h, md.h, C.byref(dd), None), gd.ctx.h)
+        out = np.empty((dd.value, 333))
+        api.check(L.lib.mclcar_samples_stats_export(gd.ctx.h, md.h, C.byref(dd), L.dptr(out)), gd.ctx.h)
+        q[off] = out[:2].T.copy()
+        if not off:
+            Zy = md.Zy
+    np.testing.assert_allclose(q[""], glm.latent_stats(W, Zy), rtol=1e-13)
+    np.testing.assert_allclose(q[""], q["1"], rtol=1e-13)
