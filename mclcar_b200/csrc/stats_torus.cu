@@ -15,6 +15,9 @@
 // is pre-loaded into a carry buffer, afterwards the last row of the previous stage serves
 // as the carry, so every byte of the sample is read from HBM exactly once (+ one halo row
 // per strip).  HBM-bound by design: algorithmic bytes per sample = n * sizeof(T).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "engine.hpp"
 
@@ -211,6 +214,138 @@ __global__ void strip_sum_kernel(const double* partial, double* q, int S, int d,
     }
 }
 
+// Linear forms X'y and (WX)'y for NON-CONSTANT design columns, a group of samples at a time.  In the streaming kernel above
+// every sample re-reads the column and its W-image (16 B per site per column against the sample's 4 or 8): the pass
+// becomes L2-bound at a quarter of the HBM rate (config 2, p = 2: 1.6 TB/s).  Here a CTA takes GS samples and a run of
+// sites: a thread reads its sites' column values ONCE and applies them to the GS samples (GS independent 16-byte loads in
+// flight), so the columns cost 16 / GS bytes per site and sample.  This is a second read of the sample matrix -- the
+// single-pass form (a group of samples per ring stage of the streaming kernel) is the next step.
+struct LinFormsParams {
+    const void* M;
+    int64_t ld, N;
+    int64_t n;          // sites per sample
+    int64_t chunk;      // sites per CTA (multiple of the vector width)
+    int nc;
+    const double* Xc[kMaxNC];
+    const double* WXc[kMaxNC];
+    double* out;        // chunks == 1: q rows directly; else partial [chunks][2 nc][ldq]
+    int64_t ldq;
+    int dst_a[kMaxNC], dst_b[kMaxNC];
+    int chunks;
+};
+
+template <typename T, int NC, int GS>
+__global__ void __launch_bounds__(256) stats_linear_forms_kernel(const LinFormsParams p) {
+    constexpr int VEC = Vec<T>::N;
+    using VT = typename Vec<T>::type;
+    __shared__ double scratch[8 * GS * 2 * NC];
+    const int64_t i0 = (int64_t)blockIdx.y * GS;
+    const int gs = (int)min((int64_t)GS, p.N - i0);
+    const int64_t s0 = (int64_t)blockIdx.x * p.chunk, s1 = min(p.n, s0 + p.chunk);
+    double acc[GS][2 * NC];
+#pragma unroll
+    for (int g = 0; g < GS; ++g)
+#pragma unroll
+        for (int l = 0; l < 2 * NC; ++l) acc[g][l] = 0.0;
+    const T* base = reinterpret_cast<const T*>(p.M) + i0 * p.ld;
+    for (int64_t s = s0 + (int64_t)threadIdx.x * VEC; s < s1; s += (int64_t)blockDim.x * VEC) {
+        double xc[NC][VEC], wc[NC][VEC];
+#pragma unroll
+        for (int l = 0; l < NC; ++l)
+#pragma unroll
+            for (int e = 0; e < VEC; e += 2) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(p.Xc[l] + s + e));
+                const double2 b = __ldg(reinterpret_cast<const double2*>(p.WXc[l] + s + e));
+                xc[l][e] = a.x; xc[l][e + 1] = a.y; wc[l][e] = b.x; wc[l][e + 1] = b.y;
+            }
+        VT v[GS];
+#pragma unroll
+        for (int g = 0; g < GS; ++g)
+            if (g < gs) v[g] = *reinterpret_cast<const VT*>(base + (int64_t)g * p.ld + s);
+#pragma unroll
+        for (int g = 0; g < GS; ++g) {
+            if (g < gs) {
+                double x[VEC];
+                unpack<T>(v[g], x);
+#pragma unroll
+                for (int l = 0; l < NC; ++l)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        acc[g][l] = fma(xc[l][e], x[e], acc[g][l]);
+                        acc[g][NC + l] = fma(wc[l][e], x[e], acc[g][NC + l]);
+                    }
+            }
+        }
+    }
+    // fixed-order reduction: lanes by shuffles, the eight warps through shared memory
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int g = 0; g < GS; ++g)
+#pragma unroll
+        for (int l = 0; l < 2 * NC; ++l) {
+            const double t = warp_sum(acc[g][l]);
+            if (lane == 0) scratch[(wid * GS + g) * 2 * NC + l] = t;
+        }
+    __syncthreads();
+    if (threadIdx.x < GS * 2 * NC) {
+        const int g = threadIdx.x / (2 * NC), l = threadIdx.x % (2 * NC);
+        if (g < gs) {
+            double a = 0.0;
+            for (int w = 0; w < 8; ++w) a += scratch[(w * GS + g) * 2 * NC + l];
+            const int row = l < NC ? p.dst_a[l] : p.dst_b[l - NC];
+            if (p.chunks == 1) p.out[(size_t)row * p.ldq + i0 + g] = a;
+            else p.out[((size_t)blockIdx.x * 2 * NC + l) * p.ldq + i0 + g] = a;
+        }
+    }
+}
+
+// partial [chunks][2 nc][ldq] -> rows dst_a / dst_b of q, chunks added in order
+__global__ void linear_forms_sum_kernel(const LinFormsParams p, double* q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.N) return;
+    for (int l = 0; l < 2 * p.nc; ++l) {
+        double a = 0.0;
+        for (int c = 0; c < p.chunks; ++c) a += p.out[((size_t)c * 2 * p.nc + l) * p.ldq + i];
+        const int row = l < p.nc ? p.dst_a[l] : p.dst_b[l - p.nc];
+        q[(size_t)row * p.ldq + i] = a;
+    }
+}
+
+template <typename T>
+int launch_linear_forms(mclcar_ctx* ctx, LinFormsParams& p, double* d_q) {
+    constexpr int VEC = Vec<T>::N;
+    const int GS = p.nc <= 2 ? 8 : 4;
+    const int64_t groups = (p.N + GS - 1) / GS;
+    // sites per CTA: whole lattice when the sample groups alone fill the machine, else split (partials added in order)
+    int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)4 * ctx->n_sm + groups - 1) / groups, p.n / (256 * VEC * 4) + 1));
+    if (chunks > 65535) chunks = 65535;
+    int64_t chunk = (p.n + chunks - 1) / chunks;
+    chunk = (chunk + VEC - 1) / VEC * VEC;
+    chunks = (int)((p.n + chunk - 1) / chunk);
+    p.chunk = chunk; p.chunks = chunks;
+    double* partial = nullptr;
+    if (chunks > 1) {
+        MCL_TRY(pool_alloc(ctx, (void**)&partial, (size_t)chunks * 2 * p.nc * p.ldq * sizeof(double)));
+        p.out = partial;
+    } else {
+        p.out = d_q;
+    }
+    if (groups > 65535) { pool_free(ctx, partial); return fail(ctx, MCLCAR_ELIMIT, "too many samples for the linear-forms kernel"); }
+    dim3 grid((unsigned)chunks, (unsigned)groups);
+    cudaStream_t st = ctx->stream;
+    switch (p.nc) {
+        case 1: stats_linear_forms_kernel<T, 1, 8><<<grid, 256, 0, st>>>(p); break;
+        case 2: stats_linear_forms_kernel<T, 2, 8><<<grid, 256, 0, st>>>(p); break;
+        case 3: stats_linear_forms_kernel<T, 3, 4><<<grid, 256, 0, st>>>(p); break;
+        default: stats_linear_forms_kernel<T, 4, 4><<<grid, 256, 0, st>>>(p); break;
+    }
+    if (chunks > 1) linear_forms_sum_kernel<<<(unsigned)((p.N + 255) / 256), 256, 0, st>>>(p, d_q);
+    cudaError_t e = cudaGetLastError();
+    pool_free(ctx, partial);    // stream-ordered reuse: later work of this context is queued behind the kernels
+    if (e != cudaSuccess) return fail(ctx, MCLCAR_ECUDA, "linear-forms kernel: %s", cudaGetErrorString(e));
+    return MCLCAR_OK;
+}
+
 template <typename T>
 int launch_typed(mclcar_ctx* ctx, const StatsTorusParams& p, int grid, size_t smem) {
     cudaStream_t st = ctx->stream;
@@ -291,12 +426,26 @@ int launch_stats_torus_fast(mclcar_ctx* ctx, const void* M, int dtype, int64_t N
     const size_t smem = carry_bytes + kStages * stage_bytes + (kStages + 2) * sizeof(uint64_t) +
                         (kThreads / 32) * (3 + 2 * kMaxNC) * sizeof(double) + 128;
     int grid = (int)std::min<int64_t>(prm.items, (int64_t)2 * ctx->n_sm);
-    ProfScope prof(ctx, PROF_STATS, S > 1 ? 2 : 1);
+    // non-constant design columns: the quadratic forms and the constant columns in the streaming pass, the linear forms
+    // of the others in the grouped kernel (MCLCAR_STATS_LINEAR=0 keeps them in the streaming pass)
+    const char* le = getenv("MCLCAR_STATS_LINEAR");
+    const bool split = prm.nc > 0 && !(le && atoi(le) == 0) && (ld % vec) == 0 && (ctx->n % vec) == 0;
+    LinFormsParams lf{};
+    if (split) {
+        lf.M = M; lf.ld = ld; lf.N = N; lf.n = ctx->n; lf.nc = prm.nc; lf.ldq = ldq;
+        for (int l = 0; l < prm.nc; ++l) { lf.Xc[l] = prm.Xc[l]; lf.WXc[l] = prm.WXc[l]; lf.dst_a[l] = prm.dst_a[l]; lf.dst_b[l] = prm.dst_b[l]; }
+        prm.nc = 0;
+    }
+    ProfScope prof(ctx, PROF_STATS, (S > 1 ? 2 : 1) + (split ? 1 : 0));
     if (dtype == MCLCAR_F32) MCL_TRY(launch_typed<float>(ctx, prm, grid, smem));
     else MCL_TRY(launch_typed<double>(ctx, prm, grid, smem));
     if (S > 1) {
         strip_sum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(partial, d_q, S, prm.d, ldq, N);
         MCL_CUDA(ctx, cudaGetLastError());
+    }
+    if (split) {   // after the strip sums: they write every row of q
+        if (dtype == MCLCAR_F32) MCL_TRY(launch_linear_forms<float>(ctx, lf, d_q));
+        else MCL_TRY(launch_linear_forms<double>(ctx, lf, d_q));
     }
     *handled = true;
     return MCLCAR_OK;
