@@ -269,7 +269,7 @@ struct TorusEmit {   // where the black half sweep of an emitting sweep writes t
 };
 int torus_fused_tile_rows(const mclcar_ctx* ctx);
 int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep,
-                const TorusEmit* emit = nullptr);
+                const TorusEmit* emit = nullptr, int want = 1, int* done = nullptr);
 int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, int dtype, int64_t ld, int64_t slot0,
                int64_t nch);
 

@@ -198,7 +198,18 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
             if (!o.keep && (st = samples_alloc_stats(ctx, s, 2 + 2 * ctx->p))) break;
             const bool fused = (ctx->n2 / 2) % 4 == 0;   // emission fused into the last black half sweep
             uint32_t sweep = 0;
-            for (int b = 0; b < burn && st == MCLCAR_OK; ++b) st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++);
+            // sweeps that emit nothing go two to a launch where the lattice allows (the tile stays in shared memory)
+            auto plain_sweeps = [&](int count) {
+                int rc = MCLCAR_OK;
+                while (count > 0 && rc == MCLCAR_OK) {
+                    int made = 1;
+                    rc = torus_sweep(ctx, tc, rho, sigma, omega, sweep, nullptr, count, &made);
+                    sweep += (uint32_t)made;
+                    count -= made;
+                }
+                return rc;
+            };
+            st = plain_sweeps(burn);
             for (int64_t e_i = 0; e_i < E && st == MCLCAR_OK; ++e_i) {
                 const int64_t nch = std::min<int64_t>(C, N - e_i * C);
                 TorusEmit em;
@@ -206,8 +217,12 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
                 em.d_mu = (mu.empty() || mu_is_const) ? nullptr : d_mu;
                 em.mu_const = mu.empty() ? 0.0 : mu[0];
                 if (fused_stats) { em.out = nullptr; em.slot0 = e_i * C; em.stats_q = s->d_q; em.stats_ldq = N; }
-                for (int t = 0; t < thin && st == MCLCAR_OK; ++t)
-                    st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++, (fused && t == thin - 1) ? &em : nullptr);
+                if (fused) {
+                    st = plain_sweeps(thin - 1);
+                    if (st == MCLCAR_OK) st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++, &em);
+                } else {
+                    st = plain_sweeps(thin);
+                }
                 if (st) break;
                 if (fused_stats) continue;
                 if (!fused) st = torus_emit(ctx, tc, d_mu, em.out, o.dtype, ld, em.slot0, nch);

@@ -360,7 +360,7 @@ __device__ __forceinline__ void sts4(const uint32_t a, const float4 v) {
 // nm: shared address of row A of the OTHER colour (rows A-1, A, B, B+1 at nm - hb .. nm + 2 hb, hb = 4 h bytes);
 // own: shared address of row A of the colour being updated; gout: the output half-lattice of the chain, offA / offB
 // the element offsets of rows A and B in it (stA / stB: whether the row is stored -- halo rows are not).
-template <bool SOR, bool PH2, int EMIT, typename TO>
+template <bool SOR, bool PH2, int EMIT, typename TO, bool STS>
 __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool valid, const uint32_t nm, const uint32_t own,
                                            float* __restrict__ gout, const uint32_t offA, const uint32_t offB, const bool stA, const bool stB,
                                            TO* __restrict__ esample, const uint32_t eoff, const double* __restrict__ mu, const uint32_t iA,
@@ -394,7 +394,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 up = lds4(nm - hb + b0a);
             const float4 cur = SOR ? lds4(own + b0a) : z4;
             const float4 v = gibbs_update4<SOR, true>(a0, up, b0, eA0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
-            if (!PH2) sts4(own + b0a, v);
+            if (STS) sts4(own + b0a, v);
             if (stA) stg4_off(gout, offA + (uint32_t)c0, v);
             if (PH2 && EMIT == 1) {
                 if (esample) emit8_off<TO, false>(p, esample, eoff + 2u * (uint32_t)c0, mu, v, a0);
@@ -405,7 +405,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 up = lds4(nm - hb + b1a);
             const float4 cur = SOR ? lds4(own + b1a) : z4;
             const float4 v = gibbs_update4<SOR, true>(a1, up, b1, eA1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
-            if (!PH2) sts4(own + b1a, v);
+            if (STS) sts4(own + b1a, v);
             if (stA) stg4_off(gout, offA + (uint32_t)c1v, v);
             if (PH2 && EMIT == 1) {
                 if (esample) emit8_off<TO, false>(p, esample, eoff + 2u * (uint32_t)c1v, mu, v, a1);
@@ -425,7 +425,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 dn = lds4(nm + 2u * hb + b0a);
             const float4 cur = SOR ? lds4(ownB + b0a) : z4;
             const float4 v = gibbs_update4<SOR, false>(b0, a0, dn, eB0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
-            if (!PH2) sts4(ownB + b0a, v);
+            if (STS) sts4(ownB + b0a, v);
             if (stB) stg4_off(gout, offB + (uint32_t)c0, v);
             if (PH2 && EMIT == 1) {
                 if (esample) emit8_off<TO, true>(p, esample, eoff + 2u * (uint32_t)(h + c0), mu, v, b0);
@@ -436,7 +436,7 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 dn = lds4(nm + 2u * hb + b1a);
             const float4 cur = SOR ? lds4(ownB + b1a) : z4;
             const float4 v = gibbs_update4<SOR, false>(b1, a1, dn, eB1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
-            if (!PH2) sts4(ownB + b1a, v);
+            if (STS) sts4(ownB + b1a, v);
             if (stB) stg4_off(gout, offB + (uint32_t)c1v, v);
             if (PH2 && EMIT == 1) {
                 if (esample) emit8_off<TO, true>(p, esample, eoff + 2u * (uint32_t)(h + c1v), mu, v, b1);
@@ -446,9 +446,15 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
     }
 }
 
-template <bool SOR, int EMIT, typename TO, int MINB>
-__global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
+// NS: sweeps per launch.  NS = 2 keeps a tile in shared memory for TWO full sweeps (red, black, red, black; the region
+// that can be advanced shrinks by one row per half sweep on either side, so the tile is loaded with 4 NS - 1 halo rows
+// per colour end and the halo is recomputed from the same Philox counters as the neighbouring tiles): the state crosses
+// HBM once per two sweeps.  Only the last sweep's rows go back to global memory; the results are those of NS single launches,
+// bit for bit.  Emission (EMIT != 0) belongs to single-sweep launches.
+template <bool SOR, int EMIT, typename TO, int MINB, int NS, int MAXT>
+__global__ void __launch_bounds__(MAXT, MINB) gibbs_torus_sweep_fused(const TorusSweepParams p, const int TR) {
     extern __shared__ __align__(128) float fsm[];
+    constexpr int HB = 2 * NS, HR = 2 * NS - 1;             // halo rows above the tile: black, red
     const int h = p.h, n1 = p.n1, hv = h >> 2, G = p.G;
     const int r0 = blockIdx.x * TR;
     const int rows = min(TR, n1 - r0);                        // even: TR and n1 are
@@ -458,15 +464,15 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
     const float* __restrict__ gblk = p.black + ch * plane;
     float* __restrict__ ored = p.red_out + ch * plane;        // write to the other pair: tiles of the
     float* __restrict__ oblk = p.black_out + ch * plane;      // same launch never see each other's output
-    float* sB = fsm;                                       // [TR + 4][h]: black rows r0-2 ..
-    float* sR = fsm + (size_t)(TR + 4) * h;                // [TR + 2][h]: red rows r0-1 ..
-    uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + (size_t)(2 * TR + 6) * h);
+    float* sB = fsm;                                       // [TR + 2 HB][h]: black rows r0 - HB ..
+    float* sR = fsm + (size_t)(TR + 2 * HB) * h;           // [TR + 2 HR][h]: red rows r0 - HR ..
+    uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + (size_t)(2 * TR + 2 * HB + 2 * HR) * h);
     const uint32_t row_bytes = (uint32_t)h * 4u;
     const uint32_t aB = smem_u32(sB), aR = smem_u32(sR);   // shared-space addresses
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
-        mbar_expect_tx(bar, row_bytes * (uint32_t)(2 * rows + 6));
+        mbar_expect_tx(bar, row_bytes * (uint32_t)(2 * rows + 2 * HB + 2 * HR));
         // rows are contiguous in HBM except at the torus wrap: at most three bulk copies per colour
         auto copy_rows = [&](float* dst, const float* src, int first, int cnt) {
             int done = 0;
@@ -478,8 +484,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
                 done += run;
             }
         };
-        copy_rows(sB, gblk, r0 - 2, rows + 4);
-        copy_rows(sR, gred, r0 - 1, rows + 2);
+        copy_rows(sB, gblk, r0 - HB, rows + 2 * HB);
+        copy_rows(sR, gred, r0 - HR, rows + 2 * HR);
 #ifdef MCLCAR_SWEEP_EXPERIMENTS
         if (p.prefetch_ahead > 0) {
             // warm L2 with the tile of the CTA that will follow this one onto the SM: CTAs are dispatched in linear
@@ -503,43 +509,57 @@ __global__ void __launch_bounds__(kFusedMaxThreads, MINB) gibbs_torus_sweep_fuse
     const uint64_t gch = (uint64_t)(p.chain0 + ch * p.chain_stride);
     const uint32_t c2 = (uint32_t)gch, c3 = (uint32_t)(gch >> 32) ^ (kTagTorus << 16);
     double acc[3] = {0.0, 0.0, 0.0};
-
-    // ---- phase 1: red rows r0-1 .. r0+rows (local 0 .. rows+1) in (rows + 2) / 2 pairs, black neighbours from sB
-    {
-        const int items = ((rows + 2) >> 1) * G;
-        for (int t0 = 0; t0 < items; t0 += blockDim.x) {         // uniform trip count: the items shuffle within their warp
-            const int t = t0 + threadIdx.x;
-            const bool valid = t < items;
-            const int q = valid ? (int)__umulhi((uint32_t)t, p.Gmagic) : 0, g = valid ? t - q * G : 0;
-            const int lA = 2 * q;                              // local red row of A; its black row in sB is lA + 1
-            int iA = r0 - 1 + lA;
-            iA = iA < 0 ? iA + n1 : iA;                        // only the first tile wraps at the top,
-            int iB = r0 + lA;
-            iB = iB >= n1 ? iB - n1 : iB;                      // only the last tile at the bottom
-            // halo rows (the first A, the last B) are recomputed, not stored
-            fused_item<SOR, false, 0, TO>(p, valid, aB + (uint32_t)(lA + 1) * row_bytes, aR + (uint32_t)lA * row_bytes, ored, (uint32_t)(iA * h),
-                                          (uint32_t)(iB * h), lA >= 1, lA + 1 <= rows, nullptr, 0u, nullptr, (uint32_t)iA, (uint32_t)iB, g, hv, h,
-                                          p.sweep * 2u, c2, c3, acc);
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: black rows r0 .. r0+rows-1 in rows / 2 pairs from the new red rows in sR
     TO* esample = nullptr;                                    // this chain's sample in the output matrix (emitting sweeps)
     if (EMIT == 1) {
         if (ch < p.nch) esample = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld;
     }
-    {
-        const int items = (rows >> 1) * G;
-        for (int t0 = 0; t0 < items; t0 += blockDim.x) {
-            const int t = t0 + threadIdx.x;
-            const bool valid = t < items;
-            const int q = valid ? (int)__umulhi((uint32_t)t, p.Gmagic) : 0, g = valid ? t - q * G : 0;
-            const int tA = 2 * q;
-            const int iA = r0 + tA, iB = iA + 1;
-            fused_item<SOR, true, EMIT, TO>(p, valid, aR + (uint32_t)(tA + 1) * row_bytes, aB + (uint32_t)(tA + 2) * row_bytes, oblk,
-                                            (uint32_t)(iA * h), (uint32_t)(iB * h), true, true, esample, (uint32_t)(iA * 2 * h), p.mu,
-                                            (uint32_t)iA, (uint32_t)iB, g, hv, h,
-                                            p.sweep * 2u + 1u, c2, c3, acc);
+
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const bool last = k == NS - 1;
+        const uint32_t swp = (p.sweep + (uint32_t)k) * 2u;
+        if (k > 0) __syncthreads();
+        // ---- red rows r0 - HR + 2k .. r0 + rows + HR - 2k - 1 (local 2k ..) in pairs, black neighbours from sB
+        {
+            const int items = ((rows + 2 * HR - 4 * k) >> 1) * G;
+            for (int t0 = 0; t0 < items; t0 += blockDim.x) {     // uniform trip count
+                const int t = t0 + threadIdx.x;
+                const bool valid = t < items;
+                const int q = valid ? (int)__umulhi((uint32_t)t, p.Gmagic) : 0, g = valid ? t - q * G : 0;
+                const int lA = 2 * k + 2 * q;                      // local red row of A in sR; its black row in sB is lA + 1
+                int iA = r0 - HR + lA;
+                iA = iA < 0 ? iA + n1 : (iA >= n1 ? iA - n1 : iA);
+                int iB = r0 - HR + lA + 1;
+                iB = iB < 0 ? iB + n1 : (iB >= n1 ? iB - n1 : iB);
+                // only the last sweep's rows inside the tile are stored (halo rows are recomputed by the neighbours)
+                const bool stA = last && lA >= HR && lA < HR + rows, stB = last && lA + 1 >= HR && lA + 1 < HR + rows;
+                fused_item<SOR, false, 0, TO, true>(p, valid, aB + (uint32_t)(lA + 1) * row_bytes, aR + (uint32_t)lA * row_bytes, ored,
+                                                    (uint32_t)(iA * h), (uint32_t)(iB * h), stA, stB, nullptr, 0u, nullptr, (uint32_t)iA,
+                                                    (uint32_t)iB, g, hv, h, swp, c2, c3, acc);
+            }
+        }
+        __syncthreads();
+        // ---- black rows r0 - HR + 2k + 1 .. (local 2k + 2 .. in sB) from the new red rows in sR
+        {
+            const int items = ((rows + 2 * HR - 2 - 4 * k) >> 1) * G;
+            for (int t0 = 0; t0 < items; t0 += blockDim.x) {
+                const int t = t0 + threadIdx.x;
+                const bool valid = t < items;
+                const int q = valid ? (int)__umulhi((uint32_t)t, p.Gmagic) : 0, g = valid ? t - q * G : 0;
+                const int lb = 2 * k + 2 + 2 * q;                  // local black row of A in sB; its red row in sR is lb - 1
+                int iA = r0 - HB + lb;
+                iA = iA < 0 ? iA + n1 : (iA >= n1 ? iA - n1 : iA);
+                int iB = r0 - HB + lb + 1;
+                iB = iB < 0 ? iB + n1 : (iB >= n1 ? iB - n1 : iB);
+                if (last)      // exactly the tile's rows: stored (and emitted)
+                    fused_item<SOR, true, EMIT, TO, false>(p, valid, aR + (uint32_t)(lb - 1) * row_bytes, aB + (uint32_t)lb * row_bytes, oblk,
+                                                           (uint32_t)(iA * h), (uint32_t)(iB * h), true, true, esample, (uint32_t)(iA * 2 * h), p.mu,
+                                                           (uint32_t)iA, (uint32_t)iB, g, hv, h, swp + 1u, c2, c3, acc);
+                else           // an inner sweep: the new black rows stay in shared memory for the next red phase
+                    fused_item<SOR, true, 0, TO, true>(p, valid, aR + (uint32_t)(lb - 1) * row_bytes, aB + (uint32_t)lb * row_bytes, oblk,
+                                                       (uint32_t)(iA * h), (uint32_t)(iB * h), false, false, nullptr, 0u, nullptr,
+                                                       (uint32_t)iA, (uint32_t)iB, g, hv, h, swp + 1u, c2, c3, acc);
+            }
         }
     }
     if (EMIT == 2) {
@@ -693,8 +713,27 @@ int torus_fused_tile_rows(const mclcar_ctx* ctx) {
 // one full sweep (both colours) of all chains; omega in [1, 2): over-relaxation factor.  When
 // `emit` is given (16-byte path only) the black half sweep also writes the samples -- or, with
 // emit->stats_q set (fused sweep, constant mean, fp32 samples), their sufficient statistics instead.
+// tile height of the two-sweeps-per-launch form (0: not available): two CTAs of <= 110 KB per SM, 4 + 3 halo rows per
+// colour and tile end
+int torus_fused2_tile_rows(const mclcar_ctx* ctx) {
+    if (!torus_fused_tile_rows(ctx)) return 0;
+    const char* e2 = getenv("MCLCAR_SWEEP_DOUBLE");
+    if (e2 && atoi(e2) == 0) return 0;
+    const size_t row_b = (size_t)(ctx->n2 / 2) * 4;
+    int TR = (int)((110 * 1024 / row_b - 14) / 2);
+    TR = std::min(TR, 64) & ~1;
+    if (const char* e = getenv("MCLCAR_SWEEP_TR2")) {
+        const int v = atoi(e);
+        if (v > 0) TR = v & ~1;
+    }
+    if (TR < 8 || ctx->n1 < TR + 8) return 0;
+    return TR;
+}
+
+// `want` >= 2 without emission: two sweeps (sweep, sweep + 1) in one launch where the lattice allows; *done = sweeps made
 int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep,
-                const TorusEmit* emit) {
+                const TorusEmit* emit, int want, int* done) {
+    if (done) *done = 1;
     TorusSweepParams p{};
     p.red = t.red; p.black = t.black; p.n1 = ctx->n1; p.h = ctx->n2 / 2; p.C = t.C;
     p.G = (p.h / 4 + 1) / 2;
@@ -717,7 +756,8 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
         }
         const bool f32 = !emit || emit->dtype == MCLCAR_F32;
         const bool want_stats = emit && emit->stats_q != nullptr;
-        const int TR = torus_fused_tile_rows(ctx);
+        const int TR2 = (want >= 2 && !emit && done) ? torus_fused2_tile_rows(ctx) : 0;
+        const int TR = TR2 ? TR2 : torus_fused_tile_rows(ctx);
         if (want_stats && (!TR || emit->d_mu || !f32))
             return fail(ctx, MCLCAR_ESTATE, "statistics-only emission needs the fused sweep, a constant mean and fp32 samples");
         if (TR) {
@@ -737,17 +777,33 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
             std::swap(t.black, t.black2);
             {   // item index -> (row pair, block) by a multiply: exact for every index a tile can have
                 p.Gmagic = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)p.G) + 1u;
-                const uint32_t tmax = (uint32_t)(((TR + 2) / 2) * p.G + kFusedMaxThreads);
+                const uint32_t tmax = (uint32_t)(((TR + 6) / 2) * p.G + 2 * kFusedMaxThreads);
                 if ((uint64_t)tmax * p.G >= ((uint64_t)1 << 32)) return fail(ctx, MCLCAR_ELIMIT, "lattice row too long for the fused sweep");
             }
             int fthreads = 256;
             if (const char* e = getenv("MCLCAR_SWEEP_THREADS")) fthreads = std::min(std::max(atoi(e), 64), kFusedMaxThreads) & ~31;
-            const size_t smem = (size_t)(2 * TR + 6) * row_b + 64 + (kFusedMaxThreads / 32) * 3 * sizeof(double);
+            size_t smem = (size_t)(2 * TR + 6) * row_b + 64 + (kFusedMaxThreads / 32) * 3 * sizeof(double);
             dim3 grid(tiles, (unsigned)t.C);
+            if (TR2) {      // two sweeps in one launch
+                constexpr int kT2 = 448;
+                int th2 = kT2;
+                if (const char* e = getenv("MCLCAR_SWEEP2_THREADS")) th2 = std::min(std::max(atoi(e), 64), kT2) & ~31;
+                smem = (size_t)(2 * TR + 14) * row_b + 64;
+                if (sor) {
+                    MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<true, 0, float, 2, 2, kT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    gibbs_torus_sweep_fused<true, 0, float, 2, 2, kT2><<<grid, th2, smem, ctx->stream>>>(p, TR);
+                } else {
+                    MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<false, 0, float, 2, 2, kT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    gibbs_torus_sweep_fused<false, 0, float, 2, 2, kT2><<<grid, th2, smem, ctx->stream>>>(p, TR);
+                }
+                MCL_CUDA(ctx, cudaGetLastError());
+                *done = 2;
+                return MCLCAR_OK;
+            }
 #define LAUNCH_FUSED_B(S, E, TO_, B_)                                                                            \
     do {                                                                                                         \
-        MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gibbs_torus_sweep_fused<S, E, TO_, B_><<<grid, fthreads, smem, ctx->stream>>>(p, TR);                   \
+        MCL_CUDA(ctx, cudaFuncSetAttribute(gibbs_torus_sweep_fused<S, E, TO_, B_, 1, kFusedMaxThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gibbs_torus_sweep_fused<S, E, TO_, B_, 1, kFusedMaxThreads><<<grid, fthreads, smem, ctx->stream>>>(p, TR);   \
     } while (0)
 #define LAUNCH_FUSED(S, E, TO_) LAUNCH_FUSED_B(S, E, TO_, 3)
             if (want_stats) {

@@ -174,6 +174,28 @@ def test_fused_sweep_is_bit_identical_to_two_half_sweeps(monkeypatch):
     assert np.abs(out[("1", 0.0)] - out[("1", 1.0)]).max() > 0.1
 
 
+@pytest.mark.parametrize("n1,n2,tr2", [(96, 128, 0), (200, 64, 0), (120, 1000, 0), (72, 256, 16)])
+def test_two_sweeps_per_launch_are_bit_identical_to_single_sweeps(n1, n2, tr2, monkeypatch):
+    """Sweeps that emit nothing run two to a launch (the tile stays in shared memory for red, black, red, black; halo
+    rows recomputed from the same Philox counters): the samples must equal those of single-sweep launches bit for bit --
+    odd and even numbers of plain sweeps, tiles that wrap around the torus, a ragged last tile, a forced small tile."""
+    n = n1 * n2
+    rng = np.random.default_rng(n1)
+    y = rng.standard_normal(n)
+    X = np.ones((n, 1))
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MCLCAR_SWEEP_DOUBLE", mode)
+        if tr2:
+            monkeypatch.setenv("MCLCAR_SWEEP_TR2", str(tr2))
+        for omega in (0.0, 1.0):
+            d = api.make_data(y, X=X, torus=(n1, n2), seed=13)
+            sd = api.mcl_prep_dCAR([0.22, 1.1, 0.4], 9, d, {"n.chains": 3, "burn": 7, "thin": 5, "omega": omega})
+            out[(mode, omega)] = sd.simY
+    for omega in (0.0, 1.0):
+        np.testing.assert_array_equal(out[("1", omega)], out[("0", omega)])
+
+
 def test_fused_sweep_fp64_samples_with_site_mean(monkeypatch):
     """Many chains, a fp64 sample matrix and a non-constant mean X beta0: the fused sweep's emission
     path is still bit-identical to the two-launch form."""
