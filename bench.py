@@ -398,8 +398,17 @@ def run_ours(args):
     try:  # measured DRAM traffic of the dominant kernel (one ncu --set full capture, profiles/)
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)["gibbs_torus_sweep_fused"]
-        if launches_per_sweep < 1.5:
-            traffic = tr["dram_bytes_per_launch"] * chains / tr["chains"]
+        # launches of a step by kind, from the schedule: emitting sweeps (one per kept state), two-sweep launches for
+        # the sweeps that emit nothing (when the library uses them), single plain sweeps for the rest
+        emits = (N_gpu + chains - 1) // chains
+        burn_, thin_ = int(diag["burn"]), int(diag["thin"])
+        per_step = sweep_launches / max(args.steps, 1)
+        doubles = burn_ // 2 + emits * ((thin_ - 1) // 2)
+        singles = burn_ % 2 + emits * ((thin_ - 1) % 2)
+        if abs(per_step - (doubles + singles + emits)) < 0.5 and "double" in tr:
+            traffic = (doubles * tr["double"] + singles * tr["plain"] + emits * tr["emitting"]) / per_step * chains / tr["chains"]
+        elif abs(per_step - (burn_ + emits * thin_)) < 0.5:
+            traffic = ((burn_ + emits * (thin_ - 1)) * tr["plain"] + emits * tr["emitting"]) / per_step * chains / tr["chains"]
     except Exception:
         pass
     line = {
@@ -420,7 +429,7 @@ def run_ours(args):
                      "frac": (sweep_gbs / peak) if sweep_gbs else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "algorithmic_bytes_per_site_update": bytes_per_update,
                      "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
-                     "launches": sweep_launches, "peak_source": peak_src,
+                     "launches": sweep_launches, "sweeps_per_launch": 1.0 / max(launches_per_sweep, 1e-9), "peak_source": peak_src,
                      "share_of_step": sweep_ms / (1e3 * t_res) if t_res > 0 else None,
                      "note": "reported against the HBM roofline as the contract asks.  ncu without the power cap (profiles/r02_ncu_sweep.md): 170 us per "
                              "launch of 130 chains = 0.93 of the HBM peak, DRAM 71 %, issue slots 65 % busy; the full-size bench runs under the 1 kW "

@@ -715,10 +715,15 @@ int torus_fused_tile_rows(const mclcar_ctx* ctx) {
 // emit->stats_q set (fused sweep, constant mean, fp32 samples), their sufficient statistics instead.
 // tile height of the two-sweeps-per-launch form (0: not available): two CTAs of <= 110 KB per SM, 4 + 3 halo rows per
 // colour and tile end
-int torus_fused2_tile_rows(const mclcar_ctx* ctx) {
+// Measured (profiles/r02_sweep_experiments.md): under the power cap of a sustained full-size run the two-sweep form is
+// 7 % faster (less energy per site update: 4.7 instead of 8 bytes of HBM traffic, SM clock 1.93 instead of 1.79 GHz);
+// in short runs at boost clocks it is 3 % slower (two larger CTAs per SM hide latency less well than three).  It is
+// therefore used for launches of >= 10^8 site updates -- the sustained regime -- unless MCLCAR_SWEEP_DOUBLE = 1 | 0 says otherwise.
+int torus_fused2_tile_rows(const mclcar_ctx* ctx, int64_t chains) {
     if (!torus_fused_tile_rows(ctx)) return 0;
     const char* e2 = getenv("MCLCAR_SWEEP_DOUBLE");
     if (e2 && atoi(e2) == 0) return 0;
+    if (!(e2 && atoi(e2) != 0) && chains * (int64_t)ctx->n < 100000000ll) return 0;
     const size_t row_b = (size_t)(ctx->n2 / 2) * 4;
     int TR = (int)((110 * 1024 / row_b - 14) / 2);
     TR = std::min(TR, 64) & ~1;
@@ -756,7 +761,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
         }
         const bool f32 = !emit || emit->dtype == MCLCAR_F32;
         const bool want_stats = emit && emit->stats_q != nullptr;
-        const int TR2 = (want >= 2 && !emit && done) ? torus_fused2_tile_rows(ctx) : 0;
+        const int TR2 = (want >= 2 && !emit && done) ? torus_fused2_tile_rows(ctx, t.C) : 0;
         const int TR = TR2 ? TR2 : torus_fused_tile_rows(ctx);
         if (want_stats && (!TR || emit->d_mu || !f32))
             return fail(ctx, MCLCAR_ESTATE, "statistics-only emission needs the fused sweep, a constant mean and fp32 samples");

@@ -4,8 +4,10 @@ S=scripts/ncu_summary.py
 {
 echo "# Round 2 - ncu \`--set full --clock-control none --import-source on\` of the torus sweep (B200, one GPU)"; echo
 echo "Command: \`scripts/profile_r02.sh\` (bench.py --config c5 --samples-per-gpu 2980 --steps 1 --warmup 1, 130 chains x 1000 x 1000; the profiled command first ran plain and exited 0)."
-echo "Launch 1 = plain sweep, launch 2 = emitting sweep (1 in 5: also writes the 520 MB of finished fp32 samples)."; echo
+echo "Launch 1 = a TWO-sweep launch (red, black, red, black on a tile of 20 rows + 14 halo rows: sweeps that emit nothing), launch 2 = emitting single sweep (1 in 5: also writes the 520 MB of finished fp32 samples)."; echo
 python $S gpurun_out/r02_prof_sweep.ncu-rep
+echo; echo "## single-sweep launches (MCLCAR_SWEEP_DOUBLE=0): plain sweep, emitting sweep"; echo
+python $S gpurun_out/r02_prof_sweep_single.ncu-rep
 echo; echo "## statistics-only emission (\`keep = 0\`: EMIT = 2, sufficient statistics accumulated in the emitting sweep instead of writing samples)"; echo
 python $S gpurun_out/r02_prof_sweep_stats.ncu-rep
 echo; echo "## config 2 (256 x 256 torus, 500 chains, TR = 64: 4 tiles per chain)"; echo
@@ -28,6 +30,6 @@ python $S gpurun_out/r02_prof_hcar.ncu-rep; } > profiles/r02_ncu_hcar.md
 { echo "# Round 2 - ncu launch lists (\`--metrics gpu__time_duration.sum --clock-control none\`) of \`bench.py --config cN --steps 1 --warmup 1\`"; echo
 echo "Cold-cache, serialised launches: compare SHARES with the bench's own CUDA-event spans (\`kernels\` / \`roofline.share_of_step\` in r02_bench_*.json), not absolutes."
 for c in c5 c2 c3 c4; do echo; echo "## $c"; echo; python scripts/launch_list_md.py gpurun_out/r02_launches_$c.csv; done; } > profiles/r02_launches.md
-for c in c1 c2 c3 c4 c5 c5_statsonly reference; do cp gpurun_out/r02_bench_$c.json profiles/r02_bench_$c.json; done
+for c in c1 c2 c3 c4 c5 c5_statsonly c5_single reference; do cp gpurun_out/r02_bench_$c.json profiles/r02_bench_$c.json; done
 cuobjdump -sass mclcar_b200/build/sampler_torus.o 2>/dev/null | awk '/Function : .*gibbs_torus_sweep_fused.*Lb1ELi0EfLi3E/{f=1;next} f&&/Function : /{f=0} f' > /tmp/fused_sass.txt
 { echo "# SASS evidence: bulk-copy engine and mbarrier instructions per kernel (\`python scripts/sass_evidence.py\`, cuobjdump -sass of the built library)"; echo; python scripts/sass_evidence.py; echo; echo "Excerpt, \`gibbs_torus_sweep_fused<SOR, EMIT = 0, float>\` tile load:"; echo '```'; grep "SYNCS\|UBLKCP\|UBLKPF" /tmp/fused_sass.txt | sed 's/^\s*//' | cut -c1-110 | head -12; echo '```'; } > profiles/r02_sass_excerpt.md

@@ -12,6 +12,7 @@ run() { echo "== $*" >> $O/r02_profile.log; "$@" >> $O/r02_profile.log 2>&1; ech
 # 1. bench lines (numbers never come from a profiled run)
 python bench.py --steps 5 --warmup 3 > $O/r02_bench_c5.json 2> $O/r02_bench_c5.err
 python bench.py --steps 5 --warmup 3 --stats-only --no-cpu-baseline > $O/r02_bench_c5_statsonly.json 2> $O/r02_bench_c5_statsonly.err
+MCLCAR_SWEEP_DOUBLE=0 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-fp64 > $O/r02_bench_c5_single.json 2> $O/r02_bench_c5_single.err
 for c in c1 c2 c3 c4; do python bench.py --config $c > $O/r02_bench_$c.json 2> $O/r02_bench_$c.err; done
 python bench.py --impl reference --steps 2 --warmup 1 > $O/r02_bench_reference.json 2> $O/r02_bench_reference.err
 
@@ -28,8 +29,9 @@ full() {  # name config kernel-regex skip count [extra bench flags]
   local name=$1 cfg=$2 k=$3 skip=$4 cnt=$5; shift 5
   run $NCU --set full --import-source on -k regex:$k --launch-skip $skip -c $cnt -f -o $O/r02_prof_$name python bench.py --config $cfg $small "$@"
 }
-full sweep        c5 'gibbs_torus_sweep_fused' 40 2 --samples-per-gpu 2980
-full sweep_stats  c5 'gibbs_torus_sweep_fused' 16 1 --samples-per-gpu 2980 --stats-only
+full sweep        c5 'gibbs_torus_sweep_fused' 40 2 --samples-per-gpu 2980     # launch 40 = a two-sweep launch, 41 = an emitting sweep
+MCLCAR_SWEEP_DOUBLE=0 full sweep_single c5 'gibbs_torus_sweep_fused' 40 2 --samples-per-gpu 2980   # single-sweep launches: plain, emitting
+full sweep_stats  c5 'gibbs_torus_sweep_fused' 17 1 --samples-per-gpu 2980 --stats-only   # 6 burn-in launches, then (double, double, emit) per kept state
 full stats_torus  c5 'stats_torus_kernel'       1 1 --samples-per-gpu 2980
 full k3           c5 'k3_moments'               1 1 --samples-per-gpu 2980
 full csr_sampler  c3 'gibbs_csr_kernel'         0 1
