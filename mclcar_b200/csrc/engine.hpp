@@ -307,7 +307,7 @@ inline uint64_t begin_draw(mclcar_ctx* ctx) {
     return ctx->draw_key;
 }
 void default_schedule(const mclcar_ctx* ctx, double rho, double* omega, int* burn, int* thin);
-int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N);
+int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N, int burn = 0, int thin = 0);
 int64_t default_torus_chains(int n, int64_t N, int burn, int thin);
 int dcar_ensure_stats(mclcar_ctx* ctx, mclcar_samples* s);
 

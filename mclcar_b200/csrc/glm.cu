@@ -868,7 +868,7 @@ int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int6
     g.qoff.resize(ctx->colidx.size());
     for (size_t e = 0; e < g.qoff.size(); ++e) g.qoff[e] = -rho * (ctx->binary ? 1.0 : ctx->val[e]) / sigma;
     int st = pool_alloc(ctx, &s->d_M, (size_t)n * s->ld * es);
-    const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
+    const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N, burn, thin);
     const uint64_t draw0 = ctx->draw;
     int64_t sweeps_total = 0;
     // z'z and z'Wz of the kept states come out of the chain kernel itself (binary W, fp32 samples): at emission the state

@@ -674,7 +674,7 @@ int mclcar_hcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int64_t N, cons
     const int64_t align = 16 / es;
     s->ld = (N + align - 1) / align * align;
     int st = pool_alloc(ctx, &s->d_M, (size_t)K * s->ld * es);
-    const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, K, N);
+    const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, K, N, burn, thin);
     const double omega = o.omega > 0 ? o.omega : 1.0;
     if (st == MCLCAR_OK)
         st = run_csr_sampler(ctx, g, FAM_GAUSS, omega, nullptr, nullptr, nullptr, nullptr, N, C, burn, thin, s->d_M,

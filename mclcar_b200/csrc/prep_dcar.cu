@@ -104,14 +104,23 @@ bool use_torus_sampler(const mclcar_ctx* ctx) {
     return ctx->kind == GRAPH_TORUS && ctx->n1 % 2 == 0 && ctx->n2 % 2 == 0 && (size_t)ctx->n * 8 * sizeof(float) > 200 * 1024;
 }
 
-int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N) {
+// Chains of the shared-memory chain sampler.  The upper end fills every SM's shared memory with chains; the schedule
+// then decides how many of them pay: C chains cost C * burn sweeps before the first kept state and N * thin after, so
+// the count is halved while the burn-in would still be more than half of the kept-state sweeps (never below two
+// blocks of chains per SM).  Measured on one B200 (scripts/exp_chains.py): 10 x 10 HCAR map, 20 000 states, 18 944
+// chains 0.43 ms -> 2 368 chains 0.24 ms; 40 x 40 binomial GLM, 10 000 states, 1 184 chains 16.8 ms -> 592 chains 15.5 ms.
+int64_t default_csr_chains(const mclcar_ctx* ctx, int n, int64_t N, int burn, int thin) {
     const size_t cap = 200 * 1024;
     int cbmax = 0;
     for (int cb : {32, 16, 8, 4, 2})
         if ((size_t)(n + 1) * cb * sizeof(float) <= cap) { cbmax = cb; break; }
     if (!cbmax) return std::min<int64_t>(N + (N & 1), (int64_t)ctx->n_sm * 2 * 32);
     int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, cap / ((size_t)n * cbmax * sizeof(float))));
-    const int64_t c_auto = (int64_t)ctx->n_sm * per_sm * cbmax;
+    int64_t c_auto = (int64_t)ctx->n_sm * per_sm * cbmax;
+    if (burn > 0 && thin > 0 && !getenv("MCLCAR_CHAINS_FILL")) {
+        const double c_pay = (double)N * thin / (2.0 * burn);
+        while ((double)c_auto > c_pay && c_auto / 2 >= (int64_t)ctx->n_sm * 4) c_auto /= 2;
+    }
     return std::max<int64_t>(2, std::min<int64_t>(c_auto, N + (N & 1)));
 }
 
@@ -253,7 +262,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         g.qoff.resize(ctx->colidx.size());
         for (size_t e = 0; e < g.qoff.size(); ++e) g.qoff[e] = -rho * (ctx->binary ? 1.0 : ctx->val[e]) / sigma;
         st = pool_alloc(ctx, &s->d_M, (size_t)n * ld * es);
-        const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
+        const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N, burn, thin);
         if (st == MCLCAR_OK)
             st = run_csr_sampler(ctx, g, FAM_GAUSS, omega, mu.empty() ? nullptr : mu.data(), nullptr, nullptr, nullptr, N, C, burn, thin,
                                  s->d_M, o.dtype == MCLCAR_F64, ld, &s->accept, &s->sweeps);
@@ -301,7 +310,7 @@ extern "C" int mclcar_dcar_plan(mclcar_ctx* ctx, double rho, int64_t N, const mc
         C = std::min<int64_t>(std::min<int64_t>(C, N), 65535);
         k = 1;
     } else {
-        C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N);
+        C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N, burn, thin);
         k = (size_t)(n + 1) * 2 * sizeof(float) <= 200 * 1024 ? 2 : 3;
     }
     if (kind) *kind = k;
