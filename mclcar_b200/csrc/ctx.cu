@@ -1,5 +1,6 @@
 // Context, model upload (graph / design / observations) and small host utilities.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <thread>
@@ -135,6 +136,20 @@ int ensure_pinned(mclcar_ctx* ctx, size_t bytes) {
     return MCLCAR_OK;
 }
 
+// MCLCAR_TRACE_HOST=1: wall-clock sections of the host-side set-up calls on stderr (scripts/exp_host_algebra.py)
+struct HostTrace {
+    const char* what;
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    explicit HostTrace(const char* w) : what(w), on(getenv("MCLCAR_TRACE_HOST") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char* section) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[host] %s: %s %.3f ms\n", what, section, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 ProfScope::ProfScope(mclcar_ctx* c, int category, int64_t n_launches) : ctx(c), cat(category) {
     ctx->launches[cat] += n_launches;
     if (ctx->profiling && cudaEventCreate(&a) == cudaSuccess) cudaEventRecord(a, ctx->stream);
@@ -184,8 +199,8 @@ static int upload_from(mclcar_ctx* ctx, T*& dptr, const T* src, size_t count) { 
 // of host threads that happen to run them), each range on its own thread.
 constexpr int kHostParts = 8;
 template <class Fn>
-static void host_parts(int n, Fn fn) {   // fn(part, begin, end)
-    if (n < (1 << 17)) {
+static void host_parts(int n, Fn fn, int64_t work = -1) {   // fn(part, begin, end); work: elements touched (default n)
+    if ((work < 0 ? (int64_t)n : work) < (1 << 17)) {
         for (int k = 0; k < kHostParts; ++k) fn(k, (int)((int64_t)n * k / kHostParts), (int)((int64_t)n * (k + 1) / kHostParts));
         return;
     }
@@ -232,7 +247,7 @@ static void spmv(const mclcar_ctx* c, const double* x, double* y) {
                     o[j] = (row[jl] + row[jr]) + (up[j] + dn[j]);
                 }
             }
-        });
+        }, (int64_t)n1 * n2);
         return;
     }
     host_parts(c->n, [&](int, int i0, int i1) {
@@ -250,6 +265,77 @@ static void invalidate_model(mclcar_ctx* ctx) {
     ctx->p = 0;
     ctx->X.clear(); ctx->WX.clear(); ctx->G0.clear(); ctx->G1.clear();
     ctx->y.clear(); ctx->ntrial.clear(); ctx->qobs.clear();
+    ctx->design_pending = ctx->obs_pending = false;
+}
+
+// The O(n) host algebra behind set_design / set_obs, formed on first use.  W X goes to the device through a pinned
+// staging buffer on the context's stream without a host wait (the device copy is consumed in stream order; the
+// staging buffer is reused only after the copy's event).
+int ensure_algebra(mclcar_ctx* ctx) {
+    if (!ctx->design_pending && !ctx->obs_pending) return MCLCAR_OK;
+    const int n = ctx->n, p = ctx->p;
+    if (ctx->design_pending) {
+        HostTrace tr("design algebra");
+        ctx->WX.resize((size_t)n * p);
+        for (int a = 0; a < p; ++a) spmv(ctx, ctx->X.data() + (size_t)a * n, ctx->WX.data() + (size_t)a * n);
+        tr.mark("W X");
+        ctx->G0.assign((size_t)p * p, 0.0);
+        ctx->G1.assign((size_t)p * p, 0.0);
+        for (int a = 0; a < p; ++a)
+            for (int b = 0; b < p; ++b) {
+                const double *xa = ctx->X.data() + (size_t)a * n, *xb = ctx->X.data() + (size_t)b * n,
+                             *wb = ctx->WX.data() + (size_t)b * n;
+                ctx->G0[(size_t)a * p + b] = dot4(xa, xb, n);
+                ctx->G1[(size_t)a * p + b] = dot4(xa, wb, n);
+            }
+        tr.mark("X'X, X'WX");
+        if (!ctx->host_only) {
+            if (ctx->d_WX) {
+                pool_free(ctx, ctx->d_WX);
+                ctx->d_WX = nullptr;
+            }
+            const size_t bytes = (size_t)n * p * sizeof(double);
+            if (bytes) {
+                MCL_TRY(pool_alloc(ctx, (void**)&ctx->d_WX, bytes));
+                if (ctx->wx_event) MCL_CUDA(ctx, cudaEventSynchronize(ctx->wx_event));   // the previous copy has left the staging buffer
+                if (ctx->h_wx_bytes < bytes) {
+                    if (ctx->h_wx) cudaFreeHost(ctx->h_wx);
+                    ctx->h_wx = nullptr; ctx->h_wx_bytes = 0;
+                    MCL_CUDA(ctx, cudaMallocHost(&ctx->h_wx, bytes));
+                    ctx->h_wx_bytes = bytes;
+                }
+                double* stage = (double*)ctx->h_wx;
+                const double* src = ctx->WX.data();
+                host_parts((int)std::min<size_t>((size_t)n * p, (size_t)INT32_MAX), [&](int, int i0, int i1) {
+                    std::memcpy(stage + i0, src + i0, (size_t)(i1 - i0) * sizeof(double));
+                });
+                MCL_CUDA(ctx, cudaMemcpyAsync(ctx->d_WX, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+                if (!ctx->wx_event) MCL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->wx_event, cudaEventDisableTiming));
+                MCL_CUDA(ctx, cudaEventRecord(ctx->wx_event, ctx->stream));
+            }
+            tr.mark("W X to the device (queued)");
+        }
+        ctx->design_pending = false;
+    }
+    if (ctx->obs_pending) {
+        HostTrace tr("observation algebra");
+        std::vector<double>& Wy = ctx->h_scratch;   // kept across calls: no 8 MB allocation and page faults per step
+        Wy.resize(n);
+        const double* y = ctx->y.data();
+        spmv(ctx, y, Wy.data());
+        tr.mark("W y");
+        ctx->qobs.assign(2 + 2 * p, 0.0);
+        ctx->qobs[0] = dot4(y, y, n);
+        ctx->qobs[1] = dot4(y, Wy.data(), n);
+        for (int a = 0; a < p; ++a) {
+            const double* xa = ctx->X.data() + (size_t)a * n;
+            ctx->qobs[2 + a] = dot4(xa, y, n);
+            ctx->qobs[2 + p + a] = dot4(xa, Wy.data(), n);
+        }
+        tr.mark("y'y, y'Wy, X'y, X'Wy");
+        ctx->obs_pending = false;
+    }
+    return MCLCAR_OK;
 }
 
 // greedy colouring in natural order (smallest free colour); colour classes keep site order
@@ -363,6 +449,8 @@ void mclcar_ctx_destroy(mclcar_ctx* ctx) {
         comm_destroy(ctx);
         for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
         if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        if (ctx->h_wx) cudaFreeHost(ctx->h_wx);
+        if (ctx->wx_event) cudaEventDestroy(ctx->wx_event);
         if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     }
     delete ctx;
@@ -609,23 +697,37 @@ int mclcar_set_design(mclcar_ctx* ctx, const double* X, int p) {
     if (p > 0 && !X) return MCLCAR_EINVAL;
     if (!ctx->host_only) MCL_TRY(require_device(ctx));
     const int n = ctx->n;
+    HostTrace tr("set_design");
     ctx->p = p;
-    ctx->X.assign(X, X + (size_t)n * p);
-    ctx->WX.resize((size_t)n * p);
-    for (int a = 0; a < p; ++a) spmv(ctx, ctx->X.data() + (size_t)a * n, ctx->WX.data() + (size_t)a * n);
-    ctx->G0.assign((size_t)p * p, 0.0);
-    ctx->G1.assign((size_t)p * p, 0.0);
-    for (int a = 0; a < p; ++a)
-        for (int b = 0; b < p; ++b) {
-            const double *xa = ctx->X.data() + (size_t)a * n, *xb = ctx->X.data() + (size_t)b * n,
-                         *wb = ctx->WX.data() + (size_t)b * n;
-            ctx->G0[(size_t)a * p + b] = dot4(xa, xb, n);
-            ctx->G1[(size_t)a * p + b] = dot4(xa, wb, n);
-        }
+    ctx->X.resize((size_t)n * p);
+    // the host copy, and in the same pass: is every column one constant?  (then X beta is one number and the
+    // statistics of the design columns follow from sum x)
+    bool all_const = true;
+    for (int a = 0; a < p; ++a) {
+        const double* src = X + (size_t)a * n;
+        double* dst = ctx->X.data() + (size_t)a * n;
+        bool part_const[kHostParts];
+        host_parts(n, [&](int k, int i0, int i1) {
+            const double x0 = src[0];
+            bool c = true;
+            for (int i = i0; i < i1; ++i) {
+                dst[i] = src[i];
+                c &= src[i] == x0;
+            }
+            part_const[k] = c;
+        });
+        for (int k = 0; k < kHostParts; ++k) all_const = all_const && part_const[k];
+    }
+    ctx->design_const = all_const;
+    tr.mark("copy X, constant columns");
     MCL_TRY(upload_from(ctx, ctx->d_X, X, (size_t)n * p));
-    MCL_TRY(upload(ctx, ctx->d_WX, ctx->WX));
+    tr.mark("upload X");
+    // W X, X'X, X'WX: formed when first needed (ensure_algebra) -- in an end-to-end step that is after the sampler's
+    // launches have been queued, so the host works while the device sweeps
+    ctx->design_pending = true;
     ctx->has_design = true;
     ctx->has_obs = false;  // qobs depends on X
+    ctx->obs_pending = false;
     return MCLCAR_OK;
 }
 
@@ -636,23 +738,20 @@ int mclcar_set_obs(mclcar_ctx* ctx, const double* y, const double* ntrial) {
         MCL_TRY(mclcar_set_design(ctx, nullptr, 0));
     }
     if (!ctx->host_only) MCL_TRY(require_device(ctx));
-    const int n = ctx->n, p = ctx->p;
-    ctx->y.assign(y, y + n);
+    const int n = ctx->n;
+    HostTrace tr("set_obs");
+    ctx->y.resize(n);
+    {
+        double* dst = ctx->y.data();
+        host_parts(n, [&](int, int i0, int i1) { std::memcpy(dst + i0, y + i0, (size_t)(i1 - i0) * sizeof(double)); });
+    }
     if (ntrial) ctx->ntrial.assign(ntrial, ntrial + n);
     else ctx->ntrial.clear();
-    std::vector<double>& Wy = ctx->h_scratch;   // kept across calls: no 8 MB allocation and page faults per step
-    Wy.resize(n);
-    spmv(ctx, ctx->y.data(), Wy.data());
-    ctx->qobs.assign(2 + 2 * p, 0.0);
-    ctx->qobs[0] = dot4(y, y, n);
-    ctx->qobs[1] = dot4(y, Wy.data(), n);
-    for (int a = 0; a < p; ++a) {
-        const double* xa = ctx->X.data() + (size_t)a * n;
-        ctx->qobs[2 + a] = dot4(xa, y, n);
-        ctx->qobs[2 + p + a] = dot4(xa, Wy.data(), n);
-    }
+    tr.mark("copy y");
     MCL_TRY(upload_from(ctx, ctx->d_y, y, (size_t)n));
     MCL_TRY(upload(ctx, ctx->d_ntrial, ctx->ntrial));
+    tr.mark("upload y");
+    ctx->obs_pending = true;   // y'y, y'Wy, X'y, X'Wy: ensure_algebra
     ctx->has_obs = true;
     return MCLCAR_OK;
 }

@@ -27,6 +27,7 @@ struct DcarAffine {
 };
 
 int build_affine(mclcar_ctx* ctx, const double* pars, int P, DcarAffine& m) {
+    MCL_TRY(ensure_algebra(ctx));
     const int p = ctx->p, d = 2 + 2 * p;
     if (P != 2 && P != 2 + p) return fail(ctx, MCLCAR_EINVAL, "parameter vector of length %d; expected 2 or %d", P, 2 + p);
     const int pb = P - 2;  // regression coefficients actually used
@@ -202,6 +203,7 @@ int dcar_finish(mclcar_ctx* ctx, const double* psi0, int P0, const double* psi, 
                 const double* rho_cons, const double* tuples, double* out0, double* out1) {
     if (!ctx || !psi0 || !psi || !tuples || !out0) return MCLCAR_EINVAL;
     if (!ctx->has_obs) return fail(ctx, MCLCAR_ESTATE, "set graph, design and observations first");
+    MCL_TRY(ensure_algebra(ctx));
     const int d = 2 + 2 * ctx->p;
     const int F = what == WHAT_LR ? 0 : P;
     const int64_t T = tuple_len(what, F, d);
@@ -302,6 +304,7 @@ int mclcar_dcar_attach(mclcar_ctx* ctx, mclcar_samples* s, const double* psi0, i
     MCL_TRY(check_ready(ctx, s, false));
     MCL_TRY(require_device(ctx));
     if (!psi0) return MCLCAR_EINVAL;
+    MCL_TRY(ensure_algebra(ctx));
     DcarAffine m0;
     MCL_TRY(build_affine(ctx, psi0, P, m0));
     s->psi0.assign(psi0, psi0 + P);

@@ -85,6 +85,12 @@ struct mclcar_ctx {
 
     // ---- observations
     bool has_obs = false;
+    bool design_const = true;    // every design column is a constant (intercept-only models): X beta is one number
+    // W X, X'X, X'WX (design) and the statistics of y (observations) are formed on first use: ensure_algebra()
+    bool design_pending = false, obs_pending = false;
+    void* h_wx = nullptr;        // pinned staging of W X on its way to the device
+    size_t h_wx_bytes = 0;
+    cudaEvent_t wx_event = nullptr;
     std::vector<double> y, ntrial;
     std::vector<double> qobs;  // (y'y, y'Wy, X'y[p], X'Wy[p])
     std::vector<double> h_scratch;  // W y of the last set_obs (host scratch)
@@ -186,6 +192,7 @@ void pool_trim(mclcar_ctx* ctx, size_t keep_bytes);
 int ensure(mclcar_ctx* ctx, DeviceBuf& b, size_t bytes);
 int ensure_pinned(mclcar_ctx* ctx, size_t bytes);
 int require_device(mclcar_ctx* ctx);
+int ensure_algebra(mclcar_ctx* ctx);   // call before reading WX, G0, G1, qobs or d_WX
 
 // ---- statistics kernels (stats_torus.cu / stats_csr.cu) -----------------------------------
 // q layout: [d][ldq]; d = 2 + 2p: (x'x, x'Wx, X'x[p], (WX)'x[p])
@@ -270,8 +277,8 @@ struct TorusEmit {   // where the black half sweep of an emitting sweep writes t
 int torus_fused_tile_rows(const mclcar_ctx* ctx);
 int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep,
                 const TorusEmit* emit = nullptr, int want = 1, int* done = nullptr);
-int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, int dtype, int64_t ld, int64_t slot0,
-               int64_t nch);
+int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, double mu_const, void* out, int dtype, int64_t ld,
+               int64_t slot0, int64_t nch);
 
 enum { FAM_GAUSS = 0, FAM_BINOM = 1, FAM_POIS = 2 };
 // host description (site order, fp64) of a Gaussian Markov random field exp(-x'Qx/2 + b'x)

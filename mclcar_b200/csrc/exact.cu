@@ -52,6 +52,7 @@ int solve_small(std::vector<double> A, std::vector<double> b, int p, double* x) 
 
 // (sigma, beta) at one rho from G0, G1 and the observed-data statistics
 int sigmabeta_one(mclcar_ctx* ctx, double rho, double* out) {
+    MCL_TRY(ensure_algebra(ctx));
     const int p = ctx->p, n = ctx->n;
     const double* q = ctx->qobs.data();
     std::vector<double> A((size_t)p * p), b(p), beta(p);
@@ -137,6 +138,7 @@ int mclcar_dcar_loglik(mclcar_ctx* ctx, const double* psi, int K, int P, const d
     std::vector<double> rho(K), ld(K);
     for (int k = 0; k < K; ++k) rho[k] = psi[(size_t)k * P];
     MCL_TRY(logdet_sums(ctx, rho.data(), K, ld.data()));
+    MCL_TRY(ensure_algebra(ctx));
     const double* q = ctx->qobs.data();
     for (int k = 0; k < K; ++k) {
         const double* t = psi + (size_t)k * P;
@@ -179,6 +181,7 @@ int mclcar_dcar_hessian_exact(mclcar_ctx* ctx, const double* pars, int P, double
     const int p = ctx->p, n = ctx->n;
     if (P != 2 && P != 2 + p) return fail(ctx, MCLCAR_EINVAL, "parameter vector of length %d; expected 2 or %d", P, 2 + p);
     MCL_TRY(ensure_spectrum(ctx));
+    MCL_TRY(ensure_algebra(ctx));
     const int pb = P - 2;
     const double rho = pars[0], sg = pars[1];
     const double* beta = pars + 2;

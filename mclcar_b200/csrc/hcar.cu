@@ -245,6 +245,7 @@ int hcar_check(mclcar_ctx* ctx, mclcar_samples* s, HcarModel** hm) {
     if (s->ctx != ctx) return fail(ctx, MCLCAR_EINVAL, "sample set belongs to another context");
     if (s->sites != (*hm)->K) return fail(ctx, MCLCAR_EINVAL, "sample matrix has %lld rows, the model has %d districts", (long long)s->sites, (*hm)->K);
     if ((*hm)->has_W) MCL_TRY(ensure_spectrum(ctx));
+    MCL_TRY(ensure_algebra(ctx));
     return MCLCAR_OK;
 }
 
@@ -322,6 +323,7 @@ int mclcar_hcar_set_model(mclcar_ctx* ctx, int K, const int* M_rowptr, const int
     if (!ctx || !M_rowptr || !M_colidx || !Z_rowptr || !Z_colidx || !eig_M) return MCLCAR_EINVAL;
     if (ctx->kind == GRAPH_NONE || !ctx->has_obs) return fail(ctx, MCLCAR_ESTATE, "set graph (W, possibly empty), design and observations first");
     if (K < 1) return fail(ctx, MCLCAR_EINVAL, "K must be positive");
+    MCL_TRY(ensure_algebra(ctx));
     const int n = ctx->n, p = ctx->p;
     HcarModel hm;
     hm.K = K; hm.has_W = has_W != 0;

@@ -149,13 +149,19 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
     const int n = ctx->n;
     const size_t es = o.dtype == MCLCAR_F32 ? 4 : 8;
 
-    // mean of the sampled field: X beta0
+    // mean of the sampled field, X beta0: one number when every design column is constant (known since the design
+    // was set), else a vector -- formed and uploaded while the burn-in sweeps run, which do not need it
+    const bool has_mu = P > 2;
+    const bool mu_is_const = !has_mu || ctx->design_const;
+    double mu0 = 0.0;
+    if (has_mu)
+        for (int l = 0; l < ctx->p; ++l) mu0 += ctx->X[(size_t)l * n] * psi0[2 + l];
     std::vector<double> mu;
-    if (P > 2) {
+    auto fill_mu = [&]() {
         mu.assign(n, 0.0);
         for (int l = 0; l < ctx->p; ++l)
             for (int i = 0; i < n; ++i) mu[i] += ctx->X[(size_t)l * n + i] * psi0[2 + l];
-    }
+    };
 
     mclcar_samples* s = new (std::nothrow) mclcar_samples();
     if (!s) return fail(ctx, MCLCAR_ENOMEM, "out of host memory");
@@ -176,35 +182,17 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         void* staging = nullptr;
         begin_draw(ctx);   // a fresh Philox stream for every mcl.prep.dCAR call (R draws fresh rnorm() each time)
         do {
-            if (!mu.empty()) {
-                if ((st = pool_alloc(ctx, (void**)&d_mu, (size_t)n * sizeof(double)))) break;
-                // fp32 samples: the emitting kernels add the mean as an fp32 pair (hi, lo) stored in the 8-byte slot
-                std::vector<double> mu_dev(mu);
-                if (o.dtype == MCLCAR_F32)
-                    for (int i = 0; i < n; ++i) {
-                        const float hi = (float)mu[i], lo = (float)(mu[i] - (double)hi);
-                        float pair[2] = {hi, lo};
-                        std::memcpy(&mu_dev[i], pair, sizeof(double));
-                    }
-                cudaError_t e = cudaMemcpyAsync(d_mu, mu_dev.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // mu is a local
-                if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ECUDA, "upload of X beta0 failed: %s", cudaGetErrorString(e)); break; }
-            }
-            // constant mean (intercept-only design): no per-site mean traffic in the emitting sweep
-            bool mu_is_const = true;
-            for (size_t i = 1; i < mu.size() && mu_is_const; ++i) mu_is_const = mu[i] == mu[0];
-            bool design_const = true;   // every design column constant: X'x and (WX)'x follow from sum x
-            for (int l = 0; l < ctx->p && design_const; ++l)
-                for (int i = 1; i < n && design_const; ++i) design_const = ctx->X[(size_t)l * n + i] == ctx->X[(size_t)l * n];
             // statistics-only sampling: the emitting sweep accumulates x'x, x'Wx and sum x of the samples it would
             // have written (no staging buffer, no statistics pass); otherwise samples go through a staging buffer of
             // one emission and the statistics kernel
-            const bool fused_stats = !o.keep && o.dtype == MCLCAR_F32 && mu_is_const && design_const &&
-                                     torus_fused_tile_rows(ctx) > 0 && !getenv("MCLCAR_NO_FUSED_STATS");
+            const bool fused_stats = o.dtype == MCLCAR_F32 && mu_is_const && ctx->design_const && torus_fused_tile_rows(ctx) > 0 &&
+                                     !getenv("MCLCAR_NO_FUSED_STATS") && !(o.keep && getenv("MCLCAR_NO_KEPT_FUSED_STATS"));
+            // kept samples under the same conditions: the emitting sweep writes the samples AND forms their statistics
+            // from the registers it writes them from -- the sample matrix is not read back by a statistics pass
             if (o.keep || !fused_stats)
                 if ((st = pool_alloc(ctx, o.keep ? &s->d_M : &staging, (size_t)(o.keep ? N : C) * ld * es))) break;
             if ((st = torus_chains_alloc(ctx, C, tc))) break;
-            if (!o.keep && (st = samples_alloc_stats(ctx, s, 2 + 2 * ctx->p))) break;
+            if ((!o.keep || fused_stats) && (st = samples_alloc_stats(ctx, s, 2 + 2 * ctx->p))) break;
             const bool fused = (ctx->n2 / 2) % 4 == 0;   // emission fused into the last black half sweep
             uint32_t sweep = 0;
             // sweeps that emit nothing go two to a launch where the lattice allows (the tile stays in shared memory)
@@ -219,13 +207,30 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
                 return rc;
             };
             st = plain_sweeps(burn);
+            if (st == MCLCAR_OK && !mu_is_const) {
+                if ((st = pool_alloc(ctx, (void**)&d_mu, (size_t)n * sizeof(double)))) break;
+                fill_mu();
+                // fp32 samples: the emitting kernels add the mean as an fp32 pair (hi, lo) stored in the 8-byte slot
+                if (o.dtype == MCLCAR_F32)
+                    for (int i = 0; i < n; ++i) {
+                        const float hi = (float)mu[i], lo = (float)(mu[i] - (double)hi);
+                        float pair[2] = {hi, lo};
+                        std::memcpy(&mu[i], pair, sizeof(double));
+                    }
+                cudaError_t e = cudaMemcpyAsync(d_mu, mu.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // mu is a local
+                if (e != cudaSuccess) { st = fail(ctx, MCLCAR_ECUDA, "upload of X beta0 failed: %s", cudaGetErrorString(e)); break; }
+            }
             for (int64_t e_i = 0; e_i < E && st == MCLCAR_OK; ++e_i) {
                 const int64_t nch = std::min<int64_t>(C, N - e_i * C);
                 TorusEmit em;
                 em.out = o.keep ? s->d_M : staging; em.dtype = o.dtype; em.ld = ld; em.slot0 = o.keep ? e_i * C : 0; em.nch = nch;
-                em.d_mu = (mu.empty() || mu_is_const) ? nullptr : d_mu;
-                em.mu_const = mu.empty() ? 0.0 : mu[0];
-                if (fused_stats) { em.out = nullptr; em.slot0 = e_i * C; em.stats_q = s->d_q; em.stats_ldq = N; }
+                em.d_mu = mu_is_const ? nullptr : d_mu;
+                em.mu_const = mu_is_const ? mu0 : 0.0;
+                if (fused_stats) {
+                    if (!o.keep) em.out = nullptr;
+                    em.slot0 = e_i * C; em.stats_q = s->d_q; em.stats_ldq = N;
+                }
                 if (fused) {
                     st = plain_sweeps(thin - 1);
                     if (st == MCLCAR_OK) st = torus_sweep(ctx, tc, rho, sigma, omega, sweep++, &em);
@@ -234,7 +239,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
                 }
                 if (st) break;
                 if (fused_stats) continue;
-                if (!fused) st = torus_emit(ctx, tc, d_mu, em.out, o.dtype, ld, em.slot0, nch);
+                if (!fused) st = torus_emit(ctx, tc, em.d_mu, em.mu_const, em.out, o.dtype, ld, em.slot0, nch);
                 if (st == MCLCAR_OK && !o.keep) {
                     bool handled = false;
                     st = launch_stats_torus_fast(ctx, staging, o.dtype, nch, ld, s->d_q + e_i * C, N, &handled);
@@ -243,7 +248,10 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
             }
             s->sweeps = sweep;
             s->chains = C;
-            if (st == MCLCAR_OK && !o.keep) {
+            // every launch of the run is queued: the host forms the algebra of a freshly set design / observations
+            // (W X, X'X, the statistics of y) now, while the device sweeps
+            if (st == MCLCAR_OK) st = ensure_algebra(ctx);
+            if (st == MCLCAR_OK && (!o.keep || fused_stats)) {
                 if ((st = samples_update_qbar(ctx, s))) break;
                 s->stats_ready = true;
             }
@@ -263,6 +271,7 @@ extern "C" int mclcar_dcar_prep(mclcar_ctx* ctx, const double* psi0, int P, int6
         for (size_t e = 0; e < g.qoff.size(); ++e) g.qoff[e] = -rho * (ctx->binary ? 1.0 : ctx->val[e]) / sigma;
         st = pool_alloc(ctx, &s->d_M, (size_t)n * ld * es);
         const int64_t C = o.n_chains > 0 ? o.n_chains + (o.n_chains & 1) : default_csr_chains(ctx, n, N, burn, thin);
+        if (has_mu) fill_mu();
         if (st == MCLCAR_OK)
             st = run_csr_sampler(ctx, g, FAM_GAUSS, omega, mu.empty() ? nullptr : mu.data(), nullptr, nullptr, nullptr, N, C, burn, thin,
                                  s->d_M, o.dtype == MCLCAR_F64, ld, &s->accept, &s->sweeps);

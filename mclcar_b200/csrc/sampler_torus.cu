@@ -356,7 +356,7 @@ __device__ __forceinline__ void sts4(const uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// EMIT: 0 none, 1 the black phase also writes the finished samples, 2 it accumulates their statistics instead.
+// EMIT: 0 none, 1 the black phase also writes the finished samples, 2 it accumulates their statistics instead, 3 both.
 // nm: shared address of row A of the OTHER colour (rows A-1, A, B, B+1 at nm - hb .. nm + 2 hb, hb = 4 h bytes);
 // own: shared address of row A of the colour being updated; gout: the output half-lattice of the chain, offA / offB
 // the element offsets of rows A and B in it (stA / stB: whether the row is stored -- halo rows are not).
@@ -396,10 +396,10 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 v = gibbs_update4<SOR, true>(a0, up, b0, eA0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
             if (STS) sts4(own + b0a, v);
             if (stA) stg4_off(gout, offA + (uint32_t)c0, v);
-            if (PH2 && EMIT == 1) {
+            if (PH2 && (EMIT == 1 || EMIT == 3)) {
                 if (esample) emit8_off<TO, false>(p, esample, eoff + 2u * (uint32_t)c0, mu, v, a0);
             }
-            if (PH2 && EMIT == 2) stats8<true>(v, a0, up, b0, eA0, m, acc);
+            if (PH2 && EMIT >= 2) stats8<true>(v, a0, up, b0, eA0, m, acc);
         }
         if (two) {
             const float4 up = lds4(nm - hb + b1a);
@@ -407,10 +407,10 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 v = gibbs_update4<SOR, true>(a1, up, b1, eA1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
             if (STS) sts4(own + b1a, v);
             if (stA) stg4_off(gout, offA + (uint32_t)c1v, v);
-            if (PH2 && EMIT == 1) {
+            if (PH2 && (EMIT == 1 || EMIT == 3)) {
                 if (esample) emit8_off<TO, false>(p, esample, eoff + 2u * (uint32_t)c1v, mu, v, a1);
             }
-            if (PH2 && EMIT == 2) stats8<true>(v, a1, up, b1, eA1, m, acc);
+            if (PH2 && EMIT >= 2) stats8<true>(v, a1, up, b1, eA1, m, acc);
         }
     }
     // ---- row B
@@ -427,10 +427,10 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 v = gibbs_update4<SOR, false>(b0, a0, dn, eB0, cur, bm_pair(blk.x, p.rad2), bm_pair(blk.y, p.rad2), p.keep, p.gain);
             if (STS) sts4(ownB + b0a, v);
             if (stB) stg4_off(gout, offB + (uint32_t)c0, v);
-            if (PH2 && EMIT == 1) {
+            if (PH2 && (EMIT == 1 || EMIT == 3)) {
                 if (esample) emit8_off<TO, true>(p, esample, eoff + 2u * (uint32_t)(h + c0), mu, v, b0);
             }
-            if (PH2 && EMIT == 2) stats8<false>(v, b0, a0, dn, eB0, m, acc);
+            if (PH2 && EMIT >= 2) stats8<false>(v, b0, a0, dn, eB0, m, acc);
         }
         if (two) {
             const float4 dn = lds4(nm + 2u * hb + b1a);
@@ -438,10 +438,10 @@ __device__ __forceinline__ void fused_item(const TorusSweepParams& p, const bool
             const float4 v = gibbs_update4<SOR, false>(b1, a1, dn, eB1, cur, bm_pair(blk.z, p.rad2), bm_pair(blk.w, p.rad2), p.keep, p.gain);
             if (STS) sts4(ownB + b1a, v);
             if (stB) stg4_off(gout, offB + (uint32_t)c1v, v);
-            if (PH2 && EMIT == 1) {
+            if (PH2 && (EMIT == 1 || EMIT == 3)) {
                 if (esample) emit8_off<TO, true>(p, esample, eoff + 2u * (uint32_t)(h + c1v), mu, v, b1);
             }
-            if (PH2 && EMIT == 2) stats8<false>(v, b1, a1, dn, eB1, m, acc);
+            if (PH2 && EMIT >= 2) stats8<false>(v, b1, a1, dn, eB1, m, acc);
         }
     }
 }
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gibbs_torus_sweep_fused(const Toru
     const uint32_t c2 = (uint32_t)gch, c3 = (uint32_t)(gch >> 32) ^ (kTagTorus << 16);
     double acc[3] = {0.0, 0.0, 0.0};
     TO* esample = nullptr;                                    // this chain's sample in the output matrix (emitting sweeps)
-    if (EMIT == 1) {
+    if (EMIT == 1 || EMIT == 3) {
         if (ch < p.nch) esample = reinterpret_cast<TO*>(p.out) + (size_t)(p.slot0 + ch) * p.ld;
     }
 
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(MAXT, MINB) gibbs_torus_sweep_fused(const Toru
             }
         }
     }
-    if (EMIT == 2) {
+    if (EMIT >= 2) {
         double* scratch = reinterpret_cast<double*>(bar + 2);
         block_sum<3>(acc, scratch);
         if (threadIdx.x == 0) {
@@ -625,8 +625,8 @@ __global__ void __launch_bounds__(256) gibbs_torus_half_sweep_v1(const TorusSwee
 // write the current state of chains [0, nch) as samples: out[(slot0 + ch)*ld + site] = mu[site] + z
 template <typename TO>
 __global__ void __launch_bounds__(256) torus_emit_kernel(const float* red, const float* black, int n1, int h,
-                                                         const double* mu, TO* out, int64_t ld, int64_t slot0,
-                                                         int64_t nch) {
+                                                         const double* mu, double mu_const, TO* out, int64_t ld,
+                                                         int64_t slot0, int64_t nch) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     const int64_t ch = blockIdx.z;
@@ -643,7 +643,13 @@ __global__ void __launch_bounds__(256) torus_emit_kernel(const float* red, const
         o[1] = (TO)add_mean_f32(par ? r : b, make_float2(mm.z, mm.w));
         return;
     }
-    const double m0 = mu ? mu[site] : 0.0, m1 = mu ? mu[site + 1] : 0.0;
+    if (mu == nullptr && sizeof(TO) == 4) {      // one mean for every site: fp32 sum, as in emit8
+        const float m = (float)mu_const;
+        o[0] = (TO)((par ? b : r) + m);
+        o[1] = (TO)((par ? r : b) + m);
+        return;
+    }
+    const double m0 = mu ? mu[site] : mu_const, m1 = mu ? mu[site + 1] : mu_const;
     const double v0 = (par ? (double)b : (double)r) + m0;
     const double v1 = (par ? (double)r : (double)b) + m1;
     o[0] = (TO)v0;
@@ -711,8 +717,9 @@ int torus_fused_tile_rows(const mclcar_ctx* ctx) {
 }
 
 // one full sweep (both colours) of all chains; omega in [1, 2): over-relaxation factor.  When
-// `emit` is given (16-byte path only) the black half sweep also writes the samples -- or, with
-// emit->stats_q set (fused sweep, constant mean, fp32 samples), their sufficient statistics instead.
+// `emit` is given (16-byte path only) the black half sweep also writes the samples; with emit->stats_q set
+// (fused sweep, constant mean, fp32 samples) it forms their sufficient statistics -- instead of the samples
+// (emit->out null) or together with them.
 // tile height of the two-sweeps-per-launch form (0: not available): two CTAs of <= 110 KB per SM, 4 + 3 halo rows per
 // colour and tile end
 // Measured (profiles/r02_sweep_experiments.md): under the power cap of a sustained full-size run the two-sweep form is
@@ -811,7 +818,11 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
         gibbs_torus_sweep_fused<S, E, TO_, B_, 1, kFusedMaxThreads><<<grid, fthreads, smem, ctx->stream>>>(p, TR);   \
     } while (0)
 #define LAUNCH_FUSED(S, E, TO_) LAUNCH_FUSED_B(S, E, TO_, 3)
-            if (want_stats) {
+            if (want_stats && emit->out) {                       // samples and their statistics from the same registers
+                // two CTAs per SM (126 registers); at three (80 registers) the fp64 accumulation spills and the sweep is 9 % slower
+                if (sor) LAUNCH_FUSED_B(true, 3, float, 2);
+                else LAUNCH_FUSED_B(false, 3, float, 2);
+            } else if (want_stats) {
                 if (sor) LAUNCH_FUSED_B(true, 2, float, 2);      // fp64 accumulators: two CTAs per SM
                 else LAUNCH_FUSED_B(false, 2, float, 2);
             } else if (emit) {
@@ -853,16 +864,16 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
     return MCLCAR_OK;
 }
 
-int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, void* out, int dtype, int64_t ld, int64_t slot0,
-               int64_t nch) {
+int torus_emit(mclcar_ctx* ctx, TorusChains& t, const double* d_mu, double mu_const, void* out, int dtype, int64_t ld,
+               int64_t slot0, int64_t nch) {
     const int h = ctx->n2 / 2;
     dim3 block(128);
     dim3 grid((h + 127) / 128, ctx->n1, (unsigned)nch);
     ProfScope prof(ctx, PROF_EMIT, 1);
     if (dtype == MCLCAR_F32)
-        torus_emit_kernel<float><<<grid, block, 0, ctx->stream>>>(t.red, t.black, ctx->n1, h, d_mu, (float*)out, ld, slot0, nch);
+        torus_emit_kernel<float><<<grid, block, 0, ctx->stream>>>(t.red, t.black, ctx->n1, h, d_mu, mu_const, (float*)out, ld, slot0, nch);
     else
-        torus_emit_kernel<double><<<grid, block, 0, ctx->stream>>>(t.red, t.black, ctx->n1, h, d_mu, (double*)out, ld, slot0, nch);
+        torus_emit_kernel<double><<<grid, block, 0, ctx->stream>>>(t.red, t.black, ctx->n1, h, d_mu, mu_const, (double*)out, ld, slot0, nch);
     MCL_CUDA(ctx, cudaGetLastError());
     return MCLCAR_OK;
 }

@@ -196,6 +196,7 @@ int launch_quadforms_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64
 
 int launch_stats_site_major(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, double* d_q,
                             int64_t ldq) {
+    MCL_TRY(ensure_algebra(ctx));   // d_WX
     const double* vecs[2 * MCLCAR_MAX_COV];
     const int p = ctx->p;
     for (int l = 0; l < p; ++l) {

@@ -370,6 +370,7 @@ int launch_typed(mclcar_ctx* ctx, const StatsTorusParams& p, int grid, size_t sm
 int launch_stats_torus_fast(mclcar_ctx* ctx, const void* M, int dtype, int64_t N, int64_t ld, double* d_q,
                             int64_t ldq, bool* handled) {
     *handled = false;
+    MCL_TRY(ensure_algebra(ctx));   // d_WX
     const int n1 = ctx->n1, n2 = ctx->n2, p = ctx->p;
     const size_t es = dtype == MCLCAR_F32 ? 4 : 8;
     const int vec = dtype == MCLCAR_F32 ? 4 : 2;

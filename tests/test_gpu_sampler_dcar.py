@@ -320,9 +320,19 @@ def test_statistics_folded_into_the_emitting_sweep(n1, n2, p, omega, monkeypatch
     N, C = (24, 8) if n < 500_000 else (12, 6)
     ctl = {"n.chains": C, "burn": 4, "thin": 2, "omega": omega}
     y = np.zeros(n)
+    # kept samples, statistics by the statistics kernel reading the matrix back
+    monkeypatch.setenv("MCLCAR_NO_KEPT_FUSED_STATS", "1")
     kept = api.mcl_prep_dCAR(psi, N, api.make_data(y, X=X, torus=(n1, n2), seed=21), dict(ctl, keep=True))
+    q_kernel = kept.stats()
+    monkeypatch.delenv("MCLCAR_NO_KEPT_FUSED_STATS")
+    # kept samples (default): the emitting sweep writes the samples and forms their statistics in one go
+    both = api.mcl_prep_dCAR(psi, N, api.make_data(y, X=X, torus=(n1, n2), seed=21), dict(ctl, keep=True))
+    np.testing.assert_allclose(both.stats(), q_kernel, rtol=1e-13)
+    if n < 500_000:
+        np.testing.assert_array_equal(both.simY, kept.simY)
     fused = api.mcl_prep_dCAR(psi, N, api.make_data(y, X=X, torus=(n1, n2), seed=21), dict(ctl, keep=False))
-    np.testing.assert_allclose(fused.stats(), kept.stats(), rtol=1e-13)
+    np.testing.assert_allclose(fused.stats(), q_kernel, rtol=1e-13)
+    np.testing.assert_array_equal(fused.stats(), both.stats())
     monkeypatch.setenv("MCLCAR_NO_FUSED_STATS", "1")
     staged = api.mcl_prep_dCAR(psi, N, api.make_data(y, X=X, torus=(n1, n2), seed=21), dict(ctl, keep=False))
     np.testing.assert_allclose(staged.stats(), kept.stats(), rtol=1e-13)
