@@ -460,6 +460,10 @@ def run_ours(args):
                      "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
                      "launches": sweep_launches, "sweeps_per_launch": 1.0 / max(launches_per_sweep, 1e-9), "peak_source": peak_src,
                      "share_of_step": sweep_ms / (1e3 * t_res) if t_res > 0 else None,
+                     # `frac` counts the 8 bytes of a site update only.  With kept samples every emitting sweep
+                     # also writes its finished fp32 samples (4 bytes per site and kept state) -- algorithmic bytes too:
+                     "frac_with_sample_writes": None if (args.stats_only or not sweep_gbs) else
+                     (bytes_per_update * updates_step + 4.0 * N_gpu * n) * args.steps / (sweep_ms * 1e-3) / 1e9 / peak,
                      "note": "reported against the HBM roofline as the contract asks.  ncu without the power cap (profiles/r02_ncu_sweep.md): 170 us per "
                              "launch of 130 chains = 0.93 of the HBM peak, DRAM 71 %, issue slots 65 % busy; the full-size bench runs under the 1 kW "
                              "power cap (sw_power_cap), where the launch time follows the energy per site update (profiles/r02_sweep_experiments.md)"},

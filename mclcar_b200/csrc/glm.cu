@@ -842,16 +842,22 @@ int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int6
     int burn = o.burn, thin = o.thin;
     double omega = 1.0;  // Metropolis-within-Gibbs: no over-relaxation
     default_schedule(ctx, rho, &omega, &burn, &thin);
-    // The accept step slows the chain below the Gibbs rate the schedule is made for, the more so the sharper the
-    // likelihood (sites with large n p (1 - p) rarely accept a draw from their prior conditional).  Start from 4x the
-    // Gibbs burn-in and 3x its thinning, then CHECK: the reference's v.lr and step rule take the draws as
-    // independent (R/mcl.bin.R:70-72), so the kept states must have an effective sample size >= 0.85 N in both
-    // z'z and z'Wz; otherwise the run was a pilot (the reference's mcl.prep.glm has one too, R/mcl.glm.R:17-26):
-    // its autocorrelation time gives the thinning that brings the lag-one autocorrelation of kept states to 5 %,
-    // and the chains are run again.  A thinning given by the caller is taken as is.
+    // Proposals come from a Gaussian approximation of each site's full conditional (sampler_csr.cu, glm_laplace; every
+    // third sweep from the prior conditional): most draws are accepted, and the data make the posterior field less
+    // dependent than the prior one the Gibbs schedule is made for -- start from twice its burn-in and half its
+    // thinning (measured on the config-3 map, scripts/exp_glm_proposal.py: effective sample size 0.94 N / 0.97 N at 6
+    // sweeps per kept state for the binomial / Poisson model; proposals from the prior conditional alone,
+    // MCLCAR_GLM_PROPOSAL=prior, are accepted 34 % / 43 % of the time and need 33 sweeps for 0.92 N).  Then CHECK: the
+    // reference's v.lr and step rule take the draws as independent (R/mcl.bin.R:70-72), so the kept states must have an
+    // effective sample size >= 0.85 N in both z'z and z'Wz; otherwise the run was a pilot (the reference's
+    // mcl.prep.glm has one too, R/mcl.glm.R:17-26): its autocorrelation time gives the thinning that brings the
+    // lag-one autocorrelation of kept states to 5 %, and the chains are run again.  A thinning given by the caller is
+    // taken as is.
     const bool tune = o.thin <= 0;
-    if (o.burn <= 0) burn = std::max(4 * burn, 200);
-    if (tune) thin = std::max(3 * thin, 10);
+    const char* pe = getenv("MCLCAR_GLM_PROPOSAL");
+    const bool prior_proposal = pe && !strcmp(pe, "prior");
+    if (o.burn <= 0) burn = prior_proposal ? std::max(4 * burn, 200) : std::max(2 * burn, 60);
+    if (tune) thin = prior_proposal ? std::max(3 * thin, 10) : std::max((thin + 1) / 2 + 1, 4);
     const int n = ctx->n;
     const size_t es = o.dtype == MCLCAR_F32 ? 4 : 8;
     std::vector<double> xb(n, 0.0);

@@ -20,6 +20,7 @@
 // site the CB chains of a CTA form one contiguous run.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "engine.hpp"
@@ -62,6 +63,14 @@ struct CsrSamplerParams {
     // site-major statistics kernel would compute from the stored matrix, without its second pass over it.  null: off
     double* stat_q;
     int64_t stat_ldq;
+    // graph on chip (MODE 2): the padded neighbour lists as 16-bit site ids, four to an 8-byte group, and one 8-byte record
+    // per position (site | groups << 16, first group) are copied into shared memory behind the state, so that a site
+    // update makes ONE global load (the second half of its CsrSite record) that nothing else waits for
+    const uint2* idx16;    // [ngroups]
+    const uint2* site8;    // [n]
+    int ngroups;
+    int laplace;           // GLM families: 1 = proposals from the Gaussian approximation of the full conditional, 0 = from the prior conditional
+    uint32_t scratch_off;  // byte offset of the statistics scratch in shared memory
 };
 
 namespace {
@@ -69,7 +78,49 @@ namespace {
 constexpr uint32_t kTagCsr = 0x4373u;
 constexpr int kMaxThreads = 1024;
 
-__device__ __forceinline__ float softplusf(float t) { return t > 15.f ? t : __logf(1.f + __expf(t)); }
+__device__ __forceinline__ float softplusf(float t) { return fmaxf(t, 0.f) + __logf(1.f + __expf(-fabsf(t))); }
+
+// log-likelihood difference of one site, f(a) - f(b):  f(z) = y z - n log(1 + e^{xb + z})  |  y z - e^{xb + z}
+template <int FAM>
+__device__ __forceinline__ float glm_logf(const float a, const float b, const float ys, const float ns, const float xbs) {
+    if (FAM == FAM_BINOM) return ys * (a - b) - ns * (softplusf(xbs + a) - softplusf(xbs + b));
+    return ys * (a - b) - (__expf(xbs + a) - __expf(xbs + b));
+}
+
+// Gaussian approximation N(mu, kInflate / tau) of the full conditional of one latent site,
+//   log pi(z) = f(z) - tau0 (z - m)^2 / 2,   m, 1 / tau0: mean and variance of its prior conditional:
+// mu = the mode, tau = tau0 - f''(mu), found by two Newton steps from the precision-weighted average of m and the
+// likelihood's own mode zb (curvature d2b there; both depend on the site's data only).  Steps are limited to four
+// standard deviations of the current approximation.  The approximation depends on the neighbours and the data, not on
+// the site's current value: proposing from it is an independence Metropolis-Hastings step with acceptance
+// min(1, w(z') / w(z)), w = pi / q -- close to one where the likelihood is sharp, which is where proposals from the
+// prior conditional are rarely accepted (config 3: 34 %).  An independence sampler is only as good as the tails of its
+// proposal: the variance is inflated a little, and every third sweep proposes from the prior conditional instead, whose
+// tails are those of the target (sites with extreme counts have a one-sided flat likelihood).
+constexpr float kInflate = 1.25f;
+template <int FAM>
+__device__ __forceinline__ void glm_laplace(const float m, const float tau0, const float ys, const float ns, const float xbs,
+                                            const float zb, const float d2b, float& mu, float& tau) {
+    float z0 = __fdividef(fmaf(tau0, m, d2b * zb), tau0 + d2b);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        float d1, d2;   // f'(z0), -f''(z0)
+        if (FAM == FAM_BINOM) {
+            const float pz = __frcp_rn(1.f + __expf(-(xbs + z0)));
+            d1 = fmaf(-ns, pz, ys);
+            d2 = ns * pz * (1.f - pz);
+        } else {
+            const float ee = __expf(fminf(xbs + z0, 80.f));
+            d1 = ys - ee;
+            d2 = ee;
+        }
+        tau = tau0 + d2;
+        const float lim = 4.f * rsqrtf(tau);
+        z0 += fminf(fmaxf(__fdividef(fmaf(tau0, m - z0, d1), tau), -lim), lim);
+    }
+    mu = z0;
+    tau *= 1.f / kInflate;
+}
 
 // The chain state of a CTA, [site][CB] floats: in shared memory (SMEM: explicit 32-bit shared-space addresses, so the
 // gathers are LDS.64 with one integer multiply-add each -- through a pointer that may be shared OR global every access
@@ -96,8 +147,19 @@ struct ChainState {
     }
 };
 
-template <int FAM, bool SMEM>
+__device__ __forceinline__ uint2 lds_u2(const uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u2(const uint32_t a, const uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// MODE: 0 chain state in global memory, 1 in shared memory, 2 in shared memory together with the graph
+template <int FAM, int MODE>
 __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSamplerParams p) {
+    constexpr bool SMEM = MODE >= 1, GOC = MODE == 2;
     const int kThreads = blockDim.x;
     extern __shared__ float sm_state[];
     const int CB = p.CB, hp = CB / 2;           // pairs per site row
@@ -108,6 +170,12 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
     x.sbase = smem_u32(sm_state);
     x.g = SMEM ? nullptr : p.state_g + (size_t)blockIdx.x * (p.n + 1) * CB;   // row n: the dummy site of the padding, always zero
     for (int t = threadIdx.x; t < (p.n + 1) * CB; t += kThreads) x.zero(t);
+    const uint32_t idx_base = x.sbase + (((uint32_t)(p.n + 1) * (uint32_t)CB * 4u + 7u) & ~7u);
+    const uint32_t site_base = idx_base + 8u * (uint32_t)p.ngroups;
+    if (GOC) {
+        for (int t = threadIdx.x; t < p.ngroups; t += kThreads) sts_u2(idx_base + 8u * (uint32_t)t, __ldg(p.idx16 + t));
+        for (int t = threadIdx.x; t < p.n; t += kThreads) sts_u2(site_base + 8u * (uint32_t)t, __ldg(p.site8 + t));
+    }
     __syncthreads();
 
     const uint64_t gpair = (uint64_t)(p.pair0 + ((int64_t)blockIdx.x * hp + pr) * p.pair_stride);
@@ -119,23 +187,48 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
         for (int col = 0; col < p.ncolors; ++col) {
             const int t1 = p.color_ptr[col + 1];
             for (int t = p.color_ptr[col] + slot; t < t1; t += nslots) {
-                const int4 ma = __ldg(reinterpret_cast<const int4*>(p.meta + t));          // s, e0, e1, hm
-                const float4 mb = __ldg(reinterpret_cast<const float4*>(p.meta + t) + 1);  // sd, y, nt, xb
-                const int s = ma.x;
-                float m0 = __int_as_float(ma.w), m1 = m0;
-                // neighbour gathers four at a time (rows are padded to whole groups): one 16-byte index load, four
-                // independent index -> shared-memory chains in flight
-                for (int e = ma.y; e < ma.z; e += 4) {
-                    const int4 j = __ldg(reinterpret_cast<const int4*>(p.colidx + e));
-                    float4 c;
-                    if (p.coef_uniform) c = make_float4(p.coef_value, p.coef_value, p.coef_value, p.coef_value);
-                    else c = __ldg(reinterpret_cast<const float4*>(p.coef + e));
-                    const float2 v0 = x.ld2(j.x * CB + 2 * pr), v1 = x.ld2(j.y * CB + 2 * pr);
-                    const float2 v2 = x.ld2(j.z * CB + 2 * pr), v3 = x.ld2(j.w * CB + 2 * pr);
-                    m0 = fmaf(c.x, v0.x, m0); m1 = fmaf(c.x, v0.y, m1);
-                    m0 = fmaf(c.y, v1.x, m0); m1 = fmaf(c.y, v1.y, m1);
-                    m0 = fmaf(c.z, v2.x, m0); m1 = fmaf(c.z, v2.y, m1);
-                    m0 = fmaf(c.w, v3.x, m0); m1 = fmaf(c.w, v3.y, m1);
+                const float4 mb = __ldg(reinterpret_cast<const float4*>(p.meta + t) + 1);  // sd, y (Gaussian family: b_s / Q_ss), nt, xb
+                int s;
+                float m0, m1;
+                if constexpr (GOC) {
+                    const uint2 rec = lds_u2(site_base + 8u * (uint32_t)t);
+                    s = (int)(rec.x & 0xffffu);
+                    m0 = m1 = FAM == FAM_GAUSS ? mb.y : 0.f;
+                    const uint32_t pbase = x.sbase + 8u * (uint32_t)pr, cb4 = 4u * (uint32_t)CB;
+                    const uint32_t gend = rec.y + (rec.x >> 16);
+                    for (uint32_t g = rec.y; g < gend; ++g) {
+                        const uint2 jj = lds_u2(idx_base + 8u * g);
+                        float4 c;
+                        if (p.coef_uniform) c = make_float4(p.coef_value, p.coef_value, p.coef_value, p.coef_value);
+                        else c = __ldg(reinterpret_cast<const float4*>(p.coef) + g);
+                        float2 v0, v1, v2, v3;
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v0.x), "=f"(v0.y) : "r"((jj.x & 0xffffu) * cb4 + pbase));
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v1.x), "=f"(v1.y) : "r"((jj.x >> 16) * cb4 + pbase));
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v2.x), "=f"(v2.y) : "r"((jj.y & 0xffffu) * cb4 + pbase));
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v3.x), "=f"(v3.y) : "r"((jj.y >> 16) * cb4 + pbase));
+                        m0 = fmaf(c.x, v0.x, m0); m1 = fmaf(c.x, v0.y, m1);
+                        m0 = fmaf(c.y, v1.x, m0); m1 = fmaf(c.y, v1.y, m1);
+                        m0 = fmaf(c.z, v2.x, m0); m1 = fmaf(c.z, v2.y, m1);
+                        m0 = fmaf(c.w, v3.x, m0); m1 = fmaf(c.w, v3.y, m1);
+                    }
+                } else {
+                    const int4 ma = __ldg(reinterpret_cast<const int4*>(p.meta + t));          // s, e0, e1, hm
+                    s = ma.x;
+                    m0 = m1 = __int_as_float(ma.w);
+                    // neighbour gathers four at a time (rows are padded to whole groups): one 16-byte index load, four
+                    // independent index -> shared-memory chains in flight
+                    for (int e = ma.y; e < ma.z; e += 4) {
+                        const int4 j = __ldg(reinterpret_cast<const int4*>(p.colidx + e));
+                        float4 c;
+                        if (p.coef_uniform) c = make_float4(p.coef_value, p.coef_value, p.coef_value, p.coef_value);
+                        else c = __ldg(reinterpret_cast<const float4*>(p.coef + e));
+                        const float2 v0 = x.ld2(j.x * CB + 2 * pr), v1 = x.ld2(j.y * CB + 2 * pr);
+                        const float2 v2 = x.ld2(j.z * CB + 2 * pr), v3 = x.ld2(j.w * CB + 2 * pr);
+                        m0 = fmaf(c.x, v0.x, m0); m1 = fmaf(c.x, v0.y, m1);
+                        m0 = fmaf(c.y, v1.x, m0); m1 = fmaf(c.y, v1.y, m1);
+                        m0 = fmaf(c.z, v2.x, m0); m1 = fmaf(c.z, v2.y, m1);
+                        m0 = fmaf(c.w, v3.x, m0); m1 = fmaf(c.w, v3.y, m1);
+                    }
                 }
                 const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)sweep, (uint32_t)gpair,
                                                 (uint32_t)(gpair >> 32) ^ (kTagCsr << 16), p.keys);
@@ -147,26 +240,45 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                     const float2 cur = x.ld2(s * CB + 2 * pr);
                     nv.x = fmaf(p.keep, cur.x, fmaf(p.gain, m0, p.noise * sdv * z0));
                     nv.y = fmaf(p.keep, cur.y, fmaf(p.gain, m1, p.noise * sdv * z1));
-                } else {
-                    nv.x = fmaf(sdv, z0, m0);
-                    nv.y = fmaf(sdv, z1, m1);
                 }
                 if constexpr (FAM != FAM_GAUSS) {
                     const float2 cur = x.ld2(s * CB + 2 * pr);
-                    const float ys = mb.y, xbs = mb.w;
-                    float la0, la1;
-                    if constexpr (FAM == FAM_BINOM) {
-                        const float ns = mb.z;
-                        la0 = ys * (nv.x - cur.x) - ns * (softplusf(xbs + nv.x) - softplusf(xbs + cur.x));
-                        la1 = ys * (nv.y - cur.y) - ns * (softplusf(xbs + nv.y) - softplusf(xbs + cur.y));
+                    const float ys = mb.y, ns = mb.z, xbs = mb.w;
+                    if (p.laplace > 0 && (p.laplace == 1 || sweep % p.laplace != p.laplace - 1)) {
+                        // independence proposal from a Gaussian approximation of the site's full conditional (see glm_laplace)
+                        const float tau0 = __frcp_rn(sdv * sdv);
+                        float zb, d2b;          // mode and curvature of the site's likelihood alone
+                        if (FAM == FAM_BINOM) {
+                            const float pb = __fdividef(ys + 0.5f, ns + 1.f);
+                            zb = __logf(__fdividef(pb, 1.f - pb)) - xbs;
+                            d2b = ns * pb * (1.f - pb);
+                        } else {
+                            zb = __logf(ys + 0.5f) - xbs;
+                            d2b = ys + 0.5f;
+                        }
+                        float mu0, mu1, t0, t1;
+                        glm_laplace<FAM>(m0, tau0, ys, ns, xbs, zb, d2b, mu0, t0);
+                        glm_laplace<FAM>(m1, tau0, ys, ns, xbs, zb, d2b, mu1, t1);
+                        nv.x = fmaf(rsqrtf(t0), z0, mu0);
+                        nv.y = fmaf(rsqrtf(t1), z1, mu1);
+                        const float la0 = glm_logf<FAM>(nv.x, cur.x, ys, ns, xbs) +
+                                          0.5f * (tau0 * ((cur.x - m0) * (cur.x - m0) - (nv.x - m0) * (nv.x - m0)) + z0 * z0 - t0 * (cur.x - mu0) * (cur.x - mu0));
+                        const float la1 = glm_logf<FAM>(nv.y, cur.y, ys, ns, xbs) +
+                                          0.5f * (tau0 * ((cur.y - m1) * (cur.y - m1) - (nv.y - m1) * (nv.y - m1)) + z1 * z1 - t1 * (cur.y - mu1) * (cur.y - mu1));
+                        const bool a0 = __logf(u01(r.z)) < la0, a1 = __logf(u01(r.w)) < la1;
+                        if (!a0) nv.x = cur.x;
+                        if (!a1) nv.y = cur.y;
+                        acc_cnt += (a0 ? 1u : 0u) + (a1 ? 1u : 0u);
                     } else {
-                        la0 = ys * (nv.x - cur.x) - (__expf(xbs + nv.x) - __expf(xbs + cur.x));
-                        la1 = ys * (nv.y - cur.y) - (__expf(xbs + nv.y) - __expf(xbs + cur.y));
+                        // proposal = the prior conditional N(m, 1 / Q_ss): the Metropolis ratio is the likelihood ratio
+                        nv.x = fmaf(sdv, z0, m0);
+                        nv.y = fmaf(sdv, z1, m1);
+                        const float la0 = glm_logf<FAM>(nv.x, cur.x, ys, ns, xbs), la1 = glm_logf<FAM>(nv.y, cur.y, ys, ns, xbs);
+                        const bool a0 = __logf(u01(r.z)) < la0, a1 = __logf(u01(r.w)) < la1;
+                        if (!a0) nv.x = cur.x;
+                        if (!a1) nv.y = cur.y;
+                        acc_cnt += (a0 ? 1u : 0u) + (a1 ? 1u : 0u);
                     }
-                    const bool a0 = __logf(u01(r.z)) < la0, a1 = __logf(u01(r.w)) < la1;
-                    if (!a0) nv.x = cur.x;
-                    if (!a1) nv.y = cur.y;
-                    acc_cnt += (a0 ? 1u : 0u) + (a1 ? 1u : 0u);
                     prop_cnt += 2u;
                 }
                 x.st2(s * CB + 2 * pr, nv);
@@ -213,7 +325,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                     zz0 += __shfl_xor_sync(0xffffffffu, zz0, o); zz1 += __shfl_xor_sync(0xffffffffu, zz1, o);
                     zw0 += __shfl_xor_sync(0xffffffffu, zw0, o); zw1 += __shfl_xor_sync(0xffffffffu, zw1, o);
                 }
-                double* sc = reinterpret_cast<double*>(sm_state + (SMEM ? (size_t)(p.n + 1) * CB : 0));   // [warps][hp][4]
+                double* sc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sm_state) + p.scratch_off);   // [warps][hp][4]
                 const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = kThreads >> 5;
                 __syncthreads();
                 if (lane < hp) {
@@ -253,6 +365,74 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
 
 }  // namespace
 
+// A colour class of size m occupies ceil(m / nslots) rounds of the CTA's site slots, so a sweep costs
+// sum_c ceil(size_c / nslots) rounds whatever the total: first-fit colouring leaves a long tail of small classes and
+// large ones just over a multiple of nslots (config-3 map, 512 slots: 1519 + 1419 + 1256 + 740 + 66 sites = 12 rounds
+// against ceil(5000 / 512) = 10).  Move the overflow of a class beyond its last full round into the spare room of
+// the other classes where the neighbourhoods allow it (any proper colouring gives a valid chromatic sweep).
+// order / cptr: colour-major site order and class boundaries, rewritten when a colouring with fewer rounds was found.
+static bool rebalance_colours(const GmrfHost& g, int nslots, std::vector<int>& order, std::vector<int>& cptr) {
+    const int n = g.n;
+    int ncol = (int)cptr.size() - 1;
+    if (nslots < 1 || ncol < 2) return false;
+    std::vector<int> col(n), size(ncol), m(ncol);
+    for (int c = 0; c < ncol; ++c) {
+        size[c] = cptr[c + 1] - cptr[c];
+        m[c] = (size[c] + nslots - 1) / nslots;
+        for (int t = cptr[c]; t < cptr[c + 1]; ++t) col[order[t]] = c;
+    }
+    auto rounds = [&]() { int r = 0; for (int c = 0; c < ncol; ++c) r += m[c]; return r; };
+    const int before = rounds(), ideal = (n + nslots - 1) / nslots;
+    if (before <= ideal) return false;
+    std::vector<char> seen(ncol);
+    for (int pass = 0; pass < 4 && rounds() > ideal; ++pass) {
+        bool improved = false;
+        std::vector<int> byover(ncol);
+        for (int c = 0; c < ncol; ++c) byover[c] = c;
+        auto over = [&](int c) { return size[c] - (m[c] - 1) * nslots; };   // sites in the last round of class c
+        std::sort(byover.begin(), byover.end(), [&](int a, int b) { return over(a) < over(b); });
+        for (int c : byover) {
+            if (m[c] < 1 || rounds() <= ideal) continue;
+            int need = over(c);
+            int room = 0;
+            for (int d = 0; d < ncol; ++d) if (d != c) room += m[d] * nslots - size[d];
+            if (need > room) continue;
+            std::vector<std::pair<int, int>> moved;   // (site, new class)
+            for (int i = 0; i < n && need > 0; ++i) {
+                if (col[i] != c) continue;
+                std::fill(seen.begin(), seen.end(), 0);
+                for (int e = (*g.rowptr)[i]; e < (*g.rowptr)[i + 1]; ++e) seen[col[(*g.colidx)[e]]] = 1;
+                int best = -1, best_room = 0;
+                for (int d = 0; d < ncol; ++d) {
+                    const int r = m[d] * nslots - size[d];
+                    if (d != c && !seen[d] && r > best_room) { best = d; best_room = r; }
+                }
+                if (best < 0) continue;
+                col[i] = best; ++size[best]; --size[c]; --need;
+                moved.push_back({i, best});
+            }
+            if (need > 0) {   // not enough movable sites: put them back
+                for (auto& mv : moved) { col[mv.first] = c; --size[mv.second]; ++size[c]; }
+            } else {
+                --m[c];
+                improved = true;
+            }
+        }
+        if (!improved) break;
+    }
+    if (rounds() >= before) return false;
+    std::vector<int> new_order, new_ptr(1, 0);
+    new_order.reserve(n);
+    for (int c = 0; c < ncol; ++c) {
+        if (!size[c]) continue;
+        for (int i = 0; i < n; ++i) if (col[i] == c) new_order.push_back(i);
+        new_ptr.push_back((int)new_order.size());
+    }
+    order.swap(new_order);
+    cptr.swap(new_ptr);
+    return true;
+}
+
 int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, const double* mu_host, const double* y,
                     const double* ntrial, const double* xb, int64_t N, int64_t C_want, int burn, int thin,
                     void* d_out, int out_f64, int64_t ld, double* accept_rate, int64_t* sweeps_out, double* d_stat_q, int64_t stat_ldq,
@@ -261,7 +441,33 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
     if (stats_done) *stats_done = false;
     begin_draw(ctx);   // a fresh Philox stream for every sampler run (the reference draws fresh rnorm() per call)
     const int n = g.n;
-    const int ncol = (int)g.color_ptr->size() - 1;
+    // ---- chains per CTA: largest CB whose state fits in shared memory and still fills the SMs
+    const size_t smem_cap = 200 * 1024;
+    int CB = 0;
+    for (int cb : {32, 16, 8, 4, 2})
+        if ((size_t)(n + 1) * cb * sizeof(float) <= smem_cap) {
+            CB = cb;
+            if ((C_want + cb - 1) / cb >= ctx->n_sm) break;
+        }
+    const bool in_smem = CB != 0;
+    if (!in_smem) CB = 32;
+    int64_t grid = (C_want + CB - 1) / CB;
+    if (grid < 1) grid = 1;
+    const int64_t C = grid * CB;
+    int E = (int)((N + C - 1) / C);
+    if (E < 1) E = 1;
+    // all warps of the CTA share the resident state: as many as the largest colour class can feed
+    std::vector<int> order(*g.order), cptr(*g.color_ptr);
+    int max_class = 1;
+    for (size_t c = 0; c + 1 < cptr.size(); ++c) max_class = std::max(max_class, cptr[c + 1] - cptr[c]);
+    int threads = 256;
+    while (threads < kMaxThreads && (threads / (CB / 2)) < max_class) threads *= 2;
+    if (const char* te = getenv("MCLCAR_CSR_THREADS")) threads = atoi(te);
+    {   // colour classes sized for whole rounds of the CTA's site slots (MCLCAR_CSR_REBALANCE=0: the graph's own colouring)
+        const char* re = getenv("MCLCAR_CSR_REBALANCE");
+        if (!(re && atoi(re) == 0)) rebalance_colours(g, threads / (CB / 2), order, cptr);
+    }
+    const int ncol = (int)cptr.size() - 1;
     // ---- permute the CSR into colour-major position order, convert to the conditional form
     // (rows padded to whole groups of four entries with the dummy site n, coefficient 0) and one 32-byte record per
     // position with everything else a site update reads
@@ -274,7 +480,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
     float coef_first = 0.f;
     bool have_first = false;
     for (int t = 0; t < n; ++t) {
-        const int s = (*g.order)[t];
+        const int s = order[t];
         const double qss = g.qdiag[s];
         if (!(qss > 0)) return fail(ctx, MCLCAR_EINVAL, "precision matrix has a non-positive diagonal at site %d", s);
         CsrSite& ms = meta[t];
@@ -291,26 +497,10 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
         ms.e1 = (int)ci.size();
         ms.hm = g.b.empty() ? 0.f : (float)(g.b[s] / qss);
         ms.sd = (float)(1.0 / std::sqrt(qss));
-        ms.y = fam != FAM_GAUSS ? (float)y[s] : 0.f;
+        ms.y = fam != FAM_GAUSS ? (float)y[s] : ms.hm;   // Gaussian family: the second half of the record carries b_s / Q_ss too
         ms.nt = fam != FAM_GAUSS ? (ntrial ? (float)ntrial[s] : 1.f) : 0.f;
         ms.xb = fam != FAM_GAUSS ? (float)xb[s] : 0.f;
     }
-    // ---- chains per CTA: largest CB whose state fits in shared memory and still fills the SMs
-    const size_t smem_cap = 200 * 1024;
-    int CB = 0;
-    for (int cb : {32, 16, 8, 4, 2})
-        if ((size_t)(n + 1) * cb * sizeof(float) <= smem_cap) {
-            CB = cb;
-            if ((C_want + cb - 1) / cb >= ctx->n_sm) break;
-        }
-    const bool in_smem = CB != 0;
-    if (!in_smem) CB = 32;
-    int64_t grid = (C_want + CB - 1) / CB;
-    if (grid < 1) grid = 1;
-    const int64_t C = grid * CB;
-    int E = (int)((N + C - 1) / C);
-    if (E < 1) E = 1;
-
     // ---- upload
     auto up = [&](const void* h, size_t bytes, void** d) -> int {
         MCL_TRY(pool_alloc(ctx, d, bytes ? bytes : 4));
@@ -328,7 +518,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
     std::vector<double> mu;
     void *d_cp = nullptr, *d_meta = nullptr, *d_ci = nullptr, *d_coef = nullptr, *d_mu = nullptr, *d_cnt = nullptr, *d_state = nullptr;
     do {
-        if ((st = upv(g.color_ptr->data(), (ncol + 1) * sizeof(int), &d_cp))) break;
+        if ((st = upv(cptr.data(), (ncol + 1) * sizeof(int), &d_cp))) break;
         if ((st = upv(meta.data(), meta.size() * sizeof(CsrSite), &d_meta))) break;
         if ((st = upv(ci.data(), ci.size() * sizeof(int), &d_ci))) break;
         if ((st = upv(coef.data(), coef.size() * sizeof(float), &d_coef))) break;
@@ -353,29 +543,59 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
         p.keep = (float)(1.0 - omega); p.gain = (float)omega; p.noise = (float)std::sqrt(omega * (2.0 - omega));
         p.pair0 = ctx->rank; p.pair_stride = ctx->world;
         p.counters = (unsigned long long*)d_cnt;
+        {   // 0: proposals from the prior conditional; 1: from the Gaussian approximation; k > 1: every k-th sweep from the prior
+            const char* le = getenv("MCLCAR_GLM_PROPOSAL");
+            p.laplace = 3;
+            if (le && !strcmp(le, "prior")) p.laplace = 0;
+            else if (le && !strncmp(le, "laplace", 7) && le[7]) p.laplace = std::max(1, atoi(le + 7));
+        }
         // statistics at emission: binary neighbourhood matrices, no mean added to the kept states, fp32 output (the
         // statistics must be those of the values written)
         const bool on_chip_stats = d_stat_q != nullptr && coef_uniform && have_first && !mu_host && !out_f64;
         if (on_chip_stats) { p.stat_q = d_stat_q; p.stat_ldq = stat_ldq; }
         if (stats_done) *stats_done = on_chip_stats;
-        size_t smem = in_smem ? (size_t)(n + 1) * CB * sizeof(float) : 0;
-        // all warps of the CTA share the resident state: as many as the largest colour class can feed
-        int max_class = 1;
-        for (int c = 0; c < ncol; ++c) max_class = std::max(max_class, (*g.color_ptr)[c + 1] - (*g.color_ptr)[c]);
-        int threads = 256;
-        while (threads < kMaxThreads && (threads / (CB / 2)) < max_class) threads *= 2;
-        if (const char* te = getenv("MCLCAR_CSR_THREADS")) threads = atoi(te);
-        if (on_chip_stats) smem += (size_t)(threads / 32) * (CB / 2) * 4 * sizeof(double);   // scratch of the statistics
+        size_t smem = in_smem ? (((size_t)(n + 1) * CB * sizeof(float) + 7) & ~(size_t)7) : 0;
+        const size_t stat_bytes = on_chip_stats ? (size_t)(threads / 32) * (CB / 2) * 4 * sizeof(double) : 0;
+        // graph on chip: 16-bit neighbour ids and the 8-byte position records behind the state, when everything fits
+        const size_t ngroups = ci.size() / 4;
+        const size_t graph_bytes = ngroups * 8 + (size_t)n * 8;
+        const char* ge = getenv("MCLCAR_CSR_GRAPH_ON_CHIP");
+        const bool goc = in_smem && n <= 65535 && ((size_t)n * sizeof(CsrSite) + ci.size() * 4 > 48 * 1024 || (ge && atoi(ge) == 1)) && ngroups <= 0x7fffffffu && (fam == FAM_GAUSS || g.b.empty()) &&
+                         smem + graph_bytes + stat_bytes <= 220 * 1024 && !(ge && atoi(ge) == 0);
+        if (goc) {
+            std::vector<uint2> idx16(ngroups), site8(n);
+            bool ok = true;
+            for (size_t q = 0; q < ngroups; ++q) {
+                idx16[q].x = (uint32_t)ci[4 * q] | ((uint32_t)ci[4 * q + 1] << 16);
+                idx16[q].y = (uint32_t)ci[4 * q + 2] | ((uint32_t)ci[4 * q + 3] << 16);
+            }
+            for (int t = 0; t < n; ++t) {
+                const uint32_t ng = (uint32_t)(meta[t].e1 - meta[t].e0) / 4;
+                ok = ok && ng <= 0xffffu;
+                site8[t].x = (uint32_t)meta[t].s | (ng << 16);
+                site8[t].y = (uint32_t)meta[t].e0 / 4;
+            }
+            if (!ok) { st = fail(ctx, MCLCAR_ELIMIT, "a site has more than 262140 neighbours"); break; }
+            void *d_i16 = nullptr, *d_s8 = nullptr;
+            if ((st = upv(idx16.data(), idx16.size() * sizeof(uint2), &d_i16))) break;
+            if ((st = upv(site8.data(), site8.size() * sizeof(uint2), &d_s8))) break;
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { st = fail(ctx, MCLCAR_ECUDA, "upload of the on-chip graph failed"); break; }   // the two vectors are locals
+            p.idx16 = (const uint2*)d_i16; p.site8 = (const uint2*)d_s8; p.ngroups = (int)ngroups;
+            smem += graph_bytes;
+        }
+        p.scratch_off = (uint32_t)smem;
+        smem += stat_bytes;   // scratch of the statistics
         cudaError_t e = cudaSuccess;
         ProfScope prof(ctx, PROF_CSR_SAMPLER, 1);
 #define LAUNCH_CSR(F_, S_)                                                                                              \
     do {                                                                                                                \
-        e = cudaFuncSetAttribute(gibbs_csr_kernel<F_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap + 20 * 1024));  \
+        e = cudaFuncSetAttribute(gibbs_csr_kernel<F_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap + 24 * 1024));  \
         if (e == cudaSuccess) gibbs_csr_kernel<F_, S_><<<(unsigned)grid, threads, smem, ctx->stream>>>(p);              \
     } while (0)
-        if (fam == FAM_GAUSS) { if (in_smem) LAUNCH_CSR(FAM_GAUSS, true); else LAUNCH_CSR(FAM_GAUSS, false); }
-        else if (fam == FAM_BINOM) { if (in_smem) LAUNCH_CSR(FAM_BINOM, true); else LAUNCH_CSR(FAM_BINOM, false); }
-        else { if (in_smem) LAUNCH_CSR(FAM_POIS, true); else LAUNCH_CSR(FAM_POIS, false); }
+        const int mode = goc ? 2 : (in_smem ? 1 : 0);
+        if (fam == FAM_GAUSS) { if (mode == 2) LAUNCH_CSR(FAM_GAUSS, 2); else if (mode == 1) LAUNCH_CSR(FAM_GAUSS, 1); else LAUNCH_CSR(FAM_GAUSS, 0); }
+        else if (fam == FAM_BINOM) { if (mode == 2) LAUNCH_CSR(FAM_BINOM, 2); else if (mode == 1) LAUNCH_CSR(FAM_BINOM, 1); else LAUNCH_CSR(FAM_BINOM, 0); }
+        else { if (mode == 2) LAUNCH_CSR(FAM_POIS, 2); else if (mode == 1) LAUNCH_CSR(FAM_POIS, 1); else LAUNCH_CSR(FAM_POIS, 0); }
 #undef LAUNCH_CSR
         if (e == cudaSuccess) e = cudaGetLastError();
         unsigned long long cnt[2] = {0, 0};
