@@ -98,6 +98,7 @@ __device__ __forceinline__ float glm_logf(const float a, const float b, const fl
 // proposal: the variance is inflated a little, and every third sweep proposes from the prior conditional instead, whose
 // tails are those of the target (sites with extreme counts have a one-sided flat likelihood).
 constexpr float kInflate = 1.25f;
+constexpr int kIcmSweeps = 4;
 template <int FAM>
 __device__ __forceinline__ void glm_laplace(const float m, const float tau0, const float ys, const float ns, const float xbs,
                                             const float zb, const float d2b, float& mu, float& tau) {
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                 if constexpr (FAM != FAM_GAUSS) {
                     const float2 cur = x.ld2(s * CB + 2 * pr);
                     const float ys = mb.y, ns = mb.z, xbs = mb.w;
-                    if (p.laplace > 0 && (p.laplace == 1 || sweep % p.laplace != p.laplace - 1)) {
+                    if (p.laplace > 0 && (sweep < kIcmSweeps || p.laplace == 1 || sweep % p.laplace != p.laplace - 1)) {
                         // independence proposal from a Gaussian approximation of the site's full conditional (see glm_laplace)
                         const float tau0 = __frcp_rn(sdv * sdv);
                         float zb, d2b;          // mode and curvature of the site's likelihood alone
@@ -261,6 +262,14 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                         glm_laplace<FAM>(m1, tau0, ys, ns, xbs, zb, d2b, mu1, t1);
                         nv.x = fmaf(rsqrtf(t0), z0, mu0);
                         nv.y = fmaf(rsqrtf(t1), z1, mu1);
+                        if (sweep < kIcmSweeps) {
+                            // start-up: the chains begin at zero, which for a site with a large count lies tens of
+                            // standard deviations out in the tail of its approximation -- a state no independence
+                            // proposal is ever accepted from.  The first sweeps move every site to the mode of its
+                            // conditional instead (iterated conditional modes); the burn-in proper starts from there.
+                            x.st2(s * CB + 2 * pr, make_float2(mu0, mu1));
+                            continue;
+                        }
                         const float la0 = glm_logf<FAM>(nv.x, cur.x, ys, ns, xbs) +
                                           0.5f * (tau0 * ((cur.x - m0) * (cur.x - m0) - (nv.x - m0) * (nv.x - m0)) + z0 * z0 - t0 * (cur.x - mu0) * (cur.x - mu0));
                         const float la1 = glm_logf<FAM>(nv.y, cur.y, ys, ns, xbs) +

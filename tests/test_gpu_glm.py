@@ -179,3 +179,50 @@ def test_latent_statistics_formed_by_the_chain_kernel(n, chains, monkeypatch):
             Zy = md.Zy
     np.testing.assert_allclose(q[""], glm.latent_stats(W, Zy), rtol=1e-13)
     np.testing.assert_allclose(q[""], q["1"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("family", ["binom", "poisson"])
+def test_both_proposals_sample_the_same_posterior(family, monkeypatch):
+    """The latent sampler proposes from a Gaussian approximation of each site's full conditional (two sweeps in three)
+    and from the prior conditional (the third); MCLCAR_GLM_PROPOSAL=prior uses the prior conditional throughout, as
+    round 1 did.  Both are Metropolis-Hastings kernels of the same target.  Reference here: a very long run of the
+    prior-proposal kernel (6000 burn-in sweeps, 400 per kept state); the default sampler at its default schedule must
+    reproduce its per-site means and variances and both quadratic statistics -- also at sites with extreme counts
+    (y = 0, y = n.trial, Poisson counts near 100), where a Gaussian approximation is poorest and where the prior-proposal
+    kernel at ITS default schedule is not converged (a site with y = 69 moves once in ~200 sweeps: variance 1.5 x too
+    large, scripts/exp_glm_site_mixing.py)."""
+    n = 400
+    W = graphs.random_planar_map(n, seed=12)
+    ew = np.linalg.eigvalsh(W.toarray())
+    rng = np.random.default_rng(12)
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    psi = np.array([0.75 / ew.max(), 1.4, 0.8, 1.0])      # eta spread over +-3: many sites with y = 0 or y = n.trial
+    od = glm.sim_glm_data(family, W, psi, X, 8.0, rng)
+    if family == "binom":
+        assert (od["y"] == 0).sum() + (od["y"] == 8).sum() > 20
+    else:
+        assert od["y"].max() > 60
+
+    def draw(prop, N, ctl):
+        monkeypatch.setenv("MCLCAR_GLM_PROPOSAL", prop)
+        gd = api.make_data(od["y"], X=X, W=W, n_trial=8 if family == "binom" else None, eigenvalues=ew, seed=5)
+        md = api.mcl_prep_glm(gd, family, psi, dict({"n.samples": N}, **ctl))
+        ess = np.empty(2)
+        api.check(L.lib.mclcar_samples_ess(gd.ctx.h, md.h, L.dptr(ess)), gd.ctx.h)
+        Z, acc = md.Zy, md.mcmc_pars["accept"]
+        md.close()
+        return Z, acc, ess / N
+
+    Nr, N = 12_000, 24_000
+    Zr, acc_r, _ = draw("prior", Nr, {"burn": 6000, "thin": 400})
+    Zd, acc_d, ess_d = draw("laplace3", N, {})
+    assert ess_d.min() > 0.8
+    assert acc_d > acc_r + 0.1                               # the approximation is accepted far more often
+    sd = Zr.std(axis=0)
+    se = sd * np.sqrt(1.0 / Nr + 1.0 / (0.8 * N))
+    assert (np.abs(Zd.mean(axis=0) - Zr.mean(axis=0)) / se).max() < 5.0
+    np.testing.assert_allclose(Zd.var(axis=0), Zr.var(axis=0), rtol=0.1)
+    for stat in (lambda z: np.einsum("ij,ij->i", z, z), lambda z: np.einsum("ij,ij->i", z, (W @ z.T).T)):
+        a, b = stat(Zr), stat(Zd)
+        assert abs(a.mean() - b.mean()) < 5.0 * a.std() * np.sqrt(1.0 / Nr + 1.0 / (0.8 * N))
+        assert b.var() == pytest.approx(a.var(), rel=0.1)
