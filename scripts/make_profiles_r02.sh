@@ -4,9 +4,9 @@ S=scripts/ncu_summary.py
 {
 echo "# Round 2 - ncu \`--set full --clock-control none --import-source on\` of the torus sweep (B200, one GPU)"; echo
 echo "Command: \`scripts/profile_r02.sh\` (bench.py --config c5 --samples-per-gpu 2980 --steps 1 --warmup 1, 130 chains x 1000 x 1000; the profiled command first ran plain and exited 0)."
-echo "Launch 1 = a TWO-sweep launch (red, black, red, black on a tile of 20 rows + 14 halo rows: sweeps that emit nothing), launch 2 = emitting single sweep (1 in 5: also writes the 520 MB of finished fp32 samples)."; echo
+echo "Launch 1 = a TWO-sweep launch (red, black, red, black on a tile of 20 rows + 14 halo rows: sweeps that emit nothing), launch 2 = emitting single sweep (1 in 5: also writes the 520 MB of finished fp32 samples and forms their statistics, EMIT = 3)."; echo
 python $S gpurun_out/r02_prof_sweep.ncu-rep
-echo; echo "## single-sweep launches (MCLCAR_SWEEP_DOUBLE=0): plain sweep, emitting sweep"; echo
+echo; echo "## single-sweep launches (MCLCAR_SWEEP_DOUBLE=0): plain sweep, emitting sweep (samples + statistics)"; echo
 python $S gpurun_out/r02_prof_sweep_single.ncu-rep
 echo; echo "## statistics-only emission (\`keep = 0\`: EMIT = 2, sufficient statistics accumulated in the emitting sweep instead of writing samples)"; echo
 python $S gpurun_out/r02_prof_sweep_stats.ncu-rep
@@ -15,7 +15,7 @@ python $S gpurun_out/r02_prof_c2_sweep.ncu-rep
 } > profiles/r02_ncu_sweep.md
 { echo "# Round 2 - ncu full captures of the likelihood kernels on config 5 (stats_torus_kernel<float>: 2980 fp32 samples = 11.92 GB; k3_moments: 200 psi x 2980 samples)"; echo
 python $S gpurun_out/r02_prof_stats_torus.ncu-rep; echo; python $S gpurun_out/r02_prof_k3.ncu-rep; } > profiles/r02_ncu_likelihood_c5.md
-{ echo "# Round 2 - ncu full capture of gibbs_csr_kernel<BINOM> (config 3: 5000-region map, 1184 chains = 8 per CTA, state in shared memory, whole chain run in one launch)"; echo
+{ echo "# Round 2 - ncu full capture of gibbs_csr_kernel<BINOM> (config 3: 5000-region map, 592 chains = 4 per CTA, state and graph in shared memory, independence proposals from the Gaussian approximation of the full conditional, whole chain run of 181 sweeps in one launch)"; echo
 python $S gpurun_out/r02_prof_csr_sampler.ncu-rep; } > profiles/r02_ncu_csr_sampler.md
 { echo "# Round 2 - ncu full capture of glm_terms_kernel (config 3: 10^4 x 5000 fp32 latent fields, binomial data term in fp64)"; echo
 echo "## final kernel: piecewise degree-8 table of log1p(exp(-a)), all betas of a tile evaluated together (first launch: the single-beta lHZy.psi pass, two-slot build; second: an 8-beta tile)"; echo
