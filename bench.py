@@ -87,7 +87,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """the timed region starts now: earlier rows (nvidia-smi needs ~0.2 s to start, so the sampler is started during the
+        last warm-up step) are dropped, unless the timed region is too short to hold any"""
+        self.t0 = time.perf_counter()
 
     def stop(self) -> dict:
         if not self.proc:
@@ -97,12 +102,18 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        timed = [r for t, r in self.rows if t >= getattr(self, "t0", 0.0)]
+        from_warmup = not timed and bool(self.rows)
+        self.rows = timed if timed else [r for _, r in self.rows]
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(sm)}
+        if from_warmup:
+            out["note"] = "timed region shorter than one sampling interval: rows from the last warm-up step (same work)"
+        return out
 
 
 # --------------------------------------------------------------------------------------
@@ -250,7 +261,10 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item()), out
 
-    for _ in range(args.warmup):
+    clocks = ClockSampler(local)
+    for w in range(args.warmup):
+        if w == args.warmup - 1 and rank == 0:
+            clocks.start()          # running by the time the timed region begins
         res = step_resident()
     assert np.all(np.isfinite(res)) or os.environ.get("MCLCAR_SWEEP_DRY"), "non-finite result in warm-up"
 
@@ -267,9 +281,10 @@ def run_ours(args):
         t_np, _ = timed(step_resident, 5)       # the step without the library's per-launch event spans
         print(f"[debug] step without event spans: {1e3 * t_np / 5:.2f} ms", file=sys.stderr)
 
-    clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        if not clocks.proc:
+            clocks.start()
+        clocks.mark()
     L.check(L.lib.mclcar_ctx_profile(ctx.h, 1), ctx.h)
     t_res, res = timed(step_resident, args.steps)
     ms_cat = np.zeros(8)

@@ -179,12 +179,18 @@ def run(args, emit):
                 "16-point batch + one gradient")
 
     # ------------------------------------------------------------------ timing
+    clocks = B.ClockSampler(0)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         res = step()
     assert np.all(np.isfinite(res)), "non-finite result in warm-up"
-    clocks = B.ClockSampler(0)
-    clocks.start()
+    # these steps take milliseconds and nvidia-smi a few hundred to start: keep the device under the same load until its
+    # first row arrives, so that the rows of the timed region are not the only chance of a reading
+    t_wait = time.perf_counter()
+    while clocks.proc and not clocks.rows and time.perf_counter() - t_wait < 2.0:
+        step()
     torch.cuda.synchronize()
+    clocks.mark()
     with _Prof(ctx, L) as prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
