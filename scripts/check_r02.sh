@@ -1,3 +1,4 @@
+# end-of-round check on one B200: GPU tests, smoke(), the default bench line, the small configurations, the reference arm
 set -u
 O=gpurun_out
 python -m pytest tests -m gpu -q > $O/r2_pytest28.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r2_pytest28.log

@@ -1,3 +1,4 @@
+# weak and strong scaling lines under torchrun (NG GPUs of one box, default 8); the bench checks the NCCL-merged results itself
 set -u
 O=gpurun_out
 G=${NG:-8}
