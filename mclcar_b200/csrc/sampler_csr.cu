@@ -69,6 +69,7 @@ struct CsrSamplerParams {
     const uint2* idx16;    // [ngroups]
     const uint2* site8;    // [n]
     int ngroups;
+    int icm;               // start-up sweeps that move every site to the mode of its approximation (never more than the burn-in)
     int laplace;           // GLM families: 1 = proposals from the Gaussian approximation of the full conditional, 0 = from the prior conditional
     uint32_t scratch_off;  // byte offset of the statistics scratch in shared memory
 };
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                 if constexpr (FAM != FAM_GAUSS) {
                     const float2 cur = x.ld2(s * CB + 2 * pr);
                     const float ys = mb.y, ns = mb.z, xbs = mb.w;
-                    if (p.laplace > 0 && (sweep < kIcmSweeps || p.laplace == 1 || sweep % p.laplace != p.laplace - 1)) {
+                    if (p.laplace > 0 && (sweep < p.icm || p.laplace == 1 || sweep % p.laplace != p.laplace - 1)) {
                         // independence proposal from a Gaussian approximation of the site's full conditional (see glm_laplace)
                         const float tau0 = __frcp_rn(sdv * sdv);
                         float zb, d2b;          // mode and curvature of the site's likelihood alone
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kMaxThreads) gibbs_csr_kernel(const CsrSampler
                         glm_laplace<FAM>(m1, tau0, ys, ns, xbs, zb, d2b, mu1, t1);
                         nv.x = fmaf(rsqrtf(t0), z0, mu0);
                         nv.y = fmaf(rsqrtf(t1), z1, mu1);
-                        if (sweep < kIcmSweeps) {
+                        if (sweep < p.icm) {
                             // start-up: the chains begin at zero, which for a site with a large count lies tens of
                             // standard deviations out in the tail of its approximation -- a state no independence
                             // proposal is ever accepted from.  The first sweeps move every site to the mode of its
@@ -557,6 +558,7 @@ int run_csr_sampler(mclcar_ctx* ctx, const GmrfHost& g, int fam, double omega, c
             p.laplace = 3;
             if (le && !strcmp(le, "prior")) p.laplace = 0;
             else if (le && !strncmp(le, "laplace", 7) && le[7]) p.laplace = std::max(1, atoi(le + 7));
+            p.icm = p.laplace > 0 ? std::min(kIcmSweeps, burn) : 0;
         }
         // statistics at emission: binary neighbourhood matrices, no mean added to the kept states, fp32 output (the
         // statistics must be those of the values written)
