@@ -408,15 +408,19 @@ def run_ours(args):
     evals = N_tot * K_PSI * args.steps
     value = evals / t_res
     # per-kernel numbers from the CUDA-event spans recorded inside the library (this rank)
-    sweep_launches = int(launches[0])
-    sweep_ms = float(ms_cat[0])
+    # sweep launches that emit nothing (category 0: two sweeps per launch where the library uses that form) and emitting
+    # launches (category 1: one sweep + the finished samples and / or their statistics) are timed apart
+    plain_launches, plain_ms = int(launches[0]), float(ms_cat[0])
+    emit_launches, emit_ms = int(launches[1]), float(ms_cat[1])
+    sweep_launches = plain_launches + emit_launches
+    sweep_ms = plain_ms + emit_ms
     sweeps_step = int(diag["sweeps"])
     chains = int(diag["chains"])      # the library's own choice unless --chains is given
     omega = float(diag["omega"])      # the library's schedule (over-relaxation factor, thin, burn)
     # algorithmic bytes per site update: read the other colour + write own colour (fp32), plus the
     # read of the current value for the over-relaxed update
     updates_step = float(chains) * n * sweeps_step
-    launches_per_sweep_ = int(launches[0]) / max(sweeps_step * args.steps, 1)
+    launches_per_sweep_ = sweep_launches / max(sweeps_step * args.steps, 1)
     # fused sweep (one launch): both colours read once + written once per sweep = 8 B per site update;
     # two-launch half sweeps: 8 B plain Gibbs, 12 B over-relaxed (the own colour is read as well)
     bytes_per_update = 8.0 if (launches_per_sweep_ < 1.5 or omega == 1.0) else 12.0
@@ -429,6 +433,24 @@ def run_ours(args):
     sweep_bytes_step = bytes_per_update * updates_step + emit_bytes_per_site * N_gpu * n
     sweep_gbs_all = sweep_bytes_step * args.steps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
     bytes_per_launch_all = sweep_bytes_step * args.steps / max(sweep_launches, 1)
+    # per launch kind.  Emitting launches of the fused sweep make one sweep each; the rest of the step's sweeps are in the
+    # plain launches.  (The two-launch fallback form emits in a separate kernel: then category 1 holds no sweeps.)
+    fused_form = launches_per_sweep_ < 1.5
+    emit_sweeps = emit_launches if fused_form else 0
+    plain_sweeps = sweeps_step * args.steps - emit_sweeps
+    kinds = {}
+    if plain_launches and plain_ms > 0:
+        b = bytes_per_update * chains * n * plain_sweeps / plain_launches
+        kinds["plain"] = {"launches": plain_launches, "sweeps_per_launch": plain_sweeps / plain_launches, "avg_launch_ms": plain_ms / plain_launches,
+                          "algorithmic_bytes_per_launch": b, "achieved_GBps": b / (plain_ms / plain_launches * 1e-3) / 1e9,
+                          "frac": b / (plain_ms / plain_launches * 1e-3) / 1e9 / peak}
+    if emit_launches and emit_ms > 0 and fused_form:
+        b = (bytes_per_update * chains * n * emit_sweeps + emit_bytes_per_site * N_gpu * n * args.steps) / emit_launches
+        kinds["emitting"] = {"launches": emit_launches, "sweeps_per_launch": 1.0, "avg_launch_ms": emit_ms / emit_launches,
+                             "algorithmic_bytes_per_launch": b, "achieved_GBps": b / (emit_ms / emit_launches * 1e-3) / 1e9,
+                             "frac": b / (emit_ms / emit_launches * 1e-3) / 1e9 / peak,
+                             "writes": "finished fp32 samples + their statistics" if not args.stats_only else "statistics only"}
+    dom_kind = max(kinds, key=lambda k: kinds[k]["avg_launch_ms"] * kinds[k]["launches"]) if kinds else None
     like_ms = float(ms_cat[2] + ms_cat[3])
     like_bytes = N_gpu * n * 4.0 * args.steps
     like_gbs = like_bytes / (like_ms * 1e-3) / 1e9 if ms_cat[2] > 0 and not args.stats_only and not stats_in_sweep else None
@@ -444,6 +466,7 @@ def run_ours(args):
                      "evals_per_s": N_gpu * K_PSI / ((k2_leg["stats_ms"] + k2_leg["reduce_ms"]) * 1e-3)}
 
     traffic = None
+    traffic_all = None
     try:  # measured DRAM traffic of the dominant kernel (one ncu --set full capture, profiles/)
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)["gibbs_torus_sweep_fused"]
@@ -454,10 +477,15 @@ def run_ours(args):
         per_step = sweep_launches / max(args.steps, 1)
         doubles = burn_ // 2 + emits * ((thin_ - 1) // 2)
         singles = burn_ % 2 + emits * ((thin_ - 1) % 2)
+        traffic_all = None
         if abs(per_step - (doubles + singles + emits)) < 0.5 and "double" in tr:
-            traffic = (doubles * tr["double"] + singles * tr["plain"] + emits * tr["emitting"]) / per_step * chains / tr["chains"]
+            traffic_all = (doubles * tr["double"] + singles * tr["plain"] + emits * tr["emitting"]) / per_step * chains / tr["chains"]
+            traffic = (doubles * tr["double"] + singles * tr["plain"]) / max(doubles + singles, 1) * chains / tr["chains"]
         elif abs(per_step - (burn_ + emits * thin_)) < 0.5:
-            traffic = ((burn_ + emits * (thin_ - 1)) * tr["plain"] + emits * tr["emitting"]) / per_step * chains / tr["chains"]
+            traffic_all = ((burn_ + emits * (thin_ - 1)) * tr["plain"] + emits * tr["emitting"]) / per_step * chains / tr["chains"]
+            traffic = tr["plain"] * chains / tr["chains"]
+        if "emitting" in kinds:
+            kinds["emitting"]["traffic"] = tr["emitting"] * chains / tr["chains"]
     except Exception:
         pass
     line = {
@@ -473,27 +501,36 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(y.nbytes + X.nbytes + psis.nbytes + PSI0.nbytes),
                 "d2h_bytes_per_step": int(K_PSI * 5 * 8 + 2 * 8)},
         "gpu_launches": int(launches.sum()),
-        "roofline": {"kernel": "gibbs_torus_sweep_fused" if launches_per_sweep < 1.5 else "gibbs_torus_half_sweep_v4",
-                     "bound": "hbm", "achieved": sweep_gbs_all, "peak": peak, "unit": "GB/s",
-                     "frac": (sweep_gbs_all / peak) if sweep_gbs_all else None, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": bytes_per_launch_all, "algorithmic_bytes_per_site_update": bytes_per_update,
-                     "algorithmic_bytes_per_emitted_site": emit_bytes_per_site,
-                     "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
-                     "launches": sweep_launches, "sweeps_per_launch": 1.0 / max(launches_per_sweep, 1e-9), "peak_source": peak_src,
-                     "share_of_step": sweep_ms / (1e3 * t_res) if t_res > 0 else None,
-                     # the strict SURVEY 8(d) figure: 8 bytes per site update and nothing for the samples the emitting sweeps write
-                     "frac_site_updates_only": (sweep_gbs / peak) if sweep_gbs else None,
-                     "note": "algorithmic bytes of the sweep launches of a step = 8 B per site update (read the other colour, write the own: SURVEY 8d) "
-                             "+ 4 B per site of every kept state (the emitting sweep writes the finished fp32 sample; its statistics are formed "
-                             "from the same registers, so no pass reads the matrix back); frac_site_updates_only leaves the sample writes out.  "
-                             "ncu without the power cap (profiles/r02_ncu_sweep.md): a plain sweep of 130 chains takes 170 us = 0.93 of the HBM "
-                             "peak, DRAM 71 %, issue slots 65 % busy; the full-size bench runs under the 1 kW power cap (sw_power_cap), where "
-                             "the launch time follows the energy per site update (profiles/r02_sweep_experiments.md)"},
+        "roofline": dict({"kernel": ("gibbs_torus_sweep_fused (launches that emit nothing: two sweeps per launch where the library uses that form)"
+                                     if launches_per_sweep < 1.5 else "gibbs_torus_half_sweep_v4"),
+                          "bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": traffic,
+                          "algorithmic_bytes_per_site_update": bytes_per_update},
+                         **({"achieved": kinds[dom_kind]["achieved_GBps"], "frac": kinds[dom_kind]["frac"],
+                             "algorithmic_bytes_per_launch": kinds[dom_kind]["algorithmic_bytes_per_launch"],
+                             "avg_launch_ms": kinds[dom_kind]["avg_launch_ms"], "launches": kinds[dom_kind]["launches"],
+                             "sweeps_per_launch": kinds[dom_kind]["sweeps_per_launch"],
+                             "share_of_step": kinds[dom_kind]["avg_launch_ms"] * kinds[dom_kind]["launches"] / (1e3 * t_res)} if dom_kind else
+                            {"achieved": None, "frac": None}),
+                         **{"launch_kinds": kinds,
+                            # every sweep launch of the step together: 8 B per site update + 4 B per site of every kept state
+                            "all_sweep_launches": {"launches": sweep_launches, "ms_per_step": sweep_ms / args.steps,
+                                                   "share_of_step": sweep_ms / (1e3 * t_res) if t_res > 0 else None,
+                                                   "algorithmic_bytes_per_emitted_site": emit_bytes_per_site,
+                                                   "achieved_GBps": sweep_gbs_all, "frac": (sweep_gbs_all / peak) if sweep_gbs_all else None,
+                                                   "frac_site_updates_only": (sweep_gbs / peak) if sweep_gbs else None,
+                                                   "traffic_per_launch": traffic_all},
+                            "note": "`frac` is the dominant kernel's: algorithmic bytes per launch = 8 B per site update (read the other colour, write the own: "
+                                    "SURVEY 8d) x the site updates of a launch, over the CUDA-event time of those launches.  launch_kinds.emitting: the "
+                                    "emitting launches apart (8 B per site update + 4 B per site for the finished fp32 sample they write; their statistics "
+                                    "are formed from the same registers, so no pass reads the matrix back).  all_sweep_launches: both together.  "
+                                    "ncu without the power cap (profiles/r02_ncu_sweep.md): a plain sweep of 130 chains takes 170 us = 0.93 of the HBM "
+                                    "peak, DRAM 71 %, issue slots 65 % busy; the full-size bench runs under the 1 kW power cap (sw_power_cap), where "
+                                    "the launch time follows the energy per site update (profiles/r02_sweep_experiments.md)"}),
         "phases": {
             "sampler": {"metric": "gibbs_site_updates_per_s", "value": site_updates_per_s, "ms_per_step": sweep_ms / args.steps,
                         "bytes_per_site_update": bytes_per_update,
                         "roofline_site_updates_per_s": peak * 1e9 / bytes_per_update * world},
-            "emit": {"ms_per_step": float(ms_cat[1]) / args.steps},
+            "emit": {"ms_per_step": float(ms_cat[1]) / args.steps, "launches_per_step": emit_launches / max(args.steps, 1)},
             "likelihood": {"metric": METRIC, "value": like_pass["evals_per_s"] * world if like_pass else
                            ((N_tot * K_PSI * args.steps / (like_ms * 1e-3)) if like_ms > 0 else None),
                            "ms_per_step": like_ms / args.steps, "achieved_GBps": like_gbs,

@@ -213,7 +213,7 @@ def run(args, emit):
         d_.close()
         info.update(sweeps=dg["sweeps"], chains=dg["chains"])
     sweeps, chains = int(info["sweeps"]), int(info["chains"])
-    samp_ms = ms[0] + ms[4]
+    samp_ms = ms[0] + ms[1] + ms[4]      # sweeps, emitting sweeps, chain kernel
     site_updates = sites * sweeps * chains / (samp_ms * 1e-3) if samp_ms > 0 else None
     # roofline of the dominant kernel
     roof = {"kernel": CATS[dom], "bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,

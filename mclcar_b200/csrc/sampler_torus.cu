@@ -779,7 +779,7 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
                 MCL_TRY(ensure(ctx, ctx->d_partial, (size_t)t.C * tiles * 3 * sizeof(double)));
                 p.stat_partial = (double*)ctx->d_partial.p;
             }
-            ProfScope prof(ctx, PROF_SWEEP, 1);
+            ProfScope prof(ctx, emit ? PROF_EMIT : PROF_SWEEP, 1);   // emitting launches are timed apart: they also write the samples
 #ifdef MCLCAR_SWEEP_EXPERIMENTS   // build with -DMCLCAR_SWEEP_EXPERIMENTS for the switches of profiles/r02_sweep_experiments.md
             if (const char* e = getenv("MCLCAR_SWEEP_PREFETCH")) p.prefetch_ahead = atoi(e);
             if (const char* e = getenv("MCLCAR_SWEEP_DRY")) { p.dry = atoi(e); if (p.dry >= 2) p.rad2 = 1e-30f; }
