@@ -633,7 +633,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --samples-per-gpu per rank (headline); strong: --total-samples split over the ranks, statistics only")
     ap.add_argument("--total-samples", type=int, default=100_000)
-    ap.add_argument("--config", default="c5", choices=["c1", "c2", "c3", "c4", "c5"],
+    ap.add_argument("--config", default="c5", choices=["c1", "c2", "c3", "c4", "c4p", "c5"],
                     help="BASELINE.json configuration; c5 is the headline (the others: bench_configs.py)")
     args = ap.parse_args()
     if args.watchdog > 0:

@@ -146,6 +146,39 @@ def run(args, emit):
             return np.concatenate([a, b])
         sites = n
         name = "BASELINE config 3: Binomial GLM with latent CAR on a synthetic 5000-region map (CSR W), Metropolis-within-Gibbs, N=10^4, 21-point rsm batch + 32 moving-beta candidates"
+    elif cfg == "c4p":
+        # config 4 as BASELINE.json words it: Poisson response.  An extension (the reference's hierarchical model is
+        # Gaussian): individual counts, district effects with a CAR prior, the GLM path on the K districts (api.PoisHcarData)
+        n_side, block, N = 100, 5, 20_000
+        n = n_side * n_side
+        ks = n_side // block
+        Kd = ks * ks
+        ii, jj = np.divmod(np.arange(n), n_side)
+        district = (ii // block) * ks + (jj // block)
+        M = _lattice(ks, ks)
+        b_ = 2 * np.cos(np.pi * np.arange(1, ks + 1) / (ks + 1))
+        X = np.column_stack([np.ones(n), rng.standard_normal(n) * 0.5])
+        psi0 = np.array([0.1, 0.5, 0.5, 0.5])
+        u = rng.standard_normal(Kd) * 0.7
+        y = rng.poisson(np.exp(X @ psi0[2:] + u[district])).astype(float)
+        pdata = api.PoisHcarData(y, X, district, M, bb=(b_[:, None] + b_[None, :]).ravel(), seed=B.SEED)
+        ctx = pdata.glm.ctx
+        ctx.set_stream(stream.cuda_stream)
+        pts = psi0[None, :] * (1 + 0.003 * rng.standard_normal((16, 4)))
+        pts[:8, 2:] = psi0[2:]                 # half of the design keeps the importance beta, half moves it
+        K = len(pts)
+        h2d = pts.nbytes + 8 * Kd * 9
+
+        def step():
+            mc = api.sim_pois_HCAR(psi0, pdata, N)
+            out = api.mcl_pois_HCAR_batch(pts, mc)
+            dg = api.sampler_diag(pdata.glm, mc.md)
+            info.update(accept=dg["accept"], sweeps=dg["sweeps"], chains=dg["chains"])
+            mc.close()
+            return out.ravel()
+        sites = Kd
+        name = ("BASELINE config 4 as worded (Poisson response; extension without a reference counterpart): 100x100 individuals, "
+                "20x20 districts, N=2x10^4, 16-point batch (8 candidates move beta)")
     else:  # c4
         n_side, block, N = 100, 5, 20_000
         n = n_side * n_side

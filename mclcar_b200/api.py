@@ -1037,3 +1037,122 @@ def mcl_HCAR_batch_multi(psis, mm: MultiMcData) -> np.ndarray:
 def mcl_grad_HCAR_multi(pars, mm: MultiMcData, Evar=False, shift=L.SHIFT_MEAN):
     g, v, _, P = _multi_family_run(lib.mclcar_multi_hcar_run, mm, np.asarray(pars)[None, :], 1, 1 if Evar else 0, shift, extra=(None,))
     return {"grad.lr": g, "grad.var": v.reshape(P, P)} if Evar else g
+
+
+# ------------------------------------------------------------------------------------------------
+# Poisson-response hierarchical model (BASELINE config 4 as worded; an EXTENSION: the reference's
+# hierarchical model is Gaussian only, R/HCAR.sim.R:42-45).
+#
+#   y_i | u ~ Poisson(exp(x_i' beta + u_{d(i)})),   u ~ N(0, sigma (I - rho M)^-1)   (district effects, CAR on M)
+#
+# Nothing new runs on the device.  Summing the individuals of a district,
+#   sum_i [y_i eta_i - e^{eta_i}] = sum_i y_i x_i' beta + sum_k [Y_k u_k - S_k(beta) e^{u_k}],
+#   Y_k = sum_{i in k} y_i,  S_k(beta) = sum_{i in k} e^{x_i' beta},
+# which is the Poisson GLM with latent CAR effects of R/mcl.pois.R on the K districts with observations Y_k
+# and the offset o_k(beta) = log S_k(beta) in the place of X beta -- up to the constant
+# c(beta) = sum_i y_i x_i' beta - sum_k Y_k o_k(beta).  The offset is not linear in beta, so a batch of
+# candidates is evaluated against a design whose columns ARE the offsets of its distinct beta values
+# (column 0: the importance beta; a candidate with the j-th beta takes the unit coefficient vector e_j):
+# the latent draws u | y, the statistics u'u, u'Mu and the reduction are those of the GLM path.
+# ------------------------------------------------------------------------------------------------
+class PoisHcarData:
+    def __init__(self, y, X, district, M, bb=None, device: int = 0, seed: int = 0, ctx: Optional[Context] = None):
+        self.y = np.ascontiguousarray(y, dtype=np.float64)
+        self.X = np.asarray(X, dtype=np.float64)
+        self.district = np.ascontiguousarray(district, dtype=np.int64)
+        self.M = sp.csr_matrix(M, dtype=np.float64)
+        self.K = self.M.shape[0]
+        if self.district.shape != self.y.shape or self.district.min() < 0 or self.district.max() >= self.K:
+            raise ValueError("district must map every individual to one of the K districts")
+        self.bb = np.linalg.eigvalsh(self.M.toarray()) if bb is None else np.asarray(bb, dtype=np.float64)
+        self.Y = np.bincount(self.district, weights=self.y, minlength=self.K)
+        self.p = self.X.shape[1]
+        # the K-district Poisson GLM; its design is replaced for every batch of candidates
+        self.glm = make_data(self.Y, X=np.zeros((self.K, 1)), W=self.M, eigenvalues=self.bb, device=device, seed=seed, ctx=ctx)
+
+    def offset(self, beta) -> np.ndarray:
+        """o_k(beta) = log sum_{i in k} exp(x_i' beta) (log-sum-exp per district)."""
+        eta = self.X @ np.asarray(beta, dtype=np.float64)
+        top = np.full(self.K, -np.inf)
+        np.maximum.at(top, self.district, eta)
+        s = np.bincount(self.district, weights=np.exp(eta - top[self.district]), minlength=self.K)
+        return top + np.log(s)
+
+    def const(self, beta, off=None) -> float:
+        off = self.offset(beta) if off is None else off
+        return float(self.y @ (self.X @ np.asarray(beta, dtype=np.float64)) - self.Y @ off)
+
+
+class PoisHcarSamples:
+    def __init__(self, data: PoisHcarData, md: McData, psi0):
+        self.data, self.md, self.psi0 = data, md, np.asarray(psi0, dtype=np.float64)
+
+    @property
+    def u_y(self) -> np.ndarray:
+        """N x K latent district effects u | y."""
+        return self.md.Zy
+
+    def close(self):
+        self.md.close()
+
+
+def sim_pois_HCAR(psi0, data: PoisHcarData, n_samples: int, control: Optional[dict] = None) -> PoisHcarSamples:
+    """Draws u | y at psi0 = (rho, sigma, beta) with the latent GLM sampler on the district graph."""
+    psi0 = np.asarray(psi0, dtype=np.float64)
+    if psi0.size != 2 + data.p:
+        raise ValueError(f"psi0 has length {psi0.size}; expected {2 + data.p}")
+    o0 = data.offset(psi0[2:])
+    set_design_obs(data.glm, o0[:, None], data.Y)
+    md = mcl_prep_glm(data.glm, "poisson", np.array([psi0[0], psi0[1], 1.0]), dict(control or {}, **{"n.samples": int(n_samples)}))
+    return PoisHcarSamples(data, md, psi0)
+
+
+def mcl_pois_HCAR_batch(psis, mc: PoisHcarSamples, shift=L.SHIFT_MEAN) -> np.ndarray:
+    """Row k = (Monte Carlo log-likelihood ratio of psis[k] against psi0, its variance estimate), the estimator of
+    mcl.pois (R/mcl.pois.R) applied to the hierarchical model."""
+    psis = np.ascontiguousarray(np.atleast_2d(psis), dtype=np.float64)
+    d = mc.data
+    if psis.shape[1] != 2 + d.p:
+        raise ValueError(f"candidates have length {psis.shape[1]}; expected {2 + d.p}")
+    beta0 = mc.psi0[2:]
+    o0 = d.offset(beta0)
+    c0 = d.const(beta0, o0)
+    out = np.empty((psis.shape[0], 2))
+    # distinct candidate betas, at most MAX_COV - 1 per pass over the latent draws
+    betas, which = np.unique(psis[:, 2:], axis=0, return_inverse=True)
+    which = np.asarray(which).ravel()
+    same0 = np.array([np.array_equal(b, beta0) for b in betas])
+    room = L.MAX_COV - 1
+    todo = [j for j in range(len(betas)) if not same0[j]]
+    groups = [todo[i:i + room] for i in range(0, len(todo), room)] or [[]]
+    first = True
+    for g in groups:
+        cols = [o0] + [d.offset(betas[j]) for j in g]
+        consts = {j: d.const(betas[j], cols[1 + t]) for t, j in enumerate(g)}
+        set_design_obs(d.glm, np.column_stack(cols), d.Y)
+        P = 2 + len(cols)
+        e0 = np.zeros(len(cols)); e0[0] = 1.0
+        psi0_t = np.concatenate([mc.psi0[:2], e0])
+        check(lib.mclcar_glm_attach(d.glm.ctx.h, mc.md.h, _FAMILY["poisson"], dptr(psi0_t), P, None), d.glm.ctx.h)
+        rows = [k for k in range(psis.shape[0]) if which[k] in g or (first and same0[which[k]])]
+        if not rows:
+            continue
+        cand = np.zeros((len(rows), P))
+        shift_c = np.zeros(len(rows))
+        for r, k in enumerate(rows):
+            cand[r, :2] = psis[k, :2]
+            j = which[k]
+            if same0[j]:
+                cand[r, 2] = 1.0
+            else:
+                cand[r, 2 + 1 + g.index(j)] = 1.0
+                shift_c[r] = consts[j] - c0
+        res = mcl_glm_batch(cand, mc.md, shift=shift)
+        out[rows, 0] = res[:, 0] + shift_c
+        out[rows, 1] = res[:, 1]
+        first = False
+    # leave the importance design in place
+    set_design_obs(d.glm, o0[:, None], d.Y)
+    p1 = np.array([mc.psi0[0], mc.psi0[1], 1.0])
+    check(lib.mclcar_glm_attach(d.glm.ctx.h, mc.md.h, _FAMILY["poisson"], dptr(p1), 3, None), d.glm.ctx.h)
+    return out

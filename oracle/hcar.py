@@ -224,3 +224,30 @@ def make_hcar_data(n_side: int, block: int, psi, p: int, rng, with_W: bool = Tru
     if with_W:
         data["aa"] = np.linalg.eigvalsh(_dense(W))
     return data
+
+
+def pois_hcar_loglik_quadrature(y, X, district, M, psi, half_width=7.0, points=61):
+    """EXTENSION (no reference counterpart: the reference's hierarchical model is Gaussian, R/HCAR.sim.R:42-45):
+    exact log-likelihood, up to the constant -sum log y_i!, of
+        y_i | u ~ Poisson(exp(x_i' beta + u_{d(i)})),   u ~ N(0, sigma (I - rho M)^-1),   psi = (rho, sigma, beta)
+    for a HANDFUL of districts (K <= 3) by the trapezoid rule on a tensor grid over u -- the brute-force check of the
+    Monte Carlo likelihood ratios of mclcar_b200.api.mcl_pois_HCAR_batch."""
+    y = np.asarray(y, dtype=np.float64)
+    X = np.asarray(X, dtype=np.float64)
+    d = np.asarray(district)
+    M = np.asarray(M.todense() if hasattr(M, "todense") else M, dtype=np.float64)
+    K = M.shape[0]
+    assert K <= 3
+    rho, sigma, beta = psi[0], psi[1], np.asarray(psi[2:], dtype=np.float64)
+    Q = (np.eye(K) - rho * M) / sigma
+    sd = np.sqrt(np.diag(np.linalg.inv(Q)))
+    axes = [np.linspace(-half_width * s, half_width * s, points) for s in sd]
+    U = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, K)
+    xb = X @ beta
+    Yk = np.bincount(d, weights=y, minlength=K)
+    Sk = np.bincount(d, weights=np.exp(xb), minlength=K)
+    logf = float(y @ xb) + U @ Yk - np.exp(U) @ Sk - 0.5 * np.einsum("ij,jk,ik->i", U, Q, U)
+    logf += 0.5 * np.linalg.slogdet(Q)[1] - 0.5 * K * np.log(2 * np.pi)
+    w = np.prod([a[1] - a[0] for a in axes])
+    m = logf.max()
+    return float(m + np.log(np.exp(logf - m).sum() * w))

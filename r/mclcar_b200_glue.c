@@ -204,6 +204,14 @@ SEXP C_mclb_samples_glm(SEXP ctx, SEXP Zy, SEXP family, SEXP psi, SEXP lHZy) { /
     if (st != MCLCAR_OK) { mclcar_samples_free(s); Rf_error("%s", mclcar_last_error(c)); }
     return wrap_samples(s);
 }
+/* a new importance point for an existing latent sample set after the design of its context was replaced: the
+ * Poisson-response hierarchical extension (r/overrides.R, mcl.HCAR.pois) evaluates the district-level draws against
+ * designs whose columns are per-candidate offsets */
+SEXP C_mclb_attach_glm(SEXP ctx, SEXP samples, SEXP family, SEXP psi) {
+    mclcar_ctx* c = ctx_of(ctx);
+    CHECK(c, mclcar_glm_attach(c, samples_of(samples), Rf_asInteger(family), REAL(psi), LENGTH(psi), NULL));
+    return R_NilValue;
+}
 /* pars: K x P -> K x 2; sub_idx / sub_ptr (doubles, 0-based, or NULL): sample subsets of the centre
  * points of Exp.CAR.glm [R/rsmSub.R:175-181] */
 SEXP C_mclb_mcl_glm(SEXP ctx, SEXP samples, SEXP pars, SEXP sub_idx, SEXP sub_ptr) {

@@ -296,3 +296,56 @@ restore.mcdata <- function(kept, data) {
     else structure(list(simY = h, t10 = NA_real_, t20 = NULL), class = "mclb_simdata", ctx = ctx, psi = kept$psi,
                    n.samples = kept$n.samples, n = kept$n)
 }
+
+## ---- Poisson-response hierarchical model (an EXTENSION: the reference's sim.HCAR / mcl.HCAR are Gaussian, R/HCAR.sim.R:42-45)
+##   y_i | u ~ Poisson(exp(x_i' beta + u_{d(i)})),  u ~ N(0, sigma (I - rho M)^-1);  psi = (rho, sigma, beta)
+## Summed over the individuals of a district this is the Poisson GLM of R/mcl.pois.R on the K districts with
+## observations Y_k = sum y_i and the offset o_k(beta) = log sum exp(x_i' beta) in the place of X beta, up to the
+## constant sum_i y_i x_i' beta - sum_k Y_k o_k(beta): the same .Call entries as the GLM path, nothing new on the device.
+## data: list(y, X, district (1..K), M, bb = eigen(M)$values)
+.mclb_pois_offset <- function(beta, data) {
+    eta <- as.numeric(data$X %*% beta)
+    top <- tapply(eta, data$district, max)
+    as.numeric(top + log(tapply(exp(eta - top[data$district]), data$district, sum)))
+}
+.mclb_pois_const <- function(beta, data, off) sum(data$y * (data$X %*% beta)) - sum(tapply(data$y, data$district, sum) * off)
+sim.HCAR.pois <- function(psi, data, n.samples) {
+    Y <- as.numeric(tapply(data$y, data$district, sum))
+    o0 <- .mclb_pois_offset(psi[-(1:2)], data)
+    ctx <- .Call(C_mclb_ctx, 0L)                 # its own context: the design is replaced for every batch of candidates
+    .mclb_graph(ctx, data$M, data$bb)
+    .Call(C_mclb_model, ctx, matrix(o0, ncol = 1), Y, NULL)
+    h <- .Call(C_mclb_prep_glm, ctx, 2L, c(psi[1:2], 1), n.samples, .mclb$control)
+    structure(list(u.y = h, psi = psi, Y = Y), ctx = ctx)
+}
+mcl.HCAR.pois <- function(pars, mcdata, data) {                             # pars: K x (2 + p) -> K x 2 (lr, v.lr)
+    pars <- matrix(as.numeric(pars), ncol = length(mcdata$psi))
+    ctx <- attr(mcdata, "ctx"); beta0 <- mcdata$psi[-(1:2)]
+    o0 <- .mclb_pois_offset(beta0, data); c0 <- .mclb_pois_const(beta0, data, o0)
+    key <- apply(pars[, -(1:2), drop = FALSE], 1, paste, collapse = " ")
+    same0 <- key == paste(beta0, collapse = " ")
+    out <- matrix(NA_real_, nrow(pars), 2)
+    todo <- unique(key[!same0]); groups <- if (length(todo)) split(todo, ceiling(seq_along(todo) / 7)) else list(character(0))
+    first <- TRUE
+    for (g in groups) {
+        rows.g <- lapply(g, function(k) which(key == k))
+        offs <- lapply(rows.g, function(r) .mclb_pois_offset(pars[r[1], -(1:2)], data))
+        Xo <- do.call(cbind, c(list(o0), offs))
+        .Call(C_mclb_model, ctx, Xo, mcdata$Y, NULL)
+        .Call(C_mclb_attach_glm, ctx, mcdata$u.y, 2L, c(mcdata$psi[1:2], 1, rep(0, length(g))))
+        rows <- c(if (first) which(same0), unlist(rows.g)); if (!length(rows)) next
+        cand <- matrix(0, length(rows), 2 + ncol(Xo)); cand[, 1:2] <- pars[rows, 1:2]; shift <- numeric(length(rows))
+        for (t in seq_along(rows)) {
+            j <- match(key[rows[t]], g)
+            if (is.na(j)) cand[t, 3] <- 1 else {
+                cand[t, 3 + j] <- 1
+                shift[t] <- .mclb_pois_const(pars[rows[t], -(1:2)], data, offs[[j]]) - c0
+            }
+        }
+        r <- .Call(C_mclb_mcl_glm, ctx, mcdata$u.y, cand, NULL, NULL)
+        out[rows, ] <- cbind(r[, 1] + shift, r[, 2]); first <- FALSE
+    }
+    .Call(C_mclb_model, ctx, matrix(o0, ncol = 1), mcdata$Y, NULL)
+    .Call(C_mclb_attach_glm, ctx, mcdata$u.y, 2L, c(mcdata$psi[1:2], 1))
+    out
+}
