@@ -1156,3 +1156,32 @@ def mcl_pois_HCAR_batch(psis, mc: PoisHcarSamples, shift=L.SHIFT_MEAN) -> np.nda
     p1 = np.array([mc.psi0[0], mc.psi0[1], 1.0])
     check(lib.mclcar_glm_attach(d.glm.ctx.h, mc.md.h, _FAMILY["poisson"], dptr(p1), 3, None), d.glm.ctx.h)
     return out
+
+
+def mcl_grad_pois_HCAR(pars, mc: PoisHcarSamples, shift=L.SHIFT_MEAN) -> np.ndarray:
+    """Gradient of the Monte Carlo log-likelihood ratio of the Poisson-response hierarchical model at pars = (rho, sigma,
+    beta), by the chain rule through the district offsets: d o_k / d beta_l = sum_{i in k} x_il e^{x_i'beta} / S_k(beta)
+    = xbar_kl, so with the design [o(beta0), o(beta), xbar_1 .. xbar_p] the GLM gradient (mcl.grad.pois, R/mcl.pois.R)
+    with respect to the coefficient of column xbar_l IS the offset part of d / d beta_l; the constant contributes
+    sum_i y_i x_il - sum_k Y_k xbar_kl.  (p <= MAX_COV - 2.)"""
+    pars = np.asarray(pars, dtype=np.float64)
+    d = mc.data
+    if pars.size != 2 + d.p:
+        raise ValueError(f"pars has length {pars.size}; expected {2 + d.p}")
+    if d.p > L.MAX_COV - 2:
+        raise ValueError("too many regression columns for the offset-derivative design")
+    beta = pars[2:]
+    o0, o1 = d.offset(mc.psi0[2:]), d.offset(beta)
+    eta = d.X @ beta
+    w = np.exp(eta - o1[d.district])                                   # e^{x_i'beta} / S_k: weights within the district
+    xbar = np.column_stack([np.bincount(d.district, weights=w * d.X[:, l], minlength=d.K) for l in range(d.p)])
+    set_design_obs(d.glm, np.column_stack([o0, o1, xbar]), d.Y)
+    P = 2 + 2 + d.p
+    psi0_t = np.concatenate([mc.psi0[:2], [1.0, 0.0], np.zeros(d.p)])
+    check(lib.mclcar_glm_attach(d.glm.ctx.h, mc.md.h, _FAMILY["poisson"], dptr(psi0_t), P, None), d.glm.ctx.h)
+    g = mcl_grad_glm(np.concatenate([pars[:2], [0.0, 1.0], np.zeros(d.p)]), mc.md, shift=shift)
+    out = np.concatenate([g[:2], g[4:] + d.X.T @ d.y - xbar.T @ d.Y])
+    set_design_obs(d.glm, o0[:, None], d.Y)
+    p1 = np.array([mc.psi0[0], mc.psi0[1], 1.0])
+    check(lib.mclcar_glm_attach(d.glm.ctx.h, mc.md.h, _FAMILY["poisson"], dptr(p1), 3, None), d.glm.ctx.h)
+    return out

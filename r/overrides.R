@@ -349,3 +349,15 @@ mcl.HCAR.pois <- function(pars, mcdata, data) {                             # pa
     .Call(C_mclb_attach_glm, ctx, mcdata$u.y, 2L, c(mcdata$psi[1:2], 1))
     out
 }
+mcl.grad.HCAR.pois <- function(pars, mcdata, data) {                        # gradient by the chain rule through the district offsets
+    ctx <- attr(mcdata, "ctx"); p <- length(pars) - 2L; beta <- pars[-(1:2)]
+    o0 <- .mclb_pois_offset(mcdata$psi[-(1:2)], data); o1 <- .mclb_pois_offset(beta, data)
+    w <- exp(as.numeric(data$X %*% beta) - o1[data$district])              # e^{x_i' beta} / S_k
+    xbar <- sapply(seq_len(p), function(l) as.numeric(tapply(w * data$X[, l], data$district, sum)))
+    .Call(C_mclb_model, ctx, cbind(o0, o1, xbar), mcdata$Y, NULL)
+    .Call(C_mclb_attach_glm, ctx, mcdata$u.y, 2L, c(mcdata$psi[1:2], 1, 0, rep(0, p)))
+    g <- .Call(C_mclb_grad_glm, ctx, mcdata$u.y, c(pars[1:2], 0, 1, rep(0, p)), FALSE)[[1]]
+    .Call(C_mclb_model, ctx, matrix(o0, ncol = 1), mcdata$Y, NULL)
+    .Call(C_mclb_attach_glm, ctx, mcdata$u.y, 2L, c(mcdata$psi[1:2], 1))
+    c(g[1:2], g[-(1:4)] + as.numeric(crossprod(data$X, data$y)) - as.numeric(crossprod(xbar, mcdata$Y)))
+}

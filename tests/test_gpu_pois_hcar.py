@@ -71,6 +71,16 @@ def test_batches_with_many_distinct_betas_and_the_gradient_direction():
     np.testing.assert_allclose(got, one, rtol=1e-9, atol=1e-10)
     toward = api.mcl_pois_HCAR_batch(np.array([psi0 + 0.5 * (psi_true - psi0), psi0 - 0.5 * (psi_true - psi0)]), mc)
     assert toward[0, 0] > toward[1, 0]
+    # gradient by the chain rule through the district offsets = central differences of the ratio on the SAME draws
+    at = psi0 * np.array([1.01, 0.99, 1.02, 0.98])
+    g = api.mcl_grad_pois_HCAR(at, mc)
+    fd = np.empty(4)
+    for j in range(4):
+        h = 1e-5 * max(abs(at[j]), 0.1)
+        e = np.zeros(4); e[j] = h
+        v = api.mcl_pois_HCAR_batch(np.array([at + e, at - e]), mc)[:, 0]
+        fd[j] = (v[0] - v[1]) / (2 * h)
+    np.testing.assert_allclose(g, fd, rtol=2e-5, atol=1e-5)
     ess = np.empty(2)
     api.check(api.lib.mclcar_samples_ess(data.glm.ctx.h, mc.md.h, api.dptr(ess)), data.glm.ctx.h)
     assert ess.min() > 0.8 * 20_000
