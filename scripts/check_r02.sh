@@ -9,7 +9,7 @@ import json
 d=json.load(open('gpurun_out/r2_bench_default.json'))
 print(d['value'], d['ms_per_step'], d['e2e'], d['roofline']['frac'], d['clocks'], d['steps'], d['warmup'], d['gpu_launches'])
 PY
-for c in c1 c3 c4; do python bench.py --config $c 2>/dev/null > $O/r2_bench_$c.json; python - <<PY
+for c in c1 c3 c4 c4p; do python bench.py --config $c 2>/dev/null > $O/r2_bench_$c.json; python - <<PY
 import json
 d=json.load(open('gpurun_out/r2_bench_$c.json'))
 print('$c', round(d['ms_per_step'],3), '%.4g'%d['value'], d['clocks'])

@@ -30,6 +30,6 @@ python $S gpurun_out/r02_prof_hcar.ncu-rep; } > profiles/r02_ncu_hcar.md
 { echo "# Round 2 - ncu launch lists (\`--metrics gpu__time_duration.sum --clock-control none\`) of \`bench.py --config cN --steps 1 --warmup 1\`"; echo
 echo "Cold-cache, serialised launches: compare SHARES with the bench's own CUDA-event spans (\`kernels\` / \`roofline.share_of_step\` in r02_bench_*.json), not absolutes."
 for c in c5 c2 c3 c4; do echo; echo "## $c"; echo; python scripts/launch_list_md.py gpurun_out/r02_launches_$c.csv; done; } > profiles/r02_launches.md
-for c in c1 c2 c3 c4 c5 c5_statsonly c5_single reference; do cp gpurun_out/r02_bench_$c.json profiles/r02_bench_$c.json; done
+for c in c2 c5 c5_statsonly c5_single reference; do cp gpurun_out/r02_bench_$c.json profiles/r02_bench_$c.json; done   # c1, c3, c4, c4p: scripts/check_r02.sh (gpurun_out/r2_bench_cN.json)
 cuobjdump -sass mclcar_b200/build/sampler_torus.o 2>/dev/null | awk '/Function : .*gibbs_torus_sweep_fused.*Lb1ELi0EfLi3E/{f=1;next} f&&/Function : /{f=0} f' > /tmp/fused_sass.txt
 { echo "# SASS evidence: bulk-copy engine and mbarrier instructions per kernel (\`python scripts/sass_evidence.py\`, cuobjdump -sass of the built library)"; echo; python scripts/sass_evidence.py; echo; echo "Excerpt, \`gibbs_torus_sweep_fused<SOR, EMIT = 0, float>\` tile load:"; echo '```'; grep "SYNCS\|UBLKCP\|UBLKPF" /tmp/fused_sass.txt | sed 's/^\s*//' | cut -c1-110 | head -12; echo '```'; } > profiles/r02_sass_excerpt.md
