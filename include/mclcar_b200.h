@@ -265,7 +265,9 @@ MCLCAR_API int mclcar_samples_from_stats(mclcar_ctx* ctx, const double* q, int64
  * W must be known (torus: analytic; CSR: mclcar_graph_set_eigenvalues) -- they replace the
  * per-call chol.spam log-determinant (R/mcl.bin.R:50-52) and eigen(W) (R/mcl.bin.R:176). */
 /* mcl.prep.glm + postZ (R/mcl.glm.R:5-40, R/postZ.R:2-14): N latent fields z | y at psi0 drawn by
- * the batched Metropolis-within-Gibbs sampler; lHZy.psi is attached implicitly. */
+ * the batched Metropolis-within-Gibbs sampler (site-wise independence proposals from a Gaussian approximation of
+ * the full conditional, every third sweep from the prior conditional; the thinning is checked against the effective
+ * sample size of z'z and z'Wz and the chains re-run when it falls short); lHZy.psi is attached implicitly. */
 MCLCAR_API int mclcar_glm_prep(mclcar_ctx* ctx, int family, const double* psi0, int P, int64_t N,
                     const mclcar_sampler_opts* opts, mclcar_samples** out);
 /* attach the importance point to the reference's own Zy; lHZy_psi NULL = recompute

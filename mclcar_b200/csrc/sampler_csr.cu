@@ -7,9 +7,11 @@
 //           - hierarchical CAR: Q = Z'Qe Z + Qu, b = Z'Qe (y - X beta): the u | y draw of sim.HCAR
 //             (R/HCAR.sim.R:64-69).
 //   BINOM / POISSON : latent CAR field of the GLM, target log pi(z) = y'z - sum n log(1+e^{xb+z})
-//           - z'Qz/2 (R/postZsub.R:431) | y'z - sum e^{xb+z} - z'Qz/2 (:976).  Per site the prior
-//           conditional N(m_s, 1/Q_ss) is the proposal, so the Metropolis ratio is the likelihood
-//           ratio only.  Replaces the single-chain whole-vector MALA of postZ (R/postZsub.R:393-529).
+//           - z'Qz/2 (R/postZsub.R:431) | y'z - sum e^{xb+z} - z'Qz/2 (:976).  Per site a Metropolis-Hastings
+//           step: two sweeps in three propose from a Gaussian approximation of the site's full conditional
+//           (independence proposal, glm_laplace below), the third from the prior conditional N(m_s, 1/Q_ss),
+//           for which the ratio is the likelihood ratio only.  Replaces the single-chain whole-vector MALA of
+//           postZ (R/postZsub.R:393-529).
 //
 // Parallelisation: chains are independent, so one CTA owns CB chains for the WHOLE run
 // (burn-in, thinning, all kept states) with their state resident in shared memory, [site][CB]
@@ -17,7 +19,8 @@
 // one launch per sample set.  One thread = (site slot, chain pair): the pair's two normals
 // and two uniforms come from ONE Philox4x32-10 call keyed by (seed; site, sweep, global pair
 // id).  Kept states are written site-major ("row = sample" of the R matrix Zy): for every
-// site the CB chains of a CTA form one contiguous run.
+// site the CB chains of a CTA form one contiguous run.  Maps whose neighbour lists fit behind the
+// state keep the graph on chip too (MODE 2: 16-bit neighbour ids, 8-byte position records).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
