@@ -307,6 +307,8 @@ inline long double spectral_sum(const mclcar_ctx* ctx, Fn f) {
 }
 // make sure the context has a spectrum: estimates one on the device when the caller supplied none
 int ensure_spectrum(mclcar_ctx* ctx);
+// sum_i w_i log(1 - rho_k lambda_i) for K values of rho (exact.cu)
+int logdet_sums(mclcar_ctx* ctx, const double* rho, int K, double* out);
 // start of a sampler run: derive this call's Philox key and advance the context's draw counter
 inline uint64_t begin_draw(mclcar_ctx* ctx) {
     ctx->draw_key = ctx->seed + ctx->draw * 0x9E3779B97F4A7C15ull + ctx->draw_salt * 0xD1B54A32D192ED03ull;

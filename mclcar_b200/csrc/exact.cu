@@ -72,11 +72,14 @@ int sigmabeta_one(mclcar_ctx* ctx, double rho, double* out) {
     return MCLCAR_OK;
 }
 
-// sum_i log(1 - rho_k lam_i) for K values of rho: device when available, host otherwise
+}  // namespace
+
+// sum_i log(1 - rho_k lam_i) for K values of rho: on the device when there is one and the sums are long enough to pay
+// for a launch and the upload of the spectrum, on the host otherwise
 int logdet_sums(mclcar_ctx* ctx, const double* rho, int K, double* out) {
     MCL_TRY(ensure_spectrum(ctx));
     const int nn = (int)ctx->eigs.size();
-    if (ctx->host_only || (int64_t)K * nn < 200000) {
+    if (ctx->host_only || (int64_t)K * nn < 20000) {
         for (int k = 0; k < K; ++k)
             out[k] = (double)spectral_sum(ctx, [&](double l) { return (long double)std::log1p(-rho[k] * l); });
         return MCLCAR_OK;
@@ -104,7 +107,6 @@ int logdet_sums(mclcar_ctx* ctx, const double* rho, int K, double* out) {
     return st;
 }
 
-}  // namespace
 }  // namespace mclcar
 
 using namespace mclcar;
