@@ -397,6 +397,23 @@ double sum_lam_ratio(const mclcar_ctx* ctx, double rho, int power) {
         return (long double)(power == 1 ? r : r * r);
     });
 }
+// sum log(1 - rho lam) of every distinct rho of a candidate batch in one go (exact.cu: one device launch when the sums
+// are long) -- half_logdet_Q finds them in ctx->logdet_tab; with n = 5000 sites and 53 candidates the per-candidate
+// host sums were 2.6 ms of a config-3 step.  The table is transient: the guard of the caller that filled it clears it.
+struct LogdetTabGuard {
+    mclcar_ctx* c;
+    bool own;
+    ~LogdetTabGuard() { if (own) c->logdet_tab.clear(); }
+};
+int fill_logdet_tab(mclcar_ctx* ctx, std::vector<double> rhos) {
+    std::sort(rhos.begin(), rhos.end());
+    rhos.erase(std::unique(rhos.begin(), rhos.end()), rhos.end());
+    std::vector<double> ld(rhos.size());
+    MCL_TRY(logdet_sums(ctx, rhos.data(), (int)rhos.size(), ld.data()));
+    ctx->logdet_tab.clear();
+    for (size_t i = 0; i < rhos.size(); ++i) ctx->logdet_tab.emplace_back(rhos[i], (long double)ld[i]);
+    return MCLCAR_OK;
+}
 // psi-independent data constant: sum(sapply(y, lchoose, n = n.trial)) | -sum(lfactorial(y))
 double glm_cterm(const mclcar_ctx* ctx, int fam) {
     const int n = ctx->n;
@@ -615,6 +632,13 @@ static int glm_run(mclcar_ctx* ctx, mclcar_samples* s, const double* psi, int K,
     if (P > MCLCAR_MAX_P) return fail(ctx, MCLCAR_ELIMIT, "P = %d exceeds MCLCAR_MAX_P", P);
     for (int k = 0; k < K; ++k)
         if (!(psi[(size_t)k * P + 1] > 0)) return fail(ctx, MCLCAR_EINVAL, "sigma must be positive (candidate %d)", k);
+    LogdetTabGuard tab_guard{ctx, ctx->logdet_tab.empty()};
+    if (tab_guard.own) {
+        std::vector<double> rhos(K + 1);
+        rhos[0] = s->psi0[0];
+        for (int k = 0; k < K; ++k) rhos[1 + k] = psi[(size_t)k * P];
+        MCL_TRY(fill_logdet_tab(ctx, std::move(rhos)));
+    }
     GlmBatch gb;
     const int mode = what == WHAT_LR ? 0 : (what == WHAT_GRAD ? 1 : 2);
     int st = glm_build_batch(ctx, s, psi, K, P, mode, gb);
@@ -708,14 +732,12 @@ int mclcar_glm_surface(mclcar_ctx* ctx, mclcar_samples* s, const double* rho, in
     const int p = ctx->p, P = 2 + p;
     MCL_TRY(glm_check(ctx, s, P));
     MCL_TRY(need_eigs(ctx));
-    struct TabGuard {
-        mclcar_ctx* c;
-        ~TabGuard() { c->logdet_tab.clear(); }
-    } guard{ctx};
-    ctx->logdet_tab.clear();
-    for (int i = 0; i < nr; ++i)
-        ctx->logdet_tab.emplace_back(rho[i], spectral_sum(ctx, [&](double l) { return (long double)std::log1p(-rho[i] * l); }));
-    std::sort(ctx->logdet_tab.begin(), ctx->logdet_tab.end());
+    LogdetTabGuard guard{ctx, true};
+    {
+        std::vector<double> rhos(rho, rho + nr);
+        rhos.push_back(s->psi0.empty() ? rho[0] : s->psi0[0]);
+        MCL_TRY(fill_logdet_tab(ctx, std::move(rhos)));
+    }
     const int64_t K = (int64_t)nr * ns, chunk = 16384;
     std::vector<double> psi((size_t)std::min(K, chunk) * P);
     for (int64_t k0 = 0; k0 < K; k0 += chunk) {
