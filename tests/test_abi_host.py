@@ -94,6 +94,15 @@ def test_sampler_plan_rules_on_a_host_only_context():
     d2 = api.make_data(np.zeros(400), X=None, torus=(20, 20), ctx=ctx2)
     p2 = api.plan_dCAR([0.2, 1.0], 1000, d2)
     assert p2["sampler"] == "chromatic, chains in shared memory" and p2["chains"] % 2 == 0 and p2["thin"] == 5
+    # chains of the shared-memory sampler follow the schedule: C * burn sweeps are paid before the first kept state and
+    # N * thin after it, so the count is halved from "every SM's shared memory full" (148 SMs x 8 blocks x 16 chains =
+    # 18,944 for 400 sites) while the burn-in is more than half of the kept-state sweeps, never below 4 blocks per SM
+    fill = 148 * 8 * 16
+    for N, want in ((1000, 592), (20_000, 2368), (200_000, fill)):
+        pl = api.plan_dCAR([0.2, 1.0], N, d2)
+        assert pl["chains"] == want
+        assert pl["chains"] == fill or pl["chains"] * pl["burn"] <= N * pl["thin"] / 2 or pl["chains"] == 4 * 148
+    assert api.plan_dCAR([0.2, 1.0], 20_000, d2, {"burn": 400, "thin": 2})["chains"] == 592     # long burn-in: the floor
 
 
 def test_effective_sample_size_of_chain_statistics():
