@@ -381,3 +381,37 @@ def test_draw_counter_bookkeeping():
     assert ctx.draw == 0
     ctx.draw = 5
     assert ctx.draw == 5
+
+
+def test_poisson_hierarchical_algebra_on_the_host():
+    """The identity the Poisson-response hierarchical extension rests on (mclcar_b200/api.py, PoisHcarData), checked without a
+    device: for any district effects u,
+        sum_i [y_i eta_i - e^{eta_i}],  eta_i = x_i'beta + u_{d(i)}
+      = sum_k [Y_k (o_k + u_k) - e^{o_k + u_k}] + c(beta),   o = offset(beta), c = const(beta)
+    -- the data term of the Poisson GLM on the districts with the offset as its linear predictor -- and the offset's
+    derivative is the within-district weighted mean of x the gradient uses."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    K, per = 7, 9
+    n = K * per
+    district = rng.permutation(np.repeat(np.arange(K), per))
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    y = rng.poisson(3.0, n).astype(float)
+    M = sp.diags([np.ones(K - 1), np.ones(K - 1)], [-1, 1]).tocsr()
+    d = api.PoisHcarData(y, X, district, M, ctx=api.Context(device=-1))
+    np.testing.assert_array_equal(d.Y, np.bincount(district, weights=y, minlength=K))
+    for beta in ([0.3, -0.4], [1.5, 0.8], [-2.0, 0.1]):
+        beta = np.array(beta)
+        o = d.offset(beta)
+        np.testing.assert_allclose(np.exp(o), np.bincount(district, weights=np.exp(X @ beta), minlength=K), rtol=1e-13)
+        u = rng.standard_normal(K)
+        eta = X @ beta + u[district]
+        lhs = y @ eta - np.exp(eta).sum()
+        rhs = d.Y @ (o + u) - np.exp(o + u).sum() + d.const(beta, o)
+        assert lhs == pytest.approx(rhs, rel=1e-12)
+        h = 1e-6
+        for l in range(2):
+            e = np.zeros(2); e[l] = h
+            fd = (d.offset(beta + e) - d.offset(beta - e)) / (2 * h)
+            w = np.exp(X @ beta - o[district])
+            np.testing.assert_allclose(fd, np.bincount(district, weights=w * X[:, l], minlength=K), rtol=1e-6, atol=1e-8)
