@@ -742,6 +742,33 @@ int torus_fused2_tile_rows(const mclcar_ctx* ctx, int64_t chains) {
     return TR;
 }
 
+// Tile height of the statistics-forming emitting sweeps.  They run two CTAs per SM (126 registers), so a tile may use
+// up to ~110 KB: taller tiles recompute fewer halo rows and pay the tile load and its barriers less often -- but a
+// phase takes ceil(items / threads) rounds of the CTA, and a height whose last round is nearly empty wastes it.  The
+// height is the one with the fewest rounds per sweep of a chain, one round charged per tile for its load; measured on
+// the 1000 x 1000 lattice (full-size bench, 84 emitting launches per step): 14 rows 0.363 ms per launch, 18 rows 0.355,
+// **22 rows 0.323** (the model's choice), 26 rows do not fit.  MCLCAR_EMIT_TR overrides.
+int torus_stats_tile_rows(const mclcar_ctx* ctx, int tr_default) {
+    const int h = ctx->n2 / 2, G = (h / 4 + 1) / 2, n1 = ctx->n1, threads = 256;
+    auto fits = [&](int tr) { return tr >= 4 && n1 >= tr + 4 && (size_t)(2 * tr + 6) * h * 4 + 1024 <= 110 * 1024; };
+    if (const char* e = getenv("MCLCAR_EMIT_TR")) {
+        const int v = atoi(e) & ~1;
+        return fits(v) ? v : tr_default;
+    }
+    auto rounds = [&](int rows) {   // red phase: rows + 2 rows in pairs; black phase: rows
+        return ((rows + 2) / 2 * G + threads - 1) / threads + (rows / 2 * G + threads - 1) / threads + 1;
+    };
+    int best = tr_default;
+    long best_cost = -1;
+    for (int tr = 64; tr >= 8; tr -= 2) {
+        if (!fits(tr)) continue;
+        const int full = n1 / tr, rest = n1 - full * tr;
+        const long cost = (long)full * rounds(tr) + (rest ? rounds(rest) : 0);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = tr; }
+    }
+    return best;
+}
+
 // `want` >= 2 without emission: two sweeps (sweep, sweep + 1) in one launch where the lattice allows; *done = sweeps made
 int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, double omega, uint32_t sweep,
                 const TorusEmit* emit, int want, int* done) {
@@ -769,7 +796,8 @@ int torus_sweep(mclcar_ctx* ctx, TorusChains& t, double rho, double sigma, doubl
         const bool f32 = !emit || emit->dtype == MCLCAR_F32;
         const bool want_stats = emit && emit->stats_q != nullptr;
         const int TR2 = (want >= 2 && !emit && done) ? torus_fused2_tile_rows(ctx, t.C) : 0;
-        const int TR = TR2 ? TR2 : torus_fused_tile_rows(ctx);
+        int TR = TR2 ? TR2 : torus_fused_tile_rows(ctx);
+        if (TR && !TR2 && want_stats) TR = torus_stats_tile_rows(ctx, TR);
         if (want_stats && (!TR || emit->d_mu || !f32))
             return fail(ctx, MCLCAR_ESTATE, "statistics-only emission needs the fused sweep, a constant mean and fp32 samples");
         if (TR) {
